@@ -1,0 +1,263 @@
+/*
+ * zgml_cuda.h — C-ABI of the B200 (sm_100a) CUDA backend for zgml's
+ * DeviceProgram interface.
+ *
+ * This is the drop-in boundary.  A thin `src/backend/cuda.zig` (see
+ * zig/cuda.zig and INTEGRATION.md) flattens zgml's Zig slices / tagged unions
+ * into the PODs below and forwards the six `Backend.VTable` slots
+ * (reference src/backend.zig:339-352) to the `zg_cuda_*` entry points, exactly
+ * as src/backend/metal.zig wraps src/backend/metal_shim.h.
+ *
+ * Plain pointers and sizes only; no C++ / torch types.  All offsets and strides
+ * are in f32 ELEMENTS unless a field says bytes (ZgIO is bytes, like ProgramIO).
+ */
+#ifndef ZGML_CUDA_H
+#define ZGML_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ── zgml `Op` ordinals (reference src/op.zig:11-61, declaration order) ───── */
+enum {
+    ZG_EW_NONE = 0, ZG_EW_VIEW = 1, ZG_EW_RESHAPE = 2, ZG_EW_TRANSPOSE = 3,
+    ZG_EW_PERMUTE = 4, ZG_EW_AS_STRIDED = 5, ZG_EW_BROADCAST_TO = 6,
+    ZG_EW_ADD = 7, ZG_EW_MUL = 8,
+    ZG_EW_NEG = 9, ZG_EW_ABS = 10, ZG_EW_SGN = 11, ZG_EW_STEP = 12, ZG_EW_RELU = 13,
+    ZG_EW_SQRT = 14, ZG_EW_RECIP = 15, ZG_EW_EXP = 16, ZG_EW_LOG = 17, ZG_EW_GELU = 18,
+    ZG_EW_SUM = 19, ZG_EW_MAX = 20, ZG_EW_REPEAT = 21
+};
+
+/* ── DeviceOp tags (reference src/backend.zig:179-249, union field order) ─── */
+typedef enum ZgOpTag {
+    ZG_OP_ELEMENTWISE = 0,
+    ZG_OP_MATMUL = 1,
+    ZG_OP_QMATMUL = 2,
+    ZG_OP_SOFTMAX = 3,
+    ZG_OP_LAYERNORM = 4,
+    ZG_OP_RMSNORM = 5,
+    ZG_OP_REDUCE = 6,
+    ZG_OP_REPEAT = 7,
+    ZG_OP_SLICE_ASSIGN = 8,
+    ZG_OP_ROPE = 9,
+    ZG_OP_ATTENTION = 10,
+    ZG_OP_FUSED_ELEMENTWISE = 11,
+    ZG_OP_COUNT = 12
+} ZgOpTag;
+
+/* MatMulGeometry — reference src/backend.zig:146-158 (all usize). */
+typedef struct ZgMatMulGeometry {
+    size_t M, N, K;
+    size_t a_row_stride, a_col_stride;
+    size_t b_row_stride, b_col_stride;
+    size_t a_offset, b_offset, dst_offset, dst_row_stride;
+} ZgMatMulGeometry;
+
+/* FusedEwStep — reference src/backend.zig:170-175. */
+typedef struct ZgFusedEwStep {
+    uint32_t op;               /* ZG_EW_* */
+    uint32_t is_swapped;       /* chain value sits in src1 position */
+    uint32_t secondary_buf;    /* u16 in zgml */
+    uint32_t secondary_offset;
+} ZgFusedEwStep;
+
+/* One DeviceOp.  Field names and meaning copied 1:1 from src/backend.zig:180-248;
+ * u16 buffer indices are widened to u32. */
+typedef struct ZgOp {
+    uint32_t tag; /* ZgOpTag */
+    uint32_t _pad;
+    union {
+        struct { uint32_t op, dst, src0, src1, n, dst_offset, src0_offset, src1_offset; } elementwise;
+        struct { uint32_t dst, a, b, _pad; ZgMatMulGeometry geom; } matmul;
+        struct {
+            uint32_t dst, input, weight_idx, M, N, K;
+            uint32_t input_offset, input_row_stride; /* stride 0 => K */
+            uint32_t dst_offset, dst_row_stride;     /* stride 0 => N */
+        } qmatmul;
+        struct { uint32_t dst, src, rows, cols, src_offset, dst_offset; } softmax;
+        struct { uint32_t dst, src, rows, cols; float eps; uint32_t src_offset, dst_offset; } layernorm;
+        struct { uint32_t dst, src, rows, cols; float eps; uint32_t src_offset, dst_offset; } rmsnorm;
+        struct { uint32_t op, dst, src, n_out, reduce_size, src_offset, dst_offset; } reduce;
+        struct {
+            uint32_t dst, src, n;
+            uint32_t src_ne[4], dst_ne[4], src_strides[4], dst_strides[4];
+            uint32_t src_offset, dst_offset;
+        } repeat;
+        struct {
+            uint32_t dst, src, rows, cols;
+            uint32_t dst_base_offset, dst_offset, dst_row_stride, dst_col_stride;
+            uint32_t src_offset, src_row_stride, src_col_stride, patch_stride;
+        } slice_assign;
+        struct {
+            uint32_t dst, src, cos_sin, half_d, seq_len;
+            uint32_t src_off, cs_off, dst_off, src_rs, src_cs, cs_cs;
+        } rope;
+        struct {
+            uint32_t dst, q, k, v, mask, has_mask;
+            uint32_t d_head, seq_q, seq_kv;
+            float scale;
+            uint32_t q_off, k_off, v_off, mask_off, dst_off;
+            uint32_t q_rs, q_cs, k_rs, k_cs, v_rs, v_cs, mask_rs, mask_cs, dst_rs, dst_cs;
+        } attention;
+        struct {
+            const ZgFusedEwStep* steps;
+            size_t n_steps;
+            uint32_t n, dst, src, dst_offset, src_offset;
+        } fused_elementwise;
+    } u;
+} ZgOp;
+
+/* ProgramIO — reference src/backend.zig:252-257.  offset/size in BYTES. */
+typedef struct ZgIO {
+    uint32_t buf_idx;
+    uint32_t offset;
+    void* host_ptr;
+    uint32_t size;
+    uint32_t _pad;
+} ZgIO;
+
+/* QuantizedWeightUpload — reference src/backend.zig:260-266.
+ * data: i8 [rows*cols] row-major [K=rows, N=cols]; scales: f32, one per
+ * `block_size` consecutive FLAT elements (scale index = (k*N+n)/block_size,
+ * reference src/quant.zig:525, src/backend/reference.zig:547). */
+typedef struct ZgQWeight {
+    const int8_t* data;
+    size_t n_data;
+    const float* scales;
+    size_t n_scales;
+    size_t rows, cols, block_size;
+} ZgQWeight;
+
+/* DeviceProgram — reference src/backend.zig:270-275. buffer_sizes in f32 elements. */
+typedef struct ZgProgram {
+    const ZgOp* ops;
+    size_t n_ops;
+    size_t n_buffers;
+    const size_t* buffer_sizes;
+    const ZgIO* initial_uploads;
+    size_t n_uploads;
+    const ZgQWeight* qweights;
+    size_t n_qweights;
+} ZgProgram;
+
+/* Subset of RuntimeProfile (reference src/profile.zig:819-842) that a CUDA
+ * backend can fill: per-tag device time + counters. */
+typedef struct ZgProfile {
+    uint64_t time_ns[ZG_OP_COUNT];
+    uint64_t backend_op_count;
+    uint64_t fallback_op_count;     /* always 0: there is no CPU fallback */
+    uint64_t backend_dispatch_count; /* kernels / graph launches issued */
+    uint64_t sync_time_ns;
+    uint64_t sync_count;
+    uint32_t call_count;
+    uint32_t _pad;
+} ZgProfile;
+
+/* Capabilities to advertise (reference src/backend.zig:14-70). */
+typedef struct ZgCapabilities {
+    uint32_t compiled_programs, host_visible_program_memory, dense_matmul_f32, dense_matmul_f16;
+    uint32_t qmatmul, fused_elementwise, max_fused_elementwise_steps /* 0 = unlimited */;
+    uint32_t dynamic_program_refresh, prefill_attention, decode_attention, quantized_kv;
+    uint32_t attention_supported, attention_max_seq_kv /* 0 = unlimited */, attention_max_d_head;
+} ZgCapabilities;
+
+typedef struct ZgCudaCtx ZgCudaCtx;
+typedef struct ZgCudaProgram ZgCudaProgram;
+
+/* ── The six vtable slots + lifecycle ─────────────────────────────────────── */
+
+/* Backend construction (MetalBackend.init analogue, src/backend/metal.zig).
+ * NULL when no CUDA device / wrong arch; see zg_cuda_last_error(). */
+ZgCudaCtx* zg_cuda_create(int device_ordinal);
+void zg_cuda_destroy(ZgCudaCtx* ctx);
+void zg_cuda_capabilities(ZgCapabilities* out);
+
+/* VTable.dense_matmul_f32 (src/backend.zig:341): host-pointer GEMM override
+ * during graph execution.  Always declines (returns 0) like the fake backend in
+ * src/device_inference.zig:750-752: host tensors are not device resident. */
+int zg_cuda_dense_matmul_f32(ZgCudaCtx* ctx, float* dst, const float* a, const float* b,
+                             const ZgMatMulGeometry* geom);
+
+/* VTable.compile_program (src/backend.zig:343): allocate zero-filled device
+ * buffers, apply initial_uploads, copy+repack every qweight into its
+ * GPU-resident packed layout, copy the op list.  NULL on any failure. */
+ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* program);
+
+/* VTable.refresh_program (src/backend.zig:345): caller's op array after
+ * patchSliceAssignOffset / patchAttentionSeqKV (src/device_inference.zig:242-256). */
+void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* prog, const ZgOp* ops, size_t n_ops);
+
+/* VTable.execute_program (src/backend.zig:347): upload inputs, run all ops in
+ * order, download outputs.  Synchronous: outputs valid on return. */
+void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* prog, const ZgIO* inputs, size_t n_inputs,
+                     const ZgIO* outputs, size_t n_outputs);
+
+/* VTable.free_program (src/backend.zig:349). */
+void zg_cuda_free(ZgCudaCtx* ctx, ZgCudaProgram* prog);
+
+/* VTable.get_runtime_profile (src/backend.zig:351). Enabled with
+ * zg_cuda_set_profiling(ctx, 1); NULL otherwise. */
+const ZgProfile* zg_cuda_profile(ZgCudaCtx* ctx, ZgCudaProgram* prog);
+void zg_cuda_set_profiling(ZgCudaCtx* ctx, int enabled);
+
+/* Error convention: NULL / no-op on failure plus this thread-unsafe string. */
+const char* zg_cuda_last_error(void);
+
+/* ── Extensions used by tests / bench (not vtable slots) ──────────────────── */
+
+/* Run work on a caller-owned stream (e.g. torch's) instead of the ctx's own. */
+void zg_cuda_set_stream(ZgCudaCtx* ctx, void* cuda_stream);
+void zg_cuda_sync(ZgCudaCtx* ctx);
+/* Kernels launched by this library since process start (claim for gpu_launches). */
+uint64_t zg_cuda_launch_count(void);
+/* 0: eager launches; 1 (default): capture the op list into a CUDA graph. */
+void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int enabled);
+/* Device pointer of program buffer `buf_idx` (for device-resident benches). */
+void* zg_cuda_program_buffer(ZgCudaProgram* prog, uint32_t buf_idx);
+/* Run the program's ops with no host<->device copies (inputs already resident);
+ * asynchronous on the ctx stream. */
+void zg_cuda_execute_device(ZgCudaCtx* ctx, ZgCudaProgram* prog);
+
+/* Packed, GPU-resident quantized weight (the src/quant.zig QuantizedWeight
+ * analogue).  Residency format is chosen losslessly at upload:
+ *   ZG_QFMT_I8_F32  36 B / 32 weights  (native fromSlice output)
+ *   ZG_QFMT_I8_F16  34 B / 32 weights  (every scale is exactly an f16: Q8_0 origin)
+ *   ZG_QFMT_I4_F16  18 B / 32 weights  (additionally all q in [-8,7]: Q4_0 origin)
+ *   ZG_QFMT_GENERIC block_size != 32 or N % 32 != 0: flat i8 + f32 scales */
+enum { ZG_QFMT_AUTO = 0, ZG_QFMT_I8_F32 = 1, ZG_QFMT_I8_F16 = 2, ZG_QFMT_I4_F16 = 3, ZG_QFMT_GENERIC = 4 };
+typedef struct ZgCudaQWeight ZgCudaQWeight;
+
+ZgCudaQWeight* zg_cuda_qweight_upload(ZgCudaCtx* ctx, const ZgQWeight* w, int fmt_hint);
+/* Direct GGUF block upload (reference src/models/gguf_loader.zig:99-154 done on
+ * device): raw = n_blocks * 34 B (ggml_type 8 = Q8_0) or 18 B (2 = Q4_0);
+ * rows = dims[0] = K, cols = dims[1] = N, zgml nibble order. */
+ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void* raw, size_t raw_bytes,
+                                           uint32_t ggml_type, size_t rows, size_t cols);
+void zg_cuda_qweight_free(ZgCudaCtx* ctx, ZgCudaQWeight* w);
+int zg_cuda_qweight_format(const ZgCudaQWeight* w);
+size_t zg_cuda_qweight_device_bytes(const ZgCudaQWeight* w);
+/* dequantizeTo (src/quant.zig:594-618) from the packed residency: host_dst gets
+ * rows*cols f32, bit-exact with the reference.  Returns 0 on success. */
+int zg_cuda_qweight_dequantize(ZgCudaCtx* ctx, const ZgCudaQWeight* w, float* host_dst);
+/* QuantizedWeight.matmul (src/quant.zig:475-578) with the DeviceOp.qmatmul
+ * stride contract, on DEVICE pointers; async on the ctx stream. */
+int zg_cuda_qmatmul_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_input,
+                           float* d_dst, uint32_t M, uint32_t input_row_stride,
+                           uint32_t dst_row_stride);
+/* Same through HOST buffers (copies inside): the e2e leg. Synchronous. */
+int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input,
+                         float* h_dst, uint32_t M);
+
+void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes);
+void zg_cuda_free_device(ZgCudaCtx* ctx, void* p);
+int zg_cuda_memcpy_h2d(ZgCudaCtx* ctx, void* d, const void* h, size_t bytes);
+int zg_cuda_memcpy_d2h(ZgCudaCtx* ctx, void* h, const void* d, size_t bytes);
+int zg_cuda_memset(ZgCudaCtx* ctx, void* d, int value, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZGML_CUDA_H */

@@ -1,0 +1,464 @@
+// C-ABI entry points: backend context, compiled DevicePrograms (device-resident
+// buffers + packed weights + CUDA-graph replay) and the direct quantized-matmul
+// calls.  Mirrors the Backend vtable contract of src/backend.zig:330-352 the way
+// src/backend/cpu.zig:55-147 implements it for the CPU.
+#include "zg_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+
+std::atomic<uint64_t> g_zg_launches{0};
+static char g_err[1024] = "";
+
+void zg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* zg_cuda_last_error(void) { return g_err; }
+extern "C" uint64_t zg_cuda_launch_count(void) { return g_zg_launches.load(); }
+
+bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cudaStream_t st) {
+    if (partial_elems > ws->partials_elems) {
+        if (ws->partials) { cudaStreamSynchronize(st); cudaFree(ws->partials); ws->partials = nullptr; }
+        ZG_CUDA_OK(cudaMalloc(&ws->partials, partial_elems * sizeof(float)));
+        ws->partials_elems = partial_elems;
+    }
+    if (counters > ws->counters_n) {
+        if (ws->counters) { cudaStreamSynchronize(st); cudaFree(ws->counters); ws->counters = nullptr; }
+        ZG_CUDA_OK(cudaMalloc(&ws->counters, counters * sizeof(uint32_t)));
+        ZG_CUDA_OK(cudaMemsetAsync(ws->counters, 0, counters * sizeof(uint32_t), st));
+        ZG_CUDA_OK(cudaStreamSynchronize(st));
+        ws->counters_n = counters;
+    }
+    return true;
+}
+void zg_gemv_ws_free(ZgGemvWs* ws) {
+    cudaFree(ws->partials); cudaFree(ws->counters);
+    *ws = ZgGemvWs();
+}
+
+struct ZgCudaProgram {
+    ZgCudaCtx* ctx = nullptr;
+    std::vector<ZgOp> ops;
+    std::vector<std::vector<ZgFusedEwStep>> steps; // owned copies, per op (empty unless fused)
+    std::vector<uint32_t> step_off;                // offset into d_steps per op
+    std::vector<float*> buffers;
+    std::vector<size_t> buffer_elems;
+    std::vector<ZgCudaQWeight*> qweights;
+    ZgDevStep* d_steps = nullptr;
+    uint32_t* d_dyn = nullptr;
+    uint32_t* h_dyn = nullptr; // pinned
+    ZgGemvWs ws;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool graph_valid = false;
+    ZgProfile profile;
+    std::vector<cudaEvent_t> prof_events;
+};
+
+// ── context ──────────────────────────────────────────────────────────────────
+extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { zg_set_error("no CUDA device available"); return nullptr; }
+    if (device_ordinal < 0 || device_ordinal >= n) { zg_set_error("device ordinal %d out of range (%d devices)", device_ordinal, n); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { zg_set_error("cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major != 10) { // kernels are built for sm_100a only; no other code path exists
+        zg_set_error("device %d is sm_%d%d; this backend is built for sm_100a (B200) only", device_ordinal, prop.major, prop.minor);
+        return nullptr;
+    }
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) { zg_set_error("cudaSetDevice failed"); return nullptr; }
+    ZgCudaCtx* ctx = new ZgCudaCtx();
+    ctx->device = device_ordinal;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
+    }
+    if (!zg_qgemv_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
+    return ctx;
+}
+
+extern "C" void zg_cuda_destroy(ZgCudaCtx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    zg_gemv_ws_free(&ctx->ws);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void zg_cuda_capabilities(ZgCapabilities* c) {
+    // modelled on Capabilities.reference_cpu (src/backend.zig:60-70) minus host-visible memory
+    memset(c, 0, sizeof(*c));
+    c->compiled_programs = 1; c->host_visible_program_memory = 0;
+    c->dense_matmul_f32 = 1; c->qmatmul = 1; c->fused_elementwise = 1; c->max_fused_elementwise_steps = 0;
+    c->dynamic_program_refresh = 1; c->prefill_attention = 1; c->decode_attention = 1;
+    c->attention_supported = 1; c->attention_max_seq_kv = 0; c->attention_max_d_head = 512;
+}
+
+extern "C" int zg_cuda_dense_matmul_f32(ZgCudaCtx*, float*, const float*, const float*, const ZgMatMulGeometry*) {
+    return 0; // decline: host tensors are not device resident
+}
+
+extern "C" void zg_cuda_set_stream(ZgCudaCtx* ctx, void* s) {
+    if (!ctx) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s;
+    ctx->owns_stream = false;
+}
+extern "C" void zg_cuda_sync(ZgCudaCtx* ctx) { if (ctx) cudaStreamSynchronize(ctx->stream); }
+extern "C" void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int e) { if (ctx) ctx->graph_mode = e != 0; }
+extern "C" void zg_cuda_set_profiling(ZgCudaCtx* ctx, int e) { if (ctx) ctx->profiling = e != 0; }
+
+// ── program ──────────────────────────────────────────────────────────────────
+static bool op_buffers_valid(const ZgOp& op, size_t nb) { // src/backend.zig:303-325
+    auto ok = [&](uint32_t i) { return (size_t)i < nb; };
+    switch (op.tag) {
+        case ZG_OP_ELEMENTWISE: return ok(op.u.elementwise.dst) && ok(op.u.elementwise.src0) && ok(op.u.elementwise.src1);
+        case ZG_OP_MATMUL: return ok(op.u.matmul.dst) && ok(op.u.matmul.a) && ok(op.u.matmul.b);
+        case ZG_OP_QMATMUL: return ok(op.u.qmatmul.dst) && ok(op.u.qmatmul.input);
+        case ZG_OP_SOFTMAX: return ok(op.u.softmax.dst) && ok(op.u.softmax.src);
+        case ZG_OP_LAYERNORM: return ok(op.u.layernorm.dst) && ok(op.u.layernorm.src);
+        case ZG_OP_RMSNORM: return ok(op.u.rmsnorm.dst) && ok(op.u.rmsnorm.src);
+        case ZG_OP_REDUCE: return ok(op.u.reduce.dst) && ok(op.u.reduce.src);
+        case ZG_OP_REPEAT: return ok(op.u.repeat.dst) && ok(op.u.repeat.src);
+        case ZG_OP_SLICE_ASSIGN: return ok(op.u.slice_assign.dst) && ok(op.u.slice_assign.src);
+        case ZG_OP_ROPE: return ok(op.u.rope.dst) && ok(op.u.rope.src) && ok(op.u.rope.cos_sin);
+        case ZG_OP_ATTENTION:
+            return ok(op.u.attention.dst) && ok(op.u.attention.q) && ok(op.u.attention.k) && ok(op.u.attention.v) && ok(op.u.attention.mask);
+        case ZG_OP_FUSED_ELEMENTWISE: {
+            if (!ok(op.u.fused_elementwise.dst) || !ok(op.u.fused_elementwise.src)) return false;
+            for (size_t s = 0; s < op.u.fused_elementwise.n_steps; s++) {
+                const ZgFusedEwStep& st = op.u.fused_elementwise.steps[s];
+                if ((st.op == ZG_EW_ADD || st.op == ZG_EW_MUL) && !ok(st.secondary_buf)) return false;
+            }
+            return true;
+        }
+        default: return false;
+    }
+}
+
+static uint32_t op_dyn_value(const ZgOp& op) {
+    if (op.tag == ZG_OP_SLICE_ASSIGN) return op.u.slice_assign.dst_offset;
+    if (op.tag == ZG_OP_ATTENTION) return op.u.attention.seq_kv;
+    return 0;
+}
+
+static void free_program(ZgCudaProgram* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->exec) cudaGraphExecDestroy(p->exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    for (float* b : p->buffers) cudaFree(b);
+    for (ZgCudaQWeight* w : p->qweights) zg_cuda_qweight_free(p->ctx, w);
+    cudaFree(p->d_steps); cudaFree(p->d_dyn);
+    if (p->h_dyn) cudaFreeHost(p->h_dyn);
+    zg_gemv_ws_free(&p->ws);
+    for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    delete p;
+}
+
+// (Re)build the device-side fused-step table from p->ops / p->steps.
+static bool upload_steps(ZgCudaProgram* p) {
+    std::vector<ZgDevStep> flat;
+    p->step_off.assign(p->ops.size(), 0);
+    for (size_t i = 0; i < p->ops.size(); i++) {
+        if (p->ops[i].tag != ZG_OP_FUSED_ELEMENTWISE) continue;
+        p->step_off[i] = (uint32_t)flat.size();
+        for (const ZgFusedEwStep& st : p->steps[i]) {
+            ZgDevStep d;
+            d.op = st.op; d.is_swapped = st.is_swapped; d.sec = nullptr;
+            if (st.op == ZG_EW_ADD || st.op == ZG_EW_MUL) d.sec = p->buffers[st.secondary_buf] + st.secondary_offset;
+            flat.push_back(d);
+        }
+    }
+    cudaFree(p->d_steps); p->d_steps = nullptr;
+    if (!flat.empty()) {
+        ZG_CUDA_OK(cudaMalloc(&p->d_steps, flat.size() * sizeof(ZgDevStep)));
+        ZG_CUDA_OK(cudaMemcpy(p->d_steps, flat.data(), flat.size() * sizeof(ZgDevStep), cudaMemcpyHostToDevice));
+    }
+    return true;
+}
+
+static bool adopt_ops(ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) {
+    p->ops.assign(ops, ops + n_ops);
+    p->steps.assign(n_ops, {});
+    for (size_t i = 0; i < n_ops; i++) {
+        if (ops[i].tag == ZG_OP_FUSED_ELEMENTWISE) {
+            const auto& f = ops[i].u.fused_elementwise;
+            p->steps[i].assign(f.steps, f.steps + f.n_steps);
+            p->ops[i].u.fused_elementwise.steps = p->steps[i].data();
+        }
+    }
+    return true;
+}
+
+static bool validate_ops(const ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) {
+    for (size_t i = 0; i < n_ops; i++) {
+        if (!op_buffers_valid(ops[i], p->buffers.size())) { zg_set_error("op %zu: invalid tag or buffer index", i); return false; }
+        if (ops[i].tag == ZG_OP_QMATMUL) { // src/backend.zig:284-292
+            const auto& q = ops[i].u.qmatmul;
+            if ((size_t)q.weight_idx >= p->qweights.size()) { zg_set_error("op %zu: weight_idx out of range", i); return false; }
+            const ZgCudaQWeight* w = p->qweights[q.weight_idx];
+            if (w->K != q.K || w->N != q.N) { zg_set_error("op %zu: qweight is [%zu,%zu], op wants [%u,%u]", i, w->K, w->N, q.K, q.N); return false; }
+        }
+        if (ops[i].tag == ZG_OP_ATTENTION && ops[i].u.attention.d_head > 512) { zg_set_error("op %zu: d_head > 512", i); return false; }
+    }
+    return true;
+}
+
+static bool reserve_workspace(ZgCudaProgram* p) {
+    size_t pe = 0, nc = 0;
+    for (const ZgOp& op : p->ops) {
+        if (op.tag != ZG_OP_QMATMUL) continue;
+        size_t a = 0, b = 0;
+        zg_qgemv_ws_need(p->ctx, p->qweights[op.u.qmatmul.weight_idx], op.u.qmatmul.M, &a, &b);
+        if (a > pe) pe = a;
+        if (b > nc) nc = b;
+    }
+    return zg_gemv_ws_reserve(&p->ws, pe, nc, p->ctx->stream);
+}
+
+extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog) {
+    if (!ctx || !prog) { zg_set_error("compile: null argument"); return nullptr; }
+    if (prog->n_buffers > 65535) { zg_set_error("compile: more than 65535 buffers"); return nullptr; }
+    cudaSetDevice(ctx->device);
+    ZgCudaProgram* p = new ZgCudaProgram();
+    p->ctx = ctx;
+    memset(&p->profile, 0, sizeof(p->profile));
+    // buffers: max(size,1) f32, zero-filled (src/backend/reference.zig:89-93)
+    p->buffers.assign(prog->n_buffers, nullptr);
+    p->buffer_elems.assign(prog->n_buffers, 0);
+    for (size_t i = 0; i < prog->n_buffers; i++) {
+        size_t n = prog->buffer_sizes[i] > 1 ? prog->buffer_sizes[i] : 1;
+        size_t bytes = (n * sizeof(float) + 15) & ~(size_t)15;
+        if (cudaMalloc(&p->buffers[i], bytes) != cudaSuccess) {
+            zg_set_error("compile: cudaMalloc(%zu B) for buffer %zu failed", bytes, i);
+            free_program(p); return nullptr;
+        }
+        cudaMemsetAsync(p->buffers[i], 0, bytes, ctx->stream);
+        p->buffer_elems[i] = n;
+    }
+    for (size_t i = 0; i < prog->n_uploads; i++) {
+        const ZgIO& io = prog->initial_uploads[i];
+        if (io.buf_idx >= prog->n_buffers || (size_t)io.offset + io.size > p->buffer_elems[io.buf_idx] * sizeof(float)) {
+            zg_set_error("compile: initial upload %zu out of range", i);
+            free_program(p); return nullptr;
+        }
+        cudaMemcpyAsync((uint8_t*)p->buffers[io.buf_idx] + io.offset, io.host_ptr, io.size, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { zg_set_error("compile: buffer initialisation failed"); free_program(p); return nullptr; }
+    for (size_t i = 0; i < prog->n_qweights; i++) {
+        ZgCudaQWeight* w = zg_cuda_qweight_upload(ctx, &prog->qweights[i], ZG_QFMT_AUTO);
+        if (!w) { free_program(p); return nullptr; }
+        p->qweights.push_back(w);
+    }
+    if (!validate_ops(p, prog->ops, prog->n_ops) || !adopt_ops(p, prog->ops, prog->n_ops) || !upload_steps(p) ||
+        !reserve_workspace(p)) {
+        free_program(p); return nullptr;
+    }
+    size_t nd = prog->n_ops ? prog->n_ops : 1;
+    if (cudaMalloc(&p->d_dyn, nd * 4) != cudaSuccess || cudaMallocHost(&p->h_dyn, nd * 4) != cudaSuccess) {
+        zg_set_error("compile: dyn table allocation failed"); free_program(p); return nullptr;
+    }
+    for (size_t i = 0; i < prog->n_ops; i++) p->h_dyn[i] = op_dyn_value(p->ops[i]);
+    return p;
+}
+
+extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) {
+    if (!ctx || !p || !ops) return;
+    bool structural = (n_ops != p->ops.size());
+    if (!structural) {
+        for (size_t i = 0; i < n_ops && !structural; i++) {
+            const ZgOp& old = p->ops[i];
+            if (ops[i].tag != old.tag) { structural = true; break; }
+            ZgOp tmp = ops[i];
+            if (tmp.tag == ZG_OP_SLICE_ASSIGN) tmp.u.slice_assign.dst_offset = old.u.slice_assign.dst_offset;
+            else if (tmp.tag == ZG_OP_ATTENTION) tmp.u.attention.seq_kv = old.u.attention.seq_kv;
+            else if (tmp.tag == ZG_OP_FUSED_ELEMENTWISE) {
+                const auto& f = ops[i].u.fused_elementwise;
+                if (f.n_steps != p->steps[i].size() ||
+                    (f.n_steps && memcmp(f.steps, p->steps[i].data(), f.n_steps * sizeof(ZgFusedEwStep)) != 0)) { structural = true; break; }
+                tmp.u.fused_elementwise.steps = old.u.fused_elementwise.steps;
+            }
+            if (memcmp(&tmp, &old, sizeof(ZgOp)) != 0) structural = true;
+        }
+    }
+    if (structural) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (!validate_ops(p, ops, n_ops)) return; // keep the previous op list; error string set
+        adopt_ops(p, ops, n_ops);
+        upload_steps(p);
+        reserve_workspace(p);
+        cudaFree(p->d_dyn); cudaFreeHost(p->h_dyn); p->d_dyn = nullptr; p->h_dyn = nullptr;
+        size_t nd = n_ops ? n_ops : 1;
+        cudaMalloc(&p->d_dyn, nd * 4); cudaMallocHost(&p->h_dyn, nd * 4);
+        p->graph_valid = false;
+    }
+    for (size_t i = 0; i < n_ops; i++) {
+        uint32_t v = op_dyn_value(ops[i]);
+        p->h_dyn[i] = v;
+        if (ops[i].tag == ZG_OP_SLICE_ASSIGN) p->ops[i].u.slice_assign.dst_offset = v;
+        else if (ops[i].tag == ZG_OP_ATTENTION) p->ops[i].u.attention.seq_kv = v;
+    }
+}
+
+static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
+    ZgCudaCtx* ctx = p->ctx;
+    size_t n = p->ops.size();
+    if (profile && p->prof_events.size() < n + 1) {
+        while (p->prof_events.size() < n + 1) { cudaEvent_t e; cudaEventCreate(&e); p->prof_events.push_back(e); }
+    }
+    if (profile) cudaEventRecord(p->prof_events[0], st);
+    for (size_t i = 0; i < n; i++) {
+        const ZgOp& op = p->ops[i];
+        bool ok;
+        if (op.tag == ZG_OP_QMATMUL) {
+            const auto& q = op.u.qmatmul;
+            ok = zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
+                                   p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &p->ws, st);
+        } else {
+            ok = zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
+        }
+        if (!ok) return false;
+        if (profile) cudaEventRecord(p->prof_events[i + 1], st);
+    }
+    return true;
+}
+
+static bool run_ops(ZgCudaProgram* p) {
+    ZgCudaCtx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    size_t n = p->ops.size();
+    if (n == 0) return true;
+    ZG_CUDA_OK(cudaMemcpyAsync(p->d_dyn, p->h_dyn, n * 4, cudaMemcpyHostToDevice, st));
+    if (ctx->profiling) {
+        if (!launch_all(p, st, true)) return false;
+        ZG_CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p->prof_events[i], p->prof_events[i + 1]);
+            p->profile.time_ns[p->ops[i].tag] += (uint64_t)(ms * 1e6);
+        }
+        p->profile.backend_op_count += n;
+        p->profile.backend_dispatch_count += n;
+        p->profile.call_count += 1;
+        return true;
+    }
+    if (!ctx->graph_mode) return launch_all(p, st, false);
+    if (!p->graph_valid) {
+        if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+        if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
+        ZG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        bool ok = launch_all(p, st, false);
+        cudaError_t e = cudaStreamEndCapture(st, &p->graph);
+        if (!ok) { if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; } return false; }
+        if (e != cudaSuccess) { zg_set_error("graph capture failed: %s", cudaGetErrorString(e)); return false; }
+        ZG_CUDA_OK(cudaGraphInstantiate(&p->exec, p->graph, 0));
+        p->graph_valid = true;
+    }
+    ZG_CUDA_OK(cudaGraphLaunch(p->exec, st));
+    return true;
+}
+
+extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in, size_t n_in, const ZgIO* out, size_t n_out) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    for (size_t i = 0; i < n_in; i++) {
+        const ZgIO& io = in[i];
+        if (io.buf_idx >= p->buffers.size() || (size_t)io.offset + io.size > p->buffer_elems[io.buf_idx] * sizeof(float)) {
+            zg_set_error("execute: input %zu out of range", i); return; // reference asserts (reference.zig:116)
+        }
+        cudaMemcpyAsync((uint8_t*)p->buffers[io.buf_idx] + io.offset, io.host_ptr, io.size, cudaMemcpyHostToDevice, st);
+    }
+    if (!run_ops(p)) { cudaStreamSynchronize(st); return; }
+    for (size_t i = 0; i < n_out; i++) {
+        const ZgIO& io = out[i];
+        if (io.buf_idx >= p->buffers.size() || (size_t)io.offset + io.size > p->buffer_elems[io.buf_idx] * sizeof(float)) {
+            zg_set_error("execute: output %zu out of range", i); continue;
+        }
+        cudaMemcpyAsync(io.host_ptr, (uint8_t*)p->buffers[io.buf_idx] + io.offset, io.size, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) zg_set_error("execute: %s", cudaGetErrorString(e));
+}
+
+extern "C" void zg_cuda_execute_device(ZgCudaCtx* ctx, ZgCudaProgram* p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    run_ops(p);
+}
+
+extern "C" void zg_cuda_free(ZgCudaCtx* ctx, ZgCudaProgram* p) { (void)ctx; free_program(p); }
+
+extern "C" const ZgProfile* zg_cuda_profile(ZgCudaCtx* ctx, ZgCudaProgram* p) {
+    if (!ctx || !p || !ctx->profiling) return nullptr;
+    return &p->profile;
+}
+
+extern "C" void* zg_cuda_program_buffer(ZgCudaProgram* p, uint32_t idx) {
+    if (!p || idx >= p->buffers.size()) return nullptr;
+    return p->buffers[idx];
+}
+
+// ── direct quantized matmul calls ────────────────────────────────────────────
+extern "C" int zg_cuda_qmatmul_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_input, float* d_dst,
+                                      uint32_t M, uint32_t input_row_stride, uint32_t dst_row_stride) {
+    if (!ctx || !w) { zg_set_error("qmatmul_device: null argument"); return -1; }
+    cudaSetDevice(ctx->device);
+    size_t pe = 0, nc = 0;
+    zg_qgemv_ws_need(ctx, w, M, &pe, &nc);
+    if (!zg_gemv_ws_reserve(&ctx->ws, pe, nc, ctx->stream)) return -1;
+    return zg_qmatmul_launch(ctx, w, d_input, d_dst, M, input_row_stride, dst_row_stride, &ctx->ws, ctx->stream) ? 0 : -1;
+}
+
+extern "C" int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, float* h_dst, uint32_t M) {
+    if (!ctx || !w) { zg_set_error("qmatmul_host: null argument"); return -1; }
+    cudaSetDevice(ctx->device);
+    float *d_in = nullptr, *d_out = nullptr;
+    size_t in_b = (size_t)M * w->K * 4, out_b = (size_t)M * w->N * 4;
+    if (cudaMalloc(&d_in, in_b ? in_b : 4) != cudaSuccess || cudaMalloc(&d_out, out_b ? out_b : 4) != cudaSuccess) {
+        zg_set_error("qmatmul_host: cudaMalloc failed"); cudaFree(d_in); cudaFree(d_out); return -1;
+    }
+    cudaMemcpyAsync(d_in, h_input, in_b, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = zg_cuda_qmatmul_device(ctx, w, d_in, d_out, M, 0, 0);
+    cudaMemcpyAsync(h_dst, d_out, out_b, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { zg_set_error("qmatmul_host: %s", cudaGetErrorString(e)); return -1; }
+    return rc;
+}
+
+// ── raw device memory helpers for tests / bench ──────────────────────────────
+extern "C" void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { zg_set_error("cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+extern "C" void zg_cuda_free_device(ZgCudaCtx* ctx, void* p) { if (ctx) cudaSetDevice(ctx->device); cudaFree(p); }
+extern "C" int zg_cuda_memcpy_h2d(ZgCudaCtx* ctx, void* d, const void* h, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { zg_set_error("memcpy_h2d: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+extern "C" int zg_cuda_memcpy_d2h(ZgCudaCtx* ctx, void* h, const void* d, size_t bytes) {
+    cudaError_t e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { zg_set_error("memcpy_d2h: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
+extern "C" int zg_cuda_memset(ZgCudaCtx* ctx, void* d, int value, size_t bytes) {
+    cudaError_t e = cudaMemsetAsync(d, value, bytes, ctx->stream);
+    if (e != cudaSuccess) { zg_set_error("memset: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}

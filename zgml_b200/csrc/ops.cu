@@ -1,0 +1,426 @@
+// The non-quantized DeviceOps a compiled zgml program contains around the
+// qmatmul anchors (elementwise, fused chains, softmax, layernorm, rmsnorm, reduce,
+// repeat, slice_assign, rope, attention, dense matmul).  Semantics follow the
+// reference executor, src/backend/reference.zig:201-497,568-672, op by op.
+//
+// Two fields change between executions (src/device_inference.zig:242-256):
+// slice_assign.dst_offset and attention.seq_kv.  They are read from a small
+// device array `dyn[op_index]` so the whole op list can live in one CUDA graph.
+#include "zg_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <bool IS_MAX>
+__device__ float block_reduce(float v, float* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = IS_MAX ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = IS_MAX ? -INFINITY : 0.0f;
+    for (int i = 0; i < nw; i++) r = IS_MAX ? fmaxf(r, sh[i]) : r + sh[i];
+    return r;
+}
+
+__device__ __forceinline__ float gelu_tanh(float a) { // reference.zig:265-269
+    float kk = 0.7978845608f * (a + 0.044715f * a * a * a);
+    return 0.5f * a * (1.0f + tanhf(kk));
+}
+
+__device__ __forceinline__ float apply_unary(uint32_t op, float v) {
+    switch (op) {
+        case ZG_EW_NEG: return -v;
+        case ZG_EW_ABS: return fabsf(v);
+        case ZG_EW_RELU: return fmaxf(v, 0.0f);
+        case ZG_EW_SQRT: return sqrtf(v);
+        case ZG_EW_RECIP: return 1.0f / v;
+        case ZG_EW_EXP: return expf(v);
+        case ZG_EW_LOG: return logf(v);
+        case ZG_EW_GELU: return gelu_tanh(v);
+        default: return v; // sgn/step/others: reference copies src0 / leaves v unchanged
+    }
+}
+
+__global__ void k_elementwise(uint32_t op, float* __restrict__ dst, const float* __restrict__ s0,
+                              const float* __restrict__ s1, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float a = s0[i];
+        float r;
+        if (op == ZG_EW_ADD) r = a + s1[i];
+        else if (op == ZG_EW_MUL) r = a * s1[i];
+        else r = apply_unary(op, a);
+        dst[i] = r;
+    }
+}
+
+__global__ void k_fused_elementwise(const ZgDevStep* __restrict__ steps, uint32_t n_steps,
+                                    float* __restrict__ dst, const float* __restrict__ src, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = src[i];
+        for (uint32_t s = 0; s < n_steps; s++) {
+            const ZgDevStep st = steps[s];
+            if (st.op == ZG_EW_ADD) { float o = st.sec[i]; v = st.is_swapped ? o + v : v + o; }
+            else if (st.op == ZG_EW_MUL) { float o = st.sec[i]; v = st.is_swapped ? o * v : v * o; }
+            else v = apply_unary(st.op, v);
+        }
+        dst[i] = v;
+    }
+}
+
+// one block per row
+__global__ void k_softmax(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols) {
+    __shared__ float sh[32];
+    const float* s = src + (size_t)blockIdx.x * cols;
+    float* d = dst + (size_t)blockIdx.x * cols;
+    float m = -INFINITY;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) m = fmaxf(m, s[j]);
+    m = block_reduce<true>(m, sh);
+    float sum = 0.0f;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) sum += expf(s[j] - m);
+    sum = block_reduce<false>(sum, sh);
+    float inv = sum > 0.0f ? 1.0f / sum : 0.0f;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) d[j] = expf(s[j] - m) * inv;
+}
+
+__global__ void k_layernorm(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols, float eps) {
+    __shared__ float sh[32];
+    const float* s = src + (size_t)blockIdx.x * cols;
+    float* d = dst + (size_t)blockIdx.x * cols;
+    float mu = 0.0f;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) mu += s[j];
+    mu = block_reduce<false>(mu, sh) / (float)cols;
+    float v = 0.0f;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) { float df = s[j] - mu; v += df * df; }
+    v = block_reduce<false>(v, sh);
+    float inv_std = 1.0f / sqrtf(v / (float)cols + eps);
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) d[j] = (s[j] - mu) * inv_std;
+}
+
+__global__ void k_rmsnorm(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols, float eps) {
+    __shared__ float sh[32];
+    const float* s = src + (size_t)blockIdx.x * cols;
+    float* d = dst + (size_t)blockIdx.x * cols;
+    float ss = 0.0f;
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) { float x = s[j]; ss += x * x; }
+    ss = block_reduce<false>(ss, sh);
+    float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+    for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) d[j] = s[j] * inv_rms;
+}
+
+// one warp per output
+__global__ void k_reduce(uint32_t is_max, float* __restrict__ dst, const float* __restrict__ src,
+                         uint32_t n_out, uint32_t rs) {
+    uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (o >= n_out) return;
+    const float* s = src + (size_t)o * rs;
+    float v = is_max ? -INFINITY : 0.0f;
+    for (uint32_t k = lane; k < rs; k += 32) v = is_max ? fmaxf(v, s[k]) : v + s[k];
+    v = is_max ? warp_max(v) : warp_sum(v);
+    if (lane == 0) dst[o] = v;
+}
+
+struct RepeatParams {
+    uint32_t mode; // 0 fill, 1 copy, 2 tile, 3 general
+    uint32_t n, src_n;
+    uint32_t src_ne[4], src_strides[4], dst_strides[4];
+    uint32_t src_offset;
+};
+// reference.zig:391-433.  `src` is the buffer base for mode 3 (it adds src_offset
+// itself), src+src_offset for the others; dst already includes dst_offset.
+__global__ void k_repeat(RepeatParams p, float* __restrict__ dst, const float* __restrict__ src) {
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.n; gid += gridDim.x * blockDim.x) {
+        float v;
+        if (p.mode == 0) v = src[0];
+        else if (p.mode == 1) v = src[gid];
+        else if (p.mode == 2) v = src[gid % p.src_n];
+        else {
+            uint32_t idx = gid, sidx = p.src_offset;
+#pragma unroll
+            for (int dim = 3; dim >= 0; dim--) {
+                uint32_t coord = idx / p.dst_strides[dim];
+                idx = idx % p.dst_strides[dim];
+                sidx += (coord % p.src_ne[dim]) * p.src_strides[dim];
+            }
+            v = src[sidx];
+        }
+        dst[gid] = v;
+    }
+}
+
+__global__ void k_slice_assign(float* __restrict__ dst, const float* __restrict__ src, uint32_t rows,
+                               uint32_t cols, const uint32_t* __restrict__ dyn_dst_offset, uint32_t drs,
+                               uint32_t dcs, uint32_t soff, uint32_t srs, uint32_t scs) {
+    const uint32_t doff = *dyn_dst_offset;
+    uint32_t total = rows * cols;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t row = i % rows, col = i / rows;
+        dst[(size_t)doff + (size_t)row * drs + (size_t)col * dcs] = src[(size_t)soff + (size_t)row * srs + (size_t)col * scs];
+    }
+}
+
+__global__ void k_rope(float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ cs,
+                       uint32_t hd, uint32_t seq_len, uint32_t s_off, uint32_t c_off, uint32_t d_off,
+                       uint32_t s_rs, uint32_t s_cs, uint32_t c_cs) {
+    uint32_t total = hd * seq_len;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t pair = i % hd, col = i / hd;
+        float x_lo = src[(size_t)s_off + (size_t)pair * s_rs + (size_t)col * s_cs];
+        float x_hi = src[(size_t)s_off + (size_t)(pair + hd) * s_rs + (size_t)col * s_cs];
+        float c = cs[(size_t)c_off + pair + (size_t)col * c_cs];
+        float sn = cs[(size_t)c_off + pair + hd + (size_t)col * c_cs];
+        // separate roundings like the reference (no FMA contraction): reference.zig:474-475
+        dst[(size_t)d_off + pair + (size_t)col * 2 * hd] = __fsub_rn(__fmul_rn(x_lo, c), __fmul_rn(x_hi, sn));
+        dst[(size_t)d_off + pair + hd + (size_t)col * 2 * hd] = __fadd_rn(__fmul_rn(x_hi, c), __fmul_rn(x_lo, sn));
+    }
+}
+
+struct AttnParams {
+    uint32_t has_mask, d_head, seq_q;
+    float scale;
+    uint32_t q_off, k_off, v_off, mask_off, dst_off;
+    uint32_t q_rs, q_cs, k_rs, k_cs, v_rs, v_cs, mask_rs, mask_cs, dst_rs, dst_cs;
+};
+constexpr int kAttnWarps = 8;
+constexpr int kAttnMaxPerLane = 16; // d_head <= 512
+
+// One CTA per query row; each warp walks kv positions warp, warp+8, ... with an
+// online softmax (reference.zig:599-671: non-finite mask / score entries skipped),
+// the 8 partial states are merged through shared memory.
+__global__ void __launch_bounds__(kAttnWarps * 32)
+k_attention(AttnParams p, float* __restrict__ dst, const float* __restrict__ q, const float* __restrict__ k,
+            const float* __restrict__ v, const float* __restrict__ mask, const uint32_t* __restrict__ dyn_seq_kv) {
+    const uint32_t seq_kv = *dyn_seq_kv;
+    const uint32_t qi = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t dh = p.d_head;
+    const size_t q_base = (size_t)p.q_off + (size_t)qi * p.q_cs;
+    const size_t m_base = (size_t)p.mask_off + (size_t)qi * p.mask_cs;
+
+    float qreg[kAttnMaxPerLane], acc[kAttnMaxPerLane];
+#pragma unroll
+    for (int j = 0; j < kAttnMaxPerLane; j++) {
+        uint32_t r = lane + 32 * j;
+        qreg[j] = (r < dh) ? q[q_base + (size_t)r * p.q_rs] : 0.0f;
+        acc[j] = 0.0f;
+    }
+    float m_val = -INFINITY, l = 0.0f;
+    for (uint32_t s = warp; s < seq_kv; s += kAttnWarps) {
+        float mask_add = p.has_mask ? mask[m_base + (size_t)s * p.mask_rs] : 0.0f;
+        if (!isfinite(mask_add)) continue; // warp-uniform
+        const size_t kb = (size_t)p.k_off + (size_t)s * p.k_cs;
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kAttnMaxPerLane; j++) {
+            uint32_t r = lane + 32 * j;
+            if (r < dh) dot = fmaf(qreg[j], k[kb + (size_t)r * p.k_rs], dot);
+        }
+        dot = warp_sum(dot);
+        float score = dot * p.scale + mask_add;
+        if (!isfinite(score)) continue;
+        float new_m = fmaxf(m_val, score);
+        float alpha = (m_val == -INFINITY) ? 0.0f : expf(m_val - new_m);
+        float w = expf(score - new_m);
+        l = l * alpha + w;
+        m_val = new_m;
+        const size_t vb = (size_t)p.v_off + (size_t)s * p.v_cs;
+#pragma unroll
+        for (int j = 0; j < kAttnMaxPerLane; j++) {
+            uint32_t r = lane + 32 * j;
+            if (r < dh) acc[j] = acc[j] * alpha + w * v[vb + (size_t)r * p.v_rs];
+        }
+    }
+    __shared__ float sh_m[kAttnWarps], sh_l[kAttnWarps];
+    __shared__ float sh_acc[kAttnWarps][512];
+    if (lane == 0) { sh_m[warp] = m_val; sh_l[warp] = l; }
+#pragma unroll
+    for (int j = 0; j < kAttnMaxPerLane; j++) {
+        uint32_t r = lane + 32 * j;
+        if (r < dh) sh_acc[warp][r] = acc[j];
+    }
+    __syncthreads();
+    float gm = -INFINITY;
+    for (int w = 0; w < kAttnWarps; w++) gm = fmaxf(gm, sh_m[w]);
+    float gl = 0.0f;
+    float wscale[kAttnWarps];
+    for (int w = 0; w < kAttnWarps; w++) {
+        wscale[w] = (sh_m[w] == -INFINITY) ? 0.0f : expf(sh_m[w] - gm);
+        gl += sh_l[w] * wscale[w];
+    }
+    float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
+    const size_t d_base = (size_t)p.dst_off + (size_t)qi * p.dst_cs;
+    for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
+        float a = 0.0f;
+        for (int w = 0; w < kAttnWarps; w++) a += sh_acc[w][r] * wscale[w];
+        dst[d_base + (size_t)r * p.dst_rs] = a * inv_l;
+    }
+}
+
+struct MMParams {
+    uint32_t M, N, K;
+    size_t a_rs, a_cs, b_rs, b_cs, a_off, b_off, d_off, d_rs;
+};
+// B contiguous along k (b_rs == 1), e.g. the tied LM head x @ token_embed^T
+// (src/models/llama.zig:162-165): one warp per output column, float4 loads.
+__global__ void k_matmul_kmajor(MMParams p, float* __restrict__ dst, const float* __restrict__ A,
+                                const float* __restrict__ B) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.N) return;
+    const uint32_t m = blockIdx.y;
+    const float* a = A + p.a_off + (size_t)m * p.a_rs;
+    const float* b = B + p.b_off + (size_t)warp * p.b_cs;
+    float acc = 0.0f;
+    if (p.a_cs == 1 && ((p.b_cs & 3) == 0) && ((p.b_off & 3) == 0) && (((p.a_off + (size_t)m * p.a_rs) & 3) == 0) && ((p.K & 3) == 0)) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        for (uint32_t k = lane; k < p.K / 4; k += 32) {
+            float4 x = a4[k], y = __ldcs(b4 + k);
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+            acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+    } else {
+        for (uint32_t k = lane; k < p.K; k += 32) acc = fmaf(a[(size_t)k * p.a_cs], b[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) dst[p.d_off + (size_t)m * p.d_rs + warp] = acc;
+}
+// general strides: one thread per output (coalesced over n when b_cs == 1)
+__global__ void k_matmul_general(MMParams p, float* __restrict__ dst, const float* __restrict__ A,
+                                 const float* __restrict__ B) {
+    uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (n >= p.N) return;
+    float acc = 0.0f;
+    for (uint32_t k = 0; k < p.K; k++)
+        acc = fmaf(A[p.a_off + (size_t)m * p.a_rs + (size_t)k * p.a_cs], B[p.b_off + (size_t)k * p.b_rs + (size_t)n * p.b_cs], acc);
+    dst[p.d_off + (size_t)m * p.d_rs + n] = acc;
+}
+
+inline unsigned blocks_for(uint32_t n, unsigned bs, unsigned cap = 4096) {
+    unsigned b = (n + bs - 1) / bs;
+    if (b < 1) b = 1;
+    return b > cap ? cap : b;
+}
+
+} // namespace
+
+bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
+                  uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st) {
+    (void)ctx;
+    switch (op.tag) {
+        case ZG_OP_ELEMENTWISE: {
+            const auto& e = op.u.elementwise;
+            if (e.n == 0) return true;
+            k_elementwise<<<blocks_for(e.n, 256), 256, 0, st>>>(e.op, bufs[e.dst] + e.dst_offset, bufs[e.src0] + e.src0_offset,
+                                                                bufs[e.src1] + e.src1_offset, e.n);
+            break;
+        }
+        case ZG_OP_FUSED_ELEMENTWISE: {
+            const auto& f = op.u.fused_elementwise;
+            if (f.n == 0) return true;
+            k_fused_elementwise<<<blocks_for(f.n, 256), 256, 0, st>>>(d_steps, (uint32_t)f.n_steps, bufs[f.dst] + f.dst_offset,
+                                                                      bufs[f.src] + f.src_offset, f.n);
+            break;
+        }
+        case ZG_OP_SOFTMAX: {
+            const auto& s = op.u.softmax;
+            if (s.rows == 0 || s.cols == 0) return true;
+            k_softmax<<<s.rows, 256, 0, st>>>(bufs[s.dst] + s.dst_offset, bufs[s.src] + s.src_offset, s.cols);
+            break;
+        }
+        case ZG_OP_LAYERNORM: {
+            const auto& l = op.u.layernorm;
+            if (l.rows == 0 || l.cols == 0) return true;
+            k_layernorm<<<l.rows, 256, 0, st>>>(bufs[l.dst] + l.dst_offset, bufs[l.src] + l.src_offset, l.cols, l.eps);
+            break;
+        }
+        case ZG_OP_RMSNORM: {
+            const auto& r = op.u.rmsnorm;
+            if (r.rows == 0 || r.cols == 0) return true;
+            k_rmsnorm<<<r.rows, 256, 0, st>>>(bufs[r.dst] + r.dst_offset, bufs[r.src] + r.src_offset, r.cols, r.eps);
+            break;
+        }
+        case ZG_OP_REDUCE: {
+            const auto& r = op.u.reduce;
+            if (r.n_out == 0) return true;
+            k_reduce<<<blocks_for(r.n_out * 32, 256, 65535), 256, 0, st>>>(r.op == ZG_EW_MAX, bufs[r.dst] + r.dst_offset,
+                                                                           bufs[r.src] + r.src_offset, r.n_out, r.reduce_size);
+            break;
+        }
+        case ZG_OP_REPEAT: {
+            const auto& rp = op.u.repeat;
+            if (rp.n == 0) return true;
+            RepeatParams p;
+            const uint32_t* ne = rp.src_ne; const uint32_t* sst = rp.src_strides;
+            size_t src_n = (size_t)ne[0] * ne[1] * ne[2] * ne[3];
+            p.n = rp.n; p.src_n = (uint32_t)src_n; p.src_offset = rp.src_offset;
+            for (int i = 0; i < 4; i++) { p.src_ne[i] = ne[i]; p.src_strides[i] = sst[i]; p.dst_strides[i] = rp.dst_strides[i]; }
+            if (src_n == 1) p.mode = 0;
+            else if (src_n >= rp.n) p.mode = 1;
+            else if (rp.n % src_n == 0 && sst[0] == 1 && (ne[1] <= 1 || sst[1] == ne[0]) && (ne[2] <= 1 || sst[2] == ne[0] * ne[1]) &&
+                     (ne[3] <= 1 || sst[3] == ne[0] * ne[1] * ne[2])) p.mode = 2;
+            else p.mode = 3;
+            const float* src = (p.mode == 3) ? bufs[rp.src] : bufs[rp.src] + rp.src_offset;
+            k_repeat<<<blocks_for(rp.n, 256), 256, 0, st>>>(p, bufs[rp.dst] + rp.dst_offset, src);
+            break;
+        }
+        case ZG_OP_SLICE_ASSIGN: {
+            const auto& sa = op.u.slice_assign;
+            if (sa.rows == 0 || sa.cols == 0) return true;
+            k_slice_assign<<<blocks_for(sa.rows * sa.cols, 256), 256, 0, st>>>(bufs[sa.dst], bufs[sa.src], sa.rows, sa.cols,
+                                                                               d_dyn + op_index, sa.dst_row_stride, sa.dst_col_stride,
+                                                                               sa.src_offset, sa.src_row_stride, sa.src_col_stride);
+            break;
+        }
+        case ZG_OP_ROPE: {
+            const auto& r = op.u.rope;
+            if (r.half_d == 0 || r.seq_len == 0) return true;
+            k_rope<<<blocks_for(r.half_d * r.seq_len, 128), 128, 0, st>>>(bufs[r.dst], bufs[r.src], bufs[r.cos_sin], r.half_d, r.seq_len,
+                                                                          r.src_off, r.cs_off, r.dst_off, r.src_rs, r.src_cs, r.cs_cs);
+            break;
+        }
+        case ZG_OP_ATTENTION: {
+            const auto& a = op.u.attention;
+            if (a.seq_q == 0 || a.d_head == 0) return true;
+            if (a.d_head > 512) { zg_set_error("attention: d_head %u > 512", a.d_head); return false; }
+            AttnParams p;
+            p.has_mask = a.has_mask; p.d_head = a.d_head; p.seq_q = a.seq_q; p.scale = a.scale;
+            p.q_off = a.q_off; p.k_off = a.k_off; p.v_off = a.v_off; p.mask_off = a.mask_off; p.dst_off = a.dst_off;
+            p.q_rs = a.q_rs; p.q_cs = a.q_cs; p.k_rs = a.k_rs; p.k_cs = a.k_cs; p.v_rs = a.v_rs; p.v_cs = a.v_cs;
+            p.mask_rs = a.mask_rs; p.mask_cs = a.mask_cs; p.dst_rs = a.dst_rs; p.dst_cs = a.dst_cs;
+            k_attention<<<a.seq_q, kAttnWarps * 32, 0, st>>>(p, bufs[a.dst], bufs[a.q], bufs[a.k], bufs[a.v], bufs[a.mask], d_dyn + op_index);
+            break;
+        }
+        case ZG_OP_MATMUL: {
+            const auto& m = op.u.matmul;
+            const ZgMatMulGeometry& g = m.geom;
+            if (g.M == 0 || g.N == 0) return true;
+            MMParams p;
+            p.M = (uint32_t)g.M; p.N = (uint32_t)g.N; p.K = (uint32_t)g.K;
+            p.a_rs = g.a_row_stride; p.a_cs = g.a_col_stride; p.b_rs = g.b_row_stride; p.b_cs = g.b_col_stride;
+            p.a_off = g.a_offset; p.b_off = g.b_offset; p.d_off = g.dst_offset; p.d_rs = g.dst_row_stride;
+            if (g.b_row_stride == 1 && g.K >= 32) {
+                dim3 grid((unsigned)((g.N * 32 + 255) / 256), (unsigned)g.M);
+                k_matmul_kmajor<<<grid, 256, 0, st>>>(p, bufs[m.dst], bufs[m.a], bufs[m.b]);
+            } else {
+                dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.M);
+                k_matmul_general<<<grid, 128, 0, st>>>(p, bufs[m.dst], bufs[m.a], bufs[m.b]);
+            }
+            break;
+        }
+        default:
+            zg_set_error("unsupported DeviceOp tag %u", op.tag);
+            return false;
+    }
+    ZG_COUNT_LAUNCH();
+    return true;
+}

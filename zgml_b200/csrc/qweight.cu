@@ -1,0 +1,322 @@
+// GPU-resident packed quantized weights: upload, lossless format selection,
+// repacking into the record layout described in zg_internal.cuh, GGUF block
+// import and dequantization back to f32 (bit-exact with the reference).
+//
+// Reference semantics restated on device:
+//   QuantizedWeightUpload           src/backend.zig:260-266
+//   scale index (k*N+n)/block_size  src/quant.zig:525, src/backend/reference.zig:547
+//   quantizedWeightFromInfo         src/models/gguf_loader.zig:99-154 (zgml nibble order)
+//   dequantizeTo                    src/quant.zig:594-618
+#include "zg_internal.cuh"
+
+namespace {
+
+__global__ void k_detect_format(const int8_t* __restrict__ data, size_t n_data,
+                                const float* __restrict__ scales, size_t n_scales,
+                                uint32_t* __restrict__ flags) {
+    // flags bit0: some scale is not exactly an f16; bit1: some q outside [-8, 7]
+    uint32_t f = 0;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_scales; i += stride) {
+        float s = scales[i];
+        float r = __half2float(__float2half_rn(s));
+        if (__float_as_uint(r) != __float_as_uint(s)) f |= 1u;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_data; i += stride) {
+        int q = data[i];
+        if (q < -8 || q > 7) f |= 2u;
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
+// int8 formats: one thread per 16-byte unit.
+__global__ void k_pack_q8(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
+                          uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_units) return;
+    size_t rec = gid >> 8;
+    uint32_t u = (uint32_t)(gid & 255);
+    size_t tile = rec / n_kc, kc = rec % n_kc;
+    uint32_t i = u >> 6, rq = (u & 63) >> 2, cg = u & 3;
+    size_t row = kc * ZG_KC + 4 * rq + i;
+    size_t col0 = tile * ZG_TN + cg * 16;
+    uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u); // q = 0 biased
+    if (row < K && col0 < N) {
+        v = *reinterpret_cast<const uint4*>(data + row * N + col0);
+        v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+    }
+    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = v;
+}
+
+// int4 format: one thread per 16-byte unit (32 weights of one quant block).
+__global__ void k_pack_q4(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
+                          uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_units) return;
+    size_t rec = gid >> 7;
+    uint32_t u = (uint32_t)(gid & 127);
+    size_t tile = rec / n_kc, kc = rec % n_kc;
+    uint32_t i = u >> 5, rq = (u & 31) >> 1, nb = u & 1;
+    size_t row = kc * ZG_KC + 4 * rq + i;
+    size_t col0 = tile * ZG_TN + nb * 32;
+    uint32_t w[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u}; // q = 0 biased by 8
+    if (row < K && col0 < N) {
+        const int8_t* src = data + row * N + col0;
+#pragma unroll
+        for (int wi = 0; wi < 4; wi++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                int j = wi * 4 + b;
+                uint32_t lo = (uint32_t)(src[j] + 8) & 0xFu;
+                uint32_t hi = (uint32_t)(src[j + 16] + 8) & 0xFu;
+                x |= (lo | (hi << 4)) << (8 * b);
+            }
+            w[wi] = x;
+        }
+    }
+    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename ST>
+__global__ void k_pack_scales(const float* __restrict__ scales, uint8_t* __restrict__ recs,
+                              uint32_t rec_bytes, uint32_t q_bytes, uint32_t n_kc, size_t K, size_t N,
+                              size_t n_total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_total) return;
+    size_t rec = gid >> 7;
+    uint32_t idx = (uint32_t)(gid & 127);
+    size_t tile = rec / n_kc, kc = rec % n_kc;
+    uint32_t rq = idx >> 3, nb = (idx >> 2) & 1, i = idx & 3;
+    size_t row = kc * ZG_KC + 4 * rq + i;
+    size_t col0 = tile * ZG_TN + nb * 32;
+    float s = 0.0f;
+    if (row < K && col0 < N) s = scales[row * (N / 32) + col0 / 32];
+    ST* dst = reinterpret_cast<ST*>(recs + rec * rec_bytes + q_bytes) + idx;
+    if constexpr (sizeof(ST) == 2) *dst = __float2half_rn(s); // exact: format was verified
+    else *dst = s;
+}
+
+// GGUF raw blocks -> flat i8 + f32 scales (src/models/gguf_loader.zig:117-145).
+__global__ void k_gguf_expand(const uint8_t* __restrict__ raw, uint32_t ggml_type, size_t n_blocks,
+                              size_t n_elems, int8_t* __restrict__ data, float* __restrict__ scales) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    size_t elems = n_elems - b * 32 < 32 ? n_elems - b * 32 : 32;
+    if (ggml_type == 8) {
+        const uint8_t* blk = raw + b * 34;
+        __half_raw hr; hr.x = (unsigned short)(blk[0] | (blk[1] << 8));
+        scales[b] = __half2float(__half(hr));
+        for (size_t i = 0; i < elems; i++) data[b * 32 + i] = (int8_t)blk[2 + i];
+    } else {
+        const uint8_t* blk = raw + b * 18;
+        __half_raw hr; hr.x = (unsigned short)(blk[0] | (blk[1] << 8));
+        scales[b] = __half2float(__half(hr));
+        for (size_t i = 0; i < elems; i++) {
+            uint8_t byte = blk[2 + i / 2];
+            uint8_t nib = (i % 2 == 0) ? (byte & 0x0F) : (byte >> 4);
+            data[b * 32 + i] = (int8_t)((int)nib - 8);
+        }
+    }
+}
+
+// dequantizeTo from the packed residency (one thread per weight).
+__global__ void k_dequant_packed(const uint8_t* __restrict__ recs, int fmt, uint32_t rec_bytes,
+                                 uint32_t q_bytes, uint32_t n_kc, size_t K, size_t N,
+                                 float* __restrict__ out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= K * N) return;
+    size_t k = gid / N, n = gid % N;
+    size_t tile = n / ZG_TN, kc = k / ZG_KC;
+    uint32_t r = (uint32_t)(k % ZG_KC), c = (uint32_t)(n % ZG_TN);
+    uint32_t rq = r >> 2, i = r & 3, nb = c >> 5;
+    const uint8_t* rec = recs + (tile * n_kc + kc) * (size_t)rec_bytes;
+    int q;
+    if (fmt == ZG_QFMT_I4_F16) {
+        uint32_t u = i * 32 + rq * 2 + nb;
+        uint32_t e = c & 31;
+        uint8_t byte = rec[u * 16 + (e & 15)];
+        q = (int)((e < 16) ? (byte & 0xF) : (byte >> 4)) - 8;
+    } else {
+        uint32_t cg = c >> 4;
+        uint32_t u = i * 64 + rq * 4 + cg;
+        q = (int)rec[u * 16 + (c & 15)] - 128;
+    }
+    uint32_t sidx = rq * 8 + nb * 4 + i;
+    float s;
+    if (fmt == ZG_QFMT_I8_F32) s = reinterpret_cast<const float*>(rec + q_bytes)[sidx];
+    else s = __half2float(reinterpret_cast<const __half*>(rec + q_bytes)[sidx]);
+    out[gid] = (float)q * s; // f32(q) * scale, src/quant.zig:612-615
+}
+
+__global__ void k_dequant_flat(const int8_t* __restrict__ data, const float* __restrict__ scales,
+                               size_t n, size_t bs, float* __restrict__ out) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    out[gid] = (float)data[gid] * scales[gid / bs];
+}
+
+inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+} // namespace
+
+ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data, const float* d_scales,
+                                           size_t K, size_t N, size_t bs, int fmt_hint) {
+    cudaStream_t st = ctx->stream;
+    size_t n_elems = K * N;
+    size_t n_blocks = (n_elems + bs - 1) / bs;
+    bool fast_ok = (bs == 32) && (N % 32 == 0) && K > 0 && N > 0;
+    int fmt = ZG_QFMT_GENERIC;
+    if (fast_ok && fmt_hint != ZG_QFMT_GENERIC) {
+        uint32_t* d_flags = nullptr;
+        uint32_t flags = 0;
+        if (cudaMalloc(&d_flags, 4) != cudaSuccess) { zg_set_error("cudaMalloc flags failed"); return nullptr; }
+        cudaMemsetAsync(d_flags, 0, 4, st);
+        unsigned blocks = (unsigned)((n_elems / 16 + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 4096) blocks = 4096;
+        k_detect_format<<<blocks, 256, 0, st>>>(d_data, n_elems, d_scales, n_blocks, d_flags);
+        ZG_COUNT_LAUNCH();
+        cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        cudaFree(d_flags);
+        int best = (flags & 1u) ? ZG_QFMT_I8_F32 : ((flags & 2u) ? ZG_QFMT_I8_F16 : ZG_QFMT_I4_F16);
+        if (fmt_hint == ZG_QFMT_AUTO) {
+            fmt = best;
+        } else {
+            // A hint may ask for a wider (still lossless) format, never a lossy one.
+            bool ok = (fmt_hint == ZG_QFMT_I8_F32) || (fmt_hint == ZG_QFMT_I8_F16 && !(flags & 1u)) ||
+                      (fmt_hint == ZG_QFMT_I4_F16 && flags == 0);
+            if (!ok) { zg_set_error("format hint %d would be lossy for this weight", fmt_hint); return nullptr; }
+            fmt = fmt_hint;
+        }
+    }
+
+    ZgCudaQWeight* w = new ZgCudaQWeight();
+    w->fmt = fmt; w->K = K; w->N = N; w->bs = bs;
+    if (fmt == ZG_QFMT_GENERIC) {
+        if (cudaMalloc(&w->g_data, n_elems ? n_elems : 1) != cudaSuccess ||
+            cudaMalloc(&w->g_scales, (n_blocks ? n_blocks : 1) * sizeof(float)) != cudaSuccess) {
+            zg_set_error("cudaMalloc for generic qweight failed");
+            cudaFree(w->g_data); cudaFree(w->g_scales); delete w; return nullptr;
+        }
+        cudaMemcpyAsync(w->g_data, d_data, n_elems, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(w->g_scales, d_scales, n_blocks * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+        w->device_bytes = n_elems + n_blocks * sizeof(float);
+        return w;
+    }
+    w->n_tiles = (uint32_t)((N + ZG_TN - 1) / ZG_TN);
+    w->n_kc = (uint32_t)((K + ZG_KC - 1) / ZG_KC);
+    w->q_bytes = zg_rec_q_bytes(fmt);
+    w->rec_bytes = w->q_bytes + zg_rec_s_bytes(fmt);
+    size_t n_rec = (size_t)w->n_tiles * w->n_kc;
+    size_t bytes = n_rec * w->rec_bytes;
+    if (cudaMalloc(&w->recs, bytes) != cudaSuccess) {
+        zg_set_error("cudaMalloc(%zu) for packed qweight failed", bytes);
+        delete w; return nullptr;
+    }
+    w->device_bytes = bytes;
+    if (fmt == ZG_QFMT_I4_F16) {
+        size_t n_units = n_rec * 128;
+        k_pack_q4<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
+    } else {
+        size_t n_units = n_rec * 256;
+        k_pack_q8<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
+    }
+    ZG_COUNT_LAUNCH();
+    size_t n_s = n_rec * 128;
+    if (fmt == ZG_QFMT_I8_F32)
+        k_pack_scales<float><<<grid_for(n_s, 256), 256, 0, st>>>(d_scales, w->recs, w->rec_bytes, w->q_bytes, w->n_kc, K, N, n_s);
+    else
+        k_pack_scales<__half><<<grid_for(n_s, 256), 256, 0, st>>>(d_scales, w->recs, w->rec_bytes, w->q_bytes, w->n_kc, K, N, n_s);
+    ZG_COUNT_LAUNCH();
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        zg_set_error("packing qweight failed: %s", cudaGetErrorString(e));
+        cudaFree(w->recs); delete w; return nullptr;
+    }
+    return w;
+}
+
+extern "C" ZgCudaQWeight* zg_cuda_qweight_upload(ZgCudaCtx* ctx, const ZgQWeight* qw, int fmt_hint) {
+    if (!ctx || !qw || qw->block_size == 0) { zg_set_error("qweight_upload: bad arguments"); return nullptr; }
+    size_t K = qw->rows, N = qw->cols, bs = qw->block_size;
+    size_t n_elems = K * N, n_blocks = (n_elems + bs - 1) / bs;
+    if (qw->n_data < n_elems || qw->n_scales < n_blocks) { // src/backend.zig:289-291
+        zg_set_error("qweight_upload: data/scales shorter than rows*cols requires");
+        return nullptr;
+    }
+    cudaSetDevice(ctx->device);
+    int8_t* d_data = nullptr; float* d_scales = nullptr;
+    if (cudaMalloc(&d_data, n_elems ? n_elems : 1) != cudaSuccess ||
+        cudaMalloc(&d_scales, (n_blocks ? n_blocks : 1) * sizeof(float)) != cudaSuccess) {
+        zg_set_error("qweight_upload: staging cudaMalloc failed");
+        cudaFree(d_data); cudaFree(d_scales); return nullptr;
+    }
+    cudaMemcpyAsync(d_data, qw->data, n_elems, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_scales, qw->scales, n_blocks * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    ZgCudaQWeight* w = zg_qweight_from_device_flat(ctx, d_data, d_scales, K, N, bs, fmt_hint);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_data); cudaFree(d_scales);
+    return w;
+}
+
+extern "C" ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void* raw, size_t raw_bytes,
+                                                      uint32_t ggml_type, size_t rows, size_t cols) {
+    if (!ctx || !raw) { zg_set_error("qweight_upload_gguf: bad arguments"); return nullptr; }
+    if (ggml_type != 8 && ggml_type != 2) { // isDirectQuantizedMatmulType, gguf_loader.zig:95-97
+        zg_set_error("qweight_upload_gguf: unsupported ggml type %u (only Q8_0=8, Q4_0=2)", ggml_type);
+        return nullptr;
+    }
+    size_t n_elems = rows * cols;
+    size_t n_blocks = (n_elems + 31) / 32;
+    size_t need = n_blocks * (ggml_type == 8 ? 34 : 18);
+    if (raw_bytes < need) { zg_set_error("qweight_upload_gguf: raw buffer too small"); return nullptr; }
+    cudaSetDevice(ctx->device);
+    uint8_t* d_raw = nullptr; int8_t* d_data = nullptr; float* d_scales = nullptr;
+    if (cudaMalloc(&d_raw, need ? need : 1) != cudaSuccess || cudaMalloc(&d_data, n_elems ? n_elems : 1) != cudaSuccess ||
+        cudaMalloc(&d_scales, (n_blocks ? n_blocks : 1) * sizeof(float)) != cudaSuccess) {
+        zg_set_error("qweight_upload_gguf: staging cudaMalloc failed");
+        cudaFree(d_raw); cudaFree(d_data); cudaFree(d_scales); return nullptr;
+    }
+    cudaMemcpyAsync(d_raw, raw, need, cudaMemcpyHostToDevice, ctx->stream);
+    if (n_blocks) {
+        k_gguf_expand<<<grid_for(n_blocks, 128), 128, 0, ctx->stream>>>(d_raw, ggml_type, n_blocks, n_elems, d_data, d_scales);
+        ZG_COUNT_LAUNCH();
+    }
+    ZgCudaQWeight* w = zg_qweight_from_device_flat(ctx, d_data, d_scales, rows, cols, 32, ZG_QFMT_AUTO);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_raw); cudaFree(d_data); cudaFree(d_scales);
+    return w;
+}
+
+extern "C" void zg_cuda_qweight_free(ZgCudaCtx* ctx, ZgCudaQWeight* w) {
+    if (!w) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(w->recs); cudaFree(w->g_data); cudaFree(w->g_scales);
+    delete w;
+}
+
+extern "C" int zg_cuda_qweight_format(const ZgCudaQWeight* w) { return w ? w->fmt : -1; }
+extern "C" size_t zg_cuda_qweight_device_bytes(const ZgCudaQWeight* w) { return w ? w->device_bytes : 0; }
+
+extern "C" int zg_cuda_qweight_dequantize(ZgCudaCtx* ctx, const ZgCudaQWeight* w, float* host_dst) {
+    if (!ctx || !w || !host_dst) { zg_set_error("qweight_dequantize: bad arguments"); return -1; }
+    cudaSetDevice(ctx->device);
+    size_t n = w->K * w->N;
+    if (n == 0) return 0;
+    float* d_out = nullptr;
+    if (cudaMalloc(&d_out, n * sizeof(float)) != cudaSuccess) { zg_set_error("qweight_dequantize: cudaMalloc failed"); return -1; }
+    if (w->fmt == ZG_QFMT_GENERIC)
+        k_dequant_flat<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->g_data, w->g_scales, n, w->bs, d_out);
+    else
+        k_dequant_packed<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->recs, w->fmt, w->rec_bytes, w->q_bytes, w->n_kc, w->K, w->N, d_out);
+    ZG_COUNT_LAUNCH();
+    cudaMemcpyAsync(host_dst, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { zg_set_error("qweight_dequantize: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
+}
