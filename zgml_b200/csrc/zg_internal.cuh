@@ -8,7 +8,10 @@
 #include <atomic>
 #include <vector>
 
+// The library is built with -fvisibility=hidden; only the C-ABI of the public header is exported.
+#pragma GCC visibility push(default)
 #include "../../include/zgml_cuda.h"
+#pragma GCC visibility pop
 
 void zg_set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_zg_launches;
