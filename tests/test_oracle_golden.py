@@ -230,32 +230,23 @@ def test_quantize_input_rule():
 
 
 # reference src/backend/conformance.zig:62-346 — the 11 core programs on the oracle executor,
-# with the answers the reference's own cpu/metal tests assert where they state them.
-def _run(program, out_idx, out_len):
+# against closed-form answers (the reference compares backend vs its executor; here the oracle
+# IS the executor restatement, so it is pinned against independently computed values).
+import pytest  # noqa: E402
+
+from conformance_programs import core_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", core_cases(), ids=lambda c: c[0])
+def test_oracle_executor_core_cases(case):
+    name, program, out_idx, out_len, want = case
     out = np.zeros(out_len, np.float32)
     oracle.run_program(program, [], [ProgramIO(out_idx, out)])
-    return out
+    np.testing.assert_allclose(out, want, atol=1e-5, rtol=0)  # conformance.zig:350 tolerance
 
 
-def test_program_matmul_known_answer():  # src/backend/cpu.zig:164-191 expects 58, 64, 139, 154
-    a = np.array([1, 2, 3, 4, 5, 6], np.float32)
-    b = np.array([7, 8, 9, 10, 11, 12], np.float32)
-    prog = DeviceProgram([DeviceOp.matmul(2, 0, 1, 2, 2, 3, 3, 1, 2, 1)], [6, 6, 4],
-                         [ProgramIO(0, a), ProgramIO(1, b)])
-    assert list(_run(prog, 2, 4)) == [58, 64, 139, 154]
-
-
-def test_program_elementwise_add_known_answer():  # src/backend/reference.zig:675-688
-    a = np.array([1, 2, 3, 4], np.float32)
-    b = np.array([10, 20, 30, 40], np.float32)
-    prog = DeviceProgram([DeviceOp.elementwise("add", 2, 0, 1, 4)], [4, 4, 4], [ProgramIO(0, a), ProgramIO(1, b)])
-    assert list(_run(prog, 2, 4)) == [11, 22, 33, 44]
-
-
-def test_program_qmatmul_with_offsets():  # src/backend/conformance.zig:81-112
-    inp = np.array([99, 1, 2, 3, 99, -1, 0.5, 4, 99], np.float32)
-    dst = np.full(9, -7, np.float32)
-    qw = QuantizedWeightUpload(np.array([2, -1, 3, 4, -2, 1, -3, 5, 2], np.int8), np.array([0.5, 0.25, 1.0], np.float32), 3, 3, 4)
-    prog = DeviceProgram([DeviceOp.qmatmul(1, 0, 0, 2, 3, 3, 1, 4, 1, 4)], [9, 9], [ProgramIO(0, inp), ProgramIO(1, dst)], [qw])
-    out = _run(prog, 1, 9)
-    np.testing.assert_allclose(out, [-7, 2.75, 2.25, 8.0, -7, -3.0, 5.25, 6.625, -7], atol=1e-6)
+def test_program_matmul_known_answer_cpu_zig():  # src/backend/cpu.zig:164-191 expects 58, 64, 139, 154 exactly
+    name, program, out_idx, out_len, want = core_cases()[0]
+    out = np.zeros(out_len, np.float32)
+    oracle.run_program(program, [], [ProgramIO(out_idx, out)])
+    assert list(out) == [58, 64, 139, 154]

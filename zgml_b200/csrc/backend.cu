@@ -51,10 +51,12 @@ struct ZgCudaProgram {
     ZgDevStep* d_steps = nullptr;
     uint32_t* d_dyn = nullptr;
     uint32_t* h_dyn = nullptr; // pinned
+    bool dyn_dirty = true;     // h_dyn differs from d_dyn
     ZgGemvWs ws;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool graph_valid = false;
+    uint64_t graph_kernels = 0; // kernel nodes captured in `graph` (added to the launch counter per replay)
     ZgProfile profile;
     std::vector<cudaEvent_t> prof_events;
 };
@@ -299,10 +301,13 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
         cudaFree(p->d_dyn); cudaFreeHost(p->h_dyn); p->d_dyn = nullptr; p->h_dyn = nullptr;
         size_t nd = n_ops ? n_ops : 1;
         cudaMalloc(&p->d_dyn, nd * 4); cudaMallocHost(&p->h_dyn, nd * 4);
+        memset(p->h_dyn, 0xFF, nd * 4);
+        p->dyn_dirty = true;
         p->graph_valid = false;
     }
     for (size_t i = 0; i < n_ops; i++) {
         uint32_t v = op_dyn_value(ops[i]);
+        if (p->h_dyn[i] != v) p->dyn_dirty = true;
         p->h_dyn[i] = v;
         if (ops[i].tag == ZG_OP_SLICE_ASSIGN) p->ops[i].u.slice_assign.dst_offset = v;
         else if (ops[i].tag == ZG_OP_ATTENTION) p->ops[i].u.attention.seq_kv = v;
@@ -337,7 +342,10 @@ static bool run_ops(ZgCudaProgram* p) {
     cudaStream_t st = ctx->stream;
     size_t n = p->ops.size();
     if (n == 0) return true;
-    ZG_CUDA_OK(cudaMemcpyAsync(p->d_dyn, p->h_dyn, n * 4, cudaMemcpyHostToDevice, st));
+    if (p->dyn_dirty) {
+        ZG_CUDA_OK(cudaMemcpyAsync(p->d_dyn, p->h_dyn, n * 4, cudaMemcpyHostToDevice, st));
+        p->dyn_dirty = false;
+    }
     if (ctx->profiling) {
         if (!launch_all(p, st, true)) return false;
         ZG_CUDA_OK(cudaStreamSynchronize(st));
@@ -356,7 +364,10 @@ static bool run_ops(ZgCudaProgram* p) {
         if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
         if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
         ZG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const uint64_t before = g_zg_launches.load();
         bool ok = launch_all(p, st, false);
+        p->graph_kernels = g_zg_launches.load() - before;
+        g_zg_launches.store(before); // captured, not launched: counted per replay below
         cudaError_t e = cudaStreamEndCapture(st, &p->graph);
         if (!ok) { if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; } return false; }
         if (e != cudaSuccess) { zg_set_error("graph capture failed: %s", cudaGetErrorString(e)); return false; }
@@ -364,6 +375,7 @@ static bool run_ops(ZgCudaProgram* p) {
         p->graph_valid = true;
     }
     ZG_CUDA_OK(cudaGraphLaunch(p->exec, st));
+    g_zg_launches.fetch_add(p->graph_kernels, std::memory_order_relaxed);
     return true;
 }
 
