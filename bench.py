@@ -35,6 +35,10 @@ sys.path.insert(0, ROOT)
 
 SHAPES = [(4096, 4096), (4096, 14336)]          # (K, N): zgml rows=K, cols=N
 FORMATS = [("i8_f32", 36), ("q8_0", 34), ("q4_0", 18)]
+if os.environ.get("ZG_BENCH_SHAPES"):            # kernel-tuning sweeps only (not the judged workload)
+    SHAPES = [tuple(int(v) for v in t.split("x")) for t in os.environ["ZG_BENCH_SHAPES"].split(",")]
+if os.environ.get("ZG_BENCH_FORMATS"):
+    FORMATS = [f for f in FORMATS if f[0] in os.environ["ZG_BENCH_FORMATS"].split(",")]
 ROTATION_BYTES = 512 << 20
 METRIC = "quant_gemv_hbm_gbps"
 UNIT = "GB/s"

@@ -5,6 +5,7 @@
 #include "zg_internal.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -76,6 +77,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     ZgCudaCtx* ctx = new ZgCudaCtx();
     ctx->device = device_ordinal;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }

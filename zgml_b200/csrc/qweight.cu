@@ -30,51 +30,54 @@ __global__ void k_detect_format(const int8_t* __restrict__ data, size_t n_data,
     if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
 }
 
-// int8 formats: one thread per 16-byte unit.
+// int8 formats: one thread per 16-byte unit = one lane's A fragment of one column tile.
 __global__ void k_pack_q8(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
-                          uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
-    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_units) return;
-    size_t rec = gid >> 8;
-    uint32_t u = (uint32_t)(gid & 255);
-    size_t tile = rec / n_kc, kc = rec % n_kc;
-    uint32_t i = u >> 6, rq = (u & 63) >> 2, cg = u & 3;
-    size_t row = kc * ZG_KC + 4 * rq + i;
-    size_t col0 = tile * ZG_TN + cg * 16;
-    uint4 v = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u); // q = 0 biased
-    if (row < K && col0 < N) {
-        v = *reinterpret_cast<const uint4*>(data + row * N + col0);
-        v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
-    }
-    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = v;
-}
-
-// int4 format: one thread per 16-byte unit (32 weights of one quant block).
-__global__ void k_pack_q4(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
                           uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_units) return;
     size_t rec = gid >> 7;
     uint32_t u = (uint32_t)(gid & 127);
     size_t tile = rec / n_kc, kc = rec % n_kc;
-    uint32_t i = u >> 5, rq = (u & 31) >> 1, nb = u & 1;
-    size_t row = kc * ZG_KC + 4 * rq + i;
-    size_t col0 = tile * ZG_TN + nb * 32;
-    uint32_t w[4] = {0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u}; // q = 0 biased by 8
-    if (row < K && col0 < N) {
-        const int8_t* src = data + row * N + col0;
+    uint32_t ct = u >> 5, L = u & 31, g = L >> 2, t = L & 3;
+    uint32_t w[4];
 #pragma unroll
-        for (int wi = 0; wi < 4; wi++) {
-            uint32_t x = 0;
+    for (int r = 0; r < 4; r++) {
+        size_t n = tile * ZG_TN + ct * 16 + g + 8 * (r & 1);
+        uint32_t x = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-                int j = wi * 4 + b;
-                uint32_t lo = (uint32_t)(src[j] + 8) & 0xFu;
-                uint32_t hi = (uint32_t)(src[j + 16] + 8) & 0xFu;
-                x |= (lo | (hi << 4)) << (8 * b);
-            }
-            w[wi] = x;
+        for (int b = 0; b < 4; b++) {
+            size_t k = kc * ZG_KR + 4 * t + b + 16 * (r >> 1);
+            uint32_t q = (k < K && n < N) ? (uint32_t)(uint8_t)data[k * N + n] : 0u;
+            x |= q << (8 * b);
         }
+        w[r] = x;
+    }
+    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// int4 format: one thread per 16-byte unit = one lane's packed fragments of a column-tile pair.
+__global__ void k_pack_q4(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
+                          uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_units) return;
+    size_t rec = gid >> 6;
+    uint32_t u = (uint32_t)(gid & 63);
+    size_t tile = rec / n_kc, kc = rec % n_kc;
+    uint32_t p = u >> 5, L = u & 31, g = L >> 2, t = L & 3;
+    uint32_t w[4];
+#pragma unroll
+    for (int wi = 0; wi < 4; wi++) {
+        uint32_t ct = 2 * p + (wi >> 1), half = wi & 1;
+        size_t n_lo = tile * ZG_TN + ct * 16 + g, n_hi = n_lo + 8;
+        uint32_t x = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            size_t k = kc * ZG_KR + 4 * t + b + 16 * half;
+            uint32_t lo = (k < K && n_lo < N) ? ((uint32_t)data[k * N + n_lo] & 0xFu) : 0u;
+            uint32_t hi = (k < K && n_hi < N) ? ((uint32_t)data[k * N + n_hi] & 0xFu) : 0u;
+            x |= (lo | (hi << 4)) << (8 * b);
+        }
+        w[wi] = x;
     }
     *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -85,17 +88,28 @@ __global__ void k_pack_scales(const float* __restrict__ scales, uint8_t* __restr
                               size_t n_total) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_total) return;
-    size_t rec = gid >> 7;
-    uint32_t idx = (uint32_t)(gid & 127);
+    size_t rec = gid >> 6;
+    uint32_t idx = (uint32_t)(gid & 63);
     size_t tile = rec / n_kc, kc = rec % n_kc;
-    uint32_t rq = idx >> 3, nb = (idx >> 2) & 1, i = idx & 3;
-    size_t row = kc * ZG_KC + 4 * rq + i;
+    uint32_t nb = idx >> 5, kk = idx & 31;
+    size_t row = kc * ZG_KR + kk;
     size_t col0 = tile * ZG_TN + nb * 32;
     float s = 0.0f;
     if (row < K && col0 < N) s = scales[row * (N / 32) + col0 / 32];
     ST* dst = reinterpret_cast<ST*>(recs + rec * rec_bytes + q_bytes) + idx;
     if constexpr (sizeof(ST) == 2) *dst = __float2half_rn(s); // exact: format was verified
     else *dst = s;
+}
+
+// max scale per 32-column quant block over all k (|s|: zgml scales are positive, but be safe).
+__global__ void k_scale_max(const float* __restrict__ scales, float* __restrict__ smax, size_t K, size_t nbN,
+                            size_t nb_padded) {
+    size_t nb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (nb >= nb_padded) return;
+    float m = 0.0f;
+    if (nb < nbN)
+        for (size_t k = 0; k < K; k++) m = fmaxf(m, fabsf(scales[k * nbN + nb]));
+    smax[nb] = m;
 }
 
 // GGUF raw blocks -> flat i8 + f32 scales (src/models/gguf_loader.zig:117-145).
@@ -128,22 +142,22 @@ __global__ void k_dequant_packed(const uint8_t* __restrict__ recs, int fmt, uint
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= K * N) return;
     size_t k = gid / N, n = gid % N;
-    size_t tile = n / ZG_TN, kc = k / ZG_KC;
-    uint32_t r = (uint32_t)(k % ZG_KC), c = (uint32_t)(n % ZG_TN);
-    uint32_t rq = r >> 2, i = r & 3, nb = c >> 5;
+    size_t tile = n / ZG_TN, kc = k / ZG_KR;
+    uint32_t kk = (uint32_t)(k % ZG_KR), c = (uint32_t)(n % ZG_TN);
+    uint32_t ct = c >> 4, cn = c & 15, g = cn & 7, r0 = cn >> 3, nb = c >> 5;
+    uint32_t half = kk >> 4, t = (kk & 15) >> 2, b = kk & 3, L = 4 * g + t;
     const uint8_t* rec = recs + (tile * n_kc + kc) * (size_t)rec_bytes;
     int q;
     if (fmt == ZG_QFMT_I4_F16) {
-        uint32_t u = i * 32 + rq * 2 + nb;
-        uint32_t e = c & 31;
-        uint8_t byte = rec[u * 16 + (e & 15)];
-        q = (int)((e < 16) ? (byte & 0xF) : (byte >> 4)) - 8;
+        uint32_t p = ct >> 1, wi = (ct & 1) * 2 + half;
+        uint8_t byte = rec[p * 512 + L * 16 + wi * 4 + b];
+        int nib = r0 ? (byte >> 4) : (byte & 0xF);
+        q = (nib ^ 8) - 8; // sign-extend the two's-complement nibble
     } else {
-        uint32_t cg = c >> 4;
-        uint32_t u = i * 64 + rq * 4 + cg;
-        q = (int)rec[u * 16 + (c & 15)] - 128;
+        uint32_t r = r0 + 2 * half;
+        q = (int)(int8_t)rec[ct * 512 + L * 16 + r * 4 + b];
     }
-    uint32_t sidx = rq * 8 + nb * 4 + i;
+    uint32_t sidx = nb * 32 + kk;
     float s;
     if (fmt == ZG_QFMT_I8_F32) s = reinterpret_cast<const float*>(rec + q_bytes)[sidx];
     else s = __half2float(reinterpret_cast<const __half*>(rec + q_bytes)[sidx]);
@@ -208,25 +222,28 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
         return w;
     }
     w->n_tiles = (uint32_t)((N + ZG_TN - 1) / ZG_TN);
-    w->n_kc = (uint32_t)((K + ZG_KC - 1) / ZG_KC);
+    w->n_kc = (uint32_t)((K + ZG_KR - 1) / ZG_KR);
     w->q_bytes = zg_rec_q_bytes(fmt);
     w->rec_bytes = w->q_bytes + zg_rec_s_bytes(fmt);
     size_t n_rec = (size_t)w->n_tiles * w->n_kc;
     size_t bytes = n_rec * w->rec_bytes;
-    if (cudaMalloc(&w->recs, bytes) != cudaSuccess) {
+    size_t nb_padded = (size_t)w->n_tiles * 2;
+    if (cudaMalloc(&w->recs, bytes) != cudaSuccess || cudaMalloc(&w->smax, nb_padded * sizeof(float)) != cudaSuccess) {
         zg_set_error("cudaMalloc(%zu) for packed qweight failed", bytes);
-        delete w; return nullptr;
+        cudaFree(w->recs); delete w; return nullptr;
     }
-    w->device_bytes = bytes;
+    w->device_bytes = bytes + nb_padded * sizeof(float);
+    k_scale_max<<<grid_for(nb_padded, 128), 128, 0, st>>>(d_scales, w->smax, K, N / 32, nb_padded);
+    ZG_COUNT_LAUNCH();
     if (fmt == ZG_QFMT_I4_F16) {
-        size_t n_units = n_rec * 128;
+        size_t n_units = n_rec * 64;
         k_pack_q4<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
     } else {
-        size_t n_units = n_rec * 256;
+        size_t n_units = n_rec * 128;
         k_pack_q8<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
     }
     ZG_COUNT_LAUNCH();
-    size_t n_s = n_rec * 128;
+    size_t n_s = n_rec * 64;
     if (fmt == ZG_QFMT_I8_F32)
         k_pack_scales<float><<<grid_for(n_s, 256), 256, 0, st>>>(d_scales, w->recs, w->rec_bytes, w->q_bytes, w->n_kc, K, N, n_s);
     else
@@ -235,7 +252,7 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         zg_set_error("packing qweight failed: %s", cudaGetErrorString(e));
-        cudaFree(w->recs); delete w; return nullptr;
+        cudaFree(w->recs); cudaFree(w->smax); delete w; return nullptr;
     }
     return w;
 }
@@ -295,7 +312,7 @@ extern "C" ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void
 extern "C" void zg_cuda_qweight_free(ZgCudaCtx* ctx, ZgCudaQWeight* w) {
     if (!w) return;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(w->recs); cudaFree(w->g_data); cudaFree(w->g_scales);
+    cudaFree(w->recs); cudaFree(w->smax); cudaFree(w->g_data); cudaFree(w->g_scales);
     delete w;
 }
 

@@ -30,20 +30,27 @@ extern std::atomic<uint64_t> g_zg_launches;
 // ── Packed, GPU-resident quantized weight ─────────────────────────────────────
 //
 // Fast formats (block_size == 32 and N % 32 == 0) are stored as RECORDS.  One
-// record covers ZG_TN = 64 output columns (2 quant blocks) x ZG_KC = 64 k-rows:
+// record covers ZG_TN = 64 output columns (2 quant blocks) x ZG_KR = 32 k-rows and
+// is laid out so that a warp's 128-bit shared-memory loads ARE the A fragments of
+// mma.sync.m16n8k32 (weights as the 16-row operand: 16 output columns x 32 k):
 //
-//   q area   int8 formats: 256 units of 16 B; unit u = i*64 + rq*4 + cg holds
-//            row 4*rq+i (i in 0..3, rq in 0..15), columns cg*16..cg*16+15, each
-//            byte = q + 128 (biased to u8 so a PRMT builds 2^23+u directly).
-//            int4 format : 128 units of 16 B; unit u = i*32 + rq*2 + nb holds
-//            row 4*rq+i, quant block nb; byte j = (q[j]+8) | (q[j+16]+8) << 4.
-//   s area   [rq 16][nb 2][i 4] scales (f16 or f32), scale of row 4*rq+i, block nb.
+//   q area   int8 formats: 4 column tiles (16 columns each) x 512 B.  Inside a column
+//            tile lane L = 4*g + t owns 16 B = regs r = 0..3, bytes b = 0..3 with
+//            column n = 16*ct + g + 8*(r & 1), row k = 4*t + b + 16*(r >> 1); the
+//            byte is q itself (two's complement).
+//            int4 format : 2 column-tile pairs x 512 B.  Lane L owns 16 B =
+//            {w0, w1 of ct = 2p, w0, w1 of ct = 2p + 1}; byte b of w0 holds rows
+//            k = 4*t + b: low nibble = q[k][n = 16*ct + g], high nibble =
+//            q[k][n = 16*ct + g + 8] (two's-complement nibbles); w1 is k + 16.
+//   s area   [nb 2][k 32] scales (f16 or f32): scale of row k, quant block nb.
 //
-// Records are laid out [n_tile][k_chunk], so the rows one CTA reduces over for one
-// column tile are ONE contiguous span -> a single cp.async.bulk per pipeline stage.
-// Rows >= K and columns >= N are zero-padded (q = 0, scale = 0).
+// Records are laid out [n_tile][k_chunk]: the whole matrix is ONE contiguous run of
+// records, so any CTA's share of the work is a single span -> one cp.async.bulk per
+// pipeline stage.  Rows >= K and columns >= N are zero-padded (q = 0, scale = 0).
+// `smax[2 * n_tiles]` = max scale of each 32-column quant block over all k (used to
+// choose the fixed-point exponent of the activation*scale products, see qgemv.cu).
 #define ZG_TN 64
-#define ZG_KC 64
+#define ZG_KR 32
 
 struct ZgCudaQWeight {
     int fmt = 0;                 // ZG_QFMT_*
@@ -51,16 +58,17 @@ struct ZgCudaQWeight {
     // fast formats
     uint32_t n_tiles = 0, n_kc = 0, rec_bytes = 0, q_bytes = 0;
     uint8_t* recs = nullptr;
+    float* smax = nullptr;
     // generic format: flat copies
     int8_t* g_data = nullptr;
     float* g_scales = nullptr;
     size_t device_bytes = 0;
 };
 
-static inline uint32_t zg_rec_q_bytes(int fmt) { return fmt == ZG_QFMT_I4_F16 ? 2048u : 4096u; }
-static inline uint32_t zg_rec_s_bytes(int fmt) { return fmt == ZG_QFMT_I8_F32 ? 512u : 256u; }
+static inline uint32_t zg_rec_q_bytes(int fmt) { return fmt == ZG_QFMT_I4_F16 ? 1024u : 2048u; }
+static inline uint32_t zg_rec_s_bytes(int fmt) { return fmt == ZG_QFMT_I8_F32 ? 256u : 128u; }
 
-// split-K scratch: partial sums [split][M][Np] + one arrival counter per column tile
+// split scratch: per-CTA partial sums of split column tiles + one arrival counter per column tile
 struct ZgGemvWs {
     float* partials = nullptr;
     size_t partials_elems = 0;
@@ -75,6 +83,7 @@ struct ZgCudaCtx {
     bool owns_stream = true;
     bool graph_mode = true;
     bool profiling = false;
+    bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
 };
 
@@ -87,9 +96,9 @@ void zg_gemv_ws_free(ZgGemvWs* ws);
 ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data, const float* d_scales,
                                            size_t K, size_t N, size_t bs, int fmt_hint);
 // qgemv.cu
-// Plan the split-K geometry for a weight (records per CTA etc.) and launch.
+// Stream-K work split for one launch (<= 8 activation rows): CTAs, ring slots, row pairs.
 struct ZgGemvPlan {
-    uint32_t n_splits = 1, rec_per_cta = 0, smem_bytes = 0, grid = 0, m_block = 1;
+    uint32_t grid = 0, n_ring = 1, smem_bytes = 0, mp = 1, max_contrib = 1;
 };
 ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M);
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
