@@ -35,14 +35,14 @@ __global__ void k_pack_q8(const int8_t* __restrict__ data, uint8_t* __restrict__
                           uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_units) return;
-    size_t rec = gid >> 7;
-    uint32_t u = (uint32_t)(gid & 127);
-    size_t tile = rec / n_kc, kc = rec % n_kc;
+    size_t rec = gid >> 6;
+    uint32_t u = (uint32_t)(gid & 63);
+    size_t nb = rec / n_kc, kc = rec % n_kc;
     uint32_t ct = u >> 5, L = u & 31, g = L >> 2, t = L & 3;
     uint32_t w[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        size_t n = tile * ZG_TN + ct * 16 + g + 8 * (r & 1);
+        size_t n = nb * ZG_TN + ct * 16 + g + 8 * (r & 1);
         uint32_t x = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
@@ -55,31 +55,41 @@ __global__ void k_pack_q8(const int8_t* __restrict__ data, uint8_t* __restrict__
     *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// int4 format: one thread per 16-byte unit = one lane's packed fragments of a column-tile pair.
+// int4 format: one thread per 16-byte unit = one lane's packed fragments of both column tiles.
+// Nibbles are the biased GGUF form u = q + 8 (padding: q = 0 -> u = 8).
 __global__ void k_pack_q4(const int8_t* __restrict__ data, uint8_t* __restrict__ recs,
                           uint32_t rec_bytes, uint32_t n_kc, size_t K, size_t N, size_t n_units) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_units) return;
-    size_t rec = gid >> 6;
-    uint32_t u = (uint32_t)(gid & 63);
-    size_t tile = rec / n_kc, kc = rec % n_kc;
-    uint32_t p = u >> 5, L = u & 31, g = L >> 2, t = L & 3;
+    size_t rec = gid >> 5;
+    uint32_t L = (uint32_t)(gid & 31), g = L >> 2, t = L & 3;
+    size_t nb = rec / n_kc, kc = rec % n_kc;
     uint32_t w[4];
 #pragma unroll
     for (int wi = 0; wi < 4; wi++) {
-        uint32_t ct = 2 * p + (wi >> 1), half = wi & 1;
-        size_t n_lo = tile * ZG_TN + ct * 16 + g, n_hi = n_lo + 8;
+        uint32_t ct = wi >> 1, half = wi & 1;
+        size_t n_lo = nb * ZG_TN + ct * 16 + g, n_hi = n_lo + 8;
         uint32_t x = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             size_t k = kc * ZG_KR + 4 * t + b + 16 * half;
-            uint32_t lo = (k < K && n_lo < N) ? ((uint32_t)data[k * N + n_lo] & 0xFu) : 0u;
-            uint32_t hi = (k < K && n_hi < N) ? ((uint32_t)data[k * N + n_hi] & 0xFu) : 0u;
-            x |= (lo | (hi << 4)) << (8 * b);
+            uint32_t lo = (k < K && n_lo < N) ? (uint32_t)(data[k * N + n_lo] + 8) : 8u;
+            uint32_t hi = (k < K && n_hi < N) ? (uint32_t)(data[k * N + n_hi] + 8) : 8u;
+            x |= ((lo & 0xFu) | ((hi & 0xFu) << 4)) << (8 * b);
         }
         w[wi] = x;
     }
-    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)u * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(recs + rec * rec_bytes + (size_t)L * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// scale slot idx = 8*t + i  <->  record row kk (zg_internal.cuh)
+__host__ __device__ inline uint32_t zg_scale_slot_row(uint32_t idx) {
+    uint32_t t = idx >> 3, i = idx & 7;
+    return i < 4 ? 4 * t + i : 16 + 4 * t + (i - 4);
+}
+__host__ __device__ inline uint32_t zg_scale_row_slot(uint32_t kk) {
+    uint32_t half = kk >> 4, t = (kk & 15) >> 2, b = kk & 3;
+    return 8 * t + 4 * half + b;
 }
 
 template <typename ST>
@@ -88,14 +98,12 @@ __global__ void k_pack_scales(const float* __restrict__ scales, uint8_t* __restr
                               size_t n_total) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_total) return;
-    size_t rec = gid >> 6;
-    uint32_t idx = (uint32_t)(gid & 63);
-    size_t tile = rec / n_kc, kc = rec % n_kc;
-    uint32_t nb = idx >> 5, kk = idx & 31;
-    size_t row = kc * ZG_KR + kk;
-    size_t col0 = tile * ZG_TN + nb * 32;
+    size_t rec = gid >> 5;
+    uint32_t idx = (uint32_t)(gid & 31);
+    size_t nb = rec / n_kc, kc = rec % n_kc;
+    size_t row = kc * ZG_KR + zg_scale_slot_row(idx);
     float s = 0.0f;
-    if (row < K && col0 < N) s = scales[row * (N / 32) + col0 / 32];
+    if (row < K) s = scales[row * (N / 32) + nb];
     ST* dst = reinterpret_cast<ST*>(recs + rec * rec_bytes + q_bytes) + idx;
     if constexpr (sizeof(ST) == 2) *dst = __float2half_rn(s); // exact: format was verified
     else *dst = s;
@@ -109,7 +117,22 @@ __global__ void k_scale_max(const float* __restrict__ scales, float* __restrict_
     float m = 0.0f;
     if (nb < nbN)
         for (size_t k = 0; k < K; k++) m = fmaxf(m, fabsf(scales[k * nbN + nb]));
-    smax[nb] = m;
+    // rounded UP to a power of two (so that per-column-group rescaling of the staged activations is exact) and
+    // clamped to [2^-60, 2^60] (an all-zero group still gets a finite reciprocal; larger scales: inf -> NaN out)
+    float p2 = 8.673617379884035e-19f; // 2^-60
+    if (m > p2) {
+        int e;
+        float f = frexpf(m, &e);           // m = f * 2^e, f in [0.5, 1)
+        p2 = (f == 0.5f) ? ldexpf(1.0f, e - 1) : ldexpf(1.0f, e);
+    }
+    if (!(m <= 1.152921504606847e18f)) p2 = m; // > 2^60, inf or NaN: keep (poisons the outputs like the reference)
+    smax[nb] = p2;
+}
+
+// the record after the last one: q = 0 everywhere (int4: biased nibbles 8), scales 0 -> contributes exactly 0;
+// the matvec kernel points idle ring slots at it instead of branching
+__global__ void k_fill_dummy(uint8_t* __restrict__ rec, uint32_t q_bytes, uint32_t rec_bytes, int is_i4) {
+    for (uint32_t i = threadIdx.x; i < rec_bytes; i += blockDim.x) rec[i] = (i < q_bytes && is_i4) ? 0x88 : 0x00;
 }
 
 // GGUF raw blocks -> flat i8 + f32 scales (src/models/gguf_loader.zig:117-145).
@@ -142,22 +165,22 @@ __global__ void k_dequant_packed(const uint8_t* __restrict__ recs, int fmt, uint
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= K * N) return;
     size_t k = gid / N, n = gid % N;
-    size_t tile = n / ZG_TN, kc = k / ZG_KR;
+    size_t nb = n / ZG_TN, kc = k / ZG_KR;
     uint32_t kk = (uint32_t)(k % ZG_KR), c = (uint32_t)(n % ZG_TN);
-    uint32_t ct = c >> 4, cn = c & 15, g = cn & 7, r0 = cn >> 3, nb = c >> 5;
+    uint32_t ct = c >> 4, cn = c & 15, g = cn & 7, r0 = cn >> 3;
     uint32_t half = kk >> 4, t = (kk & 15) >> 2, b = kk & 3, L = 4 * g + t;
-    const uint8_t* rec = recs + (tile * n_kc + kc) * (size_t)rec_bytes;
+    const uint8_t* rec = recs + (nb * n_kc + kc) * (size_t)rec_bytes;
     int q;
     if (fmt == ZG_QFMT_I4_F16) {
-        uint32_t p = ct >> 1, wi = (ct & 1) * 2 + half;
-        uint8_t byte = rec[p * 512 + L * 16 + wi * 4 + b];
+        uint32_t wi = ct * 2 + half;
+        uint8_t byte = rec[L * 16 + wi * 4 + b];
         int nib = r0 ? (byte >> 4) : (byte & 0xF);
-        q = (nib ^ 8) - 8; // sign-extend the two's-complement nibble
+        q = nib - 8; // biased nibble, src/models/gguf_loader.zig:137-141
     } else {
         uint32_t r = r0 + 2 * half;
         q = (int)(int8_t)rec[ct * 512 + L * 16 + r * 4 + b];
     }
-    uint32_t sidx = nb * 32 + kk;
+    uint32_t sidx = zg_scale_row_slot(kk);
     float s;
     if (fmt == ZG_QFMT_I8_F32) s = reinterpret_cast<const float*>(rec + q_bytes)[sidx];
     else s = __half2float(reinterpret_cast<const __half*>(rec + q_bytes)[sidx]);
@@ -221,13 +244,13 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
         w->device_bytes = n_elems + n_blocks * sizeof(float);
         return w;
     }
-    w->n_tiles = (uint32_t)((N + ZG_TN - 1) / ZG_TN);
+    w->n_nb = (uint32_t)(N / ZG_TN);
     w->n_kc = (uint32_t)((K + ZG_KR - 1) / ZG_KR);
     w->q_bytes = zg_rec_q_bytes(fmt);
     w->rec_bytes = w->q_bytes + zg_rec_s_bytes(fmt);
-    size_t n_rec = (size_t)w->n_tiles * w->n_kc;
-    size_t bytes = n_rec * w->rec_bytes;
-    size_t nb_padded = (size_t)w->n_tiles * 2;
+    size_t n_rec = (size_t)w->n_nb * w->n_kc;
+    size_t bytes = (n_rec + 1) * w->rec_bytes; // + the dummy record
+    size_t nb_padded = (size_t)w->n_nb;
     if (cudaMalloc(&w->recs, bytes) != cudaSuccess || cudaMalloc(&w->smax, nb_padded * sizeof(float)) != cudaSuccess) {
         zg_set_error("cudaMalloc(%zu) for packed qweight failed", bytes);
         cudaFree(w->recs); delete w; return nullptr;
@@ -236,14 +259,16 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
     k_scale_max<<<grid_for(nb_padded, 128), 128, 0, st>>>(d_scales, w->smax, K, N / 32, nb_padded);
     ZG_COUNT_LAUNCH();
     if (fmt == ZG_QFMT_I4_F16) {
-        size_t n_units = n_rec * 64;
+        size_t n_units = n_rec * 32;
         k_pack_q4<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
     } else {
-        size_t n_units = n_rec * 128;
+        size_t n_units = n_rec * 64;
         k_pack_q8<<<grid_for(n_units, 256), 256, 0, st>>>(d_data, w->recs, w->rec_bytes, w->n_kc, K, N, n_units);
     }
     ZG_COUNT_LAUNCH();
-    size_t n_s = n_rec * 64;
+    k_fill_dummy<<<1, 128, 0, st>>>(w->recs + n_rec * w->rec_bytes, w->q_bytes, w->rec_bytes, fmt == ZG_QFMT_I4_F16);
+    ZG_COUNT_LAUNCH();
+    size_t n_s = n_rec * 32;
     if (fmt == ZG_QFMT_I8_F32)
         k_pack_scales<float><<<grid_for(n_s, 256), 256, 0, st>>>(d_scales, w->recs, w->rec_bytes, w->q_bytes, w->n_kc, K, N, n_s);
     else

@@ -30,33 +30,34 @@ extern std::atomic<uint64_t> g_zg_launches;
 // ── Packed, GPU-resident quantized weight ─────────────────────────────────────
 //
 // Fast formats (block_size == 32 and N % 32 == 0) are stored as RECORDS.  One
-// record covers ZG_TN = 64 output columns (2 quant blocks) x ZG_KR = 32 k-rows and
-// is laid out so that a warp's 128-bit shared-memory loads ARE the A fragments of
-// mma.sync.m16n8k32 (weights as the 16-row operand: 16 output columns x 32 k):
+// record covers one quant-block column group nb (ZG_TN = 32 output columns) x
+// ZG_KR = 32 k-rows, and is laid out so that a warp's 128-bit global loads ARE the
+// A fragments of mma.sync.m16n8k32 (weights as the 16-row operand: 16 output
+// columns x 32 k), with no shared-memory staging and no unpack for int8:
 //
-//   q area   int8 formats: 4 column tiles (16 columns each) x 512 B.  Inside a column
+//   q area   int8 formats: 2 column tiles (16 columns each) x 512 B.  Inside a column
 //            tile lane L = 4*g + t owns 16 B = regs r = 0..3, bytes b = 0..3 with
 //            column n = 16*ct + g + 8*(r & 1), row k = 4*t + b + 16*(r >> 1); the
 //            byte is q itself (two's complement).
-//            int4 format : 2 column-tile pairs x 512 B.  Lane L owns 16 B =
-//            {w0, w1 of ct = 2p, w0, w1 of ct = 2p + 1}; byte b of w0 holds rows
-//            k = 4*t + b: low nibble = q[k][n = 16*ct + g], high nibble =
-//            q[k][n = 16*ct + g + 8] (two's-complement nibbles); w1 is k + 16.
-//   s area   [nb 2][k 32] scales (f16 or f32): scale of row k, quant block nb.
+//            int4 format : 512 B.  Lane L owns 16 B = {w0, w1 of ct = 0, w0, w1 of
+//            ct = 1}; byte b of w0 holds rows k = 4*t + b: low nibble = q + 8 of
+//            column n = 16*ct + g, high nibble = q + 8 of column n = 16*ct + g + 8
+//            (the GGUF Q4_0 biased nibbles); w1 is k + 16.
+//   s area   [t 4][i 8] scales (f16 or f32): lane t's eight scales, i < 4: row
+//            k = 4*t + i, i >= 4: row k = 16 + 4*t + (i - 4).
 //
-// Records are laid out [n_tile][k_chunk]: the whole matrix is ONE contiguous run of
-// records, so any CTA's share of the work is a single span -> one cp.async.bulk per
-// pipeline stage.  Rows >= K and columns >= N are zero-padded (q = 0, scale = 0).
-// `smax[2 * n_tiles]` = max scale of each 32-column quant block over all k (used to
-// choose the fixed-point exponent of the activation*scale products, see qgemv.cu).
-#define ZG_TN 64
+// Records are laid out [nb][k_chunk]: a warp walking K for one column group reads one
+// contiguous run.  Rows >= K are zero-padded (q = 0, scale = 0).
+// `smax[n_nb]` = max scale of each 32-column quant block over all k (used to choose
+// the fixed-point exponent of the activation*scale products, see qgemv.cu).
+#define ZG_TN 32
 #define ZG_KR 32
 
 struct ZgCudaQWeight {
     int fmt = 0;                 // ZG_QFMT_*
     size_t K = 0, N = 0, bs = 0; // logical [K, N], block size
     // fast formats
-    uint32_t n_tiles = 0, n_kc = 0, rec_bytes = 0, q_bytes = 0;
+    uint32_t n_nb = 0, n_kc = 0, rec_bytes = 0, q_bytes = 0;
     uint8_t* recs = nullptr;
     float* smax = nullptr;
     // generic format: flat copies
@@ -65,10 +66,10 @@ struct ZgCudaQWeight {
     size_t device_bytes = 0;
 };
 
-static inline uint32_t zg_rec_q_bytes(int fmt) { return fmt == ZG_QFMT_I4_F16 ? 1024u : 2048u; }
-static inline uint32_t zg_rec_s_bytes(int fmt) { return fmt == ZG_QFMT_I8_F32 ? 256u : 128u; }
+static inline uint32_t zg_rec_q_bytes(int fmt) { return fmt == ZG_QFMT_I4_F16 ? 512u : 1024u; }
+static inline uint32_t zg_rec_s_bytes(int fmt) { return fmt == ZG_QFMT_I8_F32 ? 128u : 64u; }
 
-// split scratch: per-CTA partial sums of split column tiles + one arrival counter per column tile
+// split-K scratch: per-split partial sums of split column groups + one arrival counter per column group
 struct ZgGemvWs {
     float* partials = nullptr;
     size_t partials_elems = 0;
@@ -84,6 +85,7 @@ struct ZgCudaCtx {
     bool graph_mode = true;
     bool profiling = false;
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
+    int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
 };
 
@@ -96,9 +98,9 @@ void zg_gemv_ws_free(ZgGemvWs* ws);
 ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data, const float* d_scales,
                                            size_t K, size_t N, size_t bs, int fmt_hint);
 // qgemv.cu
-// Stream-K work split for one launch (<= 8 activation rows): CTAs, ring slots, row pairs.
+// Work split of one launch (<= 8 activation rows): P column groups per CTA, S k-splits per column group.
 struct ZgGemvPlan {
-    uint32_t grid = 0, n_ring = 1, smem_bytes = 0, mp = 1, max_contrib = 1;
+    uint32_t grid = 0, threads = 256, P = 1, S = 1, mp = 1, G = 2, NS = 3, lcap = 1, xs_stride = 32, smem_bytes = 0;
 };
 ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M);
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
