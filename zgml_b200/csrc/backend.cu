@@ -53,13 +53,15 @@ struct ZgCudaProgram {
     uint32_t* d_dyn = nullptr;
     uint32_t* h_dyn = nullptr; // pinned
     bool dyn_dirty = true;     // h_dyn differs from d_dyn
-    ZgGemvWs ws;
+    ZgGemvWs ws;                       // split-K scratch: one private slice per qmatmul op (ops may run concurrently)
+    std::vector<size_t> ws_part_off, ws_cnt_off;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool graph_valid = false;
     uint64_t graph_kernels = 0; // kernel nodes captured in `graph` (added to the launch counter per replay)
     ZgProfile profile;
     std::vector<cudaEvent_t> prof_events;
+    std::vector<cudaEvent_t> dep_events; // capture-time fork/join markers of the concurrent graph branches
 };
 
 // ── context ──────────────────────────────────────────────────────────────────
@@ -82,6 +84,13 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
     if (!zg_qgemv_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
+    int n_branch = 7; // capture streams for independent ops of a program (ZG_CUDA_BRANCH=0: strictly serial graphs)
+    if (const char* e = getenv("ZG_CUDA_BRANCH")) n_branch = atoi(e);
+    for (int i = 0; i < n_branch && i < 31; i++) {
+        cudaStream_t b;
+        if (cudaStreamCreateWithFlags(&b, cudaStreamNonBlocking) != cudaSuccess) break;
+        ctx->branch.push_back(b);
+    }
     return ctx;
 }
 
@@ -90,6 +99,7 @@ extern "C" void zg_cuda_destroy(ZgCudaCtx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     zg_gemv_ws_free(&ctx->ws);
+    for (cudaStream_t b : ctx->branch) cudaStreamDestroy(b);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -164,6 +174,7 @@ static void free_program(ZgCudaProgram* p) {
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->dep_events) cudaEventDestroy(e);
     delete p;
 }
 
@@ -218,14 +229,73 @@ static bool validate_ops(const ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) 
 
 static bool reserve_workspace(ZgCudaProgram* p) {
     size_t pe = 0, nc = 0;
-    for (const ZgOp& op : p->ops) {
+    p->ws_part_off.assign(p->ops.size(), 0);
+    p->ws_cnt_off.assign(p->ops.size(), 0);
+    for (size_t i = 0; i < p->ops.size(); i++) {
+        const ZgOp& op = p->ops[i];
         if (op.tag != ZG_OP_QMATMUL) continue;
         size_t a = 0, b = 0;
         zg_qgemv_ws_need(p->ctx, p->qweights[op.u.qmatmul.weight_idx], op.u.qmatmul.M, &a, &b);
-        if (a > pe) pe = a;
-        if (b > nc) nc = b;
+        p->ws_part_off[i] = pe; p->ws_cnt_off[i] = nc;
+        pe += a; nc += b;
     }
     return zg_gemv_ws_reserve(&p->ws, pe, nc, p->ctx->stream);
+}
+
+// ── op dependencies (element ranges per buffer) for concurrent graph branches ─────────────────
+struct ZgRange { uint32_t buf; size_t lo, hi; bool write; };
+
+static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRange>& out) {
+    out.clear();
+    auto whole = [&](uint32_t b, bool w) { out.push_back({b, 0, p->buffer_elems[b], w}); };
+    auto span = [&](uint32_t b, size_t lo, size_t n, bool w) { out.push_back({b, lo, lo + n, w}); };
+    switch (op.tag) {
+        case ZG_OP_ELEMENTWISE: {
+            const auto& e = op.u.elementwise;
+            span(e.dst, e.dst_offset, e.n, true); span(e.src0, e.src0_offset, e.n, false); span(e.src1, e.src1_offset, e.n, false);
+            break;
+        }
+        case ZG_OP_MATMUL: whole(op.u.matmul.dst, true); whole(op.u.matmul.a, false); whole(op.u.matmul.b, false); break;
+        case ZG_OP_QMATMUL: {
+            const auto& q = op.u.qmatmul;
+            const size_t irs = q.input_row_stride ? q.input_row_stride : q.K, drs = q.dst_row_stride ? q.dst_row_stride : q.N;
+            if (q.M == 0) break;
+            span(q.dst, q.dst_offset, (size_t)(q.M - 1) * drs + q.N, true);
+            span(q.input, q.input_offset, (size_t)(q.M - 1) * irs + q.K, false);
+            break;
+        }
+        case ZG_OP_SOFTMAX: span(op.u.softmax.dst, op.u.softmax.dst_offset, (size_t)op.u.softmax.rows * op.u.softmax.cols, true);
+                            span(op.u.softmax.src, op.u.softmax.src_offset, (size_t)op.u.softmax.rows * op.u.softmax.cols, false); break;
+        case ZG_OP_LAYERNORM: span(op.u.layernorm.dst, op.u.layernorm.dst_offset, (size_t)op.u.layernorm.rows * op.u.layernorm.cols, true);
+                              span(op.u.layernorm.src, op.u.layernorm.src_offset, (size_t)op.u.layernorm.rows * op.u.layernorm.cols, false); break;
+        case ZG_OP_RMSNORM: span(op.u.rmsnorm.dst, op.u.rmsnorm.dst_offset, (size_t)op.u.rmsnorm.rows * op.u.rmsnorm.cols, true);
+                            span(op.u.rmsnorm.src, op.u.rmsnorm.src_offset, (size_t)op.u.rmsnorm.rows * op.u.rmsnorm.cols, false); break;
+        case ZG_OP_REDUCE: whole(op.u.reduce.dst, true); whole(op.u.reduce.src, false); break;
+        case ZG_OP_REPEAT: whole(op.u.repeat.dst, true); whole(op.u.repeat.src, false); break;
+        case ZG_OP_SLICE_ASSIGN: whole(op.u.slice_assign.dst, true); whole(op.u.slice_assign.src, false); break;  // offset is dynamic
+        case ZG_OP_ROPE: whole(op.u.rope.dst, true); whole(op.u.rope.src, false); whole(op.u.rope.cos_sin, false); break;
+        case ZG_OP_ATTENTION: {
+            const auto& a = op.u.attention;
+            whole(a.dst, true); whole(a.q, false); whole(a.k, false); whole(a.v, false);
+            if (a.has_mask) whole(a.mask, false);
+            break;
+        }
+        case ZG_OP_FUSED_ELEMENTWISE: {
+            const auto& f = op.u.fused_elementwise;
+            span(f.dst, f.dst_offset, f.n, true); span(f.src, f.src_offset, f.n, false);
+            for (size_t k = 0; k < f.n_steps; k++)
+                if (f.steps[k].op == ZG_EW_ADD || f.steps[k].op == ZG_EW_MUL) span(f.steps[k].secondary_buf, f.steps[k].secondary_offset, f.n, false);
+            break;
+        }
+        default: break;
+    }
+}
+
+static bool ranges_conflict(const std::vector<ZgRange>& a, const std::vector<ZgRange>& b) {
+    for (const ZgRange& x : a)
+        for (const ZgRange& y : b)
+            if ((x.write || y.write) && x.buf == y.buf && x.lo < y.hi && y.lo < x.hi) return true;
+    return false;
 }
 
 extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog) {
@@ -316,27 +386,82 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
     }
 }
 
-static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
+static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
     ZgCudaCtx* ctx = p->ctx;
+    const ZgOp& op = p->ops[i];
+    if (op.tag == ZG_OP_QMATMUL) {
+        const auto& q = op.u.qmatmul;
+        ZgGemvWs view = p->ws;
+        if (view.partials) { view.partials += p->ws_part_off[i]; view.partials_elems -= p->ws_part_off[i]; }
+        if (view.counters) { view.counters += p->ws_cnt_off[i]; view.counters_n -= p->ws_cnt_off[i]; }
+        return zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
+                                 p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &view, st);
+    }
+    return zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
+}
+
+static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
     size_t n = p->ops.size();
     if (profile && p->prof_events.size() < n + 1) {
         while (p->prof_events.size() < n + 1) { cudaEvent_t e; cudaEventCreate(&e); p->prof_events.push_back(e); }
     }
     if (profile) cudaEventRecord(p->prof_events[0], st);
     for (size_t i = 0; i < n; i++) {
-        const ZgOp& op = p->ops[i];
-        bool ok;
-        if (op.tag == ZG_OP_QMATMUL) {
-            const auto& q = op.u.qmatmul;
-            ok = zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
-                                   p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &p->ws, st);
-        } else {
-            ok = zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
-        }
-        if (!ok) return false;
+        if (!launch_one(p, i, st)) return false;
         if (profile) cudaEventRecord(p->prof_events[i + 1], st);
     }
     return true;
+}
+
+// Inside a stream capture: ops whose buffer ranges do not conflict go to different capture streams, so the
+// instantiated graph runs them as concurrent branches (q/k/v, gate/up, independent matvecs).  Results are
+// identical to program order: every read-after-write, write-after-read and write-after-write pair stays ordered.
+static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
+    ZgCudaCtx* ctx = p->ctx;
+    const size_t n = p->ops.size();
+    const int ns = 1 + (int)ctx->branch.size();
+    std::vector<cudaStream_t> strs(1, origin);
+    strs.insert(strs.end(), ctx->branch.begin(), ctx->branch.end());
+    while (p->dep_events.size() < n + (size_t)ns + 1) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { zg_set_error("cudaEventCreate failed"); return false; }
+        p->dep_events.push_back(e);
+    }
+    std::vector<std::vector<ZgRange>> rng(n);
+    std::vector<int> op_stream(n, 0);
+    std::vector<long> last_on(ns, -1), dep(ns);
+    std::vector<char> joined(ns, 0);
+    joined[0] = 1;
+    cudaEvent_t fork_ev = p->dep_events[n];
+    ZG_CUDA_OK(cudaEventRecord(fork_ev, origin));
+    int rr = 0;
+    bool ok = true;
+    for (size_t i = 0; i < n && ok; i++) {
+        op_ranges(p, p->ops[i], rng[i]);
+        std::fill(dep.begin(), dep.end(), -1L);
+        int found = 0;
+        for (long k = (long)i - 1; k >= 0 && found < ns; k--) {   // latest conflicting op of every stream
+            const int sk = op_stream[k];
+            if (dep[sk] >= 0) continue;
+            if (ranges_conflict(rng[i], rng[k])) { dep[sk] = k; found++; }
+        }
+        int s = -1;
+        for (int sk = 0; sk < ns; sk++)
+            if (dep[sk] >= 0 && last_on[sk] == dep[sk]) { s = sk; break; }   // continue the producer's stream
+        if (s < 0) { s = rr; rr = (rr + 1) % ns; }
+        if (!joined[s]) { ZG_CUDA_OK(cudaStreamWaitEvent(strs[s], fork_ev, 0)); joined[s] = 1; }
+        for (int sk = 0; sk < ns; sk++)
+            if (sk != s && dep[sk] >= 0) ZG_CUDA_OK(cudaStreamWaitEvent(strs[s], p->dep_events[dep[sk]], 0));
+        ok = launch_one(p, i, strs[s]);
+        ZG_CUDA_OK(cudaEventRecord(p->dep_events[i], strs[s]));
+        op_stream[i] = s; last_on[s] = (long)i;
+    }
+    for (int sk = 1; sk < ns; sk++) {   // join every branch back into the origin stream (also on failure: the capture must end cleanly)
+        if (!joined[sk]) continue;
+        cudaEventRecord(p->dep_events[n + 1 + sk - 1], strs[sk]);
+        cudaStreamWaitEvent(origin, p->dep_events[n + 1 + sk - 1], 0);
+    }
+    return ok;
 }
 
 static bool run_ops(ZgCudaProgram* p) {
@@ -367,7 +492,7 @@ static bool run_ops(ZgCudaProgram* p) {
         if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
         ZG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const uint64_t before = g_zg_launches.load();
-        bool ok = launch_all(p, st, false);
+        bool ok = ctx->branch.empty() ? launch_all(p, st, false) : launch_all_branched(p, st);
         p->graph_kernels = g_zg_launches.load() - before;
         g_zg_launches.store(before); // captured, not launched: counted per replay below
         cudaError_t e = cudaStreamEndCapture(st, &p->graph);

@@ -54,16 +54,6 @@ struct QGemvParams {
     uint32_t* counters;
 };
 
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-// TMA bulk prefetch global -> L2 (no registers, no shared memory): DRAM streams ahead of the register ring
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 // D(16x8, s32) += A(16x32: weights) * B(32x8, u8: digits of x*s)
 __device__ __forceinline__ void imma_s8u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -101,6 +91,17 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+constexpr uint32_t kPlaneRow = 144;   // bytes per (record, activation row) digit planes: 4 x 32 B + 16 B bank skew
+
 // FMT: ZG_QFMT_I8_F32 / ZG_QFMT_I8_F16 / ZG_QFMT_I4_F16.  MP: pairs of activation rows (M <= 2*MP).
 template <int FMT, int MP>
 __global__ void __launch_bounds__(kThreads, MP <= 2 ? 2 : 1)
@@ -114,7 +115,8 @@ qgemv_kernel(const QGemvParams p) {
 
     __shared__ float part[2][kMaxWarps][MR][ZG_TN];
     __shared__ uint32_t s_last;
-    // dynamic: [warp][row][xs_stride] scaled activations | [warp][slot][G records] weight ring | [warp][slot] mbarriers
+    // dynamic: [warp][row][xs_stride] scaled activations | [warp][slot][G records] weight ring |
+    //          [warp][G][MR][kPlaneRow] digit planes | [warp][slot] mbarriers
     extern __shared__ __align__(128) uint8_t dsm[];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
@@ -131,9 +133,13 @@ qgemv_kernel(const QGemvParams p) {
     const uint32_t total_chunks = n_chunk * (nb_end - nb_begin);
     const uint32_t slot_bytes = G * RB;
 
+    const uint32_t dsm_u32 = smem_u32(dsm);
+    const uint32_t xs_bytes = W * MR * p.xs_stride * 4, ring_bytes = W * NS * slot_bytes, plane_bytes = G * MR * kPlaneRow;
     float* xs_w = reinterpret_cast<float*>(dsm) + (size_t)warp * MR * p.xs_stride;
-    const uint32_t ring = smem_u32(dsm) + W * MR * p.xs_stride * 4 + warp * NS * slot_bytes;
-    const uint32_t bars = smem_u32(dsm) + W * MR * p.xs_stride * 4 + W * NS * slot_bytes + warp * NS * 8;
+    const uint32_t xs_u32 = dsm_u32 + warp * MR * p.xs_stride * 4;
+    const uint32_t ring = dsm_u32 + xs_bytes + warp * NS * slot_bytes;
+    const uint32_t planes = dsm_u32 + xs_bytes + ring_bytes + warp * plane_bytes;
+    const uint32_t bars = dsm_u32 + xs_bytes + ring_bytes + W * plane_bytes + warp * NS * 8;
 
     // Programmatic dependent launch: the next kernel in the stream may begin (and prefetch ITS weights, which
     // nobody writes) as soon as SM resources free up.  Everything mutable (x, out, partials, counters) is
@@ -143,19 +149,27 @@ qgemv_kernel(const QGemvParams p) {
     // ── per-warp ring of NS slots in shared memory, filled by TMA bulk copies (one per chunk of <= G
     //    consecutive records, issued by lane 0, completion on the slot's mbarrier).  The first NS chunks are
     //    requested right away. ──
-    const uint8_t* run0 = p.recs + ((size_t)nb_begin * p.n_kc + k0) * RB;   // this warp's run in the first column group
-    auto issue_chunk = [&](uint32_t ci) {   // lane 0 only; ci = linear chunk index over (column group, chunk)
-        const uint32_t nbi = ci / n_chunk, c = ci - nbi * n_chunk;
-        const uint32_t cnt = min(G, L - c * G);
-        const uint32_t slot = ci % NS;
-        const uint32_t bar = bars + slot * 8;
+    // producer cursor (lane 0): next chunk to request = chunk pf_c of column group offset pf_nb, into slot pf_slot
+    uint32_t pf_c = 0, pf_slot = 0, pf_left = total_chunks;
+    const uint8_t* pf_src = p.recs + ((size_t)nb_begin * p.n_kc + k0) * RB;   // this warp's run in the current pf column group
+    auto issue_chunk = [&]() {   // lane 0 only
+        const uint32_t cnt = min(G, L - pf_c * G);
+        const uint32_t bar = bars + pf_slot * 8;
         mbar_expect_tx(bar, cnt * RB);
-        bulk_g2s(ring + slot * slot_bytes, run0 + ((size_t)nbi * p.n_kc + c * G) * RB, cnt * RB, bar);
+        bulk_g2s(ring + pf_slot * slot_bytes, pf_src + (size_t)pf_c * G * RB, cnt * RB, bar);
+        pf_left--;
+        if (++pf_c == n_chunk) { pf_c = 0; pf_src += (size_t)p.n_kc * RB; }
+        if (++pf_slot == NS) pf_slot = 0;
     };
     if (lane == 0) {
         for (uint32_t s = 0; s < NS; s++) mbar_init(bars + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (uint32_t ci = 0; ci < NS && ci < total_chunks; ci++) issue_chunk(ci);
+        for (uint32_t i = 0; i < NS && pf_left; i++) issue_chunk();
+    }
+    // the constant ones plane (digit index 3) of every (record, row): B column of ones -> sum_k q
+    for (uint32_t i = lane; i < G * MR * 8; i += 32) {
+        const uint32_t rm = i >> 3, w4 = i & 7;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(planes + rm * kPlaneRow + 96 + w4 * 4), "r"(0x01010101u) : "memory");
     }
     __syncwarp();
     float sm_next = __ldg(p.smax + nb_begin);      // power of two >= every scale of the column group
@@ -164,48 +178,48 @@ qgemv_kernel(const QGemvParams p) {
 
     // ── stage x'[m, k] = x[m, k] * 0.499 / (max|x| * smax) of this warp's k-range in shared memory (so that
     //    |s * x'| <= 0.499).  Non-finite activations poison the partial sums (NaN out, like the reference);
-    //    rows >= M and k >= K read as zero. ──
+    //    k >= K reads as zero; only rows < M are staged (the other B columns alias row M - 1). ──
     float xm[MR];
     {
         const uint32_t kb = k0 * ZG_KR;
         const float rsm = 1.0f / sm_next;
 #pragma unroll
         for (int m = 0; m < MR; m++) {
-            const float* xr = p.x + (size_t)m * p.x_rs + kb + lane;
-            float* xd = xs_w + (size_t)m * p.xs_stride + lane;
-            const bool row_ok = (uint32_t)m < p.M;
-            float mx = 0.0f;
-            for (uint32_t i0 = 0; i0 < L; i0 += 4) {   // raw copy + max, four independent loads at a time
-                float v[4];
+            xm[m] = 0.0f;
+            if ((uint32_t)m < p.M) {
+                const float* xr = p.x + (size_t)m * p.x_rs + kb + lane;
+                float* xd = xs_w + (size_t)m * p.xs_stride + lane;
+                float v[kLcap];
+                float mx = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 4; i++)
-                    v[i] = (row_ok && i0 + i < L && kb + lane + 32 * (i0 + i) < p.K) ? xr[32 * (i0 + i)] : 0.0f;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i0 + i < L) xd[32 * (i0 + i)] = v[i];
+                for (int i = 0; i < (int)kLcap; i++) {
+                    v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? xr[32 * i] : 0.0f;
                     const float aa = fabsf(v[i]);
                     mx = (aa <= 3.0e38f) ? fmaxf(mx, aa) : INFINITY;
                 }
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            xm[m] = mx;
-            const float f = (mx <= 3.0e38f && mx >= 1.0e-30f) ? (0.499f / mx) * rsm : 0.0f;   // tiny rows flush to zero
-            for (uint32_t i = 0; i < L; i++) xd[32 * i] *= f;   // each lane rescales what it wrote
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                xm[m] = mx;
+                const float f = (mx <= 3.0e38f && mx >= 1.0e-30f) ? (0.499f / mx) * rsm : 0.0f;   // tiny rows flush to zero
+#pragma unroll
+                for (int i = 0; i < (int)kLcap; i++)
+                    if ((uint32_t)i < L) xd[32 * i] = v[i] * f;
+            }
         }
         __syncwarp();
     }
-    // this lane's B column g carries digit j (or the ones column) of activation row 2*mp + (g >> 2)
-    const uint32_t sel = j | ((4u + j) << 4);      // PRMT selector: byte j of both operands
-    const bool is_digit = j < 3;
-    uint32_t xrow[MP];   // shared address of this lane's activation row: + r * 128 is k = (k0 + r) * 32 + 4 t
+
+    // MMA role of this lane: B column g = digit j (j == 3: the ones plane) of activation row 2*mp + (g >> 2)
+    uint32_t brow[MP];
 #pragma unroll
-    for (int mp = 0; mp < MP; mp++) xrow[mp] = smem_u32(xs_w + (size_t)(2 * mp + (g >> 2)) * p.xs_stride + 4 * t);
-    const uint32_t q_off = lane * 16, s_off = QB + t * SB;
+    for (int mp = 0; mp < MP; mp++) brow[mp] = planes + min((uint32_t)(2 * mp) + (g >> 2), p.M - 1) * kPlaneRow + j * 32 + 4 * t;
+    const uint32_t q_off = lane * 16;
+    // digit-generation role of this lane: k row `lane` of each record
+    const uint32_t sc_off = QB + (kF32 ? 4u : 2u) * (8 * ((lane & 15) >> 2) + 4 * (lane >> 4) + (lane & 3));  // zg_scale_row_slot(lane)
 
     int acc[MP][2][4];
     uint32_t dsum[MP];
-    uint32_t buf = 0, ci = 0;
+    uint32_t buf = 0, slot = 0, parity = 0;
     float sm_prev = sm_next;
 
     for (uint32_t nb = nb_begin; nb < nb_end; nb++) {
@@ -214,8 +228,7 @@ qgemv_kernel(const QGemvParams p) {
         if (sm != sm_prev) {
             // re-normalise the staged activations for this column group's scale: exact (powers of two)
             const float ratio = sm_prev / sm;
-#pragma unroll
-            for (int m = 0; m < MR; m++) {
+            for (uint32_t m = 0; m < p.M && m < (uint32_t)MR; m++) {
                 float* xd = xs_w + (size_t)m * p.xs_stride + lane;
                 for (uint32_t i = 0; i < L; i++) xd[32 * i] *= ratio;
             }
@@ -231,69 +244,69 @@ qgemv_kernel(const QGemvParams p) {
                 for (int i = 0; i < 4; i++) acc[mp][ct][i] = 0;
         }
 
-        for (uint32_t c = 0; c < n_chunk; c++, ci++) {
-            const uint32_t slot = ci % NS;
+        for (uint32_t c = 0; c < n_chunk; c++) {
             const uint32_t cnt = min(G, L - c * G);
-            mbar_wait(bars + slot * 8, (ci / NS) & 1);
-            uint32_t rec = ring + slot * slot_bytes;      // shared address of the record
-            uint32_t xo = c * G * (ZG_KR * 4);            // byte offset of the record's activations in the staged row
-            for (uint32_t r = 0; r < cnt; r++, rec += RB, xo += ZG_KR * 4) {
-                // ── scales of this lane's eight k rows ──
-                float sc[8];
-                {
-                    const uint4 s0 = lds128(rec + s_off);
+            const uint32_t slot_u32 = ring + slot * slot_bytes;
+            mbar_wait(bars + slot * 8, parity);
+            // ── digit generation, lane = k: F = s * x' + 1.5 in (1, 2); the three low bytes of F are the
+            //    base-256 digits of c / E2 + 0.5 -> byte planes [record][row][digit][k] ──
+            {
+                uint32_t sa = slot_u32 + sc_off, xa = xs_u32 + (c * G * ZG_KR + lane) * 4, pa = planes + lane;
+                for (uint32_t r = 0; r < cnt; r++, sa += RB, xa += ZG_KR * 4, pa += MR * kPlaneRow) {
+                    float sc;
                     if constexpr (kF32) {
-                        const uint4 s1 = lds128(rec + s_off + 16);
-                        sc[0] = __uint_as_float(s0.x); sc[1] = __uint_as_float(s0.y); sc[2] = __uint_as_float(s0.z); sc[3] = __uint_as_float(s0.w);
-                        sc[4] = __uint_as_float(s1.x); sc[5] = __uint_as_float(s1.y); sc[6] = __uint_as_float(s1.z); sc[7] = __uint_as_float(s1.w);
+                        sc = __uint_as_float(lds32(sa));
                     } else {
-                        const uint32_t hw[4] = {s0.x, s0.y, s0.z, s0.w};
+                        unsigned short h;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sa));
+                        sc = __half2float(__ushort_as_half(h));
+                    }
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-                            sc[2 * i] = f.x; sc[2 * i + 1] = f.y;
+                    for (int m = 0; m < MR; m++) {
+                        if ((uint32_t)m < p.M) {
+                            const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + m * p.xs_stride * 4)), 1.5f));
+                            sts8(pa + m * kPlaneRow, F);
+                            sts8(pa + m * kPlaneRow + 32, F >> 8);
+                            sts8(pa + m * kPlaneRow + 64, F >> 16);
                         }
                     }
                 }
-                // ── weights: the shared-memory bytes ARE the A fragments ──
-                uint32_t a[2][4];
-                if constexpr (!kI4) {
-                    const uint4 q0 = lds128(rec + q_off), q1 = lds128(rec + q_off + 512);
-                    a[0][0] = q0.x; a[0][1] = q0.y; a[0][2] = q0.z; a[0][3] = q0.w;
-                    a[1][0] = q1.x; a[1][1] = q1.y; a[1][2] = q1.z; a[1][3] = q1.w;
-                } else {
-                    // row g: 16 u[n + 8] + u[n], row g + 8: u[n]
-                    const uint4 q0 = lds128(rec + q_off);
-                    a[0][0] = q0.x; a[0][1] = q0.x & 0x0F0F0F0Fu; a[0][2] = q0.y; a[0][3] = q0.y & 0x0F0F0F0Fu;
-                    a[1][0] = q0.z; a[1][1] = q0.z & 0x0F0F0F0Fu; a[1][2] = q0.w; a[1][3] = q0.w & 0x0F0F0F0Fu;
-                }
-#pragma unroll
-                for (int mp = 0; mp < MP; mp++) {
-                    const uint4 lo = lds128(xrow[mp] + xo), hi = lds128(xrow[mp] + xo + 64);
-                    const float xv[8] = {__uint_as_float(lo.x), __uint_as_float(lo.y), __uint_as_float(lo.z), __uint_as_float(lo.w),
-                                         __uint_as_float(hi.x), __uint_as_float(hi.y), __uint_as_float(hi.z), __uint_as_float(hi.w)};
-                    // F = s * x' + 1.5 in (1, 2): the three low bytes are the base-256 digits of c / E2 + 0.5
-                    uint32_t F[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) F[i] = __float_as_uint(fmaf(sc[i], xv[i], 1.5f));
-                    uint32_t b0 = __byte_perm(__byte_perm(F[0], F[1], sel), __byte_perm(F[2], F[3], sel), 0x5410);
-                    uint32_t b1 = __byte_perm(__byte_perm(F[4], F[5], sel), __byte_perm(F[6], F[7], sel), 0x5410);
-                    if (!is_digit) { b0 = 0x01010101u; b1 = 0x01010101u; }   // ones column: sum_k q
-                    if constexpr (kI4) {
-                        dsum[mp] = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum[mp]));
-                        imma_u8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                        imma_u8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+            }
+            __syncwarp();
+            // ── MMA: the ring's shared-memory bytes ARE the A fragments, the planes ARE the B fragments ──
+            {
+                uint32_t qa = slot_u32 + q_off, po = 0;
+                for (uint32_t r = 0; r < cnt; r++, qa += RB, po += MR * kPlaneRow) {
+                    uint32_t a[2][4];
+                    if constexpr (!kI4) {
+                        const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
+                        a[0][0] = q0.x; a[0][1] = q0.y; a[0][2] = q0.z; a[0][3] = q0.w;
+                        a[1][0] = q1.x; a[1][1] = q1.y; a[1][2] = q1.z; a[1][3] = q1.w;
                     } else {
-                        imma_s8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                        imma_s8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                        // row g: 16 u[n + 8] + u[n], row g + 8: u[n]
+                        const uint4 q0 = lds128(qa);
+                        a[0][0] = q0.x; a[0][1] = q0.x & 0x0F0F0F0Fu; a[0][2] = q0.y; a[0][3] = q0.y & 0x0F0F0F0Fu;
+                        a[1][0] = q0.z; a[1][1] = q0.z & 0x0F0F0F0Fu; a[1][2] = q0.w; a[1][3] = q0.w & 0x0F0F0F0Fu;
+                    }
+#pragma unroll
+                    for (int mp = 0; mp < MP; mp++) {
+                        const uint32_t b0 = lds32(brow[mp] + po), b1 = lds32(brow[mp] + po + 16);
+                        if constexpr (kI4) {
+                            dsum[mp] = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum[mp]));
+                            imma_u8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                            imma_u8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                        } else {
+                            imma_s8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                            imma_s8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                        }
                     }
                 }
             }
-            // ── every lane is done with the slot: lane 0 requests the chunk NS ahead into it ──
+            // ── every lane is done with the slot and the planes: lane 0 requests the chunk NS ahead ──
             __syncwarp();
-            if (lane == 0 && ci + NS < total_chunks) issue_chunk(ci + NS);
+            if (lane == 0 && pf_left) issue_chunk();
+            if (++slot == NS) { slot = 0; parity ^= 1; }
         }
-
         // ── flush: integer sums -> float partials of this warp in shared memory ──
         {
             const uint32_t kcnt = L * ZG_KR;   // rows fed to the MMA
@@ -400,7 +413,7 @@ __global__ void qmatmul_generic_kernel(const int8_t* __restrict__ data, const fl
 }
 
 template <int FMT, int MP>
-void launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
+bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
     cfg.blockDim = dim3(plan.threads);
@@ -412,16 +425,20 @@ void launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP>, p);
-    if (e != cudaSuccess) zg_set_error("qgemv launch failed: %s", cudaGetErrorString(e));
     ZG_COUNT_LAUNCH();
+    if (e != cudaSuccess) {
+        zg_set_error("qgemv launch failed: %s (grid %u, %u B shared)", cudaGetErrorString(e), plan.grid, plan.smem_bytes);
+        return false;
+    }
+    return true;
 }
 
 template <int FMT>
 bool launch_fmt(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
     switch (plan.mp) {
-        case 1: launch_fast<FMT, 1>(plan, p, st, pdl); return true;
-        case 2: launch_fast<FMT, 2>(plan, p, st, pdl); return true;
-        case 4: launch_fast<FMT, 4>(plan, p, st, pdl); return true;
+        case 1: return launch_fast<FMT, 1>(plan, p, st, pdl);
+        case 2: return launch_fast<FMT, 2>(plan, p, st, pdl);
+        case 4: return launch_fast<FMT, 4>(plan, p, st, pdl);
         default: zg_set_error("qmatmul: bad plan (row pairs %u)", plan.mp); return false;
     }
 }
@@ -439,7 +456,8 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     const uint32_t warps = kThreads / 32;
     // k-splits: each warp stages its k-range of the activations in shared memory -> at most kLcap records per
     // warp; beyond that, split K across CTAs until the grid fills the resident slots (>= 4 records per warp)
-    uint32_t S = (w->n_kc + warps * kLcap - 1) / (warps * kLcap);
+    const uint32_t lcap_max = kLcap / pl.mp;   // staged activations stay <= 32 KB per CTA
+    uint32_t S = (w->n_kc + warps * lcap_max - 1) / (warps * lcap_max);
     if (w->n_nb * S < target) {
         uint32_t fill = target / w->n_nb;
         const uint32_t by_work = w->n_kc / (warps * 4);
@@ -461,7 +479,11 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     pl.NS = ctx->tune_u ? (uint32_t)ctx->tune_u : 3;
     if (pl.G > pl.lcap) pl.G = pl.lcap;
     pl.xs_stride = pl.lcap * ZG_KR;
-    pl.smem_bytes = warps * (2 * pl.mp) * pl.xs_stride * 4 + warps * pl.NS * pl.G * rb + warps * pl.NS * 8;
+    auto smem_of = [&]() {
+        return warps * (2 * pl.mp) * pl.xs_stride * 4 + warps * pl.NS * pl.G * rb + warps * pl.G * (2 * pl.mp) * kPlaneRow + warps * pl.NS * 8;
+    };
+    while (smem_of() > 200 * 1024 && (pl.NS > 2 || pl.G > 1)) { if (pl.NS > 2) pl.NS--; else pl.G--; }
+    pl.smem_bytes = smem_of();
     pl.grid = ((w->n_nb + P - 1) / P) * S;
     return pl;
 }

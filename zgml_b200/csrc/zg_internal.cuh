@@ -87,6 +87,7 @@ struct ZgCudaCtx {
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
+    std::vector<cudaStream_t> branch; // extra capture streams: independent ops of a program become concurrent graph branches
 };
 
 // Grow-only (re)allocation; counters are zero-filled.  Never call between a graph
