@@ -32,6 +32,7 @@
 #include "zg_internal.cuh"
 
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -49,7 +50,7 @@ struct QGemvParams {
     uint32_t xs_stride;    // floats per staged activation row of a warp (shared memory: [warp][row][xs_stride])
     float* out;
     uint32_t out_rs;
-    uint32_t P, S, G, NS;
+    uint32_t P, S, NS;
     float* partials;
     uint32_t* counters;
 };
@@ -103,8 +104,9 @@ __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
 constexpr uint32_t kPlaneRow = 144;   // bytes per (record, activation row) digit planes: 4 x 32 B + 16 B bank skew
 
 // FMT: ZG_QFMT_I8_F32 / ZG_QFMT_I8_F16 / ZG_QFMT_I4_F16.  MP: pairs of activation rows (M <= 2*MP).
-template <int FMT, int MP>
-__global__ void __launch_bounds__(kThreads, MP <= 2 ? 2 : 1)
+// XR: activation rows staged per warp (1 for the decode matvec M == 1, else 2*MP).
+template <int FMT, int MP, int XR>
+__global__ void __launch_bounds__(kThreads, MP == 1 ? 3 : (MP == 2 ? 2 : 1))
 qgemv_kernel(const QGemvParams p) {
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
     constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
@@ -128,15 +130,16 @@ qgemv_kernel(const QGemvParams p) {
     const uint32_t ke = (uint32_t)(((uint64_t)(split + 1) * p.n_kc) / p.S);
     const uint32_t k0 = ks + (warp * (ke - ks)) / W, k1 = ks + ((warp + 1) * (ke - ks)) / W;
     const uint32_t L = k1 - k0;                    // records per column group for this warp (<= lcap)
-    const uint32_t G = p.G, NS = p.NS;             // records per ring slot, ring slots
+    constexpr uint32_t G = kI4 ? 4u : 2u;          // records per ring slot (one TMA bulk copy)
+    const uint32_t NS = p.NS;                      // ring slots
     const uint32_t n_chunk = (L + G - 1) / G;      // chunks (= bulk copies) per column group
     const uint32_t total_chunks = n_chunk * (nb_end - nb_begin);
-    const uint32_t slot_bytes = G * RB;
+    constexpr uint32_t slot_bytes = G * RB;
 
     const uint32_t dsm_u32 = smem_u32(dsm);
-    const uint32_t xs_bytes = W * MR * p.xs_stride * 4, ring_bytes = W * NS * slot_bytes, plane_bytes = G * MR * kPlaneRow;
-    float* xs_w = reinterpret_cast<float*>(dsm) + (size_t)warp * MR * p.xs_stride;
-    const uint32_t xs_u32 = dsm_u32 + warp * MR * p.xs_stride * 4;
+    const uint32_t xs_bytes = W * XR * p.xs_stride * 4, ring_bytes = W * NS * slot_bytes, plane_bytes = G * XR * kPlaneRow;
+    float* xs_w = reinterpret_cast<float*>(dsm) + (size_t)warp * XR * p.xs_stride;
+    const uint32_t xs_u32 = dsm_u32 + warp * XR * p.xs_stride * 4;
     const uint32_t ring = dsm_u32 + xs_bytes + warp * NS * slot_bytes;
     const uint32_t planes = dsm_u32 + xs_bytes + ring_bytes + warp * plane_bytes;
     const uint32_t bars = dsm_u32 + xs_bytes + ring_bytes + W * plane_bytes + warp * NS * 8;
@@ -167,7 +170,7 @@ qgemv_kernel(const QGemvParams p) {
         for (uint32_t i = 0; i < NS && pf_left; i++) issue_chunk();
     }
     // the constant ones plane (digit index 3) of every (record, row): B column of ones -> sum_k q
-    for (uint32_t i = lane; i < G * MR * 8; i += 32) {
+    for (uint32_t i = lane; i < G * XR * 8; i += 32) {
         const uint32_t rm = i >> 3, w4 = i & 7;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(planes + rm * kPlaneRow + 96 + w4 * 4), "r"(0x01010101u) : "memory");
     }
@@ -184,9 +187,10 @@ qgemv_kernel(const QGemvParams p) {
         const uint32_t kb = k0 * ZG_KR;
         const float rsm = 1.0f / sm_next;
 #pragma unroll
-        for (int m = 0; m < MR; m++) {
-            xm[m] = 0.0f;
-            if ((uint32_t)m < p.M) {
+        for (int m = 0; m < MR; m++) xm[m] = 0.0f;
+#pragma unroll
+        for (int m = 0; m < XR; m++) {
+            if (XR == 1 || (uint32_t)m < p.M) {
                 const float* xr = p.x + (size_t)m * p.x_rs + kb + lane;
                 float* xd = xs_w + (size_t)m * p.xs_stride + lane;
                 float v[kLcap];
@@ -212,14 +216,16 @@ qgemv_kernel(const QGemvParams p) {
     // MMA role of this lane: B column g = digit j (j == 3: the ones plane) of activation row 2*mp + (g >> 2)
     uint32_t brow[MP];
 #pragma unroll
-    for (int mp = 0; mp < MP; mp++) brow[mp] = planes + min((uint32_t)(2 * mp) + (g >> 2), p.M - 1) * kPlaneRow + j * 32 + 4 * t;
+    for (int mp = 0; mp < MP; mp++)
+        brow[mp] = planes + (XR == 1 ? 0u : min((uint32_t)(2 * mp) + (g >> 2), p.M - 1)) * kPlaneRow + j * 32 + 4 * t;
     const uint32_t q_off = lane * 16;
     // digit-generation role of this lane: k row `lane` of each record
     const uint32_t sc_off = QB + (kF32 ? 4u : 2u) * (8 * ((lane & 15) >> 2) + 4 * (lane >> 4) + (lane & 3));  // zg_scale_row_slot(lane)
 
     int acc[MP][2][4];
     uint32_t dsum[MP];
-    uint32_t buf = 0, slot = 0, parity = 0;
+    uint32_t buf = 0, slot = 0, parity = 0, slot_u32 = ring, bar_u32 = bars;
+    const uint32_t xs_row_bytes = p.xs_stride * 4;
     float sm_prev = sm_next;
 
     for (uint32_t nb = nb_begin; nb < nb_end; nb++) {
@@ -228,7 +234,7 @@ qgemv_kernel(const QGemvParams p) {
         if (sm != sm_prev) {
             // re-normalise the staged activations for this column group's scale: exact (powers of two)
             const float ratio = sm_prev / sm;
-            for (uint32_t m = 0; m < p.M && m < (uint32_t)MR; m++) {
+            for (uint32_t m = 0; m < p.M && m < (uint32_t)XR; m++) {
                 float* xd = xs_w + (size_t)m * p.xs_stride + lane;
                 for (uint32_t i = 0; i < L; i++) xd[32 * i] *= ratio;
             }
@@ -244,68 +250,75 @@ qgemv_kernel(const QGemvParams p) {
                 for (int i = 0; i < 4; i++) acc[mp][ct][i] = 0;
         }
 
-        for (uint32_t c = 0; c < n_chunk; c++) {
+        uint32_t xa = xs_u32 + lane * 4;   // this lane's (k = lane) staged activation of the chunk's first record
+        for (uint32_t c = 0; c < n_chunk; c++, xa += G * ZG_KR * 4) {
             const uint32_t cnt = min(G, L - c * G);
-            const uint32_t slot_u32 = ring + slot * slot_bytes;
-            mbar_wait(bars + slot * 8, parity);
-            // ── digit generation, lane = k: F = s * x' + 1.5 in (1, 2); the three low bytes of F are the
-            //    base-256 digits of c / E2 + 0.5 -> byte planes [record][row][digit][k] ──
-            {
-                uint32_t sa = slot_u32 + sc_off, xa = xs_u32 + (c * G * ZG_KR + lane) * 4, pa = planes + lane;
-                for (uint32_t r = 0; r < cnt; r++, sa += RB, xa += ZG_KR * 4, pa += MR * kPlaneRow) {
-                    float sc;
-                    if constexpr (kF32) {
-                        sc = __uint_as_float(lds32(sa));
-                    } else {
-                        unsigned short h;
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sa));
-                        sc = __half2float(__ushort_as_half(h));
-                    }
+            mbar_wait(bar_u32, parity);
+            auto chunk = [&](auto full_tag) {
+                constexpr bool FULL = decltype(full_tag)::value;
+                // ── digit generation, lane = k: F = s * x' + 1.5 in (1, 2); the three low bytes of F are the
+                //    base-256 digits of c / E2 + 0.5 -> byte planes [record][row][digit][k] ──
 #pragma unroll
-                    for (int m = 0; m < MR; m++) {
-                        if ((uint32_t)m < p.M) {
-                            const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + m * p.xs_stride * 4)), 1.5f));
-                            sts8(pa + m * kPlaneRow, F);
-                            sts8(pa + m * kPlaneRow + 32, F >> 8);
-                            sts8(pa + m * kPlaneRow + 64, F >> 16);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            // ── MMA: the ring's shared-memory bytes ARE the A fragments, the planes ARE the B fragments ──
-            {
-                uint32_t qa = slot_u32 + q_off, po = 0;
-                for (uint32_t r = 0; r < cnt; r++, qa += RB, po += MR * kPlaneRow) {
-                    uint32_t a[2][4];
-                    if constexpr (!kI4) {
-                        const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
-                        a[0][0] = q0.x; a[0][1] = q0.y; a[0][2] = q0.z; a[0][3] = q0.w;
-                        a[1][0] = q1.x; a[1][1] = q1.y; a[1][2] = q1.z; a[1][3] = q1.w;
-                    } else {
-                        // row g: 16 u[n + 8] + u[n], row g + 8: u[n]
-                        const uint4 q0 = lds128(qa);
-                        a[0][0] = q0.x; a[0][1] = q0.x & 0x0F0F0F0Fu; a[0][2] = q0.y; a[0][3] = q0.y & 0x0F0F0F0Fu;
-                        a[1][0] = q0.z; a[1][1] = q0.z & 0x0F0F0F0Fu; a[1][2] = q0.w; a[1][3] = q0.w & 0x0F0F0F0Fu;
-                    }
-#pragma unroll
-                    for (int mp = 0; mp < MP; mp++) {
-                        const uint32_t b0 = lds32(brow[mp] + po), b1 = lds32(brow[mp] + po + 16);
-                        if constexpr (kI4) {
-                            dsum[mp] = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum[mp]));
-                            imma_u8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                            imma_u8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                for (uint32_t r = 0; r < G; r++) {
+                    if (FULL || r < cnt) {
+                        float sc;
+                        if constexpr (kF32) {
+                            sc = __uint_as_float(lds32(slot_u32 + sc_off + r * RB));
                         } else {
-                            imma_s8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                            imma_s8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                            unsigned short h;
+                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(slot_u32 + sc_off + r * RB));
+                            sc = __half2float(__ushort_as_half(h));
+                        }
+#pragma unroll
+                        for (int m = 0; m < XR; m++) {
+                            if (XR == 1 || (uint32_t)m < p.M) {
+                                const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + r * ZG_KR * 4 + m * xs_row_bytes)), 1.5f));
+                                const uint32_t pa = planes + lane + (r * XR + m) * kPlaneRow;
+                                sts8(pa, F);
+                                sts8(pa + 32, F >> 8);
+                                sts8(pa + 64, F >> 16);
+                            }
                         }
                     }
                 }
-            }
+                __syncwarp();
+                // ── MMA: the ring's shared-memory bytes ARE the A fragments, the planes ARE the B fragments ──
+#pragma unroll
+                for (uint32_t r = 0; r < G; r++) {
+                    if (FULL || r < cnt) {
+                        const uint32_t qa = slot_u32 + q_off + r * RB;
+                        uint32_t a[2][4];
+                        if constexpr (!kI4) {
+                            const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
+                            a[0][0] = q0.x; a[0][1] = q0.y; a[0][2] = q0.z; a[0][3] = q0.w;
+                            a[1][0] = q1.x; a[1][1] = q1.y; a[1][2] = q1.z; a[1][3] = q1.w;
+                        } else {
+                            // row g: 16 u[n + 8] + u[n], row g + 8: u[n]
+                            const uint4 q0 = lds128(qa);
+                            a[0][0] = q0.x; a[0][1] = q0.x & 0x0F0F0F0Fu; a[0][2] = q0.y; a[0][3] = q0.y & 0x0F0F0F0Fu;
+                            a[1][0] = q0.z; a[1][1] = q0.z & 0x0F0F0F0Fu; a[1][2] = q0.w; a[1][3] = q0.w & 0x0F0F0F0Fu;
+                        }
+#pragma unroll
+                        for (int mp = 0; mp < MP; mp++) {
+                            const uint32_t b0 = lds32(brow[mp] + r * XR * kPlaneRow), b1 = lds32(brow[mp] + r * XR * kPlaneRow + 16);
+                            if constexpr (kI4) {
+                                dsum[mp] = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum[mp]));
+                                imma_u8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                                imma_u8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                            } else {
+                                imma_s8u8(acc[mp][0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                                imma_s8u8(acc[mp][1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                            }
+                        }
+                    }
+                }
+            };
+            if (cnt == G) chunk(std::true_type{}); else chunk(std::false_type{});
             // ── every lane is done with the slot and the planes: lane 0 requests the chunk NS ahead ──
             __syncwarp();
             if (lane == 0 && pf_left) issue_chunk();
-            if (++slot == NS) { slot = 0; parity ^= 1; }
+            slot_u32 += slot_bytes; bar_u32 += 8;
+            if (++slot == NS) { slot = 0; slot_u32 = ring; bar_u32 = bars; parity ^= 1; }
         }
         // ── flush: integer sums -> float partials of this warp in shared memory ──
         {
@@ -412,7 +425,7 @@ __global__ void qmatmul_generic_kernel(const int8_t* __restrict__ data, const fl
     out[(size_t)m * out_rs + n] = acc;
 }
 
-template <int FMT, int MP>
+template <int FMT, int MP, int XR>
 bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);
@@ -424,7 +437,7 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR>, p);
     ZG_COUNT_LAUNCH();
     if (e != cudaSuccess) {
         zg_set_error("qgemv launch failed: %s (grid %u, %u B shared)", cudaGetErrorString(e), plan.grid, plan.smem_bytes);
@@ -436,9 +449,9 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, 
 template <int FMT>
 bool launch_fmt(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
     switch (plan.mp) {
-        case 1: return launch_fast<FMT, 1>(plan, p, st, pdl);
-        case 2: return launch_fast<FMT, 2>(plan, p, st, pdl);
-        case 4: return launch_fast<FMT, 4>(plan, p, st, pdl);
+        case 1: return p.M == 1 ? launch_fast<FMT, 1, 1>(plan, p, st, pdl) : launch_fast<FMT, 1, 2>(plan, p, st, pdl);
+        case 2: return launch_fast<FMT, 2, 4>(plan, p, st, pdl);
+        case 4: return launch_fast<FMT, 4, 8>(plan, p, st, pdl);
         default: zg_set_error("qmatmul: bad plan (row pairs %u)", plan.mp); return false;
     }
 }
@@ -451,20 +464,23 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     const uint32_t rows = M > 8 ? 8 : M;
     pl.mp = rows <= 2 ? 1 : (rows <= 4 ? 2 : 4);
     pl.threads = kThreads;
-    const uint32_t occ = pl.mp <= 2 ? 2 : 1;
+    const uint32_t occ = pl.mp == 1 ? 3 : (pl.mp == 2 ? 2 : 1);
     const uint32_t target = (uint32_t)ctx->sm_count * occ;   // CTAs resident at once
     const uint32_t warps = kThreads / 32;
-    // k-splits: each warp stages its k-range of the activations in shared memory -> at most kLcap records per
-    // warp; beyond that, split K across CTAs until the grid fills the resident slots (>= 4 records per warp)
+    // k-splits: each warp stages its k-range of the activations in shared memory -> at most lcap_max records per
+    // warp.  Beyond that K is split across CTAs only until there is one CTA per SM (>= 4 records per warp): CTAs
+    // that live long amortise their fixed latencies (activation staging, flush, reduction) and leave room for the
+    // next kernel's CTAs, which is what keeps HBM busy across kernel boundaries.
     const uint32_t lcap_max = kLcap / pl.mp;   // staged activations stay <= 32 KB per CTA
     uint32_t S = (w->n_kc + warps * lcap_max - 1) / (warps * lcap_max);
-    if (w->n_nb * S < target) {
-        uint32_t fill = target / w->n_nb;
+    if (w->n_nb * S * 2 <= (uint32_t)ctx->sm_count) {
+        uint32_t fill = (uint32_t)ctx->sm_count / w->n_nb;
         const uint32_t by_work = w->n_kc / (warps * 4);
         if (fill > by_work) fill = by_work;
         if (fill > S) S = fill;
     }
     if (ctx->tune_s && (uint32_t)ctx->tune_s > S) S = (uint32_t)ctx->tune_s;
+    if (ctx->tune_smax && (uint32_t)ctx->tune_smax < S && (w->n_kc + ctx->tune_smax * warps * lcap_max - 1) / (ctx->tune_smax * warps * lcap_max) <= 1) S = (uint32_t)ctx->tune_smax;
     if (S > w->n_kc) S = w->n_kc;
     if (S < 1) S = 1;
     uint32_t P = ((uint64_t)w->n_nb * S + target - 1) / target;
@@ -475,31 +491,34 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     pl.lcap = (len_max + warps - 1) / warps;
     // weight ring per warp: NS slots of G records (one TMA bulk copy each), ~6.5 KB per warp
     const uint32_t rb = w->rec_bytes;
-    pl.G = ctx->tune_g ? (uint32_t)ctx->tune_g : (w->fmt == ZG_QFMT_I4_F16 ? 4 : 2);
+    pl.G = w->fmt == ZG_QFMT_I4_F16 ? 4 : 2;   // compile-time constant of the kernel
     pl.NS = ctx->tune_u ? (uint32_t)ctx->tune_u : 3;
-    if (pl.G > pl.lcap) pl.G = pl.lcap;
     pl.xs_stride = pl.lcap * ZG_KR;
+    const uint32_t xrows = rows == 1 ? 1 : 2 * pl.mp;
+    const uint32_t chunks = ((pl.lcap + pl.G - 1) / pl.G) * P;   // chunks a warp ever requests
+    if (pl.NS > chunks) pl.NS = chunks < 1 ? 1 : chunks;
     auto smem_of = [&]() {
-        return warps * (2 * pl.mp) * pl.xs_stride * 4 + warps * pl.NS * pl.G * rb + warps * pl.G * (2 * pl.mp) * kPlaneRow + warps * pl.NS * 8;
+        return warps * xrows * pl.xs_stride * 4 + warps * pl.NS * pl.G * rb + warps * pl.G * xrows * kPlaneRow + warps * pl.NS * 8;
     };
-    while (smem_of() > 200 * 1024 && (pl.NS > 2 || pl.G > 1)) { if (pl.NS > 2) pl.NS--; else pl.G--; }
+    while (smem_of() > 200 * 1024 && pl.NS > 1) pl.NS--;
     pl.smem_bytes = smem_of();
     pl.grid = ((w->n_nb + P - 1) / P) * S;
     return pl;
 }
 
-template <int FMT, int MP>
+template <int FMT, int MP, int XR>
 bool set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<FMT, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<FMT, MP, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemv) failed: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 template <int FMT>
-bool set_smem_attrs() { return set_smem_attr<FMT, 1>() && set_smem_attr<FMT, 2>() && set_smem_attr<FMT, 4>(); }
+bool set_smem_attrs() { return set_smem_attr<FMT, 1, 1>() && set_smem_attr<FMT, 1, 2>() && set_smem_attr<FMT, 2, 4>() && set_smem_attr<FMT, 4, 8>(); }
 
 bool zg_qgemv_init(ZgCudaCtx* ctx) {
     if (const char* e = getenv("ZG_GEMV_S")) ctx->tune_s = atoi(e);
     if (const char* e = getenv("ZG_GEMV_P")) ctx->tune_p = atoi(e);
+    if (const char* e = getenv("ZG_GEMV_SMAX")) ctx->tune_smax = atoi(e);
     if (const char* e = getenv("ZG_GEMV_NS")) ctx->tune_u = atoi(e);
     if (const char* e = getenv("ZG_GEMV_G")) ctx->tune_g = atoi(e);
     if (ctx->tune_u < 2 || ctx->tune_u > 16) ctx->tune_u = 0;
@@ -547,7 +566,7 @@ bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in
         p.x = d_in + (size_t)m0 * in_rs; p.x_rs = in_rs;
         p.xs_stride = plan.xs_stride;
         p.out = d_out + (size_t)m0 * out_rs; p.out_rs = out_rs;
-        p.P = plan.P; p.S = plan.S; p.G = plan.G; p.NS = plan.NS;
+        p.P = plan.P; p.S = plan.S; p.NS = plan.NS;
         p.partials = ws ? ws->partials : nullptr; p.counters = ws ? ws->counters : nullptr;
         bool ok;
         switch (w->fmt) {

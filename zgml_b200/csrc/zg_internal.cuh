@@ -85,7 +85,7 @@ struct ZgCudaCtx {
     bool graph_mode = true;
     bool profiling = false;
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
-    int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
+    int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
     std::vector<cudaStream_t> branch; // extra capture streams: independent ops of a program become concurrent graph branches
 };
