@@ -348,6 +348,8 @@ class CudaBackend:
             for i, o in enumerate(ops):
                 arr[i] = o
             n = len(ops)
+        elif hasattr(ops, "arr"):   # (ctypes array, length) view: no copy, like the reference's caller-owned slice
+            arr, n = ops.arr, len(ops)
         else:
             arr, n = ops, len(ops)
         self.lib.zg_cuda_refresh(self.ctx, handle.ptr, C.cast(arr, C.POINTER(abi.ZgOp)), n)

@@ -1,0 +1,317 @@
+"""Host-side mirror of zgml's LLaMA device inference for the CUDA backend.
+
+What the reference does in Zig, restated in Python over the same `Backend` interface:
+
+  * `build_program(cfg, weights, token_len)` — the DeviceProgram that
+    `DeviceInference.init` (src/device_inference.zig:61-238) lowers from the frozen plan
+    of `LLaMA.forwardCachedMasked` (src/models/llama.zig:143-168) and
+    `LLaMABlock.forwardCachedMasked` (src/models/llama_transformer.zig:192-253): per layer
+    rmsnorm -> repeat(gamma) -> mul, q/k/v qmatmul, per-KV-head rope + KV-cache slice_assign,
+    per-head rope + attention + slice_assign_rows into the concatenated buffer, o qmatmul,
+    residual add, second norm, gate/up qmatmul, SiLU chain (src/nn.zig:38-44) as a fused
+    elementwise op, down qmatmul, residual add; final norm; LM head (dense f32 matmul against
+    the tied embedding, or a quantized output projection).  Field values follow the
+    `*DeviceOp` helpers of src/device_inference.zig:464-672 (column-major tensors, ne[0] fastest).
+  * `DeviceLlamaSession.step / prefill` — the per-token host work of
+    `InferencePlan.execute` (src/llama_inference.zig:405-466): embedding row copy, causal
+    mask rewrite, RoPE cos|sin patch, then `patchSliceAssignOffset(pos)`,
+    `patchAttentionSeqKV(pos + n)` (src/device_inference.zig:240-256), `refreshProgram`,
+    `executeProgram`.
+
+Runs against any object with the Backend methods (`compile_program`, `refresh_program`,
+`execute_program`, `free_program`): the CUDA backend in production, the oracle executor in
+tests (tests/llama_reference.py).  No arithmetic on weights happens here.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .. import abi
+from ..backend import DeviceOp, DeviceProgram, ProgramIO, QuantizedWeightUpload
+
+
+@dataclass(frozen=True)
+class LlamaConfig:  # src/models/llama.zig:34-45
+    vocab_size: int
+    d_model: int
+    n_layers: int
+    n_heads: int
+    n_kv_heads: int
+    d_ff: int
+    max_seq_len: int
+    rms_norm_eps: float = 1e-5
+    rope_base: float = 10000.0
+    tied_lm_head: bool = True
+
+    @property
+    def d_head(self) -> int:
+        return self.d_model // self.n_heads
+
+    @property
+    def kv_dim(self) -> int:
+        return self.d_head * self.n_kv_heads
+
+
+# shapes of BASELINE.json's configs (public HF configs; benchmarks/llama_smollm_bench.zig:31-42 for 135M)
+SMOLLM_135M = LlamaConfig(49152, 576, 30, 9, 3, 1536, 2048, 1e-5, 1e4, True)
+SMOLLM_1_7B = LlamaConfig(49152, 2048, 24, 32, 32, 8192, 2048, 1e-5, 1e4, True)
+LLAMA3_8B = LlamaConfig(128256, 4096, 32, 32, 8, 14336, 2048, 1e-5, 5e5, False)
+LLAMA3_70B = LlamaConfig(128256, 8192, 80, 64, 8, 28672, 2048, 1e-5, 5e5, False)
+
+LINEARS = ("wq", "wk", "wv", "wo", "w_gate", "w_up", "w_down")
+
+
+def linear_shapes(cfg: LlamaConfig) -> Dict[str, tuple]:
+    """(K, N) of every per-layer linear: zgml rows = K (input), cols = N (output)."""
+    return {"wq": (cfg.d_model, cfg.d_model), "wk": (cfg.d_model, cfg.kv_dim), "wv": (cfg.d_model, cfg.kv_dim),
+            "wo": (cfg.d_model, cfg.d_model), "w_gate": (cfg.d_model, cfg.d_ff), "w_up": (cfg.d_model, cfg.d_ff),
+            "w_down": (cfg.d_ff, cfg.d_model)}
+
+
+@dataclass
+class LlamaWeights:
+    """Host form of a GGUF-direct quantized LLaMA (src/models/gguf_loader.zig:340-391): every 2-D
+    linear as i8 + f32 block scales (what `quantizedWeightFromInfo` produces), norms and the token
+    embedding as f32."""
+    cfg: LlamaConfig
+    token_embed: np.ndarray                     # f32 [vocab, d_model] (row v = embedding of token v)
+    layers: List[Dict[str, QuantizedWeightUpload]]
+    norm1: List[np.ndarray]
+    norm2: List[np.ndarray]
+    norm_f: np.ndarray
+    out_proj: Optional[QuantizedWeightUpload] = None   # untied LM head [d_model, vocab]
+
+
+def rope_tables(cfg: LlamaConfig):
+    """RoPE.init (src/nn.zig:286-313): f32 `pos / pow(base, 2i/d)`, half-split pairing, both halves filled."""
+    d = cfg.d_head
+    pos = np.arange(cfg.max_seq_len, dtype=np.float32)[:, None]
+    i = np.arange(d // 2, dtype=np.float32)[None, :]
+    freq = (pos / np.power(np.float32(cfg.rope_base), (2 * i) / np.float32(d), dtype=np.float32)).astype(np.float32)
+    cos = np.cos(freq).astype(np.float32)
+    sin = np.sin(freq).astype(np.float32)
+    return np.concatenate([cos, cos], axis=1), np.concatenate([sin, sin], axis=1)   # [max_seq, d] each
+
+
+class _Buffers:
+    def __init__(self):
+        self.sizes: List[int] = []
+        self.uploads: List[ProgramIO] = []
+
+    def new(self, n: int, init: Optional[np.ndarray] = None) -> int:
+        self.sizes.append(max(int(n), 1))
+        idx = len(self.sizes) - 1
+        if init is not None:
+            self.uploads.append(ProgramIO(idx, np.ascontiguousarray(init, dtype=np.float32).ravel()))
+        return idx
+
+
+@dataclass
+class LlamaProgram:
+    program: DeviceProgram
+    token_len: int
+    buf_token_input: int
+    buf_attn_mask: int
+    buf_rope: List[int]
+    buf_logits: int
+    slice_assign_ops: List[int]
+    attention_ops: List[int]
+    n_qmatmul: int
+
+
+def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> LlamaProgram:
+    T, D, dh, S = token_len, cfg.d_model, cfg.d_head, cfg.max_seq_len
+    hd, kvd, F = dh // 2, cfg.kv_dim, cfg.d_ff
+    n_rep = cfg.n_heads // cfg.n_kv_heads
+    B = _Buffers()
+    ops: List[abi.ZgOp] = []
+    qws: List[QuantizedWeightUpload] = []
+    sa_idx: List[int] = []
+    at_idx: List[int] = []
+
+    def qmm(dst, src, qw, K, N, src_rs=0):
+        qws.append(qw)
+        ops.append(DeviceOp.qmatmul(dst, src, len(qws) - 1, T, N, K, 0, src_rs if src_rs else K, 0, N))
+
+    def rms(dst_norm, src, gamma_buf, bare, gamma_rep):
+        # x.rmsNorm -> bare ; gamma.repeatLike(bare) ; bare.mul(rep)   (llama_transformer.zig:118-125)
+        ops.append(DeviceOp.rmsnorm(bare, src, T, D, cfg.rms_norm_eps))
+        ops.append(DeviceOp.repeat(gamma_rep, gamma_buf, D * T, (D, 1, 1, 1), (D, T, 1, 1), (1, D, D, D), (1, D, D * T, D * T)))
+        ops.append(DeviceOp.elementwise("mul", dst_norm, bare, gamma_rep, D * T))
+
+    token_input = B.new(D * T)
+    attn_mask = B.new(S * T)
+    ones_ff = B.new(F * T, np.ones(F * T, np.float32))      # `one.repeatLike(exp_neg)` of nn.silu
+    # activations are reused by every layer (the reference's workspace planner aliases them too)
+    bare, gamma_rep, norm = B.new(D * T), B.new(D * T), B.new(D * T)
+    q_proj, k_proj, v_proj = B.new(D * T), B.new(kvd * T), B.new(kvd * T)
+    k_rot = [B.new(dh * T) for _ in range(cfg.n_kv_heads)]
+    q_rot = [B.new(dh * T) for _ in range(cfg.n_heads)]
+    attn_out = [B.new(dh * T) for _ in range(cfg.n_heads)]
+    attn_buf, attn_proj, after_attn = B.new(D * T), B.new(D * T), B.new(D * T)
+    gate, up, silu, hidden, down = B.new(F * T), B.new(F * T), B.new(F * T), B.new(F * T), B.new(D * T)
+    x_bufs = [B.new(D * T), B.new(D * T)]                   # layer outputs ping-pong
+    rope_bufs: List[int] = []
+
+    x = token_input
+    for li in range(cfg.n_layers):
+        L = w.layers[li]
+        g1, g2 = B.new(D, w.norm1[li]), B.new(D, w.norm2[li])
+        k_cache, v_cache = B.new(dh * S * cfg.n_kv_heads), B.new(dh * S * cfg.n_kv_heads)
+        cs = B.new(2 * dh * T)                              # packed cos|sin leaf of this layer (patched per step)
+        rope_bufs.append(cs)
+
+        rms(norm, x, g1, bare, gamma_rep)
+        qmm(q_proj, norm, L["wq"], D, D)
+        qmm(k_proj, norm, L["wk"], D, kvd)
+        qmm(v_proj, norm, L["wv"], D, kvd)
+        for kv in range(cfg.n_kv_heads):
+            base = kv * S * dh                              # head slab = contiguous column range of the consolidated cache
+            ops.append(DeviceOp.rope(k_rot[kv], k_proj, cs, hd, T, kv * dh, 0, 0, 1, kvd, 2 * dh))
+            sa_idx.append(len(ops))
+            ops.append(DeviceOp.slice_assign(k_cache, k_rot[kv], dh, T, base, base, 1, dh, 0, 1, dh, dh))
+            sa_idx.append(len(ops))
+            ops.append(DeviceOp.slice_assign(v_cache, v_proj, dh, T, base, base, 1, dh, kv * dh, 1, kvd, dh))
+        scale = float(np.float32(1.0) / np.sqrt(np.float32(dh)))
+        for h in range(cfg.n_heads):
+            kv = h // n_rep
+            base = kv * S * dh
+            ops.append(DeviceOp.rope(q_rot[h], q_proj, cs, hd, T, h * dh, 0, 0, 1, D, 2 * dh))
+            at_idx.append(len(ops))
+            ops.append(DeviceOp.attention(attn_out[h], q_rot[h], k_cache, v_cache, attn_mask, True, dh, T, S, scale,
+                                          0, base, base, 0, 0, 1, dh, 1, dh, 1, dh, 1, S, 1, dh))
+            # sliceAssignRows(attn_out, h * d_head): patch_stride 0 (device_inference.zig:695-701)
+            ops.append(DeviceOp.slice_assign(attn_buf, attn_out[h], dh, T, 0, h * dh, 1, D, 0, 1, dh, 0))
+        qmm(attn_proj, attn_buf, L["wo"], D, D)
+        ops.append(DeviceOp.elementwise("add", after_attn, x, attn_proj, D * T))
+        rms(norm, after_attn, g2, bare, gamma_rep)
+        qmm(gate, norm, L["w_gate"], D, F)
+        qmm(up, norm, L["w_up"], D, F)
+        # silu(gate) = gate * recip(exp(-gate) + 1), then * up
+        ops.append(DeviceOp.fused_elementwise([("neg", False, 0, 0), ("exp", False, 0, 0), ("add", False, ones_ff, 0),
+                                               ("recip", False, 0, 0), ("mul", True, gate, 0)], F * T, silu, gate))
+        ops.append(DeviceOp.elementwise("mul", hidden, silu, up, F * T))
+        qmm(down, hidden, L["w_down"], F, D)
+        out = x_bufs[li % 2]
+        ops.append(DeviceOp.elementwise("add", out, after_attn, down, D * T))
+        x = out
+
+    gf = B.new(D, w.norm_f)
+    rms(norm, x, gf, bare, gamma_rep)
+    logits = B.new(cfg.vocab_size * T)
+    if cfg.tied_lm_head:
+        # x.matMul(false, token_embed, true) (models/llama.zig:162-165): dense f32, never quantized
+        emb = B.new(cfg.vocab_size * D, w.token_embed)
+        ops.append(DeviceOp.matmul(logits, norm, emb, T, cfg.vocab_size, D, D, 1, 1, D, dst_row_stride=cfg.vocab_size))
+    else:
+        qmm(logits, norm, w.out_proj, D, cfg.vocab_size)
+    prog = DeviceProgram(ops, B.sizes, B.uploads, qws)
+    return LlamaProgram(prog, T, token_input, attn_mask, rope_bufs, logits, sa_idx, at_idx, len(qws))
+
+
+class DeviceLlamaSession:
+    """LlamaInferenceSession.step/prefill over a device backend (src/llama_inference.zig:681-727,
+    benchmarks/llama_smollm_bench.zig:194-315 `runDeviceVariant`)."""
+
+    def __init__(self, backend, cfg: LlamaConfig, weights: LlamaWeights, token_len: int = 1):
+        self.be, self.cfg, self.w = backend, cfg, weights
+        self.lp = build_program(cfg, weights, token_len)
+        self.ops = self.lp.program.ops_array()              # the caller-owned, per-step mutated op array
+        self.n_ops = len(self.lp.program.ops)
+        self.handle = backend.compile_program(self.lp.program)
+        if self.handle is None:
+            raise RuntimeError("compile_program returned null")
+        T, D, S, dh = token_len, cfg.d_model, cfg.max_seq_len, cfg.d_head
+        self.token_input = np.zeros(D * T, np.float32)
+        self.attn_mask = np.zeros(S * T, np.float32)
+        self.rope_cs = np.zeros(2 * dh * T, np.float32)
+        self.logits = np.zeros(cfg.vocab_size, np.float32)
+        self.cos, self.sin = rope_tables(cfg)
+        self.pos = 0
+        self.inputs = [ProgramIO(self.lp.buf_token_input, self.token_input), ProgramIO(self.lp.buf_attn_mask, self.attn_mask)]
+        self.inputs += [ProgramIO(b, self.rope_cs) for b in self.lp.buf_rope]
+        last_off = (T - 1) * cfg.vocab_size * 4             # last-column logits (llama_inference.zig:463-465)
+        self.outputs = [ProgramIO(self.lp.buf_logits, self.logits, offset=last_off)]
+
+    def reset(self):
+        self.pos = 0
+
+    def _patch_host_inputs(self, token_ids, pos):
+        cfg, T = self.cfg, self.lp.token_len
+        D, S, dh = cfg.d_model, cfg.max_seq_len, cfg.d_head
+        assert len(token_ids) == T and pos + T <= S
+        for i, tid in enumerate(token_ids):                 # 1. embedding rows
+            self.token_input[i * D:(i + 1) * D] = self.w.token_embed[tid]
+        for j in range(T):                                  # 2. causal mask, column j = position pos + j
+            col = self.attn_mask[j * S:(j + 1) * S]
+            col[:pos + j + 1] = 0.0
+            col[pos + j + 1:] = -np.inf
+        for j in range(T):                                  # 3. packed cos|sin for positions [pos, pos + T)
+            self.rope_cs[j * 2 * dh:j * 2 * dh + dh] = self.cos[pos + j]
+            self.rope_cs[j * 2 * dh + dh:(j + 1) * 2 * dh] = self.sin[pos + j]
+
+    def _patch_ops(self, pos):
+        T = self.lp.token_len
+        for i in self.lp.slice_assign_ops:                  # patchSliceAssignOffset
+            sa = self.ops[i].u.slice_assign
+            if sa.patch_stride:
+                sa.dst_offset = sa.dst_base_offset + pos * sa.patch_stride
+        for i in self.lp.attention_ops:                     # patchAttentionSeqKV(pos + T)
+            self.ops[i].u.attention.seq_kv = pos + T
+
+    def execute_at(self, token_ids, pos) -> np.ndarray:
+        self._patch_host_inputs(token_ids, pos)
+        self._patch_ops(pos)
+        self.be.refresh_program(self.handle, _OpsView(self.ops, self.n_ops))
+        self.be.execute_program(self.handle, self.inputs, self.outputs)
+        return self.logits
+
+    def step(self, token_id: int) -> np.ndarray:
+        assert self.lp.token_len == 1
+        out = self.execute_at([token_id], self.pos)
+        self.pos += 1
+        return out
+
+    def close(self):
+        if self.handle is not None:
+            self.be.free_program(self.handle)
+            self.handle = None
+
+
+class _OpsView:
+    """ctypes op array + length, accepted by CudaBackend.refresh_program without a copy."""
+
+    def __init__(self, arr, n):
+        self.arr, self.n = arr, n
+
+    def __len__(self):
+        return self.n
+
+
+def synthetic_weights(cfg: LlamaConfig, kind: str = "q8_0", seed: int = 0, embed_scale: float = 0.05) -> LlamaWeights:
+    """Random-init GGUF-direct weights in the reference's host form: per linear
+    q ~ U{-127..127} (q8_0) / U{-8..7} (q4_0), one f16-representable scale per 32 flat elements sized so the
+    dequantized weight is ~U(-b, b) with b = sqrt(6 / K) (kaimingUniform, src/nn.zig:91-105); norms = 1;
+    token embedding ~U(-embed_scale, embed_scale)."""
+    r = np.random.default_rng(seed)
+    qmax = 127 if kind == "q8_0" else 7
+    layers = []
+
+    def make(K, N):
+        n = K * N
+        if kind == "q8_0":
+            data = r.integers(-127, 128, n, dtype=np.int8)
+        else:
+            data = r.integers(-8, 8, n, dtype=np.int8)
+        b = np.sqrt(6.0 / K)
+        scales = (r.uniform(0.5, 1.0, n // 32) * (b / qmax)).astype(np.float16).astype(np.float32)
+        return QuantizedWeightUpload(data, scales, K, N, 32)
+
+    shapes = linear_shapes(cfg)
+    for _ in range(cfg.n_layers):
+        layers.append({name: make(*shapes[name]) for name in LINEARS})
+    emb = r.uniform(-embed_scale, embed_scale, (cfg.vocab_size, cfg.d_model)).astype(np.float32)
+    ones = [np.ones(cfg.d_model, np.float32) for _ in range(cfg.n_layers)]
+    out_proj = None if cfg.tied_lm_head else make(cfg.d_model, cfg.vocab_size)
+    return LlamaWeights(cfg, emb, layers, ones, [o.copy() for o in ones], np.ones(cfg.d_model, np.float32), out_proj)
