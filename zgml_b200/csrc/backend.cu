@@ -4,6 +4,7 @@
 // src/backend/cpu.zig:55-147 implements it for the CPU.
 #include "zg_internal.cuh"
 
+#include <algorithm>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,6 +63,13 @@ struct ZgCudaProgram {
     ZgProfile profile;
     std::vector<cudaEvent_t> prof_events;
     std::vector<cudaEvent_t> dep_events; // capture-time fork/join markers of the concurrent graph branches
+    // launch schedule: ops sorted by dependency level, same-level per-head ops (rope / slice_assign / attention)
+    // of equal shape merged into one batched launch
+    struct Unit { std::vector<uint32_t> ops; uint32_t first_entry = 0; bool batched = false; };
+    std::vector<Unit> units;
+    std::vector<uint32_t> entry_of_op;   // index into d_batch for batched op kinds
+    ZgBatchEntry* d_batch = nullptr;
+    bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
 };
 
 // ── context ──────────────────────────────────────────────────────────────────
@@ -170,7 +178,7 @@ static void free_program(ZgCudaProgram* p) {
     if (p->graph) cudaGraphDestroy(p->graph);
     for (float* b : p->buffers) cudaFree(b);
     for (ZgCudaQWeight* w : p->qweights) zg_cuda_qweight_free(p->ctx, w);
-    cudaFree(p->d_steps); cudaFree(p->d_dyn);
+    cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -227,6 +235,8 @@ static bool validate_ops(const ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) 
     return true;
 }
 
+static bool build_schedule(ZgCudaProgram* p);
+
 static bool reserve_workspace(ZgCudaProgram* p) {
     size_t pe = 0, nc = 0;
     p->ws_part_off.assign(p->ops.size(), 0);
@@ -243,12 +253,14 @@ static bool reserve_workspace(ZgCudaProgram* p) {
 }
 
 // ── op dependencies (element ranges per buffer) for concurrent graph branches ─────────────────
-struct ZgRange { uint32_t buf; size_t lo, hi; bool write; };
+// dyn != 0: the range is shifted at run time by pos * dyn (slice_assign with patch_stride, i.e. KV-cache writes);
+// all such ops of a program share one pos (src/device_inference.zig:240-247), checked in zg_cuda_refresh.
+struct ZgRange { uint32_t buf; size_t lo, hi; bool write; uint32_t dyn; };
 
 static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRange>& out) {
     out.clear();
-    auto whole = [&](uint32_t b, bool w) { out.push_back({b, 0, p->buffer_elems[b], w}); };
-    auto span = [&](uint32_t b, size_t lo, size_t n, bool w) { out.push_back({b, lo, lo + n, w}); };
+    auto whole = [&](uint32_t b, bool w) { out.push_back({b, 0, p->buffer_elems[b], w, 0}); };
+    auto span = [&](uint32_t b, size_t lo, size_t n, bool w) { out.push_back({b, lo, lo + n, w, 0}); };
     switch (op.tag) {
         case ZG_OP_ELEMENTWISE: {
             const auto& e = op.u.elementwise;
@@ -272,7 +284,17 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
                             span(op.u.rmsnorm.src, op.u.rmsnorm.src_offset, (size_t)op.u.rmsnorm.rows * op.u.rmsnorm.cols, false); break;
         case ZG_OP_REDUCE: whole(op.u.reduce.dst, true); whole(op.u.reduce.src, false); break;
         case ZG_OP_REPEAT: whole(op.u.repeat.dst, true); whole(op.u.repeat.src, false); break;
-        case ZG_OP_SLICE_ASSIGN: whole(op.u.slice_assign.dst, true); whole(op.u.slice_assign.src, false); break;  // offset is dynamic
+        case ZG_OP_SLICE_ASSIGN: {
+            const auto& sa = op.u.slice_assign;
+            if (sa.rows == 0 || sa.cols == 0) break;
+            const size_t dext = (size_t)(sa.rows - 1) * sa.dst_row_stride + (size_t)(sa.cols - 1) * sa.dst_col_stride + 1;
+            const size_t sext = (size_t)(sa.rows - 1) * sa.src_row_stride + (size_t)(sa.cols - 1) * sa.src_col_stride + 1;
+            if (sa.patch_stride == 0) span(sa.dst, sa.dst_offset, dext, true);
+            else if (p->uniform_pos) out.push_back({sa.dst, sa.dst_base_offset, sa.dst_base_offset + dext, true, sa.patch_stride});
+            else whole(sa.dst, true);
+            span(sa.src, sa.src_offset, sext, false);
+            break;
+        }
         case ZG_OP_ROPE: whole(op.u.rope.dst, true); whole(op.u.rope.src, false); whole(op.u.rope.cos_sin, false); break;
         case ZG_OP_ATTENTION: {
             const auto& a = op.u.attention;
@@ -291,10 +313,16 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
     }
 }
 
+static inline bool range_conflict(const ZgRange& x, const ZgRange& y) {
+    if (x.buf != y.buf || !(x.write || y.write)) return false;
+    if (x.dyn && x.dyn == y.dyn) return x.lo < y.hi && y.lo < x.hi;   // same run-time shift: compare the bases
+    const size_t xhi = x.dyn ? (size_t)-1 : x.hi, yhi = y.dyn ? (size_t)-1 : y.hi;   // shifted range: anywhere above its base
+    return x.lo < yhi && y.lo < xhi;
+}
 static bool ranges_conflict(const std::vector<ZgRange>& a, const std::vector<ZgRange>& b) {
     for (const ZgRange& x : a)
         for (const ZgRange& y : b)
-            if ((x.write || y.write) && x.buf == y.buf && x.lo < y.hi && y.lo < x.hi) return true;
+            if (range_conflict(x, y)) return true;
     return false;
 }
 
@@ -333,7 +361,7 @@ extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog)
         p->qweights.push_back(w);
     }
     if (!validate_ops(p, prog->ops, prog->n_ops) || !adopt_ops(p, prog->ops, prog->n_ops) || !upload_steps(p) ||
-        !reserve_workspace(p)) {
+        !reserve_workspace(p) || !build_schedule(p)) {
         free_program(p); return nullptr;
     }
     size_t nd = prog->n_ops ? prog->n_ops : 1;
@@ -370,12 +398,30 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
         adopt_ops(p, ops, n_ops);
         upload_steps(p);
         reserve_workspace(p);
+        build_schedule(p);
         cudaFree(p->d_dyn); cudaFreeHost(p->h_dyn); p->d_dyn = nullptr; p->h_dyn = nullptr;
         size_t nd = n_ops ? n_ops : 1;
         cudaMalloc(&p->d_dyn, nd * 4); cudaMallocHost(&p->h_dyn, nd * 4);
         memset(p->h_dyn, 0xFF, nd * 4);
         p->dyn_dirty = true;
         p->graph_valid = false;
+    }
+    if (p->uniform_pos) {   // the schedule assumes one KV write position per step; otherwise fall back to conservative ranges
+        long pos = -1;
+        for (size_t i = 0; i < n_ops; i++) {
+            if (ops[i].tag != ZG_OP_SLICE_ASSIGN || ops[i].u.slice_assign.patch_stride == 0) continue;
+            const auto& sa = ops[i].u.slice_assign;
+            const long d = (long)sa.dst_offset - (long)sa.dst_base_offset;
+            const long q = d / (long)sa.patch_stride;
+            if (d < 0 || d % (long)sa.patch_stride != 0 || (pos >= 0 && q != pos)) {
+                cudaStreamSynchronize(ctx->stream);
+                p->uniform_pos = false;
+                build_schedule(p);
+                p->graph_valid = false;
+                break;
+            }
+            pos = q;
+        }
     }
     for (size_t i = 0; i < n_ops; i++) {
         uint32_t v = op_dyn_value(ops[i]);
@@ -384,6 +430,73 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
         if (ops[i].tag == ZG_OP_SLICE_ASSIGN) p->ops[i].u.slice_assign.dst_offset = v;
         else if (ops[i].tag == ZG_OP_ATTENTION) p->ops[i].u.attention.seq_kv = v;
     }
+}
+
+// Dependency levels (level = 1 + max level of every earlier op it conflicts with), then units in (level, program
+// order); any such order is a valid topological order of the program's dependency DAG.
+static bool build_schedule(ZgCudaProgram* p) {
+    const size_t n = p->ops.size();
+    struct Access { ZgRange r; int level; };
+    std::vector<std::vector<Access>> acc(p->buffers.size());
+    std::vector<int> level(n, 0);
+    std::vector<ZgRange> rng;
+    for (size_t i = 0; i < n; i++) {
+        op_ranges(p, p->ops[i], rng);
+        int lvl = 0;
+        for (const ZgRange& r : rng)
+            for (const Access& a : acc[r.buf])
+                if (a.level + 1 > lvl && range_conflict(r, a.r)) lvl = a.level + 1;
+        level[i] = lvl;
+        for (const ZgRange& r : rng) {
+            // a write covering the whole buffer orders everything after it: older accesses need not be kept
+            if (r.write && !r.dyn && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
+            acc[r.buf].push_back({r, lvl});
+        }
+    }
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
+    p->units.clear();
+    p->entry_of_op.assign(n, 0);
+    std::vector<ZgBatchEntry> entries;
+    size_t pos = 0;
+    while (pos < n) {
+        size_t end = pos;
+        while (end < n && level[order[end]] == level[order[pos]]) end++;
+        std::vector<std::pair<uint64_t, size_t>> open;   // batch signature -> unit index (within this level)
+        for (size_t k = pos; k < end; k++) {
+            const uint32_t i = order[k];
+            const ZgOp& op = p->ops[i];
+            if (!zg_op_is_batched(op.tag)) { ZgCudaProgram::Unit u; u.ops.push_back(i); p->units.push_back(u); continue; }
+            const uint64_t sig = zg_batch_signature(op);
+            size_t ui = (size_t)-1;
+            for (auto& o : open) if (o.first == sig) { ui = o.second; break; }
+            if (ui == (size_t)-1) {
+                ZgCudaProgram::Unit u; u.batched = true;
+                p->units.push_back(u);
+                ui = p->units.size() - 1;
+                open.push_back({sig, ui});
+            }
+            p->units[ui].ops.push_back(i);
+        }
+        pos = end;
+    }
+    for (auto& u : p->units) {
+        if (!u.batched) continue;
+        u.first_entry = (uint32_t)entries.size();
+        for (uint32_t i : u.ops) {
+            ZgBatchEntry e;
+            if (!zg_fill_batch_entry(p->ops[i], p->buffers.data(), i, &e)) return false;
+            p->entry_of_op[i] = (uint32_t)entries.size();
+            entries.push_back(e);
+        }
+    }
+    cudaFree(p->d_batch); p->d_batch = nullptr;
+    if (!entries.empty()) {
+        ZG_CUDA_OK(cudaMalloc(&p->d_batch, entries.size() * sizeof(ZgBatchEntry)));
+        ZG_CUDA_OK(cudaMemcpy(p->d_batch, entries.data(), entries.size() * sizeof(ZgBatchEntry), cudaMemcpyHostToDevice));
+    }
+    return true;
 }
 
 static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
@@ -397,7 +510,13 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
         return zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
                                  p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &view, st);
     }
+    if (zg_op_is_batched(op.tag)) return zg_launch_batch(op, p->d_batch + p->entry_of_op[i], 1, p->d_dyn, st);
     return zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
+}
+
+static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
+    if (!u.batched) return launch_one(p, u.ops[0], st);
+    return zg_launch_batch(p->ops[u.ops[0]], p->d_batch + u.first_entry, (uint32_t)u.ops.size(), p->d_dyn, st);
 }
 
 static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
@@ -405,10 +524,15 @@ static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
     if (profile && p->prof_events.size() < n + 1) {
         while (p->prof_events.size() < n + 1) { cudaEvent_t e; cudaEventCreate(&e); p->prof_events.push_back(e); }
     }
-    if (profile) cudaEventRecord(p->prof_events[0], st);
-    for (size_t i = 0; i < n; i++) {
+    if (!profile) {   // schedule order: dependency levels, per-head ops batched
+        for (const auto& u : p->units)
+            if (!launch_unit(p, u, st)) return false;
+        return true;
+    }
+    cudaEventRecord(p->prof_events[0], st);
+    for (size_t i = 0; i < n; i++) {   // program order, one launch per op: per-tag device times
         if (!launch_one(p, i, st)) return false;
-        if (profile) cudaEventRecord(p->prof_events[i + 1], st);
+        cudaEventRecord(p->prof_events[i + 1], st);
     }
     return true;
 }
@@ -418,7 +542,7 @@ static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
 // identical to program order: every read-after-write, write-after-read and write-after-write pair stays ordered.
 static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
     ZgCudaCtx* ctx = p->ctx;
-    const size_t n = p->ops.size();
+    const size_t n = p->units.size();
     const int ns = 1 + (int)ctx->branch.size();
     std::vector<cudaStream_t> strs(1, origin);
     strs.insert(strs.end(), ctx->branch.begin(), ctx->branch.end());
@@ -428,7 +552,8 @@ static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
         p->dep_events.push_back(e);
     }
     std::vector<std::vector<ZgRange>> rng(n);
-    std::vector<int> op_stream(n, 0);
+    std::vector<ZgRange> tmp;
+    std::vector<int> unit_stream(n, 0);
     std::vector<long> last_on(ns, -1), dep(ns);
     std::vector<char> joined(ns, 0);
     joined[0] = 1;
@@ -437,11 +562,14 @@ static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
     int rr = 0;
     bool ok = true;
     for (size_t i = 0; i < n && ok; i++) {
-        op_ranges(p, p->ops[i], rng[i]);
+        for (uint32_t oi : p->units[i].ops) {   // a unit reads / writes the union of its ops' ranges
+            op_ranges(p, p->ops[oi], tmp);
+            rng[i].insert(rng[i].end(), tmp.begin(), tmp.end());
+        }
         std::fill(dep.begin(), dep.end(), -1L);
         int found = 0;
-        for (long k = (long)i - 1; k >= 0 && found < ns; k--) {   // latest conflicting op of every stream
-            const int sk = op_stream[k];
+        for (long k = (long)i - 1; k >= 0 && found < ns; k--) {   // latest conflicting unit of every stream
+            const int sk = unit_stream[k];
             if (dep[sk] >= 0) continue;
             if (ranges_conflict(rng[i], rng[k])) { dep[sk] = k; found++; }
         }
@@ -452,9 +580,9 @@ static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
         if (!joined[s]) { ZG_CUDA_OK(cudaStreamWaitEvent(strs[s], fork_ev, 0)); joined[s] = 1; }
         for (int sk = 0; sk < ns; sk++)
             if (sk != s && dep[sk] >= 0) ZG_CUDA_OK(cudaStreamWaitEvent(strs[s], p->dep_events[dep[sk]], 0));
-        ok = launch_one(p, i, strs[s]);
+        ok = launch_unit(p, p->units[i], strs[s]);
         ZG_CUDA_OK(cudaEventRecord(p->dep_events[i], strs[s]));
-        op_stream[i] = s; last_on[s] = (long)i;
+        unit_stream[i] = s; last_on[s] = (long)i;
     }
     for (int sk = 1; sk < ns; sk++) {   // join every branch back into the origin stream (also on failure: the capture must end cleanly)
         if (!joined[sk]) continue;

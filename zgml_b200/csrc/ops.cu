@@ -8,6 +8,8 @@
 // device array `dyn[op_index]` so the whole op list can live in one CUDA graph.
 #include "zg_internal.cuh"
 
+#include <string.h>
+
 namespace {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -158,10 +160,15 @@ __global__ void k_repeat(RepeatParams p, float* __restrict__ dst, const float* _
     }
 }
 
-__global__ void k_slice_assign(float* __restrict__ dst, const float* __restrict__ src, uint32_t rows,
-                               uint32_t cols, const uint32_t* __restrict__ dyn_dst_offset, uint32_t drs,
-                               uint32_t dcs, uint32_t soff, uint32_t srs, uint32_t scs) {
-    const uint32_t doff = *dyn_dst_offset;
+// The three per-head op kinds of a decode program (rope, slice_assign, attention) are launched in BATCHES:
+// blockIdx.y selects one op's parameter entry from a device table built at compile time, so all heads of a
+// layer (mutually independent ops of one dependency level) cost one launch instead of one each.
+__global__ void k_slice_assign(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    const ZgBatchEntry e = tab[blockIdx.y];
+    const uint32_t rows = e.u[0], cols = e.u[1], drs = e.u[2], dcs = e.u[3], soff = e.u[4], srs = e.u[5], scs = e.u[6];
+    const uint32_t doff = d_dyn[e.dyn];
+    float* __restrict__ dst = e.dst;
+    const float* __restrict__ src = e.s0;
     uint32_t total = rows * cols;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t row = i % rows, col = i / rows;
@@ -169,9 +176,12 @@ __global__ void k_slice_assign(float* __restrict__ dst, const float* __restrict_
     }
 }
 
-__global__ void k_rope(float* __restrict__ dst, const float* __restrict__ src, const float* __restrict__ cs,
-                       uint32_t hd, uint32_t seq_len, uint32_t s_off, uint32_t c_off, uint32_t d_off,
-                       uint32_t s_rs, uint32_t s_cs, uint32_t c_cs) {
+__global__ void k_rope(const ZgBatchEntry* __restrict__ tab) {
+    const ZgBatchEntry e = tab[blockIdx.y];
+    const uint32_t hd = e.u[0], seq_len = e.u[1], s_off = e.u[2], c_off = e.u[3], d_off = e.u[4], s_rs = e.u[5], s_cs = e.u[6], c_cs = e.u[7];
+    float* __restrict__ dst = e.dst;
+    const float* __restrict__ src = e.s0;
+    const float* __restrict__ cs = e.s1;
     uint32_t total = hd * seq_len;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         uint32_t pair = i % hd, col = i / hd;
@@ -198,9 +208,19 @@ constexpr int kAttnMaxPerLane = 16; // d_head <= 512
 // online softmax (reference.zig:599-671: non-finite mask / score entries skipped),
 // the 8 partial states are merged through shared memory.
 __global__ void __launch_bounds__(kAttnWarps * 32)
-k_attention(AttnParams p, float* __restrict__ dst, const float* __restrict__ q, const float* __restrict__ k,
-            const float* __restrict__ v, const float* __restrict__ mask, const uint32_t* __restrict__ dyn_seq_kv) {
-    const uint32_t seq_kv = *dyn_seq_kv;
+k_attention(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    const ZgBatchEntry e = tab[blockIdx.y];
+    AttnParams p;
+    p.has_mask = e.u[0]; p.d_head = e.u[1]; p.seq_q = e.u[2]; p.scale = e.f;
+    p.q_off = e.u[3]; p.k_off = e.u[4]; p.v_off = e.u[5]; p.mask_off = e.u[6]; p.dst_off = e.u[7];
+    p.q_rs = e.u[8]; p.q_cs = e.u[9]; p.k_rs = e.u[10]; p.k_cs = e.u[11]; p.v_rs = e.u[12]; p.v_cs = e.u[13];
+    p.mask_rs = e.u[14]; p.mask_cs = e.u[15]; p.dst_rs = e.u[16]; p.dst_cs = e.u[17];
+    float* __restrict__ dst = e.dst;
+    const float* __restrict__ q = e.s0;
+    const float* __restrict__ k = e.s1;
+    const float* __restrict__ v = e.s2;
+    const float* __restrict__ mask = e.s3;
+    const uint32_t seq_kv = d_dyn[e.dyn];
     const uint32_t qi = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t dh = p.d_head;
@@ -264,6 +284,103 @@ k_attention(AttnParams p, float* __restrict__ dst, const float* __restrict__ q, 
         for (int w = 0; w < kAttnWarps; w++) a += sh_acc[w][r] * wscale[w];
         dst[d_base + (size_t)r * p.dst_rs] = a * inv_l;
     }
+}
+
+// Decode / prefill attention fast path (unit row strides, d_head % 4 == 0, d_head <= 256): within a warp lane =
+// kv position for the scores (each lane dots its own contiguous K row against q in shared memory, 128-bit loads),
+// then lane = head dimension for the V accumulation (coalesced rows, weights broadcast by shuffle).  32 positions
+// per warp step instead of one, so the kv scan is no longer a chain of dependent global loads.  Same online
+// softmax and skip rules as reference.zig:599-671; only the summation order differs (1e-6 relative).
+__global__ void __launch_bounds__(kAttnWarps * 32)
+k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    const ZgBatchEntry e = tab[blockIdx.y];
+    const uint32_t has_mask = e.u[0], dh = e.u[1];
+    const float scale = e.f;
+    const uint32_t q_off = e.u[3], k_off = e.u[4], v_off = e.u[5], mask_off = e.u[6], dst_off = e.u[7];
+    const uint32_t q_cs = e.u[9], k_cs = e.u[11], v_cs = e.u[13], mask_rs = e.u[14], mask_cs = e.u[15], dst_cs = e.u[17];
+    float* __restrict__ dst = e.dst;
+    const float* __restrict__ q = e.s0;
+    const float* __restrict__ k = e.s1;
+    const float* __restrict__ v = e.s2;
+    const float* __restrict__ mask = e.s3;
+    const uint32_t seq_kv = d_dyn[e.dyn];
+    const uint32_t qi = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    __shared__ __align__(16) float sq[256];
+    __shared__ float sh_m[kAttnWarps], sh_l[kAttnWarps];
+    __shared__ float sh_acc[kAttnWarps][256];
+    for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) sq[r] = q[(size_t)q_off + (size_t)qi * q_cs + r];
+    __syncthreads();
+    const size_t m_base = (size_t)mask_off + (size_t)qi * mask_cs;
+    const uint32_t dh4 = dh >> 2;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    float m_val = -INFINITY, l = 0.0f;
+    for (uint32_t s0 = warp * 32; s0 < seq_kv; s0 += kAttnWarps * 32) {
+        const uint32_t s = s0 + lane;
+        float mask_add = -INFINITY;
+        if (s < seq_kv) mask_add = has_mask ? mask[m_base + (size_t)s * mask_rs] : 0.0f;
+        bool ok = isfinite(mask_add);
+        float score = -INFINITY;
+        if (ok) {
+            const float4* kr = reinterpret_cast<const float4*>(k + (size_t)k_off + (size_t)s * k_cs);
+            const float4* q4 = reinterpret_cast<const float4*>(sq);
+            float dot = 0.0f;
+            for (uint32_t d = 0; d < dh4; d++) {
+                const float4 kv4 = kr[d], qv = q4[d];
+                dot = fmaf(qv.x, kv4.x, dot); dot = fmaf(qv.y, kv4.y, dot); dot = fmaf(qv.z, kv4.z, dot); dot = fmaf(qv.w, kv4.w, dot);
+            }
+            score = dot * scale + mask_add;
+            ok = isfinite(score);
+            if (!ok) score = -INFINITY;
+        }
+        float bm = score;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        if (bm == -INFINITY) continue;   // warp-uniform: nothing attendable in this block
+        const float new_m = fmaxf(m_val, bm);
+        const float alpha = (m_val == -INFINITY) ? 0.0f : expf(m_val - new_m);
+        const float wgt = ok ? expf(score - new_m) : 0.0f;
+        l = l * alpha + warp_sum(wgt);
+        m_val = new_m;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] *= alpha;
+        const uint32_t nj = min(32u, seq_kv - s0);
+        const float* vb = v + (size_t)v_off + (size_t)s0 * v_cs + lane;
+        for (uint32_t j = 0; j < nj; j++, vb += v_cs) {
+            const float wj = __shfl_sync(0xffffffffu, wgt, j);
+            if (wj == 0.0f) continue;   // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (lane + 32 * i < dh) acc[i] = fmaf(wj, vb[32 * i], acc[i]);
+        }
+    }
+    if (lane == 0) { sh_m[warp] = m_val; sh_l[warp] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (lane + 32 * i < dh) sh_acc[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    float gm = -INFINITY;
+    for (int w = 0; w < kAttnWarps; w++) gm = fmaxf(gm, sh_m[w]);
+    float gl = 0.0f;
+    float wscale[kAttnWarps];
+    for (int w = 0; w < kAttnWarps; w++) {
+        wscale[w] = (sh_m[w] == -INFINITY) ? 0.0f : expf(sh_m[w] - gm);
+        gl += sh_l[w] * wscale[w];
+    }
+    const float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
+    for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
+        float a = 0.0f;
+        for (int w = 0; w < kAttnWarps; w++) a += sh_acc[w][r] * wscale[w];
+        dst[(size_t)dst_off + (size_t)qi * dst_cs + r] = a * inv_l;
+    }
+}
+
+static inline bool attn_fast_ok(const ZgOp& op) {
+    const auto& a = op.u.attention;
+    return a.q_rs == 1 && a.k_rs == 1 && a.v_rs == 1 && a.dst_rs == 1 && (a.d_head % 4) == 0 && a.d_head <= 256 &&
+           (a.k_off % 4) == 0 && (a.k_cs % 4) == 0;
 }
 
 struct MMParams {
@@ -373,33 +490,11 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
             k_repeat<<<blocks_for(rp.n, 256), 256, 0, st>>>(p, bufs[rp.dst] + rp.dst_offset, src);
             break;
         }
-        case ZG_OP_SLICE_ASSIGN: {
-            const auto& sa = op.u.slice_assign;
-            if (sa.rows == 0 || sa.cols == 0) return true;
-            k_slice_assign<<<blocks_for(sa.rows * sa.cols, 256), 256, 0, st>>>(bufs[sa.dst], bufs[sa.src], sa.rows, sa.cols,
-                                                                               d_dyn + op_index, sa.dst_row_stride, sa.dst_col_stride,
-                                                                               sa.src_offset, sa.src_row_stride, sa.src_col_stride);
-            break;
-        }
-        case ZG_OP_ROPE: {
-            const auto& r = op.u.rope;
-            if (r.half_d == 0 || r.seq_len == 0) return true;
-            k_rope<<<blocks_for(r.half_d * r.seq_len, 128), 128, 0, st>>>(bufs[r.dst], bufs[r.src], bufs[r.cos_sin], r.half_d, r.seq_len,
-                                                                          r.src_off, r.cs_off, r.dst_off, r.src_rs, r.src_cs, r.cs_cs);
-            break;
-        }
-        case ZG_OP_ATTENTION: {
-            const auto& a = op.u.attention;
-            if (a.seq_q == 0 || a.d_head == 0) return true;
-            if (a.d_head > 512) { zg_set_error("attention: d_head %u > 512", a.d_head); return false; }
-            AttnParams p;
-            p.has_mask = a.has_mask; p.d_head = a.d_head; p.seq_q = a.seq_q; p.scale = a.scale;
-            p.q_off = a.q_off; p.k_off = a.k_off; p.v_off = a.v_off; p.mask_off = a.mask_off; p.dst_off = a.dst_off;
-            p.q_rs = a.q_rs; p.q_cs = a.q_cs; p.k_rs = a.k_rs; p.k_cs = a.k_cs; p.v_rs = a.v_rs; p.v_cs = a.v_cs;
-            p.mask_rs = a.mask_rs; p.mask_cs = a.mask_cs; p.dst_rs = a.dst_rs; p.dst_cs = a.dst_cs;
-            k_attention<<<a.seq_q, kAttnWarps * 32, 0, st>>>(p, bufs[a.dst], bufs[a.q], bufs[a.k], bufs[a.v], bufs[a.mask], d_dyn + op_index);
-            break;
-        }
+        case ZG_OP_SLICE_ASSIGN:
+        case ZG_OP_ROPE:
+        case ZG_OP_ATTENTION:
+            zg_set_error("internal: batched op kind %u reached the single-op launcher", op.tag);
+            return false;
         case ZG_OP_MATMUL: {
             const auto& m = op.u.matmul;
             const ZgMatMulGeometry& g = m.geom;
@@ -420,6 +515,81 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
         default:
             zg_set_error("unsupported DeviceOp tag %u", op.tag);
             return false;
+    }
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
+// ── batched per-head ops ────────────────────────────────────────────────────────────────────────
+bool zg_op_is_batched(uint32_t tag) { return tag == ZG_OP_SLICE_ASSIGN || tag == ZG_OP_ROPE || tag == ZG_OP_ATTENTION; }
+
+// Two ops may share a launch when their kind and work shape agree (grid dimensions are common to the batch).
+uint64_t zg_batch_signature(const ZgOp& op) {
+    switch (op.tag) {
+        case ZG_OP_SLICE_ASSIGN: return ((uint64_t)op.tag << 56) | ((uint64_t)(op.u.slice_assign.rows & 0xFFFFFFF) << 28) | (op.u.slice_assign.cols & 0xFFFFFFF);
+        case ZG_OP_ROPE: return ((uint64_t)op.tag << 56) | ((uint64_t)(op.u.rope.half_d & 0xFFFFFFF) << 28) | (op.u.rope.seq_len & 0xFFFFFFF);
+        case ZG_OP_ATTENTION: return ((uint64_t)op.tag << 56) | ((uint64_t)attn_fast_ok(op) << 55) | ((uint64_t)(op.u.attention.d_head & 0x7FFFFFF) << 28) | (op.u.attention.seq_q & 0xFFFFFFF);
+        default: return 0;
+    }
+}
+
+bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, ZgBatchEntry* e) {
+    memset(e, 0, sizeof(*e));
+    e->dyn = op_index;
+    switch (op.tag) {
+        case ZG_OP_SLICE_ASSIGN: {
+            const auto& sa = op.u.slice_assign;
+            e->dst = bufs[sa.dst]; e->s0 = bufs[sa.src];
+            e->u[0] = sa.rows; e->u[1] = sa.cols; e->u[2] = sa.dst_row_stride; e->u[3] = sa.dst_col_stride;
+            e->u[4] = sa.src_offset; e->u[5] = sa.src_row_stride; e->u[6] = sa.src_col_stride;
+            return true;
+        }
+        case ZG_OP_ROPE: {
+            const auto& r = op.u.rope;
+            e->dst = bufs[r.dst]; e->s0 = bufs[r.src]; e->s1 = bufs[r.cos_sin];
+            e->u[0] = r.half_d; e->u[1] = r.seq_len; e->u[2] = r.src_off; e->u[3] = r.cs_off; e->u[4] = r.dst_off;
+            e->u[5] = r.src_rs; e->u[6] = r.src_cs; e->u[7] = r.cs_cs;
+            return true;
+        }
+        case ZG_OP_ATTENTION: {
+            const auto& a = op.u.attention;
+            if (a.d_head > 512) { zg_set_error("attention: d_head %u > 512", a.d_head); return false; }
+            e->dst = bufs[a.dst]; e->s0 = bufs[a.q]; e->s1 = bufs[a.k]; e->s2 = bufs[a.v]; e->s3 = bufs[a.mask];
+            e->f = a.scale;
+            e->u[0] = a.has_mask; e->u[1] = a.d_head; e->u[2] = a.seq_q;
+            e->u[3] = a.q_off; e->u[4] = a.k_off; e->u[5] = a.v_off; e->u[6] = a.mask_off; e->u[7] = a.dst_off;
+            e->u[8] = a.q_rs; e->u[9] = a.q_cs; e->u[10] = a.k_rs; e->u[11] = a.k_cs; e->u[12] = a.v_rs; e->u[13] = a.v_cs;
+            e->u[14] = a.mask_rs; e->u[15] = a.mask_cs; e->u[16] = a.dst_rs; e->u[17] = a.dst_cs;
+            return true;
+        }
+        default: zg_set_error("internal: op kind %u has no batch entry", op.tag); return false;
+    }
+}
+
+// `first` = any op of the batch (all share the work shape); `d_entries` = `count` consecutive table entries.
+bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st) {
+    if (count == 0) return true;
+    switch (first.tag) {
+        case ZG_OP_SLICE_ASSIGN: {
+            const auto& sa = first.u.slice_assign;
+            if (sa.rows == 0 || sa.cols == 0) return true;
+            k_slice_assign<<<dim3(blocks_for(sa.rows * sa.cols, 256), count), 256, 0, st>>>(d_entries, d_dyn);
+            break;
+        }
+        case ZG_OP_ROPE: {
+            const auto& r = first.u.rope;
+            if (r.half_d == 0 || r.seq_len == 0) return true;
+            k_rope<<<dim3(blocks_for(r.half_d * r.seq_len, 128), count), 128, 0, st>>>(d_entries);
+            break;
+        }
+        case ZG_OP_ATTENTION: {
+            const auto& a = first.u.attention;
+            if (a.seq_q == 0 || a.d_head == 0) return true;
+            if (attn_fast_ok(first)) k_attention_fast<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
+            else k_attention<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
+            break;
+        }
+        default: zg_set_error("internal: op kind %u is not batched", first.tag); return false;
     }
     ZG_COUNT_LAUNCH();
     return true;

@@ -112,5 +112,11 @@ bool zg_qgemv_init(ZgCudaCtx* ctx);
 
 // ops.cu : one launcher per DeviceOp tag (buffers = device pointer table)
 struct ZgDevStep { uint32_t op, is_swapped; const float* sec; };
+// one op's parameters in the device table of the batched per-head kernels (rope, slice_assign, attention)
+struct ZgBatchEntry { float* dst; const float* s0; const float* s1; const float* s2; const float* s3; uint32_t u[18]; float f; uint32_t dyn; };
+bool zg_op_is_batched(uint32_t tag);
+uint64_t zg_batch_signature(const ZgOp& op);
+bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, ZgBatchEntry* e);
+bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
 bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
                   uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st);

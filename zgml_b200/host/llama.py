@@ -233,6 +233,7 @@ class DeviceLlamaSession:
         self.inputs += [ProgramIO(b, self.rope_cs) for b in self.lp.buf_rope]
         last_off = (T - 1) * cfg.vocab_size * 4             # last-column logits (llama_inference.zig:463-465)
         self.outputs = [ProgramIO(self.lp.buf_logits, self.logits, offset=last_off)]
+        self._init_patch_views()
 
     def reset(self):
         self.pos = 0
@@ -251,14 +252,25 @@ class DeviceLlamaSession:
             self.rope_cs[j * 2 * dh:j * 2 * dh + dh] = self.cos[pos + j]
             self.rope_cs[j * 2 * dh + dh:(j + 1) * 2 * dh] = self.sin[pos + j]
 
+    def _init_patch_views(self):
+        """u32 view of the caller-owned op array + word indices of the per-step patched fields, so that
+        patchSliceAssignOffset / patchAttentionSeqKV are two vectorised stores instead of a Python loop."""
+        import ctypes as C
+        self._ops_u32 = np.frombuffer((C.c_char * C.sizeof(self.ops)).from_buffer(self.ops), dtype=np.uint32)
+        op_words = C.sizeof(abi.ZgOp) // 4
+        u_off = abi.ZgOp.u.offset
+        sa_t, at_t = type(self.ops[0].u.slice_assign), type(self.ops[0].u.attention)
+        w_sa = (u_off + sa_t.dst_offset.offset) // 4
+        w_at = (u_off + at_t.seq_kv.offset) // 4
+        sa = [i for i in self.lp.slice_assign_ops if self.ops[i].u.slice_assign.patch_stride]
+        self._sa_words = np.array([i * op_words + w_sa for i in sa], dtype=np.int64)
+        self._sa_base = np.array([self.ops[i].u.slice_assign.dst_base_offset for i in sa], dtype=np.uint32)
+        self._sa_stride = np.array([self.ops[i].u.slice_assign.patch_stride for i in sa], dtype=np.uint32)
+        self._at_words = np.array([i * op_words + w_at for i in self.lp.attention_ops], dtype=np.int64)
+
     def _patch_ops(self, pos):
-        T = self.lp.token_len
-        for i in self.lp.slice_assign_ops:                  # patchSliceAssignOffset
-            sa = self.ops[i].u.slice_assign
-            if sa.patch_stride:
-                sa.dst_offset = sa.dst_base_offset + pos * sa.patch_stride
-        for i in self.lp.attention_ops:                     # patchAttentionSeqKV(pos + T)
-            self.ops[i].u.attention.seq_kv = pos + T
+        self._ops_u32[self._sa_words] = self._sa_base + np.uint32(pos) * self._sa_stride   # patchSliceAssignOffset
+        self._ops_u32[self._at_words] = np.uint32(pos + self.lp.token_len)                 # patchAttentionSeqKV(pos + T)
 
     def execute_at(self, token_ids, pos) -> np.ndarray:
         self._patch_host_inputs(token_ids, pos)
