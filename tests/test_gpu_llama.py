@@ -71,3 +71,15 @@ def test_smollm_135m_shape_q8_0_greedy_decode(cuda_backend):  # BASELINE.json co
     assert got_t == want_t
     for g, wv in zip(got_l, want_l):
         assert rel(g, wv) < 1e-3
+
+
+def test_prefill_chunk_on_tensor_core_path(cuda_backend):  # token_len > 8: every linear runs the tcgen05 GEMM
+    cfg = TINY
+    w = synthetic_weights(cfg, "q4_0", seed=9, embed_scale=1.0)
+    toks = [(7 * i + 3) % cfg.vocab_size for i in range(24)]
+    pre = DeviceLlamaSession(cuda_backend, cfg, w, len(toks))
+    got = pre.execute_at(toks, 0).copy()
+    ref = DeviceLlamaSession(OracleBackend(), cfg, w, len(toks))
+    want = ref.execute_at(toks, 0).copy()
+    pre.close(); ref.close()
+    assert rel(got, want) < 1e-3 and int(np.argmax(got)) == int(np.argmax(want))

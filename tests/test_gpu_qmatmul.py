@@ -278,3 +278,43 @@ def test_program_rejects_bad_descriptors(cuda_backend):  # reference src/backend
     assert cuda_backend.compile_program(bad_idx) is None
     bad_buf = DeviceProgram([DeviceOp.qmatmul(5, 0, 0, 1, 32, 64)], [64, 32], [], [qw])
     assert cuda_backend.compile_program(bad_buf) is None
+
+
+# ── prefill path: M > 8 on the tcgen05 tensor cores (3xTF32 operands, fp32 accumulate) ──────────
+@pytest.mark.parametrize("K,N", [(64, 64), (100, 160), (576, 1536), (1536, 576), (2048, 2048)])
+@pytest.mark.parametrize("M", [9, 64, 128, 200, 257])
+@pytest.mark.parametrize("kind", ["i8_f32", "q8_0", "q4_0"])
+def test_qmatmul_prefill_tensor_core_path_vs_oracle(cuda_backend, K, N, M, kind):
+    if K * N * M > 600e6:
+        pytest.skip("oracle time")
+    r = rng(K + 3 * N + M)
+    if kind == "i8_f32":
+        o = oracle.QuantizedWeight.from_slice(r.uniform(-1, 1, K * N).astype(np.float32), K, N, 32)
+        w = QuantizedWeight.upload(cuda_backend, o.data, o.scales, K, N, 32)
+    else:
+        t = 8 if kind == "q8_0" else 2
+        if K * N % 32:
+            pytest.skip("GGUF blocks need K*N % 32 == 0")
+        raw = make_q8_0_raw(K, N, 5 + K) if t == 8 else make_q4_0_raw(K, N, 5 + K)
+        o = oracle.QuantizedWeight.from_gguf(raw, t, K, N)
+        w = QuantizedWeight.from_gguf_blocks(cuda_backend, raw, t, K, N)
+    x = r.standard_normal((M, K)).astype(np.float32)
+    got = w.matmul(x, M)
+    want = o.matmul(x, M, threads=8)
+    e = rel_err(got, want)
+    assert e < REL_TOL, e          # north-star tolerance
+    assert e < 5e-5, e             # 3xTF32 (hi/lo split of both operands) is fp32-class (tensor-core fp32 accumulation order)
+    w.free()
+
+
+def test_prefill_rows_match_decode_rows(cuda_backend):
+    """Row i of an M = 40 tensor-core matmul equals the exact M = 1 matvec of that row within the TF32 envelope."""
+    K, N = 576, 1536
+    raw = make_q8_0_raw(K, N, 77)
+    w = QuantizedWeight.from_gguf_blocks(cuda_backend, raw, 8, K, N)
+    x = rng(3).standard_normal((40, K)).astype(np.float32)
+    big = w.matmul(x, 40)
+    for i in (0, 7, 39):
+        one = w.matmul(x[i:i + 1], 1)
+        assert rel_err(big[i], one[0]) < 5e-5
+    w.free()

@@ -22,7 +22,12 @@ void zg_set_error(const char* fmt, ...) {
 extern "C" const char* zg_cuda_last_error(void) { return g_err; }
 extern "C" uint64_t zg_cuda_launch_count(void) { return g_zg_launches.load(); }
 
-bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cudaStream_t st) {
+bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cudaStream_t st, size_t gemm_scratch_elems) {
+    if (gemm_scratch_elems > ws->gemm_scratch_elems) {
+        if (ws->gemm_scratch) { cudaStreamSynchronize(st); cudaFree(ws->gemm_scratch); ws->gemm_scratch = nullptr; }
+        ZG_CUDA_OK(cudaMalloc(&ws->gemm_scratch, gemm_scratch_elems * sizeof(float)));
+        ws->gemm_scratch_elems = gemm_scratch_elems;
+    }
     if (partial_elems > ws->partials_elems) {
         if (ws->partials) { cudaStreamSynchronize(st); cudaFree(ws->partials); ws->partials = nullptr; }
         ZG_CUDA_OK(cudaMalloc(&ws->partials, partial_elems * sizeof(float)));
@@ -38,7 +43,7 @@ bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cud
     return true;
 }
 void zg_gemv_ws_free(ZgGemvWs* ws) {
-    cudaFree(ws->partials); cudaFree(ws->counters);
+    cudaFree(ws->partials); cudaFree(ws->counters); cudaFree(ws->gemm_scratch);
     *ws = ZgGemvWs();
 }
 
@@ -91,7 +96,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
-    if (!zg_qgemv_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
+    if (!zg_qgemv_init(ctx) || !zg_qgemm_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
     int n_branch = 7; // capture streams for independent ops of a program (ZG_CUDA_BRANCH=0: strictly serial graphs)
     if (const char* e = getenv("ZG_CUDA_BRANCH")) n_branch = atoi(e);
     for (int i = 0; i < n_branch && i < 31; i++) {
@@ -238,7 +243,7 @@ static bool validate_ops(const ZgCudaProgram* p, const ZgOp* ops, size_t n_ops) 
 static bool build_schedule(ZgCudaProgram* p);
 
 static bool reserve_workspace(ZgCudaProgram* p) {
-    size_t pe = 0, nc = 0;
+    size_t pe = 0, nc = 0, gs = 0;
     p->ws_part_off.assign(p->ops.size(), 0);
     p->ws_cnt_off.assign(p->ops.size(), 0);
     for (size_t i = 0; i < p->ops.size(); i++) {
@@ -248,8 +253,10 @@ static bool reserve_workspace(ZgCudaProgram* p) {
         zg_qgemv_ws_need(p->ctx, p->qweights[op.u.qmatmul.weight_idx], op.u.qmatmul.M, &a, &b);
         p->ws_part_off[i] = pe; p->ws_cnt_off[i] = nc;
         pe += a; nc += b;
+        const size_t g = zg_qgemm_scratch_elems(p->qweights[op.u.qmatmul.weight_idx], op.u.qmatmul.M);
+        if (g > gs) gs = g;
     }
-    return zg_gemv_ws_reserve(&p->ws, pe, nc, p->ctx->stream);
+    return zg_gemv_ws_reserve(&p->ws, pe, nc, p->ctx->stream, gs);
 }
 
 // ── op dependencies (element ranges per buffer) for concurrent graph branches ─────────────────
@@ -274,6 +281,8 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
             if (q.M == 0) break;
             span(q.dst, q.dst_offset, (size_t)(q.M - 1) * drs + q.N, true);
             span(q.input, q.input_offset, (size_t)(q.M - 1) * irs + q.K, false);
+            // the tensor-core path stages its rounded activations in ONE shared scratch: a virtual buffer orders its users
+            if (zg_qgemm_scratch_elems(p->qweights[q.weight_idx], q.M)) span((uint32_t)p->buffers.size(), 0, 1, true);
             break;
         }
         case ZG_OP_SOFTMAX: span(op.u.softmax.dst, op.u.softmax.dst_offset, (size_t)op.u.softmax.rows * op.u.softmax.cols, true);
@@ -437,7 +446,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 static bool build_schedule(ZgCudaProgram* p) {
     const size_t n = p->ops.size();
     struct Access { ZgRange r; int level; };
-    std::vector<std::vector<Access>> acc(p->buffers.size());
+    std::vector<std::vector<Access>> acc(p->buffers.size() + 1);   // + the virtual GEMM-scratch buffer
     std::vector<int> level(n, 0);
     std::vector<ZgRange> rng;
     for (size_t i = 0; i < n; i++) {
@@ -449,7 +458,7 @@ static bool build_schedule(ZgCudaProgram* p) {
         level[i] = lvl;
         for (const ZgRange& r : rng) {
             // a write covering the whole buffer orders everything after it: older accesses need not be kept
-            if (r.write && !r.dyn && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
+            if (r.write && !r.dyn && r.buf < p->buffer_elems.size() && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
             acc[r.buf].push_back({r, lvl});
         }
     }
@@ -682,7 +691,7 @@ extern "C" int zg_cuda_qmatmul_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, co
     cudaSetDevice(ctx->device);
     size_t pe = 0, nc = 0;
     zg_qgemv_ws_need(ctx, w, M, &pe, &nc);
-    if (!zg_gemv_ws_reserve(&ctx->ws, pe, nc, ctx->stream)) return -1;
+    if (!zg_gemv_ws_reserve(&ctx->ws, pe, nc, ctx->stream, zg_qgemm_scratch_elems(w, M))) return -1;
     return zg_qmatmul_launch(ctx, w, d_input, d_dst, M, input_row_stride, dst_row_stride, &ctx->ws, ctx->stream) ? 0 : -1;
 }
 

@@ -1,0 +1,391 @@
+// Prefill-path quantized matmul for sm_100a: dst[M, N] = x[M, K] * dequant(W)[K, N], M > 8.
+//
+// zgml's W8·f32 algorithm (QuantizedWeight.matmul, src/quant.zig:475-578; DeviceOp.qmatmul,
+// src/backend/reference.zig:499-566) as a dense contraction on the 5th-generation tensor cores:
+//
+//   * tcgen05.mma.cta_group::1.kind::tf32, 128 x 256 output tile per CTA, fp32 accumulators in TMEM
+//     (128 lanes x 256 columns), issued by one thread; K advances 32 per pipeline stage (4 MMAs of K = 8).
+//   * A = activations: split once into TF32 terms x = x_hi + x_lo (each round-to-nearest, so the tensor core's
+//     operand truncation is exact) in a dense scratch, then TMA (cp.async.bulk.tensor.2d, 128B swizzle)
+//     straight into the canonical K-major shared-memory layout.
+//   * B = weights: eight dequantize warps read the packed records (zg_internal.cuh) with 128-bit loads, form
+//     w = f32(q) * s exactly like dequantizeTo (src/quant.zig:594-618), round to TF32 and store 16-byte
+//     chunks into the same swizzled K-major layout (a record's 16 bytes per lane are four k-runs of four
+//     weights = four chunks).  Weights are dequantized once per 128 activation rows, in shared memory only.
+//   * 4-stage mbarrier pipeline: TMA warp / dequant warps -> MMA warp -> (tcgen05.commit) -> stage free;
+//     the dequant warps turn into the epilogue (tcgen05.ld 32x32b -> global stores) at the end.
+//
+// Numerics: "3xTF32" — both operands are split hi + lo (22 significant bits), D += hi*hi + hi*lo + lo*hi with
+// fp32 accumulation in TMEM: ~1e-6 relative on outputs (fp32-class; a single rounded term would give ~4e-4 and
+// does not survive 200+ chained linears inside the 1e-3 logit budget).  ZG_GEMM_TF32X1=1 selects the single-term
+// mode (3x fewer MMAs) for throughput experiments.  The exact fixed-point matvec (qgemv.cu) stays the path for M <= 8.
+#include "zg_internal.cuh"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr uint32_t BM = 128, BN = 256, BK = 32;
+constexpr uint32_t kTileA = BM * BK * 4, kTileB = BN * BK * 4;      // one TF32 operand tile: 16 KB (A), 32 KB (B)
+constexpr uint32_t kGemmThreads = 320;                             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: dequant + epilogue
+constexpr uint32_t kTmemCols = 256;
+// NT = TF32 terms per operand.  NT = 2 (default): x = x_hi + x_lo, w = w_hi + w_lo, D += hi*hi + hi*lo + lo*hi
+// ("3xTF32": ~1e-6 relative, fp32-class); NT = 1: one rounded term each (~4e-4 relative, 3x fewer MMAs).
+__host__ __device__ constexpr uint32_t stages_of(int NT) { return NT == 1 ? 4u : 2u; }
+__host__ __device__ constexpr uint32_t smem_of(int NT) { return stages_of(NT) * NT * (kTileA + kTileB) + 1024 /* alignment slack */ + 256 /* barriers */; }
+
+struct QGemmParams {
+    const uint8_t* recs;
+    uint32_t n_kc, n_nb;
+    uint32_t M, N;
+    float* out;
+    uint32_t out_rs;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)1 << 16;                               // leading byte offset (ignored)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset
+    d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+
+// hi = rn_tf32(x), lo = rn_tf32(x - hi) into dense [Mp][Kp] planes (plane 1 only when NT == 2); zero padding
+__global__ void k_round_tf32(const float* __restrict__ x, uint32_t x_rs, float* __restrict__ xr, uint32_t xr_rs,
+                             uint32_t M, uint32_t K, size_t plane_elems, int NT) {
+    const uint32_t m = blockIdx.y;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < xr_rs; k += gridDim.x * blockDim.x) {
+        const float v = (m < M && k < K) ? x[(size_t)m * x_rs + k] : 0.0f;
+        const float hi = __uint_as_float(to_tf32(v));
+        xr[(size_t)m * xr_rs + k] = hi;
+        if (NT == 2) xr[plane_elems + (size_t)m * xr_rs + k] = __uint_as_float(to_tf32(v - hi));
+    }
+}
+
+template <int FMT, int NT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo, const QGemmParams p) {
+    constexpr uint32_t kStages = stages_of(NT);
+    constexpr uint32_t kStageA = NT * kTileA, kStageB = NT * kTileB;   // [hi | lo] tiles
+    constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
+    constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
+    constexpr uint32_t QB = kI4 ? 512u : 1024u;
+    constexpr uint32_t SB = kF32 ? 32u : 16u;
+    constexpr uint32_t RB = QB + 4 * SB;
+
+    extern __shared__ uint8_t dsm_raw[];
+    const uint32_t base = (smem_u32(dsm_raw) + 1023u) & ~1023u;        // 128B-swizzle atoms need 1024-byte alignment
+    const uint32_t sA = base, sB = base + kStages * kStageA;
+    const uint32_t bars = sB + kStages * kStageB;
+    const uint32_t full_a = bars, full_b = bars + 8 * kStages, empty = bars + 16 * kStages, tmem_full = bars + 24 * kStages;
+    const uint32_t tmem_slot = tmem_full + 8;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile_n = blockIdx.x, tile_m = blockIdx.y;
+    const uint32_t n_k = p.n_kc;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kStages; s++) {
+            mbar_init(full_a + 8 * s, 1);
+            mbar_init(full_b + 8 * s, 8);      // one arrive per dequant warp
+            mbar_init(empty + 8 * s, 1);       // tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM accumulator: 128 columns x 128 lanes of fp32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ── TMA producer: activations ──
+        if (lane == 0) {
+            for (uint32_t kt = 0; kt < n_k; kt++) {
+                const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
+                mbar_wait(empty + 8 * s, ph ^ 1);
+                mbar_expect_tx(full_a + 8 * s, kStageA);
+                tma_load_2d(sA + s * kStageA, &tmap_a, kt * BK, tile_m * BM, full_a + 8 * s);
+                if constexpr (NT == 2) tma_load_2d(sA + s * kStageA + kTileA, &tmap_a_lo, kt * BK, tile_m * BM, full_a + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        // ── MMA issuer ──
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+        for (uint32_t kt = 0; kt < n_k; kt++) {
+            const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
+            mbar_wait(full_a + 8 * s, ph);
+            mbar_wait(full_b + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+#pragma unroll
+                for (uint32_t k = 0; k < BK / 8; k++) {
+                    // term 0: hi*hi; NT == 2 adds hi*lo and lo*hi (lo*lo is below fp32 resolution)
+#pragma unroll
+                    for (int term = 0; term < (NT == 2 ? 3 : 1); term++) {
+                        const uint32_t a_off = (term == 2) ? kTileA : 0u, b_off = (term == 1) ? kTileB : 0u;
+                        const uint64_t da = make_desc(sA + s * kStageA + a_off + k * 32), db = make_desc(sB + s * kStageB + b_off + k * 32);
+                        const uint32_t accumulate = (kt | k | (uint32_t)term) ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+                    }
+                }
+                // frees the stage when the MMAs that read it have completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty + 8 * s) : "memory");
+                if (kt + 1 == n_k)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        // ── dequantize warps: warp dw owns column group dw (one record = 32 columns x 32 k) of the CTA tile per k-step ──
+        const uint32_t dw = warp - 2;                    // 0..7
+        const uint32_t g = lane >> 2, t = lane & 3;
+        const uint32_t nb = tile_n * (BN / 32) + dw;
+        const bool nb_ok = nb < p.n_nb;
+        const uint8_t* rec = p.recs + (size_t)(nb_ok ? nb : 0) * p.n_kc * RB;
+        // register ring: the records of the next kPf k-steps are in flight while the current one is converted
+        constexpr int kPf = 3;
+        uint4 rq[kPf], rq1[kPf], rs0[kPf], rs1[kPf];
+        auto load_rec = [&](int slot, uint32_t kt) {
+            rq[slot] = make_uint4(0, 0, 0, 0); rq1[slot] = rq[slot]; rs0[slot] = rq[slot]; rs1[slot] = rq[slot];
+            if (nb_ok && kt < n_k) {
+                const uint8_t* r = rec + (size_t)kt * RB;
+                rq[slot] = __ldg(reinterpret_cast<const uint4*>(r + lane * 16));
+                if constexpr (!kI4) rq1[slot] = __ldg(reinterpret_cast<const uint4*>(r + 512 + lane * 16));
+                rs0[slot] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB));
+                if constexpr (kF32) rs1[slot] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB + 16));
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < kPf; i++) load_rec(i, i);
+        for (uint32_t kt0 = 0; kt0 < n_k; kt0 += kPf) {
+#pragma unroll
+          for (int slot = 0; slot < kPf; slot++) {
+            const uint32_t kt = kt0 + slot;
+            if (kt >= n_k) break;
+            const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
+            const uint4 qa = rq[slot], qb = rq1[slot], s0 = rs0[slot], s1 = rs1[slot];
+            load_rec(slot, kt + kPf);
+            float sc[8];   // scales of rows k = 4t + i (i < 4) and 16 + 4t + (i - 4)
+            if constexpr (kF32) {
+                sc[0] = __uint_as_float(s0.x); sc[1] = __uint_as_float(s0.y); sc[2] = __uint_as_float(s0.z); sc[3] = __uint_as_float(s0.w);
+                sc[4] = __uint_as_float(s1.x); sc[5] = __uint_as_float(s1.y); sc[6] = __uint_as_float(s1.z); sc[7] = __uint_as_float(s1.w);
+            } else {
+                const uint32_t hw[4] = {s0.x, s0.y, s0.z, s0.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+                    sc[2 * i] = f.x; sc[2 * i + 1] = f.y;
+                }
+            }
+            mbar_wait(empty + 8 * s, ph ^ 1);
+            const uint32_t stage = sB + s * kStageB;
+#pragma unroll
+            for (int ct = 0; ct < 2; ct++) {
+            const uint32_t row_lo = dw * 32 + ct * 16 + g;   // B-tile rows of this lane in column tile ct: row_lo and row_lo + 8
+            uint4 q;
+            if constexpr (kI4) { q.x = ct ? qa.z : qa.x; q.y = ct ? qa.w : qa.y; q.z = 0; q.w = 0; }
+            else q = ct ? qb : qa;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                // unit r: column n = row_lo + 8 (r & 1), rows k = 4 t + b + 16 (r >> 1), b = 0..3.
+                // int -> float through the mantissa: bits 0x4B000000 | u are the float 2^23 + u exactly.
+                float qf[4];
+                if constexpr (!kI4) {
+                    const uint32_t w = (r == 0 ? q.x : (r == 1 ? q.y : (r == 2 ? q.z : q.w))) ^ 0x80808080u;   // u = q + 128
+#pragma unroll
+                    for (int b = 0; b < 4; b++) qf[b] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + b)) - 8388736.0f;
+                } else {
+                    // {w0, w1}: byte b low nibble = column g, high nibble = column g + 8 (both biased by 8)
+                    const uint32_t w = (r >> 1) ? q.y : q.x;
+                    const uint32_t nib = (r & 1) ? ((w >> 4) & 0x0F0F0F0Fu) : (w & 0x0F0F0F0Fu);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) qf[b] = __uint_as_float(__byte_perm(nib, 0x4B000000u, 0x7650 + b)) - 8388616.0f;
+                }
+                const uint32_t n = row_lo + 8 * (r & 1);
+                const uint32_t chunk = t + 4 * (r >> 1);                        // 16-byte chunk = four consecutive k
+                float wv[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) wv[b] = qf[b] * sc[4 * (r >> 1) + b];   // f32(q) * scale, src/quant.zig:612-615
+                uint4 o;
+                o.x = to_tf32(wv[0]); o.y = to_tf32(wv[1]); o.z = to_tf32(wv[2]); o.w = to_tf32(wv[3]);
+                const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                if constexpr (NT == 2) {
+                    uint4 l;
+                    l.x = to_tf32(wv[0] - __uint_as_float(o.x)); l.y = to_tf32(wv[1] - __uint_as_float(o.y));
+                    l.z = to_tf32(wv[2] - __uint_as_float(o.z)); l.w = to_tf32(wv[3] - __uint_as_float(o.w));
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kTileB), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w) : "memory");
+                }
+            }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_b + 8 * s);
+          }
+        }
+        // ── epilogue: TMEM -> registers -> global.  Warp w may touch TMEM lanes 32 (w % 4) .. + 31 ──
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t quarter = warp & 3;
+        const uint32_t m = tile_m * BM + quarter * 32 + lane;
+        const uint32_t c_begin = (dw >> 2) * (BN / 2);   // the two warps of a TMEM lane quarter split the columns
+#pragma unroll 1
+        for (uint32_t c0 = c_begin; c0 < c_begin + BN / 2; c0 += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t n0 = tile_n * BN + c0;
+            if (m < p.M && n0 < p.N) {
+                float* dstp = p.out + (size_t)m * p.out_rs + n0;
+#pragma unroll
+                for (int i = 0; i < 32; i++) dstp[i] = __uint_as_float(v[i]);   // N % 32 == 0: whole column groups only
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+bool get_encode() {
+    if (g_encode) return true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+        zg_set_error("cuTensorMapEncodeTiled entry point not available");
+        return false;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    return true;
+}
+
+template <int FMT, int NT>
+bool launch_gemm(const CUtensorMap& map, const CUtensorMap& map_lo, const QGemmParams& p, cudaStream_t st) {
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+    qgemm_tf32_kernel<FMT, NT><<<grid, kGemmThreads, smem_of(NT), st>>>(map, map_lo, p);
+    ZG_COUNT_LAUNCH();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { zg_set_error("qgemm launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+}
+
+template <int FMT, int NT>
+bool set_attr() {
+    cudaError_t e = cudaFuncSetAttribute(qgemm_tf32_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(NT));
+    if (e != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemm) failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+}
+
+int g_terms = 2;   // ZG_GEMM_TF32X1=1 selects the single-term (fast, ~4e-4) mode
+
+} // namespace
+
+bool zg_qgemm_init(ZgCudaCtx*) {
+    if (const char* e = getenv("ZG_GEMM_TF32X1")) g_terms = (e[0] == '1') ? 1 : 2;
+    return set_attr<ZG_QFMT_I8_F32, 1>() && set_attr<ZG_QFMT_I8_F16, 1>() && set_attr<ZG_QFMT_I4_F16, 1>() &&
+           set_attr<ZG_QFMT_I8_F32, 2>() && set_attr<ZG_QFMT_I8_F16, 2>() && set_attr<ZG_QFMT_I4_F16, 2>() && get_encode();
+}
+
+// TF32 hi (and lo) planes of the activations the GEMM's TMA reads: 2 x [round_up(M, 128)][n_kc * 32] floats.
+size_t zg_qgemm_scratch_elems(const ZgCudaQWeight* w, uint32_t M) {
+    if (w->fmt == ZG_QFMT_GENERIC || M <= 8) return 0;
+    return 2 * (size_t)((M + BM - 1) / BM * BM) * ((size_t)w->n_kc * ZG_KR);
+}
+
+bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out, uint32_t M, uint32_t in_rs,
+                     uint32_t out_rs, float* scratch, cudaStream_t st) {
+    (void)ctx;
+    if (!get_encode()) return false;
+    const uint32_t Kp = w->n_kc * ZG_KR, Mp = (M + BM - 1) / BM * BM;
+    const size_t plane = (size_t)Mp * Kp;
+    const int NT = g_terms;
+    k_round_tf32<<<dim3((Kp + 255) / 256, Mp), 256, 0, st>>>(d_in, in_rs, scratch, Kp, M, (uint32_t)w->K, plane, NT);
+    ZG_COUNT_LAUNCH();
+    CUtensorMap map[2];
+    const cuuint64_t gdim[2] = {Kp, Mp};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Kp * 4};
+    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 2; i++) {
+        CUresult r = g_encode(&map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch + (size_t)i * plane, gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { zg_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
+    }
+    QGemmParams p;
+    p.recs = w->recs; p.n_kc = w->n_kc; p.n_nb = w->n_nb; p.M = M; p.N = (uint32_t)w->N; p.out = d_out; p.out_rs = out_rs;
+    if (NT == 1) {
+        switch (w->fmt) {
+            case ZG_QFMT_I8_F32: return launch_gemm<ZG_QFMT_I8_F32, 1>(map[0], map[1], p, st);
+            case ZG_QFMT_I8_F16: return launch_gemm<ZG_QFMT_I8_F16, 1>(map[0], map[1], p, st);
+            case ZG_QFMT_I4_F16: return launch_gemm<ZG_QFMT_I4_F16, 1>(map[0], map[1], p, st);
+            default: break;
+        }
+    } else {
+        switch (w->fmt) {
+            case ZG_QFMT_I8_F32: return launch_gemm<ZG_QFMT_I8_F32, 2>(map[0], map[1], p, st);
+            case ZG_QFMT_I8_F16: return launch_gemm<ZG_QFMT_I8_F16, 2>(map[0], map[1], p, st);
+            case ZG_QFMT_I4_F16: return launch_gemm<ZG_QFMT_I4_F16, 2>(map[0], map[1], p, st);
+            default: break;
+        }
+    }
+    zg_set_error("qgemm: unknown weight format %d", w->fmt);
+    return false;
+}

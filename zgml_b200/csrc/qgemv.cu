@@ -530,7 +530,7 @@ bool zg_qgemv_init(ZgCudaCtx* ctx) {
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
                       size_t* counters) {
     *partial_elems = 0; *counters = 0;
-    if (w->fmt == ZG_QFMT_GENERIC || M == 0) return;
+    if (w->fmt == ZG_QFMT_GENERIC || M == 0 || M > 8) return;
     ZgGemvPlan plan = zg_qgemv_plan(ctx, w, M);
     if (plan.S > 1) {
         *partial_elems = (size_t)w->n_nb * plan.S * (2 * plan.mp) * ZG_TN;
@@ -549,6 +549,11 @@ bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in
                                                       d_out, out_rs, M, (uint32_t)w->N, (uint32_t)w->K);
         ZG_COUNT_LAUNCH();
         return true;
+    }
+    if (M > 8) {   // prefill: dense contraction on the tcgen05 tensor cores (qgemm.cu)
+        const size_t need = zg_qgemm_scratch_elems(w, M);
+        if (!ws || ws->gemm_scratch_elems < need) { zg_set_error("internal: GEMM scratch too small (%zu needed)", need); return false; }
+        return zg_qgemm_launch(ctx, w, d_in, d_out, M, in_rs, out_rs, ws->gemm_scratch, st);
     }
     size_t pe = 0, nc = 0;
     zg_qgemv_ws_need(ctx, w, M, &pe, &nc);

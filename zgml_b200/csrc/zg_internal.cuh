@@ -75,6 +75,8 @@ struct ZgGemvWs {
     size_t partials_elems = 0;
     uint32_t* counters = nullptr;
     size_t counters_n = 0;
+    float* gemm_scratch = nullptr;   // TF32-rounded activations of the prefill GEMM (one op at a time uses it)
+    size_t gemm_scratch_elems = 0;
 };
 
 struct ZgCudaCtx {
@@ -92,7 +94,7 @@ struct ZgCudaCtx {
 
 // Grow-only (re)allocation; counters are zero-filled.  Never call between a graph
 // capture and its replays: programs own a workspace sized once at compile time.
-bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cudaStream_t st);
+bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cudaStream_t st, size_t gemm_scratch_elems = 0);
 void zg_gemv_ws_free(ZgGemvWs* ws);
 
 // qweight.cu
@@ -109,6 +111,11 @@ void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, 
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
                        uint32_t M, uint32_t in_rs, uint32_t out_rs, const ZgGemvWs* ws, cudaStream_t st);
 bool zg_qgemv_init(ZgCudaCtx* ctx);
+// qgemm.cu : M > 8 on tcgen05 tensor cores
+bool zg_qgemm_init(ZgCudaCtx* ctx);
+size_t zg_qgemm_scratch_elems(const ZgCudaQWeight* w, uint32_t M);
+bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out, uint32_t M, uint32_t in_rs,
+                     uint32_t out_rs, float* scratch, cudaStream_t st);
 
 // ops.cu : one launcher per DeviceOp tag (buffers = device pointer table)
 struct ZgDevStep { uint32_t op, is_swapped; const float* sec; };
