@@ -326,6 +326,9 @@ def run_b200(args):
                     "h2d_bytes_per_step": sum(4 * c["K"] for c in cases), "d2h_bytes_per_step": sum(4 * c["R"] * c["N"] for c in cases)},
             "gpu_launches": int(launches), "roofline": roofline, "cases": case_out}
 
+    if rank == 0 and world == 1 and not args.no_extras:
+        with torch.cuda.stream(stream):
+            line["extras"] = run_extras(be, torch)
     if rank == 0 and world == 1 and not args.no_cpu:
         gb, sec, passes, ccases = cpu_leg(1, args.cpu_seconds, 200)
         line["cpu_baseline"] = {"value": round(gb, 3), "unit": UNIT, "cores": 1, "kind": "port",
@@ -341,6 +344,56 @@ def run_b200(args):
         print(json.dumps(line))
 
 
+def run_extras(be, torch):
+    """Bounded side measurements of the other BASELINE.json configs (never part of `value`): the tcgen05 prefill
+    GEMM at Llama-3-8B shapes (config 4) and greedy decode of a SmolLM-135M-shape Q8_0 program (config 1)."""
+    out = {}
+    try:
+        from zgml_b200 import QuantizedWeight
+        r = np.random.default_rng(3)
+        M, gem = 2048, []
+        for (K, N) in [(4096, 4096), (4096, 14336)]:
+            data = r.integers(-127, 128, K * N, dtype=np.int8)
+            scales = r.uniform(1e-3, 1e-2, K * N // 32).astype(np.float16).astype(np.float32)
+            ws = [QuantizedWeight.upload(be, data, scales, K, N, 32) for _ in range(2)]
+            x = torch.randn(M, K, device="cuda")
+            y = torch.empty(M, N, device="cuda")
+            for w in ws:
+                w.matmul_device(x.data_ptr(), y.data_ptr(), M)
+            be.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st = torch.cuda.current_stream()
+            e0.record(st)
+            for i in range(10):
+                ws[i % 2].matmul_device(x.data_ptr(), y.data_ptr(), M)
+            e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            gem.append({"M": M, "K": K, "N": N, "format": "q8_0", "ms": round(ms, 4), "tflops": round(2.0 * M * N * K / ms / 1e9, 1)})
+            for w in ws:
+                w.free()
+        out["prefill_qgemm_tcgen05"] = {"mode": "3xTF32 (hi/lo split, fp32 accumulate in TMEM)", "cases": gem,
+                                        "tf32_mma_tflops_issued": round(3 * max(g["tflops"] for g in gem), 1)}
+    except Exception as e:  # extras never break the contract line
+        out["prefill_error"] = repr(e)
+    try:
+        from zgml_b200.host import llama
+        cfg = llama.SMOLLM_135M
+        sess = llama.DeviceLlamaSession(be, cfg, llama.synthetic_weights(cfg, "q8_0", seed=0), 1)
+        tok = int(np.argmax(sess.step(1)))
+        t0 = time.perf_counter()
+        n = 64
+        for _ in range(n):
+            tok = int(np.argmax(sess.step(tok)))
+        dt = time.perf_counter() - t0
+        out["decode_smollm_135m_q8_0"] = {"tok_s": round(n / dt, 1), "ms_per_token": round(1e3 * dt / n, 3), "ops_per_token": sess.n_ops,
+                                          "path": "DeviceProgram through execute_program (host copies inside), greedy"}
+        sess.close()
+    except Exception as e:
+        out["decode_error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -350,6 +403,7 @@ def main():
     ap.add_argument("--rotation-mb", type=int, default=ROTATION_BYTES >> 20)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
