@@ -45,7 +45,11 @@ typedef enum ZgOpTag {
     ZG_OP_ROPE = 9,
     ZG_OP_ATTENTION = 10,
     ZG_OP_FUSED_ELEMENTWISE = 11,
-    ZG_OP_COUNT = 12
+    ZG_OP_COUNT = 12,
+    /* Extensions (no zgml counterpart: the reference has no distributed layer).  Emitted only by
+     * the sharded session of this repo; need zg_cuda_comm_init().  One NCCL collective each, in program order. */
+    ZG_OP_ALLREDUCE = 12, /* buf[offset .. offset + n) = sum over ranks, in place */
+    ZG_OP_ALLGATHER = 13  /* dst[dst_offset + r * n ..) = rank r's src[src_offset .. + n), every rank */
 } ZgOpTag;
 
 /* MatMulGeometry — reference src/backend.zig:146-158 (all usize). */
@@ -107,6 +111,8 @@ typedef struct ZgOp {
             size_t n_steps;
             uint32_t n, dst, src, dst_offset, src_offset;
         } fused_elementwise;
+        struct { uint32_t buf, offset, n; } allreduce;
+        struct { uint32_t dst, src, n, dst_offset, src_offset; } allgather;
     } u;
 } ZgOp;
 
@@ -130,6 +136,13 @@ typedef struct ZgQWeight {
     size_t n_scales;
     size_t rows, cols, block_size;
 } ZgQWeight;
+
+/* Extension (direct GGUF->device upload): a descriptor with block_size == ZG_QWEIGHT_RESIDENT
+ * refers to a weight already packed in HBM — `data` is the ZgCudaQWeight* that zg_cuda_qweight_upload /
+ * zg_cuda_qweight_upload_gguf returned, rows/cols must match it, the other fields are ignored.  The program
+ * borrows it (the caller frees it after zg_cuda_free).  Lets a loader stream a model into HBM one tensor at a
+ * time instead of holding every expanded i8 copy in host memory until compile (70B: 69.5 GB). */
+#define ZG_QWEIGHT_RESIDENT ((size_t)-1)
 
 /* DeviceProgram — reference src/backend.zig:270-275. buffer_sizes in f32 elements. */
 typedef struct ZgProgram {
@@ -250,6 +263,12 @@ int zg_cuda_qmatmul_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* 
 /* Same through HOST buffers (copies inside): the e2e leg. Synchronous. */
 int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input,
                          float* h_dst, uint32_t M);
+
+/* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
+ * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */
+int zg_cuda_comm_unique_id(void* id128);
+int zg_cuda_comm_init(ZgCudaCtx* ctx, const void* id128, int rank, int world);
+void zg_cuda_comm_destroy(ZgCudaCtx* ctx);
 
 void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes);
 void zg_cuda_free_device(ZgCudaCtx* ctx, void* p);

@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Row-sharded LLaMA decode tok/s (BASELINE.json config 5: Llama-3-70B-shape Q4_0, weights sharded over the GPUs
+of one box, NCCL all-reduce / all-gather inside the decode CUDA graph).  One process per GPU:
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+      scripts/bench_sharded.py --model llama3-70b --kind q4_0 --tokens 32 --batch 1
+
+Every rank streams its own random-init shard into HBM (host memory: one tensor at a time), decodes greedily from
+`--context`, and rank 0 prints one JSON line: tok/s through step() (host patching + copies inside, e2e) and the
+device-only graph replay time, max over ranks.  `--batch T` runs T-token programs (zgml's token_len)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from zgml_b200 import CudaBackend  # noqa: E402
+from zgml_b200.host import llama  # noqa: E402
+
+MODELS = {"smollm-135m": llama.SMOLLM_135M, "smollm-1.7b": llama.SMOLLM_1_7B, "llama3-8b": llama.LLAMA3_8B, "llama3-70b": llama.LLAMA3_70B}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="llama3-70b", choices=sorted(MODELS))
+    ap.add_argument("--kind", default="q4_0", choices=["q8_0", "q4_0"])
+    ap.add_argument("--tokens", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--context", type=int, default=0)
+    ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--max-seq", type=int, default=0)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")
+    cfg = MODELS[args.model]
+    over = {}
+    if args.layers:
+        over["n_layers"] = args.layers
+    if args.max_seq:
+        over["max_seq_len"] = args.max_seq
+    if over:
+        cfg = llama.LlamaConfig(**{**cfg.__dict__, **over})
+    be = CudaBackend(local)
+    if world > 1:
+        be.comm_init_torch()
+    t0 = time.perf_counter()
+    w, handles = llama.synthetic_resident_shard(be, cfg, args.kind, seed=0, rank=rank, world=world)
+    t_load = time.perf_counter() - t0
+    dev_bytes = sum(h.device_bytes for h in handles)
+    T = args.batch
+    sess = llama.DeviceLlamaSession(be, cfg, w, T)
+    pos = args.context
+    toks = [(i + 1) % cfg.vocab_size for i in range(T)]
+    lg = sess.execute_at(toks, pos)  # warm-up: captures the graph
+    pos += T
+    if world > 1:
+        dist.barrier()
+    launches0 = be.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.tokens):
+        lg = sess.execute_at(toks, pos)
+        toks = toks[1:] + [int(np.argmax(lg))]
+        pos += T
+    dt = time.perf_counter() - t0
+    launches = be.launch_count() - launches0
+    be.sync()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.tokens):
+        be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
+    be.sync()
+    dt_dev = time.perf_counter() - t1
+    if world > 1:
+        t = torch.tensor([dt, dt_dev], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_dev = t.tolist()
+    line = {"metric": "llama_decode_tok_s_sharded", "model": args.model, "kind": args.kind, "n_layers": cfg.n_layers, "n_gpus": world,
+            "batch": T, "value": round(T * args.tokens / dt, 1), "unit": "tok/s", "ms_per_step": round(1e3 * dt / args.tokens, 3),
+            "device_ms_per_step": round(1e3 * dt_dev / args.tokens, 3), "device_tok_s": round(T * args.tokens / dt_dev, 1),
+            "steps": args.tokens, "context": args.context, "ops_per_step": sess.n_ops, "kernels_per_step": launches // args.tokens,
+            "weight_bytes_per_gpu": dev_bytes, "hbm_gbps_per_gpu_on_weights": round(dev_bytes / (dt_dev / args.tokens) / 1e9, 1),
+            "load_s": round(t_load, 1), "collectives_per_step": 2 * cfg.n_layers + 1 if world > 1 else 0,
+            "data": "synthetic random-init GGUF blocks, streamed per shard", "last_token": int(np.argmax(lg))}
+    sess.close()
+    for h in handles:
+        h.free()
+    be.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

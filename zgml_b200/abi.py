@@ -17,6 +17,8 @@ EW_NAMES = {"add": 7, "mul": 8, "neg": 9, "abs": 10, "sgn": 11, "step": 12, "rel
 (OP_ELEMENTWISE, OP_MATMUL, OP_QMATMUL, OP_SOFTMAX, OP_LAYERNORM, OP_RMSNORM, OP_REDUCE,
  OP_REPEAT, OP_SLICE_ASSIGN, OP_ROPE, OP_ATTENTION, OP_FUSED_ELEMENTWISE) = range(12)
 OP_COUNT = 12
+OP_ALLREDUCE, OP_ALLGATHER = 12, 13   # multi-GPU extensions (need comm_init)
+QWEIGHT_RESIDENT = (1 << 64) - 1
 OP_TAG_NAMES = ["elementwise", "matmul", "qmatmul", "softmax", "layernorm", "rmsnorm", "reduce",
                 "repeat", "slice_assign", "rope", "attention", "fused_elementwise"]
 
@@ -90,11 +92,20 @@ class _FusedElementwise(C.Structure):
                 ("src", u32), ("dst_offset", u32), ("src_offset", u32)]
 
 
+class _AllReduce(C.Structure):
+    _fields_ = [(n, u32) for n in ("buf", "offset", "n")]
+
+
+class _AllGather(C.Structure):
+    _fields_ = [(n, u32) for n in ("dst", "src", "n", "dst_offset", "src_offset")]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("elementwise", _Elementwise), ("matmul", _MatMul), ("qmatmul", _QMatMul),
                 ("softmax", _Softmax), ("layernorm", _Norm), ("rmsnorm", _Norm), ("reduce", _Reduce),
                 ("repeat", _Repeat), ("slice_assign", _SliceAssign), ("rope", _Rope),
-                ("attention", _Attention), ("fused_elementwise", _FusedElementwise)]
+                ("attention", _Attention), ("fused_elementwise", _FusedElementwise),
+                ("allreduce", _AllReduce), ("allgather", _AllGather)]
 
 
 class ZgOp(C.Structure):
@@ -158,6 +169,9 @@ SYMBOLS = [
     ("zg_cuda_qweight_dequantize", C.c_int, [vp, vp, vp]),
     ("zg_cuda_qmatmul_device", C.c_int, [vp, vp, vp, vp, u32, u32, u32]),
     ("zg_cuda_qmatmul_host", C.c_int, [vp, vp, vp, vp, u32]),
+    ("zg_cuda_comm_unique_id", C.c_int, [vp]),
+    ("zg_cuda_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
+    ("zg_cuda_comm_destroy", None, [vp]),
     ("zg_cuda_malloc", vp, [vp, sz]),
     ("zg_cuda_free_device", None, [vp, vp]),
     ("zg_cuda_memcpy_h2d", C.c_int, [vp, vp, vp, sz]),

@@ -175,6 +175,20 @@ class DeviceOp:
         o._steps_keepalive = arr  # the caller owns `steps` (src/device_inference.zig:291-298)
         return o
 
+    # Multi-GPU extensions (no zgml counterpart).  One NCCL collective each.
+    @staticmethod
+    def allreduce(buf, n, offset=0):
+        o = DeviceOp._mk(abi.OP_ALLREDUCE)
+        o.u.allreduce.buf, o.u.allreduce.offset, o.u.allreduce.n = buf, offset, n
+        return o
+
+    @staticmethod
+    def allgather(dst, src, n, dst_offset=0, src_offset=0):
+        o = DeviceOp._mk(abi.OP_ALLGATHER)
+        g = o.u.allgather
+        g.dst, g.src, g.n, g.dst_offset, g.src_offset = dst, src, n, dst_offset, src_offset
+        return o
+
 
 @dataclass
 class ProgramIO:  # reference src/backend.zig:252-257 (offset/size in bytes)
@@ -206,6 +220,28 @@ class QuantizedWeightUpload:  # reference src/backend.zig:260-266
         q.data, q.n_data = self.data.ctypes.data, self.data.size
         q.scales, q.n_scales = self.scales.ctypes.data, self.scales.size
         q.rows, q.cols, q.block_size = self.rows, self.cols, self.block_size
+        return q
+
+
+@dataclass
+class ResidentQuantizedWeight:
+    """Descriptor of a weight already packed in HBM (ZG_QWEIGHT_RESIDENT, include/zgml_cuda.h): the program
+    borrows `weight` (a `QuantizedWeight`); the caller keeps it alive and frees it after free_program."""
+    weight: "QuantizedWeight"
+
+    @property
+    def rows(self):
+        return self.weight.rows
+
+    @property
+    def cols(self):
+        return self.weight.cols
+
+    block_size = abi.QWEIGHT_RESIDENT
+
+    def to_c(self) -> abi.ZgQWeight:
+        q = abi.ZgQWeight()
+        q.data, q.rows, q.cols, q.block_size = self.weight.ptr, self.weight.rows, self.weight.cols, abi.QWEIGHT_RESIDENT
         return q
 
 
@@ -273,6 +309,28 @@ class CudaBackend:
         caps = abi.ZgCapabilities()
         self.lib.zg_cuda_capabilities(C.byref(caps))
         self.capabilities = caps
+        self.rank, self.world, self.comm_ready = 0, 1, False
+
+    # Multi-GPU: one process per GPU, one NCCL communicator per backend (csrc/comm.cu)
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.zg_cuda_comm_unique_id(buf) != 0:
+            raise BackendError(f"comm_unique_id failed: {last_error()}")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        if self.lib.zg_cuda_comm_init(self.ctx, buf, rank, world) != 0:
+            raise BackendError(f"comm_init failed: {last_error()}")
+        self.rank, self.world, self.comm_ready = rank, world, True
+
+    def comm_init_torch(self):
+        """Exchange the NCCL id over an initialised torch.distributed group (any backend) and join."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], rank, world)
 
     def close(self):
         if self.ctx:
@@ -302,6 +360,8 @@ class CudaBackend:
                 qw = program.qweights[q.weight_idx]
                 if qw.block_size == 0 or qw.rows != q.K or qw.cols != q.N:
                     return False
+                if qw.block_size == abi.QWEIGHT_RESIDENT:
+                    continue
                 n_elems = q.K * q.N
                 n_blocks = (n_elems + qw.block_size - 1) // qw.block_size
                 if qw.data.size < n_elems or qw.scales.size < n_blocks:
@@ -325,6 +385,8 @@ class CudaBackend:
                 for i in range(f.n_steps):
                     if not (abi.EW_ADD <= f.steps[i].op <= abi.EW_GELU):
                         return False
+            elif t in (abi.OP_ALLREDUCE, abi.OP_ALLGATHER):
+                pass   # world 1 (no comm_init): identity / local copy
             elif t >= abi.OP_COUNT:
                 return False
         return True

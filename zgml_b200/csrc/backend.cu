@@ -55,6 +55,7 @@ struct ZgCudaProgram {
     std::vector<float*> buffers;
     std::vector<size_t> buffer_elems;
     std::vector<ZgCudaQWeight*> qweights;
+    std::vector<bool> qweight_owned;   // false: resident weight borrowed from the caller (ZG_QWEIGHT_RESIDENT)
     ZgDevStep* d_steps = nullptr;
     uint32_t* d_dyn = nullptr;
     uint32_t* h_dyn = nullptr; // pinned
@@ -111,6 +112,7 @@ extern "C" void zg_cuda_destroy(ZgCudaCtx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    zg_cuda_comm_destroy(ctx);
     zg_gemv_ws_free(&ctx->ws);
     for (cudaStream_t b : ctx->branch) cudaStreamDestroy(b);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
@@ -165,6 +167,8 @@ static bool op_buffers_valid(const ZgOp& op, size_t nb) { // src/backend.zig:303
             }
             return true;
         }
+        case ZG_OP_ALLREDUCE: return ok(op.u.allreduce.buf);
+        case ZG_OP_ALLGATHER: return ok(op.u.allgather.dst) && ok(op.u.allgather.src);
         default: return false;
     }
 }
@@ -182,7 +186,8 @@ static void free_program(ZgCudaProgram* p) {
     if (p->exec) cudaGraphExecDestroy(p->exec);
     if (p->graph) cudaGraphDestroy(p->graph);
     for (float* b : p->buffers) cudaFree(b);
-    for (ZgCudaQWeight* w : p->qweights) zg_cuda_qweight_free(p->ctx, w);
+    for (size_t i = 0; i < p->qweights.size(); i++)
+        if (p->qweight_owned[i]) zg_cuda_qweight_free(p->ctx, p->qweights[i]);
     cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
@@ -318,6 +323,15 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
                 if (f.steps[k].op == ZG_EW_ADD || f.steps[k].op == ZG_EW_MUL) span(f.steps[k].secondary_buf, f.steps[k].secondary_offset, f.n, false);
             break;
         }
+        case ZG_OP_ALLREDUCE:
+            span(op.u.allreduce.buf, op.u.allreduce.offset, op.u.allreduce.n, true);
+            span((uint32_t)p->buffers.size() + 1, 0, 1, true);   // one communicator: collectives stay in program order
+            break;
+        case ZG_OP_ALLGATHER:
+            span(op.u.allgather.dst, op.u.allgather.dst_offset, (size_t)op.u.allgather.n * p->ctx->world, true);
+            span(op.u.allgather.src, op.u.allgather.src_offset, op.u.allgather.n, false);
+            span((uint32_t)p->buffers.size() + 1, 0, 1, true);
+            break;
         default: break;
     }
 }
@@ -365,9 +379,16 @@ extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog)
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { zg_set_error("compile: buffer initialisation failed"); free_program(p); return nullptr; }
     for (size_t i = 0; i < prog->n_qweights; i++) {
-        ZgCudaQWeight* w = zg_cuda_qweight_upload(ctx, &prog->qweights[i], ZG_QFMT_AUTO);
+        const ZgQWeight& d = prog->qweights[i];
+        if (d.block_size == ZG_QWEIGHT_RESIDENT) {   // already packed in HBM by zg_cuda_qweight_upload*: borrow it
+            ZgCudaQWeight* w = (ZgCudaQWeight*)d.data;
+            if (!w || w->K != d.rows || w->N != d.cols) { zg_set_error("compile: resident qweight %zu is null or not [%zu,%zu]", i, d.rows, d.cols); free_program(p); return nullptr; }
+            p->qweights.push_back(w); p->qweight_owned.push_back(false);
+            continue;
+        }
+        ZgCudaQWeight* w = zg_cuda_qweight_upload(ctx, &d, ZG_QFMT_AUTO);
         if (!w) { free_program(p); return nullptr; }
-        p->qweights.push_back(w);
+        p->qweights.push_back(w); p->qweight_owned.push_back(true);
     }
     if (!validate_ops(p, prog->ops, prog->n_ops) || !adopt_ops(p, prog->ops, prog->n_ops) || !upload_steps(p) ||
         !reserve_workspace(p) || !build_schedule(p)) {
@@ -446,7 +467,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 static bool build_schedule(ZgCudaProgram* p) {
     const size_t n = p->ops.size();
     struct Access { ZgRange r; int level; };
-    std::vector<std::vector<Access>> acc(p->buffers.size() + 1);   // + the virtual GEMM-scratch buffer
+    std::vector<std::vector<Access>> acc(p->buffers.size() + 2);   // + the virtual GEMM-scratch and communicator buffers
     std::vector<int> level(n, 0);
     std::vector<ZgRange> rng;
     for (size_t i = 0; i < n; i++) {
@@ -519,6 +540,10 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
         return zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
                                  p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &view, st);
     }
+    if (op.tag == ZG_OP_ALLREDUCE) return zg_comm_allreduce(ctx, p->buffers[op.u.allreduce.buf] + op.u.allreduce.offset, op.u.allreduce.n, st);
+    if (op.tag == ZG_OP_ALLGATHER)
+        return zg_comm_allgather(ctx, p->buffers[op.u.allgather.src] + op.u.allgather.src_offset,
+                                 p->buffers[op.u.allgather.dst] + op.u.allgather.dst_offset, op.u.allgather.n, st);
     if (zg_op_is_batched(op.tag)) return zg_launch_batch(op, p->d_batch + p->entry_of_op[i], 1, p->d_dyn, st);
     return zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
 }
@@ -616,7 +641,7 @@ static bool run_ops(ZgCudaProgram* p) {
         for (size_t i = 0; i < n; i++) {
             float ms = 0;
             cudaEventElapsedTime(&ms, p->prof_events[i], p->prof_events[i + 1]);
-            p->profile.time_ns[p->ops[i].tag] += (uint64_t)(ms * 1e6);
+            if (p->ops[i].tag < ZG_OP_COUNT) p->profile.time_ns[p->ops[i].tag] += (uint64_t)(ms * 1e6);
         }
         p->profile.backend_op_count += n;
         p->profile.backend_dispatch_count += n;

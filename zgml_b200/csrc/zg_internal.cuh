@@ -89,6 +89,8 @@ struct ZgCudaCtx {
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
+    void* nccl_comm = nullptr;   // ncclComm_t (comm.cu), null unless zg_cuda_comm_init ran
+    int rank = 0, world = 1;
     std::vector<cudaStream_t> branch; // extra capture streams: independent ops of a program become concurrent graph branches
 };
 
@@ -127,3 +129,7 @@ bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, 
 bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
 bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
                   uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st);
+
+// comm.cu : NCCL through dlopen (no link-time dependency)
+bool zg_comm_allreduce(ZgCudaCtx* ctx, float* buf, size_t n, cudaStream_t st);
+bool zg_comm_allgather(ZgCudaCtx* ctx, const float* src, float* dst, size_t n_per_rank, cudaStream_t st);

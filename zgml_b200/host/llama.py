@@ -28,7 +28,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from .. import abi
-from ..backend import DeviceOp, DeviceProgram, ProgramIO, QuantizedWeightUpload
+from ..backend import DeviceOp, DeviceProgram, ProgramIO, QuantizedWeightUpload, ResidentQuantizedWeight
 
 
 @dataclass(frozen=True)
@@ -81,6 +81,11 @@ class LlamaWeights:
     norm2: List[np.ndarray]
     norm_f: np.ndarray
     out_proj: Optional[QuantizedWeightUpload] = None   # untied LM head [d_model, vocab]
+    # Row-sharded form: `shard = (rank, world)`; every linear then holds only this rank's slab
+    # (see `shard_weights`), `head_rows` the rank's vocab rows of the tied embedding.  token_embed stays whole
+    # (host-side row lookup); anything indexable by token id works.
+    shard: Optional[tuple] = None
+    head_rows: Optional[np.ndarray] = None
 
 
 def rope_tables(cfg: LlamaConfig):
@@ -92,6 +97,56 @@ def rope_tables(cfg: LlamaConfig):
     cos = np.cos(freq).astype(np.float32)
     sin = np.sin(freq).astype(np.float32)
     return np.concatenate([cos, cos], axis=1), np.concatenate([sin, sin], axis=1)   # [max_seq, d] each
+
+
+def check_shardable(cfg: LlamaConfig, world: int):
+    """Slab boundaries must fall on multiples of 32 so that no quant block is split."""
+    if world == 1:
+        return
+    if cfg.n_heads % world or cfg.n_kv_heads % world:
+        raise ValueError(f"{cfg.n_heads}/{cfg.n_kv_heads} heads do not divide over {world} GPUs")
+    widths = {"q": cfg.d_model // world, "kv": cfg.kv_dim // world, "ff": cfg.d_ff // world}
+    if not cfg.tied_lm_head:
+        widths["vocab"] = cfg.vocab_size // world
+    if cfg.d_ff % world or cfg.vocab_size % world or any(v % 32 for v in widths.values()):
+        raise ValueError(f"shard widths {widths} over {world} GPUs are not multiples of the 32-element quant block")
+
+
+def slice_columns(qw: QuantizedWeightUpload, n0: int, n1: int) -> QuantizedWeightUpload:
+    """Output-column slab [n0, n1) of a [K, N] weight.  Blocks run along n inside one k row (flat index k*N + n,
+    src/quant.zig:525), so with N, n0, n1 multiples of the block size the slab keeps whole blocks: exact."""
+    K, N, bs = qw.rows, qw.cols, qw.block_size
+    assert N % bs == 0 and n0 % bs == 0 and n1 % bs == 0 and 0 <= n0 < n1 <= N
+    data = np.ascontiguousarray(qw.data.reshape(K, N)[:, n0:n1]).ravel()
+    scales = np.ascontiguousarray(qw.scales.reshape(K, N // bs)[:, n0 // bs:n1 // bs]).ravel()
+    return QuantizedWeightUpload(data, scales, K, n1 - n0, bs)
+
+
+def slice_rows(qw: QuantizedWeightUpload, k0: int, k1: int) -> QuantizedWeightUpload:
+    """Input-row slab [k0, k1): a contiguous run of the flat array, block-aligned whenever N is."""
+    K, N, bs = qw.rows, qw.cols, qw.block_size
+    assert (k0 * N) % bs == 0 and (k1 * N) % bs == 0 and 0 <= k0 < k1 <= K
+    return QuantizedWeightUpload(np.ascontiguousarray(qw.data[k0 * N:k1 * N]), np.ascontiguousarray(qw.scales[k0 * N // bs:k1 * N // bs]),
+                                 k1 - k0, N, bs)
+
+
+def shard_weights(w: LlamaWeights, rank: int, world: int) -> LlamaWeights:
+    """This rank's slabs of a whole model (tests and small models; big models are generated per shard)."""
+    cfg = w.cfg
+    check_shardable(cfg, world)
+    if world == 1:
+        return w
+    Dq, kvd, F, V = cfg.d_model // world, cfg.kv_dim // world, cfg.d_ff // world, cfg.vocab_size // world
+    col = {"wq": Dq, "wk": kvd, "wv": kvd, "w_gate": F, "w_up": F}
+    row = {"wo": Dq, "w_down": F}
+    layers = []
+    for L in w.layers:
+        d = {n: slice_columns(L[n], rank * c, (rank + 1) * c) for n, c in col.items()}
+        d.update({n: slice_rows(L[n], rank * r, (rank + 1) * r) for n, r in row.items()})
+        layers.append(d)
+    out_proj = None if w.out_proj is None else slice_columns(w.out_proj, rank * V, (rank + 1) * V)
+    head_rows = np.ascontiguousarray(w.token_embed[rank * V:(rank + 1) * V]) if cfg.tied_lm_head else None
+    return LlamaWeights(cfg, w.token_embed, layers, w.norm1, w.norm2, w.norm_f, out_proj, (rank, world), head_rows)
 
 
 class _Buffers:
@@ -118,12 +173,21 @@ class LlamaProgram:
     slice_assign_ops: List[int]
     attention_ops: List[int]
     n_qmatmul: int
+    logits_offset: int = 0          # f32 element offset of the last position's logits in buf_logits
 
 
 def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> LlamaProgram:
+    """Unsharded (w.shard is None): the reference lowering.  Sharded over `world` GPUs: q/k/v/gate/up
+    hold this rank's output columns (its heads, its slice of d_ff), wo/down this rank's input rows followed by an
+    all-reduce of the d_model partial sums, the LM head this rank's vocab slice followed by an all-gather of the
+    last position's logits.  Activations are replicated; the KV cache is sharded by KV head."""
+    rank, world = w.shard if w.shard else (0, 1)
+    check_shardable(cfg, world)
     T, D, dh, S = token_len, cfg.d_model, cfg.d_head, cfg.max_seq_len
-    hd, kvd, F = dh // 2, cfg.kv_dim, cfg.d_ff
+    hd = dh // 2
     n_rep = cfg.n_heads // cfg.n_kv_heads
+    n_heads, n_kv = cfg.n_heads // world, cfg.n_kv_heads // world      # local heads
+    Dq, kvd, F, V = n_heads * dh, n_kv * dh, cfg.d_ff // world, cfg.vocab_size // world   # local widths
     B = _Buffers()
     ops: List[abi.ZgOp] = []
     qws: List[QuantizedWeightUpload] = []
@@ -145,11 +209,11 @@ def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> Llam
     ones_ff = B.new(F * T, np.ones(F * T, np.float32))      # `one.repeatLike(exp_neg)` of nn.silu
     # activations are reused by every layer (the reference's workspace planner aliases them too)
     bare, gamma_rep, norm = B.new(D * T), B.new(D * T), B.new(D * T)
-    q_proj, k_proj, v_proj = B.new(D * T), B.new(kvd * T), B.new(kvd * T)
-    k_rot = [B.new(dh * T) for _ in range(cfg.n_kv_heads)]
-    q_rot = [B.new(dh * T) for _ in range(cfg.n_heads)]
-    attn_out = [B.new(dh * T) for _ in range(cfg.n_heads)]
-    attn_buf, attn_proj, after_attn = B.new(D * T), B.new(D * T), B.new(D * T)
+    q_proj, k_proj, v_proj = B.new(Dq * T), B.new(kvd * T), B.new(kvd * T)
+    k_rot = [B.new(dh * T) for _ in range(n_kv)]
+    q_rot = [B.new(dh * T) for _ in range(n_heads)]
+    attn_out = [B.new(dh * T) for _ in range(n_heads)]
+    attn_buf, attn_proj, after_attn = B.new(Dq * T), B.new(D * T), B.new(D * T)
     gate, up, silu, hidden, down = B.new(F * T), B.new(F * T), B.new(F * T), B.new(F * T), B.new(D * T)
     x_bufs = [B.new(D * T), B.new(D * T)]                   # layer outputs ping-pong
     rope_bufs: List[int] = []
@@ -158,15 +222,15 @@ def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> Llam
     for li in range(cfg.n_layers):
         L = w.layers[li]
         g1, g2 = B.new(D, w.norm1[li]), B.new(D, w.norm2[li])
-        k_cache, v_cache = B.new(dh * S * cfg.n_kv_heads), B.new(dh * S * cfg.n_kv_heads)
+        k_cache, v_cache = B.new(dh * S * n_kv), B.new(dh * S * n_kv)
         cs = B.new(2 * dh * T)                              # packed cos|sin leaf of this layer (patched per step)
         rope_bufs.append(cs)
 
         rms(norm, x, g1, bare, gamma_rep)
-        qmm(q_proj, norm, L["wq"], D, D)
+        qmm(q_proj, norm, L["wq"], D, Dq)
         qmm(k_proj, norm, L["wk"], D, kvd)
         qmm(v_proj, norm, L["wv"], D, kvd)
-        for kv in range(cfg.n_kv_heads):
+        for kv in range(n_kv):
             base = kv * S * dh                              # head slab = contiguous column range of the consolidated cache
             ops.append(DeviceOp.rope(k_rot[kv], k_proj, cs, hd, T, kv * dh, 0, 0, 1, kvd, 2 * dh))
             sa_idx.append(len(ops))
@@ -174,16 +238,18 @@ def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> Llam
             sa_idx.append(len(ops))
             ops.append(DeviceOp.slice_assign(v_cache, v_proj, dh, T, base, base, 1, dh, kv * dh, 1, kvd, dh))
         scale = float(np.float32(1.0) / np.sqrt(np.float32(dh)))
-        for h in range(cfg.n_heads):
+        for h in range(n_heads):
             kv = h // n_rep
             base = kv * S * dh
-            ops.append(DeviceOp.rope(q_rot[h], q_proj, cs, hd, T, h * dh, 0, 0, 1, D, 2 * dh))
+            ops.append(DeviceOp.rope(q_rot[h], q_proj, cs, hd, T, h * dh, 0, 0, 1, Dq, 2 * dh))
             at_idx.append(len(ops))
             ops.append(DeviceOp.attention(attn_out[h], q_rot[h], k_cache, v_cache, attn_mask, True, dh, T, S, scale,
                                           0, base, base, 0, 0, 1, dh, 1, dh, 1, dh, 1, S, 1, dh))
             # sliceAssignRows(attn_out, h * d_head): patch_stride 0 (device_inference.zig:695-701)
-            ops.append(DeviceOp.slice_assign(attn_buf, attn_out[h], dh, T, 0, h * dh, 1, D, 0, 1, dh, 0))
-        qmm(attn_proj, attn_buf, L["wo"], D, D)
+            ops.append(DeviceOp.slice_assign(attn_buf, attn_out[h], dh, T, 0, h * dh, 1, Dq, 0, 1, dh, 0))
+        qmm(attn_proj, attn_buf, L["wo"], Dq, D)
+        if world > 1:
+            ops.append(DeviceOp.allreduce(attn_proj, D * T))
         ops.append(DeviceOp.elementwise("add", after_attn, x, attn_proj, D * T))
         rms(norm, after_attn, g2, bare, gamma_rep)
         qmm(gate, norm, L["w_gate"], D, F)
@@ -193,21 +259,28 @@ def build_program(cfg: LlamaConfig, w: LlamaWeights, token_len: int = 1) -> Llam
                                                ("recip", False, 0, 0), ("mul", True, gate, 0)], F * T, silu, gate))
         ops.append(DeviceOp.elementwise("mul", hidden, silu, up, F * T))
         qmm(down, hidden, L["w_down"], F, D)
+        if world > 1:
+            ops.append(DeviceOp.allreduce(down, D * T))
         out = x_bufs[li % 2]
         ops.append(DeviceOp.elementwise("add", out, after_attn, down, D * T))
         x = out
 
     gf = B.new(D, w.norm_f)
     rms(norm, x, gf, bare, gamma_rep)
-    logits = B.new(cfg.vocab_size * T)
+    logits = B.new(V * T)
     if cfg.tied_lm_head:
         # x.matMul(false, token_embed, true) (models/llama.zig:162-165): dense f32, never quantized
-        emb = B.new(cfg.vocab_size * D, w.token_embed)
-        ops.append(DeviceOp.matmul(logits, norm, emb, T, cfg.vocab_size, D, D, 1, 1, D, dst_row_stride=cfg.vocab_size))
+        emb = B.new(V * D, w.head_rows if w.shard else w.token_embed)
+        ops.append(DeviceOp.matmul(logits, norm, emb, T, V, D, D, 1, 1, D, dst_row_stride=V))
     else:
-        qmm(logits, norm, w.out_proj, D, cfg.vocab_size)
+        qmm(logits, norm, w.out_proj, D, V)
+    logits_off = (T - 1) * V                                # last-column logits (llama_inference.zig:463-465)
+    if world > 1:
+        full = B.new(cfg.vocab_size)
+        ops.append(DeviceOp.allgather(full, logits, V, 0, logits_off))
+        logits, logits_off = full, 0
     prog = DeviceProgram(ops, B.sizes, B.uploads, qws)
-    return LlamaProgram(prog, T, token_input, attn_mask, rope_bufs, logits, sa_idx, at_idx, len(qws))
+    return LlamaProgram(prog, T, token_input, attn_mask, rope_bufs, logits, sa_idx, at_idx, len(qws), logits_off)
 
 
 class DeviceLlamaSession:
@@ -231,8 +304,7 @@ class DeviceLlamaSession:
         self.pos = 0
         self.inputs = [ProgramIO(self.lp.buf_token_input, self.token_input), ProgramIO(self.lp.buf_attn_mask, self.attn_mask)]
         self.inputs += [ProgramIO(b, self.rope_cs) for b in self.lp.buf_rope]
-        last_off = (T - 1) * cfg.vocab_size * 4             # last-column logits (llama_inference.zig:463-465)
-        self.outputs = [ProgramIO(self.lp.buf_logits, self.logits, offset=last_off)]
+        self.outputs = [ProgramIO(self.lp.buf_logits, self.logits, offset=self.lp.logits_offset * 4)]
         self._init_patch_views()
 
     def reset(self):
@@ -327,3 +399,66 @@ def synthetic_weights(cfg: LlamaConfig, kind: str = "q8_0", seed: int = 0, embed
     ones = [np.ones(cfg.d_model, np.float32) for _ in range(cfg.n_layers)]
     out_proj = None if cfg.tied_lm_head else make(cfg.d_model, cfg.vocab_size)
     return LlamaWeights(cfg, emb, layers, ones, [o.copy() for o in ones], np.ones(cfg.d_model, np.float32), out_proj)
+
+
+class SyntheticEmbedding:
+    """Token-embedding rows generated on demand (row v ~ U(-scale, scale), seeded by v): big-vocabulary synthetic
+    models need no [vocab, d_model] f32 table on the host."""
+
+    def __init__(self, vocab_size: int, d_model: int, seed: int = 0, scale: float = 0.05):
+        self.shape, self.seed, self.scale = (vocab_size, d_model), seed, scale
+
+    def __getitem__(self, tid: int) -> np.ndarray:
+        return np.random.default_rng([self.seed, int(tid)]).uniform(-self.scale, self.scale, self.shape[1]).astype(np.float32)
+
+
+GGML_Q4_0, GGML_Q8_0 = 2, 8
+
+
+def synthetic_gguf_blocks(r: np.random.Generator, K: int, N: int, kind: str) -> np.ndarray:
+    """Raw GGUF block bytes of a random [K, N] weight (src/gguf.zig:65-112: Q8_0 = f16 scale + 32 i8 = 34 B,
+    Q4_0 = f16 scale + 16 nibble bytes = 18 B per 32 flat elements), dequantized magnitude ~ sqrt(6 / K)."""
+    nb = K * N // 32
+    bb, qmax = (34, 127) if kind == "q8_0" else (18, 7)
+    raw = np.frombuffer(r.bytes(nb * bb), dtype=np.uint8).reshape(nb, bb).copy()
+    if kind == "q8_0":
+        q = raw[:, 2:].view(np.int8)
+        np.maximum(q, -127, out=q)
+    scales = (r.uniform(0.5, 1.0, nb) * (np.sqrt(6.0 / K) / qmax)).astype(np.float16)
+    raw[:, :2] = scales.view(np.uint8).reshape(nb, 2)
+    return raw.ravel()
+
+
+def synthetic_resident_shard(be, cfg: LlamaConfig, kind: str, seed: int, rank: int = 0, world: int = 1,
+                             embed_scale: float = 0.05):
+    """This rank's shard of a random-init GGUF model, streamed tensor by tensor straight into HBM
+    (`QuantizedWeight.from_gguf_blocks` = quantizedWeightFromInfo on device): host memory stays at one tensor,
+    which is what makes Llama-3-70B-shape Q4_0 (39 GB of blocks) loadable next to 7 other ranks.  Returns
+    (LlamaWeights of ResidentQuantizedWeight descriptors, the QuantizedWeight handles to free afterwards)."""
+    from ..backend import QuantizedWeight
+    check_shardable(cfg, world)
+    ggml = GGML_Q8_0 if kind == "q8_0" else GGML_Q4_0
+    D, kvd, F, V = cfg.d_model, cfg.kv_dim, cfg.d_ff, cfg.vocab_size
+    local = {"wq": (D, D // world), "wk": (D, kvd // world), "wv": (D, kvd // world), "wo": (D // world, D),
+             "w_gate": (D, F // world), "w_up": (D, F // world), "w_down": (F // world, D)}
+    r = np.random.default_rng([seed, rank, world])
+    handles, layers = [], []
+
+    def make(K, N):
+        h = QuantizedWeight.from_gguf_blocks(be, synthetic_gguf_blocks(r, K, N, kind), ggml, K, N)
+        handles.append(h)
+        return ResidentQuantizedWeight(h)
+
+    for _ in range(cfg.n_layers):
+        layers.append({n: make(*local[n]) for n in LINEARS})
+    ones = [np.ones(D, np.float32) for _ in range(cfg.n_layers)]
+    out_proj, head_rows = None, None
+    if cfg.tied_lm_head:
+        emb = np.random.default_rng([seed, 7]).uniform(-embed_scale, embed_scale, (V, D)).astype(np.float32)
+        head_rows = np.ascontiguousarray(emb[rank * (V // world):(rank + 1) * (V // world)])
+    else:
+        emb = SyntheticEmbedding(V, D, seed, embed_scale)
+        out_proj = make(D, V // world)
+    w = LlamaWeights(cfg, emb, layers, ones, [o.copy() for o in ones], np.ones(D, np.float32), out_proj,
+                     (rank, world) if world > 1 else None, head_rows if world > 1 else None)
+    return w, handles
