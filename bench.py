@@ -329,6 +329,20 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         with torch.cuda.stream(stream):
             line["extras"] = run_extras(be, torch)
+    if world > 1 and not args.no_extras:
+        # BASELINE.json config 5 beside the weak-scaling GEMV number: Llama-3-70B-shape Q4_0 decode with every linear
+        # row-sharded over the N GPUs (collectives on the data path), batch 1 and 8.  Never part of `value`.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_sharded
+            from zgml_b200.host import llama
+            be.comm_init_torch()
+            with torch.cuda.stream(stream):
+                res = bench_sharded.run_sharded_decode(be, llama.LLAMA3_70B, "q4_0", rank, world, dist, tokens=16, batches=(1, 8),
+                                                       context=512, model_name="llama3-70b")
+            line["extras"] = {"llama3_70b_q4_0_decode_sharded": res}
+        except Exception as e:  # extras never break the contract line
+            line["extras"] = {"sharded_decode_error": repr(e)}
     if rank == 0 and world == 1 and not args.no_cpu:
         gb, sec, passes, ccases = cpu_leg(1, args.cpu_seconds, 200)
         line["cpu_baseline"] = {"value": round(gb, 3), "unit": UNIT, "cores": 1, "kind": "port",

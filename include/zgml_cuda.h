@@ -269,6 +269,8 @@ int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_
 int zg_cuda_comm_unique_id(void* id128);
 int zg_cuda_comm_init(ZgCudaCtx* ctx, const void* id128, int rank, int world);
 void zg_cuda_comm_destroy(ZgCudaCtx* ctx);
+/* 0 = no communicator, 1 = NCCL only, 2 = small all-reduces over NVLink peer memory (cudaIpc) + NCCL for the rest. */
+int zg_cuda_comm_mode(const ZgCudaCtx* ctx);
 
 void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes);
 void zg_cuda_free_device(ZgCudaCtx* ctx, void* p);

@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Row-sharded LLaMA decode tok/s (BASELINE.json config 5: Llama-3-70B-shape Q4_0, weights sharded over the GPUs
-of one box, NCCL all-reduce / all-gather inside the decode CUDA graph).  One process per GPU:
+of one box; all-reduce of the d_model partial sums over NVLink peer memory, all-gather of the logits over NCCL,
+both inside the decode CUDA graph).  One process per GPU:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
-      scripts/bench_sharded.py --model llama3-70b --kind q4_0 --tokens 32 --batch 1
+      scripts/bench_sharded.py --model llama3-70b --kind q4_0 --tokens 32 --batch 1,8
 
 Every rank streams its own random-init shard into HBM (host memory: one tensor at a time), decodes greedily from
-`--context`, and rank 0 prints one JSON line: tok/s through step() (host patching + copies inside, e2e) and the
-device-only graph replay time, max over ranks.  `--batch T` runs T-token programs (zgml's token_len)."""
+`--context`, and rank 0 prints one JSON line per batch size: tok/s through step() (host patching + copies inside,
+e2e) and the device-only graph replay time, max over ranks.  `--batch T` runs T-token programs (zgml's token_len)."""
 import argparse
 import json
 import os
@@ -24,12 +25,62 @@ from zgml_b200.host import llama  # noqa: E402
 MODELS = {"smollm-135m": llama.SMOLLM_135M, "smollm-1.7b": llama.SMOLLM_1_7B, "llama3-8b": llama.LLAMA3_8B, "llama3-70b": llama.LLAMA3_70B}
 
 
+def run_sharded_decode(be, cfg, kind, rank, world, dist, tokens=32, batches=(1,), context=0, model_name=""):
+    """Load this rank's shard once, then time one session per batch size.  Returns the result dicts (every rank)."""
+    import torch
+    t0 = time.perf_counter()
+    w, handles = llama.synthetic_resident_shard(be, cfg, kind, seed=0, rank=rank, world=world)
+    t_load = time.perf_counter() - t0
+    dev_bytes = sum(h.device_bytes for h in handles)
+    out = []
+    for T in batches:
+        sess = llama.DeviceLlamaSession(be, cfg, w, T)
+        pos = context
+        toks = [(i + 1) % cfg.vocab_size for i in range(T)]
+        lg = sess.execute_at(toks, pos)  # warm-up: captures the graph
+        pos += T
+        if world > 1:
+            dist.barrier()
+        launches0 = be.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(tokens):
+            lg = sess.execute_at(toks, pos)
+            toks = toks[1:] + [int(np.argmax(lg))]
+            pos += T
+        dt = time.perf_counter() - t0
+        launches = be.launch_count() - launches0
+        be.sync()
+        if world > 1:
+            dist.barrier()
+        t1 = time.perf_counter()
+        for _ in range(tokens):
+            be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
+        be.sync()
+        dt_dev = time.perf_counter() - t1
+        if world > 1:
+            t = torch.tensor([dt, dt_dev], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, dt_dev = t.tolist()
+        out.append({"metric": "llama_decode_tok_s_sharded", "model": model_name, "kind": kind, "n_layers": cfg.n_layers, "n_gpus": world,
+                    "batch": T, "value": round(T * tokens / dt, 1), "unit": "tok/s", "ms_per_step": round(1e3 * dt / tokens, 3),
+                    "device_ms_per_step": round(1e3 * dt_dev / tokens, 3), "device_tok_s": round(T * tokens / dt_dev, 1),
+                    "steps": tokens, "context": context, "ops_per_step": sess.n_ops, "kernels_per_step": launches // tokens,
+                    "weight_bytes_per_gpu": dev_bytes, "hbm_gbps_per_gpu_on_weights": round(dev_bytes / (dt_dev / tokens) / 1e9, 1),
+                    "hbm_floor_ms_per_step": round(dev_bytes / 6540.8e6, 3),
+                    "load_s": round(t_load, 1), "comm": be.comm_mode(), "collectives_per_step": 2 * cfg.n_layers + 1 if world > 1 else 0,
+                    "data": "synthetic random-init GGUF blocks, streamed per shard", "last_token": int(np.argmax(lg))})
+        sess.close()
+    for h in handles:
+        h.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="llama3-70b", choices=sorted(MODELS))
     ap.add_argument("--kind", default="q4_0", choices=["q8_0", "q4_0"])
     ap.add_argument("--tokens", type=int, default=32)
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch", default="1")
     ap.add_argument("--context", type=int, default=0)
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--max-seq", type=int, default=0)
@@ -51,53 +102,13 @@ def main():
     be = CudaBackend(local)
     if world > 1:
         be.comm_init_torch()
-    t0 = time.perf_counter()
-    w, handles = llama.synthetic_resident_shard(be, cfg, args.kind, seed=0, rank=rank, world=world)
-    t_load = time.perf_counter() - t0
-    dev_bytes = sum(h.device_bytes for h in handles)
-    T = args.batch
-    sess = llama.DeviceLlamaSession(be, cfg, w, T)
-    pos = args.context
-    toks = [(i + 1) % cfg.vocab_size for i in range(T)]
-    lg = sess.execute_at(toks, pos)  # warm-up: captures the graph
-    pos += T
-    if world > 1:
-        dist.barrier()
-    launches0 = be.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.tokens):
-        lg = sess.execute_at(toks, pos)
-        toks = toks[1:] + [int(np.argmax(lg))]
-        pos += T
-    dt = time.perf_counter() - t0
-    launches = be.launch_count() - launches0
-    be.sync()
-    if world > 1:
-        dist.barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.tokens):
-        be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
-    be.sync()
-    dt_dev = time.perf_counter() - t1
-    if world > 1:
-        t = torch.tensor([dt, dt_dev], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_dev = t.tolist()
-    line = {"metric": "llama_decode_tok_s_sharded", "model": args.model, "kind": args.kind, "n_layers": cfg.n_layers, "n_gpus": world,
-            "batch": T, "value": round(T * args.tokens / dt, 1), "unit": "tok/s", "ms_per_step": round(1e3 * dt / args.tokens, 3),
-            "device_ms_per_step": round(1e3 * dt_dev / args.tokens, 3), "device_tok_s": round(T * args.tokens / dt_dev, 1),
-            "steps": args.tokens, "context": args.context, "ops_per_step": sess.n_ops, "kernels_per_step": launches // args.tokens,
-            "weight_bytes_per_gpu": dev_bytes, "hbm_gbps_per_gpu_on_weights": round(dev_bytes / (dt_dev / args.tokens) / 1e9, 1),
-            "load_s": round(t_load, 1), "collectives_per_step": 2 * cfg.n_layers + 1 if world > 1 else 0,
-            "data": "synthetic random-init GGUF blocks, streamed per shard", "last_token": int(np.argmax(lg))}
-    sess.close()
-    for h in handles:
-        h.free()
+    res = run_sharded_decode(be, cfg, args.kind, rank, world, dist, args.tokens, [int(b) for b in args.batch.split(",")], args.context, args.model)
     be.close()
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        for line in res:
+            print(json.dumps(line))
 
 
 if __name__ == "__main__":

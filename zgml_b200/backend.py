@@ -324,6 +324,9 @@ class CudaBackend:
             raise BackendError(f"comm_init failed: {last_error()}")
         self.rank, self.world, self.comm_ready = rank, world, True
 
+    def comm_mode(self) -> str:
+        return {0: "none", 1: "nccl", 2: "nvlink-peer+nccl"}[self.lib.zg_cuda_comm_mode(self.ctx)]
+
     def comm_init_torch(self):
         """Exchange the NCCL id over an initialised torch.distributed group (any backend) and join."""
         import torch.distributed as dist

@@ -71,10 +71,14 @@ struct ZgCudaProgram {
     std::vector<cudaEvent_t> dep_events; // capture-time fork/join markers of the concurrent graph branches
     // launch schedule: ops sorted by dependency level, same-level per-head ops (rope / slice_assign / attention)
     // of equal shape merged into one batched launch
-    struct Unit { std::vector<uint32_t> ops; uint32_t first_entry = 0; bool batched = false; };
+    // ... and runs of small ops (norms, broadcasts, residual adds, rope, cache stores, SiLU chains) spanning
+    // consecutive levels chained into one single-CTA launch (ops.cu k_chain)
+    struct Unit { std::vector<uint32_t> ops; uint32_t first_entry = 0; bool batched = false; bool chain = false; };
     std::vector<Unit> units;
     std::vector<uint32_t> entry_of_op;   // index into d_batch for batched op kinds
+    std::vector<uint32_t> peer_entry;    // index into d_chain of a peer-memory all-reduce's standalone entry (UINT32_MAX: NCCL)
     ZgBatchEntry* d_batch = nullptr;
+    ZgChainOp* d_chain = nullptr;
     bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
 };
 
@@ -94,6 +98,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     ctx->device = device_ordinal;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
+    if (const char* e = getenv("ZG_CUDA_CHAIN")) ctx->chain_max = (size_t)atol(e);   // 0: one launch per small op
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
@@ -188,7 +193,7 @@ static void free_program(ZgCudaProgram* p) {
     for (float* b : p->buffers) cudaFree(b);
     for (size_t i = 0; i < p->qweights.size(); i++)
         if (p->qweight_owned[i]) zg_cuda_qweight_free(p->ctx, p->qweights[i]);
-    cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch);
+    cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch); cudaFree(p->d_chain);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -489,14 +494,80 @@ static bool build_schedule(ZgCudaProgram* p) {
     p->units.clear();
     p->entry_of_op.assign(n, 0);
     std::vector<ZgBatchEntry> entries;
+    std::vector<ZgChainOp> chain_ops;
+    // Chains: walking the levels upwards, small ops join the open chain (first op of a new level = block barrier).
+    // A level that also holds big ops (matvecs, attention, dense matmul, collectives) closes the chain BEFORE them:
+    // they may consume the chain's earlier levels, and nothing in the chain depends on them (same level = no
+    // conflict; later levels start a new chain).  The unit order stays a topological order of the dependency DAG.
+    const size_t chain_max = p->ctx->chain_max;
+    auto chain_work = [&](const ZgOp& op) -> size_t {
+        if (op.tag == ZG_OP_ALLREDUCE)   // peer-memory all-reduce runs inside the chain kernel; NCCL ones are "big" ops
+            return zg_peer_allreduce_ok(p->ctx, op.u.allreduce.n) ? (size_t)op.u.allreduce.n * p->ctx->world / 4 + 1 : 0;
+        return zg_chain_work(op);
+    };
+    p->peer_entry.assign(n, UINT32_MAX);
+    for (size_t i = 0; i < n; i++) {   // standalone single-op entries: eager / profiling launches and chaining switched off
+        if (p->ops[i].tag != ZG_OP_ALLREDUCE || !zg_peer_allreduce_ok(p->ctx, p->ops[i].u.allreduce.n)) continue;
+        ZgChainOp c;
+        if (!zg_fill_chain_op(p->ops[i], p->buffers.data(), (uint32_t)i, nullptr, false, &c)) return false;
+        p->peer_entry[i] = (uint32_t)chain_ops.size();
+        chain_ops.push_back(c);
+    }
+    ZgCudaProgram::Unit chain; chain.chain = true;
+    std::vector<char> chain_sync, chain_tiny;
+    auto close_chain = [&]() {
+        if (chain.ops.empty()) return true;
+        if (chain.ops.size() == 1 && !zg_op_is_batched(p->ops[chain.ops[0]].tag) && p->ops[chain.ops[0]].tag != ZG_OP_ALLREDUCE) {
+            ZgCudaProgram::Unit u; u.ops = chain.ops; p->units.push_back(u);   // a lone op: its own (wider) kernel is as good
+        } else {
+            chain.first_entry = (uint32_t)chain_ops.size();
+            for (size_t k = 0; k < chain.ops.size(); k++) {
+                ZgChainOp c;
+                const uint32_t i = chain.ops[k];
+                if (!zg_fill_chain_op(p->ops[i], p->buffers.data(), i, p->d_steps + p->step_off[i], chain_sync[k] != 0, &c)) return false;
+                chain_ops.push_back(c);
+            }
+            // runs of >= 2 tiny ops inside one level execute warp-parallel (group = run length on the run's first op)
+            for (size_t k = 0; k < chain.ops.size();) {
+                size_t e = k;
+                if (chain_tiny[k]) { e = k + 1; while (e < chain.ops.size() && chain_tiny[e] && !chain_sync[e]) e++; }
+                if (e - k >= 2) { chain_ops[chain.first_entry + k].group = (uint32_t)(e - k); k = e; }
+                else k++;
+            }
+            p->units.push_back(chain);
+        }
+        chain.ops.clear(); chain_sync.clear(); chain_tiny.clear();
+        return true;
+    };
+    auto is_tiny = [&](const ZgOp& op) {
+        return op.tag != ZG_OP_RMSNORM && op.tag != ZG_OP_ALLREDUCE && zg_chain_work(op) <= 512;
+    };
     size_t pos = 0;
     while (pos < n) {
         size_t end = pos;
         while (end < n && level[order[end]] == level[order[pos]]) end++;
+        bool first_small = true, has_big = false;
+        for (int pass = 0; pass < 2; pass++) {   // CTA-wide ops first, then the level's tiny ops as one warp-parallel run
+            for (size_t k = pos; k < end; k++) {
+                const uint32_t i = order[k];
+                const size_t wk = chain_max ? chain_work(p->ops[i]) : 0;
+                if (wk == 0 || wk > chain_max) { has_big = true; continue; }
+                const bool tiny = is_tiny(p->ops[i]);
+                if (tiny != (pass == 1)) continue;
+                if (chain.ops.size() >= kZgChainMaxOps) { if (!close_chain()) return false; }   // kernel boundary = barrier
+                chain_sync.push_back(first_small && !chain.ops.empty());
+                chain_tiny.push_back(tiny);
+                chain.ops.push_back(i);
+                first_small = false;
+            }
+        }
+        if (has_big && !close_chain()) return false;
         std::vector<std::pair<uint64_t, size_t>> open;   // batch signature -> unit index (within this level)
         for (size_t k = pos; k < end; k++) {
             const uint32_t i = order[k];
             const ZgOp& op = p->ops[i];
+            const size_t wk = chain_max ? chain_work(op) : 0;
+            if (wk != 0 && wk <= chain_max) continue;   // chained above
             if (!zg_op_is_batched(op.tag)) { ZgCudaProgram::Unit u; u.ops.push_back(i); p->units.push_back(u); continue; }
             const uint64_t sig = zg_batch_signature(op);
             size_t ui = (size_t)-1;
@@ -511,6 +582,7 @@ static bool build_schedule(ZgCudaProgram* p) {
         }
         pos = end;
     }
+    if (!close_chain()) return false;
     for (auto& u : p->units) {
         if (!u.batched) continue;
         u.first_entry = (uint32_t)entries.size();
@@ -520,6 +592,11 @@ static bool build_schedule(ZgCudaProgram* p) {
             p->entry_of_op[i] = (uint32_t)entries.size();
             entries.push_back(e);
         }
+    }
+    cudaFree(p->d_chain); p->d_chain = nullptr;
+    if (!chain_ops.empty()) {
+        ZG_CUDA_OK(cudaMalloc(&p->d_chain, chain_ops.size() * sizeof(ZgChainOp)));
+        ZG_CUDA_OK(cudaMemcpy(p->d_chain, chain_ops.data(), chain_ops.size() * sizeof(ZgChainOp), cudaMemcpyHostToDevice));
     }
     cudaFree(p->d_batch); p->d_batch = nullptr;
     if (!entries.empty()) {
@@ -540,6 +617,7 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
         return zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
                                  p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &view, st);
     }
+    if (op.tag == ZG_OP_ALLREDUCE && p->peer_entry[i] != UINT32_MAX) return zg_launch_chain(p->d_chain + p->peer_entry[i], 1, p->d_dyn, ctx->peer, st);
     if (op.tag == ZG_OP_ALLREDUCE) return zg_comm_allreduce(ctx, p->buffers[op.u.allreduce.buf] + op.u.allreduce.offset, op.u.allreduce.n, st);
     if (op.tag == ZG_OP_ALLGATHER)
         return zg_comm_allgather(ctx, p->buffers[op.u.allgather.src] + op.u.allgather.src_offset,
@@ -549,6 +627,7 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 }
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
+    if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, (uint32_t)u.ops.size(), p->d_dyn, p->ctx->peer, st);
     if (!u.batched) return launch_one(p, u.ops[0], st);
     return zg_launch_batch(p->ops[u.ops[0]], p->d_batch + u.first_entry, (uint32_t)u.ops.size(), p->d_dyn, st);
 }

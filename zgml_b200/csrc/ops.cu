@@ -289,9 +289,13 @@ k_attention(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d
 // Decode / prefill attention fast path (unit row strides, d_head % 4 == 0, d_head <= 256): within a warp lane =
 // kv position for the scores (each lane dots its own contiguous K row against q in shared memory, 128-bit loads),
 // then lane = head dimension for the V accumulation (coalesced rows, weights broadcast by shuffle).  32 positions
-// per warp step instead of one, so the kv scan is no longer a chain of dependent global loads.  Same online
-// softmax and skip rules as reference.zig:599-671; only the summation order differs (1e-6 relative).
-__global__ void __launch_bounds__(kAttnWarps * 32)
+// per warp step, 16 warps per CTA, and every global load of a step is issued before its first use (K: 4 float4 per
+// lane in flight, V: 8 rows in flight), so a 512-token context is ONE pass of independent loads instead of a chain
+// of dependent ones.  Same online softmax and skip rules as reference.zig:599-671; only the summation order
+// differs (1e-6 relative).  NI = ceil(d_head / 32) values per lane.
+constexpr int kAttnFastWarps = 16;
+template <int NI>
+__global__ void __launch_bounds__(kAttnFastWarps * 32)
 k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
     const ZgBatchEntry e = tab[blockIdx.y];
     const uint32_t has_mask = e.u[0], dh = e.u[1];
@@ -306,18 +310,18 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
     const uint32_t seq_kv = d_dyn[e.dyn];
     const uint32_t qi = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    __shared__ __align__(16) float sq[256];
-    __shared__ float sh_m[kAttnWarps], sh_l[kAttnWarps];
-    __shared__ float sh_acc[kAttnWarps][256];
-    for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) sq[r] = q[(size_t)q_off + (size_t)qi * q_cs + r];
+    __shared__ __align__(16) float sq[NI * 32];
+    __shared__ float sh_m[kAttnFastWarps], sh_l[kAttnFastWarps];
+    __shared__ float sh_acc[kAttnFastWarps][NI * 32];
+    for (uint32_t r = threadIdx.x; r < NI * 32; r += blockDim.x) sq[r] = r < dh ? q[(size_t)q_off + (size_t)qi * q_cs + r] : 0.0f;
     __syncthreads();
     const size_t m_base = (size_t)mask_off + (size_t)qi * mask_cs;
     const uint32_t dh4 = dh >> 2;
-    float acc[8];
+    float acc[NI];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    for (int i = 0; i < NI; i++) acc[i] = 0.0f;
     float m_val = -INFINITY, l = 0.0f;
-    for (uint32_t s0 = warp * 32; s0 < seq_kv; s0 += kAttnWarps * 32) {
+    for (uint32_t s0 = warp * 32; s0 < seq_kv; s0 += kAttnFastWarps * 32) {
         const uint32_t s = s0 + lane;
         float mask_add = -INFINITY;
         if (s < seq_kv) mask_add = has_mask ? mask[m_base + (size_t)s * mask_rs] : 0.0f;
@@ -326,12 +330,21 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
         if (ok) {
             const float4* kr = reinterpret_cast<const float4*>(k + (size_t)k_off + (size_t)s * k_cs);
             const float4* q4 = reinterpret_cast<const float4*>(sq);
-            float dot = 0.0f;
-            for (uint32_t d = 0; d < dh4; d++) {
-                const float4 kv4 = kr[d], qv = q4[d];
-                dot = fmaf(qv.x, kv4.x, dot); dot = fmaf(qv.y, kv4.y, dot); dot = fmaf(qv.z, kv4.z, dot); dot = fmaf(qv.w, kv4.w, dot);
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            uint32_t d = 0;
+            for (; d + 4 <= dh4; d += 4) {
+                const float4 a = kr[d], b = kr[d + 1], c = kr[d + 2], f = kr[d + 3];
+                const float4 qa = q4[d], qb = q4[d + 1], qc = q4[d + 2], qf = q4[d + 3];
+                d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
+                d1 = fmaf(qb.x, b.x, d1); d1 = fmaf(qb.y, b.y, d1); d1 = fmaf(qb.z, b.z, d1); d1 = fmaf(qb.w, b.w, d1);
+                d2 = fmaf(qc.x, c.x, d2); d2 = fmaf(qc.y, c.y, d2); d2 = fmaf(qc.z, c.z, d2); d2 = fmaf(qc.w, c.w, d2);
+                d3 = fmaf(qf.x, f.x, d3); d3 = fmaf(qf.y, f.y, d3); d3 = fmaf(qf.z, f.z, d3); d3 = fmaf(qf.w, f.w, d3);
             }
-            score = dot * scale + mask_add;
+            for (; d < dh4; d++) {
+                const float4 a = kr[d], qa = q4[d];
+                d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
+            }
+            score = ((d0 + d1) + (d2 + d3)) * scale + mask_add;
             ok = isfinite(score);
             if (!ok) score = -INFINITY;
         }
@@ -341,38 +354,48 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
         if (bm == -INFINITY) continue;   // warp-uniform: nothing attendable in this block
         const float new_m = fmaxf(m_val, bm);
         const float alpha = (m_val == -INFINITY) ? 0.0f : expf(m_val - new_m);
-        const float wgt = ok ? expf(score - new_m) : 0.0f;
+        const float wgt = ok ? expf(score - new_m) : 0.0f;   // lanes past seq_kv and skipped entries weigh 0
         l = l * alpha + warp_sum(wgt);
         m_val = new_m;
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] *= alpha;
+        for (int i = 0; i < NI; i++) acc[i] *= alpha;
         const uint32_t nj = min(32u, seq_kv - s0);
         const float* vb = v + (size_t)v_off + (size_t)s0 * v_cs + lane;
-        for (uint32_t j = 0; j < nj; j++, vb += v_cs) {
-            const float wj = __shfl_sync(0xffffffffu, wgt, j);
-            if (wj == 0.0f) continue;   // warp-uniform
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < nj; j0 += 8) {
+            float vv[8][NI];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (lane + 32 * i < dh) acc[i] = fmaf(wj, vb[32 * i], acc[i]);
+            for (int jj = 0; jj < 8; jj++) {
+                const bool in = j0 + jj < nj;
+#pragma unroll
+                for (int i = 0; i < NI; i++) vv[jj][i] = (in && lane + 32 * i < dh) ? vb[(size_t)(j0 + jj) * v_cs + 32 * i] : 0.0f;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const float wj = __shfl_sync(0xffffffffu, wgt, (j0 + jj) & 31);
+#pragma unroll
+                for (int i = 0; i < NI; i++) acc[i] = fmaf(wj, vv[jj][i], acc[i]);
+            }
         }
     }
     if (lane == 0) { sh_m[warp] = m_val; sh_l[warp] = l; }
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (lane + 32 * i < dh) sh_acc[warp][lane + 32 * i] = acc[i];
+    for (int i = 0; i < NI; i++) sh_acc[warp][lane + 32 * i] = acc[i];
     __syncthreads();
     float gm = -INFINITY;
-    for (int w = 0; w < kAttnWarps; w++) gm = fmaxf(gm, sh_m[w]);
+    for (int w = 0; w < kAttnFastWarps; w++) gm = fmaxf(gm, sh_m[w]);
     float gl = 0.0f;
-    float wscale[kAttnWarps];
-    for (int w = 0; w < kAttnWarps; w++) {
+    float wscale[kAttnFastWarps];
+#pragma unroll
+    for (int w = 0; w < kAttnFastWarps; w++) {
         wscale[w] = (sh_m[w] == -INFINITY) ? 0.0f : expf(sh_m[w] - gm);
         gl += sh_l[w] * wscale[w];
     }
     const float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
     for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
         float a = 0.0f;
-        for (int w = 0; w < kAttnWarps; w++) a += sh_acc[w][r] * wscale[w];
+#pragma unroll
+        for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
         dst[(size_t)dst_off + (size_t)qi * dst_cs + r] = a * inv_l;
     }
 }
@@ -422,6 +445,217 @@ __global__ void k_matmul_general(MMParams p, float* __restrict__ dst, const floa
     dst[p.d_off + (size_t)m * p.d_rs + n] = acc;
 }
 
+// ── chained small ops ───────────────────────────────────────────────────────────────────────────
+// A decode step is a long dependency chain of tiny ops between the matvecs (norms, gamma broadcast, residual adds,
+// RoPE, KV-cache stores, the SiLU chain): a few thousand floats each, so a launch per op is pure latency
+// (~4 us per dependent kernel, ~1 us of work).  Runs of such ops are executed by ONE CTA instead: ops in table
+// order, every op exactly as its DeviceOp defines it (all intermediate buffers are written), `sync` marks the first
+// op of a new dependency level (block barrier: CTA-scope visibility of the previous level's global writes).
+// Plain (coherent) loads only: data read here may have been written earlier in the same kernel.
+constexpr int kChainThreads = 1024;
+static_assert(sizeof(ZgChainOp) % 4 == 0, "table is copied word-wise");
+
+__device__ __forceinline__ float chain_block_sum(float v, float* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kChainThreads / 32; i++) r += sh[i];
+    return r;
+}
+
+// The element-parallel op kinds, run by `nt` cooperating threads (a whole CTA, or one warp of it).
+__device__ __forceinline__ void chain_small_op(const ZgChainOp* o, uint32_t t, uint32_t nt, const uint32_t* __restrict__ d_dyn) {
+    float* dst = o->dst;
+    const float* s0 = o->s0;
+    const float* s1 = o->s1;
+    switch (o->kind) {
+        case ZG_OP_ELEMENTWISE: {
+            const uint32_t op = o->u[0], n = o->u[1];
+            for (uint32_t j = t; j < n; j += nt) {
+                const float a = s0[j];
+                float r;
+                if (op == ZG_EW_ADD) r = a + s1[j];
+                else if (op == ZG_EW_MUL) r = a * s1[j];
+                else r = apply_unary(op, a);
+                dst[j] = r;
+            }
+            break;
+        }
+        case ZG_OP_FUSED_ELEMENTWISE: {
+            const uint32_t n_steps = o->u[0], n = o->u[1];
+            const ZgDevStep* steps = o->steps;
+            for (uint32_t j = t; j < n; j += nt) {
+                float v = s0[j];
+                for (uint32_t s = 0; s < n_steps; s++) {
+                    const uint32_t sop = steps[s].op, sw = steps[s].is_swapped;
+                    if (sop == ZG_EW_ADD) { const float x = steps[s].sec[j]; v = sw ? x + v : v + x; }
+                    else if (sop == ZG_EW_MUL) { const float x = steps[s].sec[j]; v = sw ? x * v : v * x; }
+                    else v = apply_unary(sop, v);
+                }
+                dst[j] = v;
+            }
+            break;
+        }
+        case ZG_OP_REPEAT: {
+            const uint32_t mode = o->u[0], n = o->u[1], src_n = o->u[2], src_offset = o->u[15];
+            for (uint32_t gid = t; gid < n; gid += nt) {
+                float v;
+                if (mode == 0) v = s0[0];
+                else if (mode == 1) v = s0[gid];
+                else if (mode == 2) v = s0[gid % src_n];
+                else {
+                    uint32_t idx = gid, sidx = src_offset;
+#pragma unroll
+                    for (int dim = 3; dim >= 0; dim--) {
+                        const uint32_t ds = o->u[11 + dim];
+                        const uint32_t coord = idx / ds;
+                        idx = idx % ds;
+                        sidx += (coord % o->u[3 + dim]) * o->u[7 + dim];
+                    }
+                    v = s0[sidx];
+                }
+                dst[gid] = v;
+            }
+            break;
+        }
+        case ZG_OP_SLICE_ASSIGN: {
+            const uint32_t rows = o->u[0], cols = o->u[1], drs = o->u[2], dcs = o->u[3], soff = o->u[4], srs = o->u[5], scs = o->u[6];
+            const uint32_t doff = d_dyn[o->dyn];
+            const uint32_t total = rows * cols;
+            for (uint32_t j = t; j < total; j += nt) {
+                const uint32_t row = j % rows, col = j / rows;
+                dst[(size_t)doff + (size_t)row * drs + (size_t)col * dcs] = s0[(size_t)soff + (size_t)row * srs + (size_t)col * scs];
+            }
+            break;
+        }
+        case ZG_OP_ROPE: {
+            const uint32_t hd = o->u[0], seq_len = o->u[1], s_off = o->u[2], c_off = o->u[3], d_off = o->u[4], s_rs = o->u[5], s_cs = o->u[6], c_cs = o->u[7];
+            const uint32_t total = hd * seq_len;
+            for (uint32_t j = t; j < total; j += nt) {
+                const uint32_t pair = j % hd, col = j / hd;
+                const float x_lo = s0[(size_t)s_off + (size_t)pair * s_rs + (size_t)col * s_cs];
+                const float x_hi = s0[(size_t)s_off + (size_t)(pair + hd) * s_rs + (size_t)col * s_cs];
+                const float c = s1[(size_t)c_off + pair + (size_t)col * c_cs];
+                const float sn = s1[(size_t)c_off + pair + hd + (size_t)col * c_cs];
+                dst[(size_t)d_off + pair + (size_t)col * 2 * hd] = __fsub_rn(__fmul_rn(x_lo, c), __fmul_rn(x_hi, sn));
+                dst[(size_t)d_off + pair + hd + (size_t)col * 2 * hd] = __fadd_rn(__fmul_rn(x_hi, c), __fmul_rn(x_lo, sn));
+            }
+            break;
+        }
+        default: break;
+    }
+}
+
+__global__ void __launch_bounds__(kChainThreads)
+k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __restrict__ d_dyn, const ZgPeerComm pc) {
+    __shared__ float sh[32];
+    __shared__ uint32_t s_seq;
+    __shared__ __align__(16) ZgChainOp s_tab[kZgChainMaxOps];   // the whole op table: one coalesced read instead of a dependent load per op
+    const uint32_t tid = threadIdx.x;
+    {
+        const uint32_t words = count * (uint32_t)(sizeof(ZgChainOp) / 4);
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(tab);
+        uint32_t* l = reinterpret_cast<uint32_t*>(s_tab);
+        for (uint32_t j = tid; j < words; j += kChainThreads) l[j] = __ldg(g + j);
+    }
+    __syncthreads();
+    uint32_t i = 0;
+    while (i < count) {
+        const ZgChainOp* o = s_tab + i;
+        if (o->sync) __syncthreads();
+        if (o->group) {   // a run of tiny independent ops of one dependency level (per-head rope / cache stores): one warp each
+            const uint32_t g = o->group;
+            for (uint32_t k = tid >> 5; k < g; k += kChainThreads / 32) chain_small_op(o + k, tid & 31, 32, d_dyn);
+            i += g;
+            continue;
+        }
+        i++;
+        float* dst = o->dst;
+        const float* s0 = o->s0;
+        switch (o->kind) {
+            case ZG_OP_RMSNORM: {   // same arithmetic as k_rmsnorm (rows run one after the other)
+                const uint32_t rows = o->u[0], cols = o->u[1];
+                const float eps = o->f;
+                for (uint32_t r = 0; r < rows; r++) {
+                    const float* s = s0 + (size_t)r * cols;
+                    float* d = dst + (size_t)r * cols;
+                    float ss = 0.0f;
+                    for (uint32_t j = tid; j < cols; j += kChainThreads) { const float x = s[j]; ss += x * x; }
+                    ss = chain_block_sum(ss, sh);
+                    const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+                    for (uint32_t j = tid; j < cols; j += kChainThreads) d[j] = s[j] * inv_rms;
+                }
+                break;
+            }
+            case ZG_OP_ALLREDUCE: {
+                // One-shot all-reduce over NVLink peer memory: push this rank's vector into every peer's slot, raise a
+                // release flag there, wait for the peers' flags here, then sum the slots in RANK ORDER (every rank gets
+                // bit-identical sums).  Slot sets alternate per all-reduce: a rank can only be two all-reduces ahead of a
+                // peer after that peer finished reading the older set (it has to send its flag for the one in between).
+                const uint32_t n = o->u[0], n4 = (n & 3u) == 0 && ((size_t)dst & 15u) == 0 ? n >> 2 : 0;
+                if (tid == 0) s_seq = *(volatile uint32_t*)pc.seq;
+                __syncthreads();
+                const uint32_t seq = s_seq, set = seq % kZgPeerSets, epoch = seq + 1;
+                const size_t my_slot = ((size_t)set * pc.world + pc.rank) * pc.max_n;
+                for (int pr = 0; pr < pc.world; pr++) {
+                    if (pr == pc.rank) continue;
+                    float* ps = pc.slots[pr] + my_slot;
+                    if (n4) {
+                        float4* p4 = reinterpret_cast<float4*>(ps);
+                        const float4* i4 = reinterpret_cast<const float4*>(dst);
+                        for (uint32_t j = tid; j < n4; j += kChainThreads) p4[j] = i4[j];
+                    } else {
+                        for (uint32_t j = tid; j < n; j += kChainThreads) ps[j] = dst[j];
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid < (uint32_t)pc.world && tid != (uint32_t)pc.rank) {
+                    uint32_t* f = pc.flags[tid] + set * kZgMaxRanks + pc.rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+                    const uint32_t* mine = pc.flags[pc.rank] + set * kZgMaxRanks + tid;
+                    uint32_t got = 0;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+                        if (got != epoch && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
+                    } while (got != epoch);
+                }
+                __syncthreads();
+                const float* base = pc.slots[pc.rank] + (size_t)set * pc.world * pc.max_n;
+                if (n4) {
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    for (uint32_t j = tid; j < n4; j += kChainThreads) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int r = 0; r < pc.world; r++) {
+                            const float4 v = (r == pc.rank) ? d4[j] : __ldcv(reinterpret_cast<const float4*>(base + (size_t)r * pc.max_n) + j);
+                            if (r == 0) acc = v;
+                            else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+                        }
+                        d4[j] = acc;
+                    }
+                } else {
+                    for (uint32_t j = tid; j < n; j += kChainThreads) {
+                        float acc = 0.f;
+                        for (int r = 0; r < pc.world; r++) {
+                            const float v = (r == pc.rank) ? dst[j] : __ldcv(base + (size_t)r * pc.max_n + j);
+                            acc = (r == 0) ? v : acc + v;
+                        }
+                        dst[j] = acc;
+                    }
+                }
+                if (tid == 0) *(volatile uint32_t*)pc.seq = epoch;
+                break;
+            }
+            default: chain_small_op(o, tid, kChainThreads, d_dyn); break;
+        }
+    }
+}
+
 inline unsigned blocks_for(uint32_t n, unsigned bs, unsigned cap = 4096) {
     unsigned b = (n + bs - 1) / bs;
     if (b < 1) b = 1;
@@ -429,6 +663,18 @@ inline unsigned blocks_for(uint32_t n, unsigned bs, unsigned cap = 4096) {
 }
 
 } // namespace
+
+static uint32_t repeat_mode(const ZgOp& op, size_t* src_n_out) {
+    const auto& rp = op.u.repeat;
+    const uint32_t* ne = rp.src_ne; const uint32_t* sst = rp.src_strides;
+    const size_t src_n = (size_t)ne[0] * ne[1] * ne[2] * ne[3];
+    *src_n_out = src_n;
+    if (src_n == 1) return 0;
+    if (src_n >= rp.n) return 1;
+    if (rp.n % src_n == 0 && sst[0] == 1 && (ne[1] <= 1 || sst[1] == ne[0]) && (ne[2] <= 1 || sst[2] == ne[0] * ne[1]) &&
+        (ne[3] <= 1 || sst[3] == ne[0] * ne[1] * ne[2])) return 2;
+    return 3;
+}
 
 bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
                   uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st) {
@@ -477,15 +723,10 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
             const auto& rp = op.u.repeat;
             if (rp.n == 0) return true;
             RepeatParams p;
-            const uint32_t* ne = rp.src_ne; const uint32_t* sst = rp.src_strides;
-            size_t src_n = (size_t)ne[0] * ne[1] * ne[2] * ne[3];
+            size_t src_n = 0;
+            p.mode = repeat_mode(op, &src_n);
             p.n = rp.n; p.src_n = (uint32_t)src_n; p.src_offset = rp.src_offset;
-            for (int i = 0; i < 4; i++) { p.src_ne[i] = ne[i]; p.src_strides[i] = sst[i]; p.dst_strides[i] = rp.dst_strides[i]; }
-            if (src_n == 1) p.mode = 0;
-            else if (src_n >= rp.n) p.mode = 1;
-            else if (rp.n % src_n == 0 && sst[0] == 1 && (ne[1] <= 1 || sst[1] == ne[0]) && (ne[2] <= 1 || sst[2] == ne[0] * ne[1]) &&
-                     (ne[3] <= 1 || sst[3] == ne[0] * ne[1] * ne[2])) p.mode = 2;
-            else p.mode = 3;
+            for (int i = 0; i < 4; i++) { p.src_ne[i] = rp.src_ne[i]; p.src_strides[i] = rp.src_strides[i]; p.dst_strides[i] = rp.dst_strides[i]; }
             const float* src = (p.mode == 3) ? bufs[rp.src] : bufs[rp.src] + rp.src_offset;
             k_repeat<<<blocks_for(rp.n, 256), 256, 0, st>>>(p, bufs[rp.dst] + rp.dst_offset, src);
             break;
@@ -516,6 +757,82 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
             zg_set_error("unsupported DeviceOp tag %u", op.tag);
             return false;
     }
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
+// ── chained small ops: host side ─────────────────────────────────────────────────────────────────
+// Elements one CTA would have to walk for this op, or 0 when the op kind cannot be chained.
+size_t zg_chain_work(const ZgOp& op) {
+    switch (op.tag) {
+        case ZG_OP_ELEMENTWISE: return op.u.elementwise.n ? op.u.elementwise.n : 1;
+        case ZG_OP_FUSED_ELEMENTWISE: return op.u.fused_elementwise.n ? (size_t)op.u.fused_elementwise.n * (1 + op.u.fused_elementwise.n_steps) : 1;   // transcendental chains: one CTA is slow
+        case ZG_OP_RMSNORM: return op.u.rmsnorm.rows <= 8 ? (size_t)op.u.rmsnorm.rows * op.u.rmsnorm.cols + 1 : 0;
+        case ZG_OP_REPEAT: return op.u.repeat.n ? op.u.repeat.n : 1;
+        case ZG_OP_SLICE_ASSIGN: return (size_t)op.u.slice_assign.rows * op.u.slice_assign.cols + 1;
+        case ZG_OP_ROPE: return (size_t)op.u.rope.half_d * op.u.rope.seq_len * 2 + 1;
+        default: return 0;
+    }
+}
+
+bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c) {
+    memset(c, 0, sizeof(*c));
+    c->kind = op.tag; c->sync = sync ? 1u : 0u; c->dyn = op_index;
+    switch (op.tag) {
+        case ZG_OP_ELEMENTWISE: {
+            const auto& e = op.u.elementwise;
+            c->dst = bufs[e.dst] + e.dst_offset; c->s0 = bufs[e.src0] + e.src0_offset; c->s1 = bufs[e.src1] + e.src1_offset;
+            c->u[0] = e.op; c->u[1] = e.n;
+            return true;
+        }
+        case ZG_OP_FUSED_ELEMENTWISE: {
+            const auto& f = op.u.fused_elementwise;
+            c->dst = bufs[f.dst] + f.dst_offset; c->s0 = bufs[f.src] + f.src_offset; c->steps = d_steps;
+            c->u[0] = (uint32_t)f.n_steps; c->u[1] = f.n;
+            return true;
+        }
+        case ZG_OP_RMSNORM: {
+            const auto& r = op.u.rmsnorm;
+            c->dst = bufs[r.dst] + r.dst_offset; c->s0 = bufs[r.src] + r.src_offset;
+            c->u[0] = r.rows; c->u[1] = r.cols; c->f = r.eps;
+            return true;
+        }
+        case ZG_OP_REPEAT: {
+            const auto& rp = op.u.repeat;
+            size_t src_n = 0;
+            const uint32_t mode = repeat_mode(op, &src_n);
+            c->dst = bufs[rp.dst] + rp.dst_offset;
+            c->s0 = (mode == 3) ? bufs[rp.src] : bufs[rp.src] + rp.src_offset;
+            c->u[0] = mode; c->u[1] = rp.n; c->u[2] = (uint32_t)src_n; c->u[15] = rp.src_offset;
+            for (int i = 0; i < 4; i++) { c->u[3 + i] = rp.src_ne[i]; c->u[7 + i] = rp.src_strides[i]; c->u[11 + i] = rp.dst_strides[i]; }
+            return true;
+        }
+        case ZG_OP_SLICE_ASSIGN: {
+            const auto& sa = op.u.slice_assign;
+            c->dst = bufs[sa.dst]; c->s0 = bufs[sa.src];
+            c->u[0] = sa.rows; c->u[1] = sa.cols; c->u[2] = sa.dst_row_stride; c->u[3] = sa.dst_col_stride;
+            c->u[4] = sa.src_offset; c->u[5] = sa.src_row_stride; c->u[6] = sa.src_col_stride;
+            return true;
+        }
+        case ZG_OP_ROPE: {
+            const auto& r = op.u.rope;
+            c->dst = bufs[r.dst]; c->s0 = bufs[r.src]; c->s1 = bufs[r.cos_sin];
+            c->u[0] = r.half_d; c->u[1] = r.seq_len; c->u[2] = r.src_off; c->u[3] = r.cs_off; c->u[4] = r.dst_off;
+            c->u[5] = r.src_rs; c->u[6] = r.src_cs; c->u[7] = r.cs_cs;
+            return true;
+        }
+        case ZG_OP_ALLREDUCE: {
+            const auto& a = op.u.allreduce;
+            c->dst = bufs[a.buf] + a.offset; c->u[0] = a.n;
+            return true;
+        }
+        default: zg_set_error("internal: op kind %u cannot be chained", op.tag); return false;
+    }
+}
+
+bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st) {
+    if (count == 0) return true;
+    k_chain<<<1, kChainThreads, 0, st>>>(d_ops, count, d_dyn, pc);
     ZG_COUNT_LAUNCH();
     return true;
 }
@@ -585,8 +902,12 @@ bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t 
         case ZG_OP_ATTENTION: {
             const auto& a = first.u.attention;
             if (a.seq_q == 0 || a.d_head == 0) return true;
-            if (attn_fast_ok(first)) k_attention_fast<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
-            else k_attention<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
+            if (attn_fast_ok(first)) {
+                const dim3 grid(a.seq_q, count);
+                if (a.d_head <= 64) k_attention_fast<2><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
+                else if (a.d_head <= 128) k_attention_fast<4><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
+                else k_attention_fast<8><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
+            } else k_attention<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
             break;
         }
         default: zg_set_error("internal: op kind %u is not batched", first.tag); return false;

@@ -79,6 +79,18 @@ struct ZgGemvWs {
     size_t gemm_scratch_elems = 0;
 };
 
+// One-shot all-reduce over NVLink peer memory (comm.cu): every rank owns `slots[set][src_rank][max_n]` floats and
+// `flags[set][src_rank]`; peers store their vector + a release flag straight into them.  Passed to k_chain by value.
+constexpr int kZgMaxRanks = 8;
+constexpr uint32_t kZgPeerSets = 2;
+struct ZgPeerComm {
+    int rank = 0, world = 1;
+    uint32_t max_n = 0;                 // floats per slot; 0 = peer path unavailable (NCCL is used instead)
+    float* slots[kZgMaxRanks] = {};     // slot base of every rank (own entry = local pointer)
+    uint32_t* flags[kZgMaxRanks] = {};  // flag base of every rank
+    uint32_t* seq = nullptr;            // local: number of all-reduces this rank has completed; [1] = timeout marker
+};
+
 struct ZgCudaCtx {
     int device = 0;
     int sm_count = 148;
@@ -89,6 +101,10 @@ struct ZgCudaCtx {
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
+    size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
+    ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
+    void* peer_mem = nullptr;    // this rank's slots + flags + seq (cudaMalloc, exported by cudaIpc)
+    void* peer_mapped[kZgMaxRanks] = {};   // cudaIpcOpenMemHandle mappings to close
     void* nccl_comm = nullptr;   // ncclComm_t (comm.cu), null unless zg_cuda_comm_init ran
     int rank = 0, world = 1;
     std::vector<cudaStream_t> branch; // extra capture streams: independent ops of a program become concurrent graph branches
@@ -123,6 +139,13 @@ bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, 
 struct ZgDevStep { uint32_t op, is_swapped; const float* sec; };
 // one op's parameters in the device table of the batched per-head kernels (rope, slice_assign, attention)
 struct ZgBatchEntry { float* dst; const float* s0; const float* s1; const float* s2; const float* s3; uint32_t u[18]; float f; uint32_t dyn; };
+// one op of a chained run of small ops (ops.cu k_chain): executed by a single CTA in table order
+struct ZgChainOp { float* dst; const float* s0; const float* s1; const ZgDevStep* steps; uint32_t u[18]; float f; uint32_t dyn, kind, sync, group, _pad; };
+constexpr uint32_t kZgChainMaxOps = 256;   // ops per chain launch (the table lives in shared memory)
+size_t zg_chain_work(const ZgOp& op);
+bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
+bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st);
+bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n);   // comm.cu: the peer path can take an n-float all-reduce
 bool zg_op_is_batched(uint32_t tag);
 uint64_t zg_batch_signature(const ZgOp& op);
 bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, ZgBatchEntry* e);

@@ -417,15 +417,19 @@ GGML_Q4_0, GGML_Q8_0 = 2, 8
 
 def synthetic_gguf_blocks(r: np.random.Generator, K: int, N: int, kind: str) -> np.ndarray:
     """Raw GGUF block bytes of a random [K, N] weight (src/gguf.zig:65-112: Q8_0 = f16 scale + 32 i8 = 34 B,
-    Q4_0 = f16 scale + 16 nibble bytes = 18 B per 32 flat elements), dequantized magnitude ~ sqrt(6 / K)."""
+    Q4_0 = f16 scale + 16 nibble bytes = 18 B per 32 flat elements).  Everything comes from ONE stream of random
+    bytes (this has to produce tens of GB for the 70B shape): quants are the bytes themselves, the f16 scale keeps
+    its 10 random mantissa bits under a fixed exponent, i.e. uniform in [2^e, 2^(e+1)) with 2^(e+1) <= sqrt(6/K)/qmax,
+    so the dequantized magnitude is ~ sqrt(6 / K) like kaimingUniform (src/nn.zig:91-105)."""
     nb = K * N // 32
     bb, qmax = (34, 127) if kind == "q8_0" else (18, 7)
-    raw = np.frombuffer(r.bytes(nb * bb), dtype=np.uint8).reshape(nb, bb).copy()
+    raw = r.integers(0, 1 << 64, (nb * bb + 7) // 8, dtype=np.uint64).view(np.uint8)[:nb * bb].reshape(nb, bb)
     if kind == "q8_0":
         q = raw[:, 2:].view(np.int8)
         np.maximum(q, -127, out=q)
-    scales = (r.uniform(0.5, 1.0, nb) * (np.sqrt(6.0 / K) / qmax)).astype(np.float16)
-    raw[:, :2] = scales.view(np.uint8).reshape(nb, 2)
+    e = int(np.floor(np.log2(np.sqrt(6.0 / K) / qmax))) - 1 + 15          # biased f16 exponent (normal range)
+    assert 1 <= e <= 30
+    raw[:, 1] = (raw[:, 1] & 3) | np.uint8(e << 2)                          # sign 0 | exponent | top 2 mantissa bits
     return raw.ravel()
 
 
