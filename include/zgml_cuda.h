@@ -272,6 +272,12 @@ void zg_cuda_comm_destroy(ZgCudaCtx* ctx);
 /* 0 = no communicator, 1 = NCCL only, 2 = small all-reduces over NVLink peer memory (cudaIpc) + NCCL for the rest. */
 int zg_cuda_comm_mode(const ZgCudaCtx* ctx);
 
+/* Debug timeline of a program's kernels (off by default): records of 3 x u64 {kind << 56 | t_entry, t_after_wait, t_exit},
+ * %globaltimer ns stamped by block 0 of each kernel; kinds: 1 elementwise, 2 fused_elementwise, 3 rmsnorm, 4 repeat,
+ * 5 slice_assign, 6 rope, 7 attention, 8 chain, 9 dense matmul, 10 quantized matvec. */
+int zg_cuda_trace(ZgCudaCtx* ctx, int enable);
+size_t zg_cuda_trace_read(ZgCudaCtx* ctx, unsigned long long* host, size_t max_records);
+
 void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes);
 void zg_cuda_free_device(ZgCudaCtx* ctx, void* p);
 int zg_cuda_memcpy_h2d(ZgCudaCtx* ctx, void* d, const void* h, size_t bytes);

@@ -84,6 +84,8 @@ def main():
     ap.add_argument("--context", type=int, default=0)
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--max-seq", type=int, default=0)
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="single process: run rank 0's shard of an N-way split with the collectives as identity (per-rank compute profile)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -102,6 +104,10 @@ def main():
     be = CudaBackend(local)
     if world > 1:
         be.comm_init_torch()
+    if args.emulate_world:
+        world_shape = args.emulate_world
+        orig = llama.synthetic_resident_shard
+        llama.synthetic_resident_shard = lambda be_, cfg_, kind_, seed=0, rank=0, world=1, **kw: orig(be_, cfg_, kind_, seed, 0, world_shape, **kw)
     res = run_sharded_decode(be, cfg, args.kind, rank, world, dist, args.tokens, [int(b) for b in args.batch.split(",")], args.context, args.model)
     be.close()
     if world > 1:

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+for m in smollm-135m:q8_0:0 smollm-1.7b:q4_0:512; do
+  IFS=: read model kind ctx <<< "$m"
+  timeout 300 python scripts/bench_decode.py --model $model --kind $kind --tokens 128 --context $ctx --cpu-tokens 2 > gpurun_out/decode_${model}.log 2>&1
+done
+timeout 300 python scripts/bench_sharded.py --model llama3-70b --layers 16 --emulate-world 8 --tokens 32 --batch 1 --context 512 > gpurun_out/shard8_emul.log 2>&1
+timeout 600 python bench.py > gpurun_out/bench_default.log 2> gpurun_out/bench_default.err
+tail -n 2 gpurun_out/pytest_gpu.log
+for f in gpurun_out/decode_smollm-135m.log gpurun_out/decode_smollm-1.7b.log gpurun_out/shard8_emul.log; do grep -h '^{' $f | cut -c1-700; done
+tail -c 1500 gpurun_out/bench_default.log

@@ -83,3 +83,29 @@ def test_prefill_chunk_on_tensor_core_path(cuda_backend):  # token_len > 8: ever
     want = ref.execute_at(toks, 0).copy()
     pre.close(); ref.close()
     assert rel(got, want) < 1e-3 and int(np.argmax(got)) == int(np.argmax(want))
+
+
+@pytest.mark.parametrize("token_len", [1, 3])
+def test_every_program_buffer_matches_oracle_with_fused_patterns(cuda_backend, token_len):
+    """The backend evaluates the lowering's fixed op runs (add/rmsnorm/repeat/mul, SiLU chain * up, attention + head
+    store, chained small ops) in single passes; every DeviceOp's output buffer must still hold what op-by-op
+    execution (the oracle executor) leaves there — not just the logits."""
+    from zgml_b200 import ProgramIO
+    cfg = TINY_UNTIED
+    w = synthetic_weights(cfg, "q8_0", seed=21, embed_scale=1.0)
+    dev, ref = DeviceLlamaSession(cuda_backend, cfg, w, token_len), DeviceLlamaSession(OracleBackend(), cfg, w, token_len)
+    sizes = dev.lp.program.buffer_sizes
+    got = [np.zeros(n, np.float32) for n in sizes]
+    want = [np.zeros(n, np.float32) for n in sizes]
+    dev.outputs = [ProgramIO(i, got[i]) for i in range(len(sizes))]
+    ref.outputs = [ProgramIO(i, want[i]) for i in range(len(sizes))]
+    toks = [5, 77, 130][:token_len]
+    for pos in (0, token_len):
+        dev.execute_at(toks, pos)
+        ref.execute_at(toks, pos)
+        for i, (g, wv) in enumerate(zip(got, want)):
+            scale = float(np.max(np.abs(wv[np.isfinite(wv)]))) if np.isfinite(wv).any() else 0.0
+            fin = np.isfinite(wv)
+            assert np.array_equal(np.isfinite(g), fin), f"buffer {i}"
+            assert np.max(np.abs(g[fin] - wv[fin]), initial=0.0) <= 1e-4 * scale + 1e-6, f"buffer {i} at pos {pos}"
+    dev.close(); ref.close()

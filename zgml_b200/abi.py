@@ -173,6 +173,8 @@ SYMBOLS = [
     ("zg_cuda_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("zg_cuda_comm_destroy", None, [vp]),
     ("zg_cuda_comm_mode", C.c_int, [vp]),
+    ("zg_cuda_trace", C.c_int, [vp, C.c_int]),
+    ("zg_cuda_trace_read", sz, [vp, vp, sz]),
     ("zg_cuda_malloc", vp, [vp, sz]),
     ("zg_cuda_free_device", None, [vp, vp]),
     ("zg_cuda_memcpy_h2d", C.c_int, [vp, vp, vp, sz]),

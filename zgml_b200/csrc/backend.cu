@@ -5,6 +5,8 @@
 #include "zg_internal.cuh"
 
 #include <algorithm>
+#include <initializer_list>
+#include <map>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -73,9 +75,17 @@ struct ZgCudaProgram {
     // of equal shape merged into one batched launch
     // ... and runs of small ops (norms, broadcasts, residual adds, rope, cache stores, SiLU chains) spanning
     // consecutive levels chained into one single-CTA launch (ops.cu k_chain)
-    struct Unit { std::vector<uint32_t> ops; uint32_t first_entry = 0; bool batched = false; bool chain = false; };
+    struct Unit {
+        std::vector<uint32_t> ops;         // every DeviceOp the launch executes (its dependency footprint)
+        std::vector<uint32_t> entry_ops;   // batched: the ops that own a table entry (absorbed slice_assigns do not)
+        std::map<uint32_t, uint32_t> store_of;   // batched attention op -> the slice_assign absorbed into it
+        uint32_t first_entry = 0, n_entries = 0;
+        bool batched = false, chain = false, ewmul = false;
+        ZgEwMulMacro em = {};
+    };
     std::vector<Unit> units;
     std::vector<uint32_t> entry_of_op;   // index into d_batch for batched op kinds
+    std::vector<uint32_t> single_entry;  // index into d_batch of a batched-kind op's own plain entry (per-op launches)
     std::vector<uint32_t> peer_entry;    // index into d_chain of a peer-memory all-reduce's standalone entry (UINT32_MAX: NCCL)
     ZgBatchEntry* d_batch = nullptr;
     ZgChainOp* d_chain = nullptr;
@@ -98,6 +108,8 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     ctx->device = device_ordinal;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
+    g_zg_pdl = ctx->pdl;
+    if (const char* e = getenv("ZG_CUDA_FUSE")) ctx->fuse = (e[0] != '0');   // 0: no macro patterns (one chain / batch entry per DeviceOp)
     if (const char* e = getenv("ZG_CUDA_CHAIN")) ctx->chain_max = (size_t)atol(e);   // 0: one launch per small op
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
@@ -469,41 +481,140 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 
 // Dependency levels (level = 1 + max level of every earlier op it conflicts with), then units in (level, program
 // order); any such order is a valid topological order of the program's dependency DAG.
+// ── macro patterns: consecutive DeviceOps that the lowering always emits together ────────────────────────────
+// Each is evaluated in ONE pass (values kept in registers, every op's output buffer still written), so the result of
+// every op is what the op-by-op execution gives.  Matching is deliberately strict: consecutive in program order, whole
+// contiguous vectors, all buffers distinct.
+struct ZgItem { uint32_t first = 0, count = 1, kind = 0; };   // kind 0: one op; 1: [add,] rmsnorm, repeat, mul; 2: fused_elementwise, mul; 3: attention, slice_assign
+enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3 };
+
+static bool distinct(std::initializer_list<uint32_t> bufs) {
+    std::vector<uint32_t> v(bufs);
+    std::sort(v.begin(), v.end());
+    return std::adjacent_find(v.begin(), v.end()) == v.end();
+}
+
+// [elementwise add(sum = a + b)] ; rmsnorm(bare = norm(sum)) ; repeat(gamma_rep = gamma tiled over rows) ; mul(dst = bare * gamma_rep)
+static uint32_t match_norm(const ZgCudaProgram* p, size_t i, ZgNormMacro* m) {
+    const size_t n = p->ops.size();
+    const bool has_add = p->ops[i].tag == ZG_OP_ELEMENTWISE && p->ops[i].u.elementwise.op == ZG_EW_ADD;
+    const size_t r0 = i + (has_add ? 1 : 0);
+    if (r0 + 2 >= n) return 0;
+    const ZgOp &rn = p->ops[r0], &rp = p->ops[r0 + 1], &ml = p->ops[r0 + 2];
+    if (rn.tag != ZG_OP_RMSNORM || rp.tag != ZG_OP_REPEAT || ml.tag != ZG_OP_ELEMENTWISE || ml.u.elementwise.op != ZG_EW_MUL) return 0;
+    const auto& r = rn.u.rmsnorm;
+    const auto& q = rp.u.repeat;
+    const auto& e = ml.u.elementwise;
+    const uint32_t rows = r.rows, cols = r.cols, tot = rows * cols;
+    if (rows == 0 || rows > 8 || cols == 0 || (cols & 3u) || cols > 8192 || tot > p->ctx->chain_max) return 0;   // 4 float4 x 512 threads per row
+    if (r.src_offset || r.dst_offset || q.src_offset || q.dst_offset || e.dst_offset || e.src0_offset || e.src1_offset) return 0;
+    if (q.n != tot || e.n != tot) return 0;
+    // gamma: a contiguous [cols] vector tiled over the rows
+    if (q.src_ne[0] != cols || q.src_ne[1] != 1 || q.src_ne[2] != 1 || q.src_ne[3] != 1 || q.src_strides[0] != 1) return 0;
+    if (q.dst_ne[0] != cols || q.dst_ne[1] != rows || q.dst_ne[2] != 1 || q.dst_ne[3] != 1 || q.dst_strides[0] != 1 || (rows > 1 && q.dst_strides[1] != cols)) return 0;
+    if (e.src0 != r.dst || e.src1 != q.dst) return 0;
+    uint32_t a_buf = r.src, b_buf = UINT32_MAX, sum_buf = UINT32_MAX;
+    if (has_add) {
+        const auto& ad = p->ops[i].u.elementwise;
+        if (ad.n != tot || ad.dst_offset || ad.src0_offset || ad.src1_offset || ad.dst != r.src) return 0;
+        a_buf = ad.src0; b_buf = ad.src1; sum_buf = ad.dst;
+        if (!distinct({ad.src0, ad.src1, ad.dst, r.dst, q.src, q.dst, e.dst})) return 0;
+    } else if (!distinct({r.src, r.dst, q.src, q.dst, e.dst})) return 0;
+    for (uint32_t b : {a_buf, r.dst, q.dst, e.dst}) if (p->buffer_elems[b] < tot) return 0;
+    if (p->buffer_elems[q.src] < cols) return 0;
+    m->a = p->buffers[a_buf]; m->b = has_add ? p->buffers[b_buf] : nullptr; m->sum = has_add ? p->buffers[sum_buf] : nullptr;
+    m->bare = p->buffers[r.dst]; m->gamma = p->buffers[q.src]; m->gamma_rep = p->buffers[q.dst]; m->norm = p->buffers[e.dst];
+    m->rows = rows; m->cols = cols; m->eps = r.eps;
+    return has_add ? 4 : 3;
+}
+
+// fused_elementwise(mid = chain(src)) ; mul(dst = mid * other)
+static uint32_t match_ewmul(const ZgCudaProgram* p, size_t i, ZgEwMulMacro* m) {
+    if (i + 1 >= p->ops.size()) return 0;
+    const ZgOp &fo = p->ops[i], &mo = p->ops[i + 1];
+    if (fo.tag != ZG_OP_FUSED_ELEMENTWISE || mo.tag != ZG_OP_ELEMENTWISE || mo.u.elementwise.op != ZG_EW_MUL) return 0;
+    const auto& f = fo.u.fused_elementwise;
+    const auto& e = mo.u.elementwise;
+    if (f.n == 0 || f.n != e.n || f.dst_offset || f.src_offset || e.dst_offset || e.src0_offset || e.src1_offset) return 0;
+    if (e.src0 != f.dst || e.src1 == f.dst || e.dst == f.dst || e.dst == f.src || e.dst == e.src1 || f.dst == f.src) return 0;
+    for (const ZgFusedEwStep& st : p->steps[i])
+        if ((st.op == ZG_EW_ADD || st.op == ZG_EW_MUL) && (st.secondary_buf == f.dst || st.secondary_buf == e.dst)) return 0;
+    m->src = p->buffers[f.src]; m->mid = p->buffers[f.dst]; m->other = p->buffers[e.src1]; m->dst = p->buffers[e.dst];
+    m->steps = p->d_steps + p->step_off[i]; m->n_steps = (uint32_t)f.n_steps; m->n = f.n;
+    return 2;
+}
+
+// attention(out) ; slice_assign(concat[...] = out): the copy of a head's whole output into the concatenated buffer
+static uint32_t match_attn_store(const ZgCudaProgram* p, size_t i) {
+    if (i + 1 >= p->ops.size()) return 0;
+    const ZgOp &ao = p->ops[i], &so = p->ops[i + 1];
+    if (ao.tag != ZG_OP_ATTENTION || so.tag != ZG_OP_SLICE_ASSIGN) return 0;
+    const auto& a = ao.u.attention;
+    const auto& sa = so.u.slice_assign;
+    if (sa.patch_stride != 0 || sa.src != a.dst || sa.dst == a.dst || sa.dst == a.q || sa.dst == a.k || sa.dst == a.v || sa.dst == a.mask) return 0;
+    if (sa.rows != a.d_head || sa.cols != a.seq_q || sa.src_offset != a.dst_off || sa.src_row_stride != a.dst_rs || sa.src_col_stride != a.dst_cs) return 0;
+    return 2;
+}
+
+// Dependency levels over ITEMS (level = 1 + max level of every earlier item it conflicts with), then units in (level,
+// program order); any such order is a valid topological order of the program's dependency DAG.
 static bool build_schedule(ZgCudaProgram* p) {
     const size_t n = p->ops.size();
+    const size_t chain_max = p->ctx->chain_max;
+    std::vector<ZgItem> items;
+    std::vector<ZgNormMacro> norm_of;     // per item (kind ITEM_NORM)
+    std::vector<ZgEwMulMacro> ewmul_of;   // per item (kind ITEM_EWMUL)
+    for (size_t i = 0; i < n;) {
+        ZgItem it; it.first = (uint32_t)i;
+        ZgNormMacro nm = {}; ZgEwMulMacro em = {};
+        uint32_t c = 0;
+        if (chain_max && p->ctx->fuse && (c = match_norm(p, i, &nm))) it.kind = ITEM_NORM;
+        else if (p->ctx->fuse && (c = match_ewmul(p, i, &em))) it.kind = ITEM_EWMUL;
+        else if (p->ctx->fuse && (c = match_attn_store(p, i))) it.kind = ITEM_ATTN_STORE;
+        else c = 1;
+        it.count = c;
+        items.push_back(it); norm_of.push_back(nm); ewmul_of.push_back(em);
+        i += c;
+    }
+    const size_t ni = items.size();
     struct Access { ZgRange r; int level; };
     std::vector<std::vector<Access>> acc(p->buffers.size() + 2);   // + the virtual GEMM-scratch and communicator buffers
-    std::vector<int> level(n, 0);
-    std::vector<ZgRange> rng;
-    for (size_t i = 0; i < n; i++) {
-        op_ranges(p, p->ops[i], rng);
+    std::vector<int> level(ni, 0);
+    std::vector<ZgRange> rng, tmp;
+    for (size_t k = 0; k < ni; k++) {
+        rng.clear();
+        for (uint32_t j = 0; j < items[k].count; j++) { op_ranges(p, p->ops[items[k].first + j], tmp); rng.insert(rng.end(), tmp.begin(), tmp.end()); }
         int lvl = 0;
         for (const ZgRange& r : rng)
             for (const Access& a : acc[r.buf])
                 if (a.level + 1 > lvl && range_conflict(r, a.r)) lvl = a.level + 1;
-        level[i] = lvl;
+        level[k] = lvl;
         for (const ZgRange& r : rng) {
             // a write covering the whole buffer orders everything after it: older accesses need not be kept
             if (r.write && !r.dyn && r.buf < p->buffer_elems.size() && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
             acc[r.buf].push_back({r, lvl});
         }
     }
-    std::vector<uint32_t> order(n);
-    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::vector<uint32_t> order(ni);
+    for (size_t k = 0; k < ni; k++) order[k] = (uint32_t)k;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
     p->units.clear();
     p->entry_of_op.assign(n, 0);
     std::vector<ZgBatchEntry> entries;
     std::vector<ZgChainOp> chain_ops;
-    // Chains: walking the levels upwards, small ops join the open chain (first op of a new level = block barrier).
-    // A level that also holds big ops (matvecs, attention, dense matmul, collectives) closes the chain BEFORE them:
-    // they may consume the chain's earlier levels, and nothing in the chain depends on them (same level = no
+    // Chains: walking the levels upwards, small items join the open chain (first item of a new level = block barrier).
+    // A level that also holds big ops (matvecs, attention, dense matmul, NCCL collectives) closes the chain BEFORE
+    // them: they may consume the chain's earlier levels, and nothing in the chain depends on them (same level = no
     // conflict; later levels start a new chain).  The unit order stays a topological order of the dependency DAG.
-    const size_t chain_max = p->ctx->chain_max;
-    auto chain_work = [&](const ZgOp& op) -> size_t {
+    auto chain_work = [&](const ZgItem& it) -> size_t {
+        if (it.kind == ITEM_NORM) return 1;   // size-checked by the matcher
+        if (it.kind == ITEM_EWMUL) return ewmul_of[&it - items.data()].n <= 1024 ? 1 : 0;   // transcendental chains: one CTA only when tiny
+        if (it.kind != ITEM_OP) return 0;
+        const ZgOp& op = p->ops[it.first];
         if (op.tag == ZG_OP_ALLREDUCE)   // peer-memory all-reduce runs inside the chain kernel; NCCL ones are "big" ops
-            return zg_peer_allreduce_ok(p->ctx, op.u.allreduce.n) ? (size_t)op.u.allreduce.n * p->ctx->world / 4 + 1 : 0;
-        return zg_chain_work(op);
+            return zg_peer_allreduce_ok(p->ctx, op.u.allreduce.n) ? 1 : 0;
+        const size_t wk = zg_chain_work(op);
+        return wk <= chain_max ? wk : 0;
     };
     p->peer_entry.assign(n, UINT32_MAX);
     for (size_t i = 0; i < n; i++) {   // standalone single-op entries: eager / profiling launches and chaining switched off
@@ -513,62 +624,82 @@ static bool build_schedule(ZgCudaProgram* p) {
         p->peer_entry[i] = (uint32_t)chain_ops.size();
         chain_ops.push_back(c);
     }
-    ZgCudaProgram::Unit chain; chain.chain = true;
+    std::vector<uint32_t> chain_items;
     std::vector<char> chain_sync, chain_tiny;
     auto close_chain = [&]() {
-        if (chain.ops.empty()) return true;
-        if (chain.ops.size() == 1 && !zg_op_is_batched(p->ops[chain.ops[0]].tag) && p->ops[chain.ops[0]].tag != ZG_OP_ALLREDUCE) {
-            ZgCudaProgram::Unit u; u.ops = chain.ops; p->units.push_back(u);   // a lone op: its own (wider) kernel is as good
+        if (chain_items.empty()) return true;
+        const ZgItem& only = items[chain_items[0]];
+        if (chain_items.size() == 1 && only.kind == ITEM_OP && !zg_op_is_batched(p->ops[only.first].tag) && p->ops[only.first].tag != ZG_OP_ALLREDUCE) {
+            ZgCudaProgram::Unit u; u.ops.push_back(only.first); p->units.push_back(u);   // a lone op: its own (wider) kernel is as good
         } else {
+            ZgCudaProgram::Unit chain; chain.chain = true;
             chain.first_entry = (uint32_t)chain_ops.size();
-            for (size_t k = 0; k < chain.ops.size(); k++) {
+            chain.n_entries = (uint32_t)chain_items.size();
+            for (size_t k = 0; k < chain_items.size(); k++) {
                 ZgChainOp c;
-                const uint32_t i = chain.ops[k];
-                if (!zg_fill_chain_op(p->ops[i], p->buffers.data(), i, p->d_steps + p->step_off[i], chain_sync[k] != 0, &c)) return false;
+                const ZgItem& it = items[chain_items[k]];
+                const bool sync = chain_sync[k] != 0;
+                bool ok;
+                if (it.kind == ITEM_NORM) ok = zg_fill_chain_norm(norm_of[chain_items[k]], sync, &c);
+                else if (it.kind == ITEM_EWMUL) ok = zg_fill_chain_ewmul(ewmul_of[chain_items[k]], sync, &c);
+                else ok = zg_fill_chain_op(p->ops[it.first], p->buffers.data(), it.first, p->d_steps + p->step_off[it.first], sync, &c);
+                if (!ok) return false;
                 chain_ops.push_back(c);
+                for (uint32_t j = 0; j < it.count; j++) chain.ops.push_back(it.first + j);
             }
             // runs of >= 2 tiny ops inside one level execute warp-parallel (group = run length on the run's first op)
-            for (size_t k = 0; k < chain.ops.size();) {
+            for (size_t k = 0; k < chain_items.size();) {
                 size_t e = k;
-                if (chain_tiny[k]) { e = k + 1; while (e < chain.ops.size() && chain_tiny[e] && !chain_sync[e]) e++; }
+                if (chain_tiny[k]) { e = k + 1; while (e < chain_items.size() && chain_tiny[e] && !chain_sync[e]) e++; }
                 if (e - k >= 2) { chain_ops[chain.first_entry + k].group = (uint32_t)(e - k); k = e; }
                 else k++;
             }
             p->units.push_back(chain);
         }
-        chain.ops.clear(); chain_sync.clear(); chain_tiny.clear();
+        chain_items.clear(); chain_sync.clear(); chain_tiny.clear();
         return true;
     };
-    auto is_tiny = [&](const ZgOp& op) {
+    auto is_tiny = [&](const ZgItem& it) {
+        if (it.kind != ITEM_OP) return false;
+        const ZgOp& op = p->ops[it.first];
         return op.tag != ZG_OP_RMSNORM && op.tag != ZG_OP_ALLREDUCE && zg_chain_work(op) <= 512;
     };
     size_t pos = 0;
-    while (pos < n) {
+    while (pos < ni) {
         size_t end = pos;
-        while (end < n && level[order[end]] == level[order[pos]]) end++;
+        while (end < ni && level[order[end]] == level[order[pos]]) end++;
         bool first_small = true, has_big = false;
+        // per-head ops (rope, cache stores): one warp each inside a chain is only a win for a handful of heads; a wide
+        // level (32 heads x 4 ops) is better served by the batched multi-CTA kernels
+        size_t n_tiny = 0;
+        for (size_t k = pos; k < end; k++) n_tiny += (chain_max && chain_work(items[order[k]]) && is_tiny(items[order[k]])) ? 1 : 0;
+        const bool tiny_in_chain = n_tiny <= 8;
+        auto in_chain = [&](const ZgItem& it) { return chain_max && chain_work(it) != 0 && (tiny_in_chain || !is_tiny(it)); };
         for (int pass = 0; pass < 2; pass++) {   // CTA-wide ops first, then the level's tiny ops as one warp-parallel run
             for (size_t k = pos; k < end; k++) {
-                const uint32_t i = order[k];
-                const size_t wk = chain_max ? chain_work(p->ops[i]) : 0;
-                if (wk == 0 || wk > chain_max) { has_big = true; continue; }
-                const bool tiny = is_tiny(p->ops[i]);
+                const ZgItem& it = items[order[k]];
+                if (!in_chain(it)) { has_big = true; continue; }
+                const bool tiny = is_tiny(it);
                 if (tiny != (pass == 1)) continue;
-                if (chain.ops.size() >= kZgChainMaxOps) { if (!close_chain()) return false; }   // kernel boundary = barrier
-                chain_sync.push_back(first_small && !chain.ops.empty());
+                if (chain_items.size() >= kZgChainMaxOps) { if (!close_chain()) return false; }   // kernel boundary = barrier
+                chain_sync.push_back(first_small && !chain_items.empty());
                 chain_tiny.push_back(tiny);
-                chain.ops.push_back(i);
+                chain_items.push_back(order[k]);
                 first_small = false;
             }
         }
         if (has_big && !close_chain()) return false;
         std::vector<std::pair<uint64_t, size_t>> open;   // batch signature -> unit index (within this level)
         for (size_t k = pos; k < end; k++) {
-            const uint32_t i = order[k];
-            const ZgOp& op = p->ops[i];
-            const size_t wk = chain_max ? chain_work(op) : 0;
-            if (wk != 0 && wk <= chain_max) continue;   // chained above
-            if (!zg_op_is_batched(op.tag)) { ZgCudaProgram::Unit u; u.ops.push_back(i); p->units.push_back(u); continue; }
+            const ZgItem& it = items[order[k]];
+            if (in_chain(it)) continue;   // chained above
+            const ZgOp& op = p->ops[it.first];
+            if (it.kind == ITEM_EWMUL) {   // fused_elementwise + mul as one multi-CTA launch
+                ZgCudaProgram::Unit u; u.ops.push_back(it.first); u.ops.push_back(it.first + 1);
+                u.ewmul = true; u.em = ewmul_of[order[k]];
+                p->units.push_back(u); continue;
+            }
+            if (!zg_op_is_batched(op.tag)) { ZgCudaProgram::Unit u; u.ops.push_back(it.first); p->units.push_back(u); continue; }
             const uint64_t sig = zg_batch_signature(op);
             size_t ui = (size_t)-1;
             for (auto& o : open) if (o.first == sig) { ui = o.second; break; }
@@ -578,7 +709,9 @@ static bool build_schedule(ZgCudaProgram* p) {
                 ui = p->units.size() - 1;
                 open.push_back({sig, ui});
             }
-            p->units[ui].ops.push_back(i);
+            p->units[ui].entry_ops.push_back(it.first);
+            for (uint32_t j = 0; j < it.count; j++) p->units[ui].ops.push_back(it.first + j);
+            if (it.kind == ITEM_ATTN_STORE) p->units[ui].store_of[it.first] = it.first + 1;
         }
         pos = end;
     }
@@ -586,12 +719,27 @@ static bool build_schedule(ZgCudaProgram* p) {
     for (auto& u : p->units) {
         if (!u.batched) continue;
         u.first_entry = (uint32_t)entries.size();
-        for (uint32_t i : u.ops) {
+        u.n_entries = (uint32_t)u.entry_ops.size();
+        for (uint32_t i : u.entry_ops) {
             ZgBatchEntry e;
             if (!zg_fill_batch_entry(p->ops[i], p->buffers.data(), i, &e)) return false;
+            auto st = u.store_of.find(i);
+            if (st != u.store_of.end()) {   // the absorbed slice_assign: second destination of the attention output
+                const auto& sa = p->ops[st->second].u.slice_assign;
+                e.dst2 = p->buffers[sa.dst]; e.d2_off = sa.dst_offset; e.d2_rs = sa.dst_row_stride; e.d2_cs = sa.dst_col_stride;
+            }
             p->entry_of_op[i] = (uint32_t)entries.size();
             entries.push_back(e);
         }
+    }
+    // single-op launches (profiling / eager per-op mode) of batched kinds need their own plain entries
+    p->single_entry.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (!zg_op_is_batched(p->ops[i].tag)) continue;
+        ZgBatchEntry e;
+        if (!zg_fill_batch_entry(p->ops[i], p->buffers.data(), (uint32_t)i, &e)) return false;
+        p->single_entry[i] = (uint32_t)entries.size();
+        entries.push_back(e);
     }
     cudaFree(p->d_chain); p->d_chain = nullptr;
     if (!chain_ops.empty()) {
@@ -622,14 +770,15 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
     if (op.tag == ZG_OP_ALLGATHER)
         return zg_comm_allgather(ctx, p->buffers[op.u.allgather.src] + op.u.allgather.src_offset,
                                  p->buffers[op.u.allgather.dst] + op.u.allgather.dst_offset, op.u.allgather.n, st);
-    if (zg_op_is_batched(op.tag)) return zg_launch_batch(op, p->d_batch + p->entry_of_op[i], 1, p->d_dyn, st);
+    if (zg_op_is_batched(op.tag)) return zg_launch_batch(op, p->d_batch + p->single_entry[i], 1, p->d_dyn, st);
     return zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
 }
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
-    if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, (uint32_t)u.ops.size(), p->d_dyn, p->ctx->peer, st);
+    if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, p->ctx->peer, st);
+    if (u.ewmul) return zg_launch_ewmul(u.em, st);
     if (!u.batched) return launch_one(p, u.ops[0], st);
-    return zg_launch_batch(p->ops[u.ops[0]], p->d_batch + u.first_entry, (uint32_t)u.ops.size(), p->d_dyn, st);
+    return zg_launch_batch(p->ops[u.entry_ops[0]], p->d_batch + u.first_entry, u.n_entries, p->d_dyn, st);
 }
 
 static bool launch_all(ZgCudaProgram* p, cudaStream_t st, bool profile) {
@@ -777,6 +926,30 @@ extern "C" void zg_cuda_execute_device(ZgCudaCtx* ctx, ZgCudaProgram* p) {
 }
 
 extern "C" void zg_cuda_free(ZgCudaCtx* ctx, ZgCudaProgram* p) { (void)ctx; free_program(p); }
+
+// Debug timeline: enable (allocates the device buffer) / disable, and copy out {kind, t_entry, t_after_wait, t_exit} records.
+static unsigned long long* g_trace_buf = nullptr;
+extern "C" int zg_cuda_trace(ZgCudaCtx* ctx, int enable) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (enable && !g_trace_buf) { if (cudaMalloc(&g_trace_buf, (1 + 3 * 16000) * 8) != cudaSuccess) return -1; }
+    if (g_trace_buf) cudaMemset(g_trace_buf, 0, (1 + 3 * 16000) * 8);
+    zg_trace_set_ops(enable ? g_trace_buf : nullptr);
+    zg_trace_set_gemv(enable ? g_trace_buf : nullptr);
+    return 0;
+}
+extern "C" size_t zg_cuda_trace_read(ZgCudaCtx* ctx, unsigned long long* host, size_t max_records) {
+    if (!ctx || !g_trace_buf || !host) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    unsigned long long n = 0;
+    cudaMemcpy(&n, g_trace_buf, 8, cudaMemcpyDeviceToHost);
+    if (n > 16000) n = 16000;
+    if (n > max_records) n = max_records;
+    cudaMemcpy(host, g_trace_buf + 1, n * 3 * 8, cudaMemcpyDeviceToHost);
+    return (size_t)n;
+}
 
 extern "C" const ZgProfile* zg_cuda_profile(ZgCudaCtx* ctx, ZgCudaProgram* p) {
     if (!ctx || !p || !ctx->profiling) return nullptr;

@@ -10,7 +10,32 @@
 
 #include <string.h>
 
+ZG_TRACE_DECL
+void zg_trace_set_ops(unsigned long long* d_buf) { cudaMemcpyToSymbol(c_zg_trace, &d_buf, sizeof(d_buf)); }
+
+bool g_zg_pdl = true;   // programmatic dependent launch for every kernel of a program (ZG_CUDA_PDL=0 disables)
+
 namespace {
+
+// Programmatic dependent launch, both directions: let the NEXT kernel of the stream become resident right away (a
+// matvec then streams its immutable weights while this kernel still runs), and hold THIS kernel — launched early the
+// same way — until the previous one has fully completed.  Nothing mutable is touched before the wait.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_zg_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -55,6 +80,10 @@ __device__ __forceinline__ float apply_unary(uint32_t op, float v) {
 
 __global__ void k_elementwise(uint32_t op, float* __restrict__ dst, const float* __restrict__ s0,
                               const float* __restrict__ s1, uint32_t n) {
+    ZG_TRACE_BEGIN(1)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
+#pragma unroll 4
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float a = s0[i];
         float r;
@@ -63,10 +92,14 @@ __global__ void k_elementwise(uint32_t op, float* __restrict__ dst, const float*
         else r = apply_unary(op, a);
         dst[i] = r;
     }
+    ZG_TRACE_MARK(2)
 }
 
 __global__ void k_fused_elementwise(const ZgDevStep* __restrict__ steps, uint32_t n_steps,
                                     float* __restrict__ dst, const float* __restrict__ src, uint32_t n) {
+    ZG_TRACE_BEGIN(2)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float v = src[i];
         for (uint32_t s = 0; s < n_steps; s++) {
@@ -77,10 +110,33 @@ __global__ void k_fused_elementwise(const ZgDevStep* __restrict__ steps, uint32_
         }
         dst[i] = v;
     }
+    ZG_TRACE_MARK(2)
+}
+
+// fused_elementwise chain -> mid, then mid * other -> dst (SiLU(gate) * up): one launch for the two ops
+__global__ void k_fused_ew_mul(const ZgDevStep* __restrict__ steps, uint32_t n_steps, float* __restrict__ mid,
+                               const float* __restrict__ src, uint32_t n, const float* __restrict__ other, float* __restrict__ dst) {
+    ZG_TRACE_BEGIN(2)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = src[i];
+        const float o2 = other[i];
+        for (uint32_t s = 0; s < n_steps; s++) {
+            const ZgDevStep st = steps[s];
+            if (st.op == ZG_EW_ADD) { float o = st.sec[i]; v = st.is_swapped ? o + v : v + o; }
+            else if (st.op == ZG_EW_MUL) { float o = st.sec[i]; v = st.is_swapped ? o * v : v * o; }
+            else v = apply_unary(st.op, v);
+        }
+        mid[i] = v;
+        dst[i] = v * o2;
+    }
+    ZG_TRACE_MARK(2)
 }
 
 // one block per row
 __global__ void k_softmax(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols) {
+    pdl_enter();
     __shared__ float sh[32];
     const float* s = src + (size_t)blockIdx.x * cols;
     float* d = dst + (size_t)blockIdx.x * cols;
@@ -95,6 +151,7 @@ __global__ void k_softmax(float* __restrict__ dst, const float* __restrict__ src
 }
 
 __global__ void k_layernorm(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols, float eps) {
+    pdl_enter();
     __shared__ float sh[32];
     const float* s = src + (size_t)blockIdx.x * cols;
     float* d = dst + (size_t)blockIdx.x * cols;
@@ -109,10 +166,27 @@ __global__ void k_layernorm(float* __restrict__ dst, const float* __restrict__ s
 }
 
 __global__ void k_rmsnorm(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols, float eps) {
+    ZG_TRACE_BEGIN(3)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     __shared__ float sh[32];
     const float* s = src + (size_t)blockIdx.x * cols;
     float* d = dst + (size_t)blockIdx.x * cols;
     float ss = 0.0f;
+    if ((cols & 3u) == 0 && (((size_t)s | (size_t)d) & 15u) == 0) {   // 128-bit loads, 4 in flight per thread (latency-bound otherwise)
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        float4* d4 = reinterpret_cast<float4*>(d);
+        const uint32_t c4 = cols >> 2;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll 4
+        for (uint32_t j = threadIdx.x; j < c4; j += blockDim.x) { const float4 x = s4[j]; p0 += x.x * x.x; p1 += x.y * x.y; p2 += x.z * x.z; p3 += x.w * x.w; }
+        ss = block_reduce<false>((p0 + p1) + (p2 + p3), sh);
+        const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+#pragma unroll 4
+        for (uint32_t j = threadIdx.x; j < c4; j += blockDim.x) { const float4 x = s4[j]; d4[j] = make_float4(x.x * inv_rms, x.y * inv_rms, x.z * inv_rms, x.w * inv_rms); }
+        ZG_TRACE_MARK(2)
+        return;
+    }
     for (uint32_t j = threadIdx.x; j < cols; j += blockDim.x) { float x = s[j]; ss += x * x; }
     ss = block_reduce<false>(ss, sh);
     float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
@@ -122,6 +196,7 @@ __global__ void k_rmsnorm(float* __restrict__ dst, const float* __restrict__ src
 // one warp per output
 __global__ void k_reduce(uint32_t is_max, float* __restrict__ dst, const float* __restrict__ src,
                          uint32_t n_out, uint32_t rs) {
+    pdl_enter();
     uint32_t o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t lane = threadIdx.x & 31;
     if (o >= n_out) return;
@@ -141,6 +216,9 @@ struct RepeatParams {
 // reference.zig:391-433.  `src` is the buffer base for mode 3 (it adds src_offset
 // itself), src+src_offset for the others; dst already includes dst_offset.
 __global__ void k_repeat(RepeatParams p, float* __restrict__ dst, const float* __restrict__ src) {
+    ZG_TRACE_BEGIN(4)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < p.n; gid += gridDim.x * blockDim.x) {
         float v;
         if (p.mode == 0) v = src[0];
@@ -158,12 +236,16 @@ __global__ void k_repeat(RepeatParams p, float* __restrict__ dst, const float* _
         }
         dst[gid] = v;
     }
+    ZG_TRACE_MARK(2)
 }
 
 // The three per-head op kinds of a decode program (rope, slice_assign, attention) are launched in BATCHES:
 // blockIdx.y selects one op's parameter entry from a device table built at compile time, so all heads of a
 // layer (mutually independent ops of one dependency level) cost one launch instead of one each.
 __global__ void k_slice_assign(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    ZG_TRACE_BEGIN(5)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     const ZgBatchEntry e = tab[blockIdx.y];
     const uint32_t rows = e.u[0], cols = e.u[1], drs = e.u[2], dcs = e.u[3], soff = e.u[4], srs = e.u[5], scs = e.u[6];
     const uint32_t doff = d_dyn[e.dyn];
@@ -174,9 +256,13 @@ __global__ void k_slice_assign(const ZgBatchEntry* __restrict__ tab, const uint3
         uint32_t row = i % rows, col = i / rows;
         dst[(size_t)doff + (size_t)row * drs + (size_t)col * dcs] = src[(size_t)soff + (size_t)row * srs + (size_t)col * scs];
     }
+    ZG_TRACE_MARK(2)
 }
 
 __global__ void k_rope(const ZgBatchEntry* __restrict__ tab) {
+    ZG_TRACE_BEGIN(6)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     const ZgBatchEntry e = tab[blockIdx.y];
     const uint32_t hd = e.u[0], seq_len = e.u[1], s_off = e.u[2], c_off = e.u[3], d_off = e.u[4], s_rs = e.u[5], s_cs = e.u[6], c_cs = e.u[7];
     float* __restrict__ dst = e.dst;
@@ -193,6 +279,7 @@ __global__ void k_rope(const ZgBatchEntry* __restrict__ tab) {
         dst[(size_t)d_off + pair + (size_t)col * 2 * hd] = __fsub_rn(__fmul_rn(x_lo, c), __fmul_rn(x_hi, sn));
         dst[(size_t)d_off + pair + hd + (size_t)col * 2 * hd] = __fadd_rn(__fmul_rn(x_hi, c), __fmul_rn(x_lo, sn));
     }
+    ZG_TRACE_MARK(2)
 }
 
 struct AttnParams {
@@ -209,6 +296,7 @@ constexpr int kAttnMaxPerLane = 16; // d_head <= 512
 // the 8 partial states are merged through shared memory.
 __global__ void __launch_bounds__(kAttnWarps * 32)
 k_attention(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    pdl_enter();
     const ZgBatchEntry e = tab[blockIdx.y];
     AttnParams p;
     p.has_mask = e.u[0]; p.d_head = e.u[1]; p.seq_q = e.u[2]; p.scale = e.f;
@@ -283,6 +371,7 @@ k_attention(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d
         float a = 0.0f;
         for (int w = 0; w < kAttnWarps; w++) a += sh_acc[w][r] * wscale[w];
         dst[d_base + (size_t)r * p.dst_rs] = a * inv_l;
+        if (e.dst2) e.dst2[(size_t)e.d2_off + (size_t)r * e.d2_rs + (size_t)qi * e.d2_cs] = a * inv_l;
     }
 }
 
@@ -297,7 +386,24 @@ constexpr int kAttnFastWarps = 16;
 template <int NI>
 __global__ void __launch_bounds__(kAttnFastWarps * 32)
 k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    ZG_TRACE_BEGIN(7)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const ZgBatchEntry e = tab[blockIdx.y];
+    {   // While the producer kernels still run: pull this head's K and V rows into L2 (one 128-byte line per prefetch).
+        // The op table and seq_kv are fixed before the step starts; the cache rows are only read after the wait (the
+        // row written by this step just gets prefetched a little early — L2 is the point of coherence).
+        const uint32_t seq_kv0 = d_dyn[e.dyn], dhb = e.u[1] * 4;
+        const char* kb = reinterpret_cast<const char*>(e.s1 + e.u[4]);
+        const char* vb0 = reinterpret_cast<const char*>(e.s2 + e.u[5]);
+        if (blockIdx.x == 0)
+            for (uint32_t s = threadIdx.x; s < seq_kv0; s += blockDim.x)
+                for (uint32_t b = 0; b < dhb; b += 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (size_t)s * e.u[11] * 4 + b));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(vb0 + (size_t)s * e.u[13] * 4 + b));
+                }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
     const uint32_t has_mask = e.u[0], dh = e.u[1];
     const float scale = e.f;
     const uint32_t q_off = e.u[3], k_off = e.u[4], v_off = e.u[5], mask_off = e.u[6], dst_off = e.u[7];
@@ -332,13 +438,18 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
             const float4* q4 = reinterpret_cast<const float4*>(sq);
             float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
             uint32_t d = 0;
-            for (; d + 4 <= dh4; d += 4) {
-                const float4 a = kr[d], b = kr[d + 1], c = kr[d + 2], f = kr[d + 3];
-                const float4 qa = q4[d], qb = q4[d + 1], qc = q4[d + 2], qf = q4[d + 3];
-                d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
-                d1 = fmaf(qb.x, b.x, d1); d1 = fmaf(qb.y, b.y, d1); d1 = fmaf(qb.z, b.z, d1); d1 = fmaf(qb.w, b.w, d1);
-                d2 = fmaf(qc.x, c.x, d2); d2 = fmaf(qc.y, c.y, d2); d2 = fmaf(qc.z, c.z, d2); d2 = fmaf(qc.w, c.w, d2);
-                d3 = fmaf(qf.x, f.x, d3); d3 = fmaf(qf.y, f.y, d3); d3 = fmaf(qf.z, f.z, d3); d3 = fmaf(qf.w, f.w, d3);
+            for (; d + 8 <= dh4; d += 8) {   // 8 independent 128-bit loads in flight per lane
+                float4 kk[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) kk[u] = kr[d + u];
+#pragma unroll
+                for (int u = 0; u < 8; u += 4) {
+                    const float4 qa = q4[d + u], qb = q4[d + u + 1], qc = q4[d + u + 2], qf = q4[d + u + 3];
+                    d0 = fmaf(qa.x, kk[u].x, d0); d0 = fmaf(qa.y, kk[u].y, d0); d0 = fmaf(qa.z, kk[u].z, d0); d0 = fmaf(qa.w, kk[u].w, d0);
+                    d1 = fmaf(qb.x, kk[u + 1].x, d1); d1 = fmaf(qb.y, kk[u + 1].y, d1); d1 = fmaf(qb.z, kk[u + 1].z, d1); d1 = fmaf(qb.w, kk[u + 1].w, d1);
+                    d2 = fmaf(qc.x, kk[u + 2].x, d2); d2 = fmaf(qc.y, kk[u + 2].y, d2); d2 = fmaf(qc.z, kk[u + 2].z, d2); d2 = fmaf(qc.w, kk[u + 2].w, d2);
+                    d3 = fmaf(qf.x, kk[u + 3].x, d3); d3 = fmaf(qf.y, kk[u + 3].y, d3); d3 = fmaf(qf.z, kk[u + 3].z, d3); d3 = fmaf(qf.w, kk[u + 3].w, d3);
+                }
             }
             for (; d < dh4; d++) {
                 const float4 a = kr[d], qa = q4[d];
@@ -397,7 +508,9 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
 #pragma unroll
         for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
         dst[(size_t)dst_off + (size_t)qi * dst_cs + r] = a * inv_l;
+        if (e.dst2) e.dst2[(size_t)e.d2_off + (size_t)r * e.d2_rs + (size_t)qi * e.d2_cs] = a * inv_l;
     }
+    ZG_TRACE_MARK(2)
 }
 
 static inline bool attn_fast_ok(const ZgOp& op) {
@@ -414,6 +527,9 @@ struct MMParams {
 // (src/models/llama.zig:162-165): one warp per output column, float4 loads.
 __global__ void k_matmul_kmajor(MMParams p, float* __restrict__ dst, const float* __restrict__ A,
                                 const float* __restrict__ B) {
+    ZG_TRACE_BEGIN(9)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.N) return;
     const uint32_t m = blockIdx.y;
@@ -437,6 +553,7 @@ __global__ void k_matmul_kmajor(MMParams p, float* __restrict__ dst, const float
 // general strides: one thread per output (coalesced over n when b_cs == 1)
 __global__ void k_matmul_general(MMParams p, float* __restrict__ dst, const float* __restrict__ A,
                                  const float* __restrict__ B) {
+    pdl_enter();
     uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
     if (n >= p.N) return;
     float acc = 0.0f;
@@ -452,7 +569,7 @@ __global__ void k_matmul_general(MMParams p, float* __restrict__ dst, const floa
 // order, every op exactly as its DeviceOp defines it (all intermediate buffers are written), `sync` marks the first
 // op of a new dependency level (block barrier: CTA-scope visibility of the previous level's global writes).
 // Plain (coherent) loads only: data read here may have been written earlier in the same kernel.
-constexpr int kChainThreads = 1024;
+constexpr int kChainThreads = 256;   // x 64 registers = 16K: fits next to two resident matvec CTAs (2 x 20K), so PDL can make it resident early
 static_assert(sizeof(ZgChainOp) % 4 == 0, "table is copied word-wise");
 
 __device__ __forceinline__ float chain_block_sum(float v, float* sh) {
@@ -475,6 +592,22 @@ __device__ __forceinline__ void chain_small_op(const ZgChainOp* o, uint32_t t, u
     switch (o->kind) {
         case ZG_OP_ELEMENTWISE: {
             const uint32_t op = o->u[0], n = o->u[1];
+            if ((op == ZG_EW_ADD || op == ZG_EW_MUL) && (n & 3u) == 0 && (((size_t)dst | (size_t)s0 | (size_t)s1) & 15u) == 0) {
+                // 128-bit accesses, two in flight per thread: these ops are pure load latency
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                const float4* a4 = reinterpret_cast<const float4*>(s0);
+                const float4* b4 = reinterpret_cast<const float4*>(s1);
+                const uint32_t n4 = n >> 2;
+                for (uint32_t j = t; j < n4; j += 2 * nt) {
+                    const uint32_t j2 = j + nt;
+                    const float4 a = a4[j], b = b4[j];
+                    float4 c = make_float4(0.f, 0.f, 0.f, 0.f), e = c;
+                    if (j2 < n4) { c = a4[j2]; e = b4[j2]; }
+                    d4[j] = op == ZG_EW_ADD ? make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w) : make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+                    if (j2 < n4) d4[j2] = op == ZG_EW_ADD ? make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w) : make_float4(c.x * e.x, c.y * e.y, c.z * e.z, c.w * e.w);
+                }
+                break;
+            }
             for (uint32_t j = t; j < n; j += nt) {
                 const float a = s0[j];
                 float r;
@@ -502,6 +635,13 @@ __device__ __forceinline__ void chain_small_op(const ZgChainOp* o, uint32_t t, u
         }
         case ZG_OP_REPEAT: {
             const uint32_t mode = o->u[0], n = o->u[1], src_n = o->u[2], src_offset = o->u[15];
+            if ((mode == 1 || mode == 2) && ((n | src_n) & 3u) == 0 && (((size_t)dst | (size_t)s0) & 15u) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                const float4* a4 = reinterpret_cast<const float4*>(s0);
+                const uint32_t n4 = n >> 2, sn4 = src_n >> 2;
+                for (uint32_t j = t; j < n4; j += nt) d4[j] = a4[mode == 1 ? j : j % sn4];
+                break;
+            }
             for (uint32_t gid = t; gid < n; gid += nt) {
                 float v;
                 if (mode == 0) v = s0[0];
@@ -550,18 +690,23 @@ __device__ __forceinline__ void chain_small_op(const ZgChainOp* o, uint32_t t, u
     }
 }
 
-__global__ void __launch_bounds__(kChainThreads)
+__global__ void __launch_bounds__(kChainThreads, 4)
 k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __restrict__ d_dyn, const ZgPeerComm pc) {
     __shared__ float sh[32];
     __shared__ uint32_t s_seq;
+    __shared__ ZgDevStep s_steps[16];
     __shared__ __align__(16) ZgChainOp s_tab[kZgChainMaxOps];   // the whole op table: one coalesced read instead of a dependent load per op
     const uint32_t tid = threadIdx.x;
-    {
+    ZG_TRACE_BEGIN(8)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    {   // the op table is immutable while programs run: copy it before waiting for the previous kernel
         const uint32_t words = count * (uint32_t)(sizeof(ZgChainOp) / 4);
         const uint32_t* g = reinterpret_cast<const uint32_t*>(tab);
         uint32_t* l = reinterpret_cast<uint32_t*>(s_tab);
         for (uint32_t j = tid; j < words; j += kChainThreads) l[j] = __ldg(g + j);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
     __syncthreads();
     uint32_t i = 0;
     while (i < count) {
@@ -584,10 +729,132 @@ k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __res
                     const float* s = s0 + (size_t)r * cols;
                     float* d = dst + (size_t)r * cols;
                     float ss = 0.0f;
+                    if ((cols & 3u) == 0 && (((size_t)s | (size_t)d) & 15u) == 0 && cols <= 16 * kChainThreads) {   // <= 4096
+                        // the row stays in registers between the two passes (<= 4 float4 per thread)
+                        const float4* s4 = reinterpret_cast<const float4*>(s);
+                        const uint32_t c4 = cols >> 2;
+                        float4 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { const uint32_t j = tid + u * kChainThreads; x[u] = j < c4 ? s4[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) ss += (x[u].x * x[u].x + x[u].y * x[u].y) + (x[u].z * x[u].z + x[u].w * x[u].w);
+                        ss = chain_block_sum(ss, sh);
+                        const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+                        float4* d4 = reinterpret_cast<float4*>(d);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t j = tid + u * kChainThreads;
+                            if (j < c4) d4[j] = make_float4(x[u].x * inv_rms, x[u].y * inv_rms, x[u].z * inv_rms, x[u].w * inv_rms);
+                        }
+                        continue;
+                    }
                     for (uint32_t j = tid; j < cols; j += kChainThreads) { const float x = s[j]; ss += x * x; }
                     ss = chain_block_sum(ss, sh);
                     const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
                     for (uint32_t j = tid; j < cols; j += kChainThreads) d[j] = s[j] * inv_rms;
+                }
+                break;
+            }
+            case kZgChainFusedNorm: {
+                // [a + b ->] sum ; rmsnorm(sum) -> bare ; gamma broadcast -> gamma_rep ; bare * gamma_rep -> dst, one pass in
+                // registers (cols <= 8192, cols % 4 == 0): one load round, one block reduction, one store round per row.
+                const uint32_t rows = o->u[0], cols = o->u[1], c4 = cols >> 2;
+                const float eps = o->f;
+                const float4* a4 = reinterpret_cast<const float4*>(s0);
+                const float4* b4 = reinterpret_cast<const float4*>(o->s1);
+                float4* sum4 = reinterpret_cast<float4*>(((uint64_t)o->u[3] << 32) | o->u[2]);
+                float4* bare4 = reinterpret_cast<float4*>(((uint64_t)o->u[5] << 32) | o->u[4]);
+                const float4* g4 = reinterpret_cast<const float4*>(((uint64_t)o->u[7] << 32) | o->u[6]);
+                float4* grep4 = reinterpret_cast<float4*>(((uint64_t)o->u[9] << 32) | o->u[8]);
+                float4* n4 = reinterpret_cast<float4*>(dst);
+                constexpr int NV = 4;   // float4 per thread held in registers: cols <= 4 * NV * kChainThreads = 4096 in one read
+                if (c4 <= NV * kChainThreads) {
+                    float4 gam[NV];
+#pragma unroll
+                    for (int u = 0; u < NV; u++) { const uint32_t j = tid + u * kChainThreads; gam[u] = j < c4 ? g4[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
+                    for (uint32_t r = 0; r < rows; r++) {
+                        const size_t ro = (size_t)r * c4;
+                        float4 x[NV];
+#pragma unroll
+                        for (int u = 0; u < NV; u++) { const uint32_t j = tid + u * kChainThreads; x[u] = j < c4 ? a4[ro + j] : make_float4(0.f, 0.f, 0.f, 0.f); }
+                        if (b4) {
+#pragma unroll
+                            for (int u = 0; u < NV; u++) {
+                                const uint32_t j = tid + u * kChainThreads;
+                                if (j >= c4) continue;
+                                const float4 t = b4[ro + j];
+                                x[u] = make_float4(x[u].x + t.x, x[u].y + t.y, x[u].z + t.z, x[u].w + t.w);
+                                sum4[ro + j] = x[u];
+                            }
+                        }
+                        float ss = 0.0f;
+#pragma unroll
+                        for (int u = 0; u < NV; u++) ss += (x[u].x * x[u].x + x[u].y * x[u].y) + (x[u].z * x[u].z + x[u].w * x[u].w);
+                        ss = chain_block_sum(ss, sh);
+                        const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+#pragma unroll
+                        for (int u = 0; u < NV; u++) {
+                            const uint32_t j = tid + u * kChainThreads;
+                            if (j >= c4) continue;
+                            const float4 bz = make_float4(x[u].x * inv_rms, x[u].y * inv_rms, x[u].z * inv_rms, x[u].w * inv_rms);
+                            bare4[ro + j] = bz; grep4[ro + j] = gam[u];
+                            n4[ro + j] = make_float4(bz.x * gam[u].x, bz.y * gam[u].y, bz.z * gam[u].z, bz.w * gam[u].w);
+                        }
+                    }
+                } else {   // long rows: sum pass, then a second read of the (L2-resident) inputs
+                    for (uint32_t r = 0; r < rows; r++) {
+                        const size_t ro = (size_t)r * c4;
+                        float ss = 0.0f;
+#pragma unroll 4
+                        for (uint32_t j = tid; j < c4; j += kChainThreads) {
+                            float4 x = a4[ro + j];
+                            if (b4) { const float4 t = b4[ro + j]; x = make_float4(x.x + t.x, x.y + t.y, x.z + t.z, x.w + t.w); sum4[ro + j] = x; }
+                            ss += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+                        }
+                        ss = chain_block_sum(ss, sh);   // its barriers also publish sum4 to the whole CTA
+                        const float inv_rms = 1.0f / sqrtf(ss / (float)cols + eps);
+                        const float4* x4 = b4 ? sum4 : a4;
+#pragma unroll 4
+                        for (uint32_t j = tid; j < c4; j += kChainThreads) {
+                            const float4 x = x4[ro + j], g = g4[j];
+                            const float4 bz = make_float4(x.x * inv_rms, x.y * inv_rms, x.z * inv_rms, x.w * inv_rms);
+                            bare4[ro + j] = bz; grep4[ro + j] = g;
+                            n4[ro + j] = make_float4(bz.x * g.x, bz.y * g.y, bz.z * g.z, bz.w * g.w);
+                        }
+                    }
+                }
+                break;
+            }
+            case kZgChainEwMul: {
+                // fused_elementwise chain -> mid ; mid * other -> dst, four independent elements in flight per thread
+                const uint32_t n_steps = o->u[0], n = o->u[1];
+                __syncthreads();
+                if (tid < n_steps && tid < 16) s_steps[tid] = o->steps[tid];
+                __syncthreads();
+                const ZgDevStep* steps = s_steps;
+                float* mid = reinterpret_cast<float*>(((uint64_t)o->u[3] << 32) | o->u[2]);
+                const float* other = o->s1;
+                for (uint32_t jb = tid; jb < n; jb += 4 * kChainThreads) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const uint32_t j = jb + u * kChainThreads; v[u] = j < n ? s0[j] : 0.0f; }
+                    for (uint32_t st = 0; st < n_steps; st++) {
+                        const uint32_t sop = steps[st].op, sw = steps[st].is_swapped;
+                        const float* sec = steps[st].sec;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t j = jb + u * kChainThreads;
+                            if (j >= n) continue;
+                            if (sop == ZG_EW_ADD) { const float t = sec[j]; v[u] = sw ? t + v[u] : v[u] + t; }
+                            else if (sop == ZG_EW_MUL) { const float t = sec[j]; v[u] = sw ? t * v[u] : v[u] * t; }
+                            else v[u] = apply_unary(sop, v[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = jb + u * kChainThreads;
+                        if (j < n) { mid[j] = v[u]; dst[j] = v[u] * other[j]; }
+                    }
                 }
                 break;
             }
@@ -628,21 +895,25 @@ k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __res
                 __syncthreads();
                 const float* base = pc.slots[pc.rank] + (size_t)set * pc.world * pc.max_n;
                 if (n4) {
+                    // all ranks' values of an element are requested before the first add (L2-coherent loads: peers wrote
+                    // them over NVLink; the acquire above ordered them), then summed in rank order
                     float4* d4 = reinterpret_cast<float4*>(dst);
                     for (uint32_t j = tid; j < n4; j += kChainThreads) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int r = 0; r < pc.world; r++) {
-                            const float4 v = (r == pc.rank) ? d4[j] : __ldcv(reinterpret_cast<const float4*>(base + (size_t)r * pc.max_n) + j);
-                            if (r == 0) acc = v;
-                            else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
-                        }
+                        float4 v[kZgMaxRanks];
+#pragma unroll
+                        for (int r = 0; r < kZgMaxRanks; r++)
+                            if (r < pc.world) v[r] = (r == pc.rank) ? d4[j] : __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * pc.max_n) + j);
+                        float4 acc = v[0];
+#pragma unroll
+                        for (int r = 1; r < kZgMaxRanks; r++)
+                            if (r < pc.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
                         d4[j] = acc;
                     }
                 } else {
                     for (uint32_t j = tid; j < n; j += kChainThreads) {
                         float acc = 0.f;
                         for (int r = 0; r < pc.world; r++) {
-                            const float v = (r == pc.rank) ? dst[j] : __ldcv(base + (size_t)r * pc.max_n + j);
+                            const float v = (r == pc.rank) ? dst[j] : __ldcg(base + (size_t)r * pc.max_n + j);
                             acc = (r == 0) ? v : acc + v;
                         }
                         dst[j] = acc;
@@ -654,6 +925,7 @@ k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __res
             default: chain_small_op(o, tid, kChainThreads, d_dyn); break;
         }
     }
+    ZG_TRACE_MARK(2)
 }
 
 inline unsigned blocks_for(uint32_t n, unsigned bs, unsigned cap = 4096) {
@@ -683,39 +955,39 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
         case ZG_OP_ELEMENTWISE: {
             const auto& e = op.u.elementwise;
             if (e.n == 0) return true;
-            k_elementwise<<<blocks_for(e.n, 256), 256, 0, st>>>(e.op, bufs[e.dst] + e.dst_offset, bufs[e.src0] + e.src0_offset,
+            launch_k(k_elementwise, dim3(blocks_for(e.n, 256)), dim3(256), st, e.op, bufs[e.dst] + e.dst_offset, bufs[e.src0] + e.src0_offset,
                                                                 bufs[e.src1] + e.src1_offset, e.n);
             break;
         }
         case ZG_OP_FUSED_ELEMENTWISE: {
             const auto& f = op.u.fused_elementwise;
             if (f.n == 0) return true;
-            k_fused_elementwise<<<blocks_for(f.n, 256), 256, 0, st>>>(d_steps, (uint32_t)f.n_steps, bufs[f.dst] + f.dst_offset,
+            launch_k(k_fused_elementwise, dim3(blocks_for(f.n, 256)), dim3(256), st, d_steps, (uint32_t)f.n_steps, bufs[f.dst] + f.dst_offset,
                                                                       bufs[f.src] + f.src_offset, f.n);
             break;
         }
         case ZG_OP_SOFTMAX: {
             const auto& s = op.u.softmax;
             if (s.rows == 0 || s.cols == 0) return true;
-            k_softmax<<<s.rows, 256, 0, st>>>(bufs[s.dst] + s.dst_offset, bufs[s.src] + s.src_offset, s.cols);
+            launch_k(k_softmax, dim3(s.rows), dim3(256), st, bufs[s.dst] + s.dst_offset, bufs[s.src] + s.src_offset, s.cols);
             break;
         }
         case ZG_OP_LAYERNORM: {
             const auto& l = op.u.layernorm;
             if (l.rows == 0 || l.cols == 0) return true;
-            k_layernorm<<<l.rows, 256, 0, st>>>(bufs[l.dst] + l.dst_offset, bufs[l.src] + l.src_offset, l.cols, l.eps);
+            launch_k(k_layernorm, dim3(l.rows), dim3(256), st, bufs[l.dst] + l.dst_offset, bufs[l.src] + l.src_offset, l.cols, l.eps);
             break;
         }
         case ZG_OP_RMSNORM: {
             const auto& r = op.u.rmsnorm;
             if (r.rows == 0 || r.cols == 0) return true;
-            k_rmsnorm<<<r.rows, 256, 0, st>>>(bufs[r.dst] + r.dst_offset, bufs[r.src] + r.src_offset, r.cols, r.eps);
+            launch_k(k_rmsnorm, dim3(r.rows), dim3(1024), st, bufs[r.dst] + r.dst_offset, bufs[r.src] + r.src_offset, r.cols, r.eps);
             break;
         }
         case ZG_OP_REDUCE: {
             const auto& r = op.u.reduce;
             if (r.n_out == 0) return true;
-            k_reduce<<<blocks_for(r.n_out * 32, 256, 65535), 256, 0, st>>>(r.op == ZG_EW_MAX, bufs[r.dst] + r.dst_offset,
+            launch_k(k_reduce, dim3(blocks_for(r.n_out * 32, 256, 65535)), dim3(256), st, r.op == ZG_EW_MAX, bufs[r.dst] + r.dst_offset,
                                                                            bufs[r.src] + r.src_offset, r.n_out, r.reduce_size);
             break;
         }
@@ -728,7 +1000,7 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
             p.n = rp.n; p.src_n = (uint32_t)src_n; p.src_offset = rp.src_offset;
             for (int i = 0; i < 4; i++) { p.src_ne[i] = rp.src_ne[i]; p.src_strides[i] = rp.src_strides[i]; p.dst_strides[i] = rp.dst_strides[i]; }
             const float* src = (p.mode == 3) ? bufs[rp.src] : bufs[rp.src] + rp.src_offset;
-            k_repeat<<<blocks_for(rp.n, 256), 256, 0, st>>>(p, bufs[rp.dst] + rp.dst_offset, src);
+            launch_k(k_repeat, dim3(blocks_for(rp.n, 256)), dim3(256), st, p, bufs[rp.dst] + rp.dst_offset, src);
             break;
         }
         case ZG_OP_SLICE_ASSIGN:
@@ -746,10 +1018,10 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
             p.a_off = g.a_offset; p.b_off = g.b_offset; p.d_off = g.dst_offset; p.d_rs = g.dst_row_stride;
             if (g.b_row_stride == 1 && g.K >= 32) {
                 dim3 grid((unsigned)((g.N * 32 + 255) / 256), (unsigned)g.M);
-                k_matmul_kmajor<<<grid, 256, 0, st>>>(p, bufs[m.dst], bufs[m.a], bufs[m.b]);
+                launch_k(k_matmul_kmajor, dim3(grid), dim3(256), st, p, bufs[m.dst], bufs[m.a], bufs[m.b]);
             } else {
                 dim3 grid((unsigned)((g.N + 127) / 128), (unsigned)g.M);
-                k_matmul_general<<<grid, 128, 0, st>>>(p, bufs[m.dst], bufs[m.a], bufs[m.b]);
+                launch_k(k_matmul_general, dim3(grid), dim3(128), st, p, bufs[m.dst], bufs[m.a], bufs[m.b]);
             }
             break;
         }
@@ -830,9 +1102,38 @@ bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, con
     }
 }
 
+static inline void put_ptr(ZgChainOp* c, int at, const void* ptr) {
+    c->u[at] = (uint32_t)((uint64_t)ptr & 0xFFFFFFFFu); c->u[at + 1] = (uint32_t)((uint64_t)ptr >> 32);
+}
+
+bool zg_fill_chain_norm(const ZgNormMacro& m, bool sync, ZgChainOp* c) {
+    memset(c, 0, sizeof(*c));
+    c->kind = kZgChainFusedNorm; c->sync = sync ? 1u : 0u;
+    c->dst = m.norm; c->s0 = m.a; c->s1 = m.b; c->f = m.eps;
+    c->u[0] = m.rows; c->u[1] = m.cols;
+    put_ptr(c, 2, m.sum); put_ptr(c, 4, m.bare); put_ptr(c, 6, m.gamma); put_ptr(c, 8, m.gamma_rep);
+    return true;
+}
+
+bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c) {
+    memset(c, 0, sizeof(*c));
+    c->kind = kZgChainEwMul; c->sync = sync ? 1u : 0u;
+    c->dst = m.dst; c->s0 = m.src; c->s1 = m.other; c->steps = m.steps;
+    c->u[0] = m.n_steps; c->u[1] = m.n;
+    put_ptr(c, 2, m.mid);
+    return true;
+}
+
+bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st) {
+    if (m.n == 0) return true;
+    launch_k(k_fused_ew_mul, dim3(blocks_for(m.n, 128)), dim3(128), st, m.steps, m.n_steps, m.mid, m.src, m.n, m.other, m.dst);
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
 bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st) {
     if (count == 0) return true;
-    k_chain<<<1, kChainThreads, 0, st>>>(d_ops, count, d_dyn, pc);
+    launch_k(k_chain, dim3(1), dim3(kChainThreads), st, d_ops, count, d_dyn, pc);
     ZG_COUNT_LAUNCH();
     return true;
 }
@@ -890,13 +1191,13 @@ bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t 
         case ZG_OP_SLICE_ASSIGN: {
             const auto& sa = first.u.slice_assign;
             if (sa.rows == 0 || sa.cols == 0) return true;
-            k_slice_assign<<<dim3(blocks_for(sa.rows * sa.cols, 256), count), 256, 0, st>>>(d_entries, d_dyn);
+            launch_k(k_slice_assign, dim3(dim3(blocks_for(sa.rows * sa.cols, 256), count)), dim3(256), st, d_entries, d_dyn);
             break;
         }
         case ZG_OP_ROPE: {
             const auto& r = first.u.rope;
             if (r.half_d == 0 || r.seq_len == 0) return true;
-            k_rope<<<dim3(blocks_for(r.half_d * r.seq_len, 128), count), 128, 0, st>>>(d_entries);
+            launch_k(k_rope, dim3(dim3(blocks_for(r.half_d * r.seq_len, 128), count)), dim3(128), st, d_entries);
             break;
         }
         case ZG_OP_ATTENTION: {
@@ -904,10 +1205,10 @@ bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t 
             if (a.seq_q == 0 || a.d_head == 0) return true;
             if (attn_fast_ok(first)) {
                 const dim3 grid(a.seq_q, count);
-                if (a.d_head <= 64) k_attention_fast<2><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
-                else if (a.d_head <= 128) k_attention_fast<4><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
-                else k_attention_fast<8><<<grid, kAttnFastWarps * 32, 0, st>>>(d_entries, d_dyn);
-            } else k_attention<<<dim3(a.seq_q, count), kAttnWarps * 32, 0, st>>>(d_entries, d_dyn);
+                if (a.d_head <= 64) launch_k(k_attention_fast<2>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
+                else if (a.d_head <= 128) launch_k(k_attention_fast<4>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
+                else launch_k(k_attention_fast<8>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
+            } else launch_k(k_attention, dim3(dim3(a.seq_q, count)), dim3(kAttnWarps * 32), st, d_entries, d_dyn);
             break;
         }
         default: zg_set_error("internal: op kind %u is not batched", first.tag); return false;

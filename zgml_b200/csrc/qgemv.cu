@@ -34,6 +34,9 @@
 #include <stdlib.h>
 #include <type_traits>
 
+ZG_TRACE_DECL
+void zg_trace_set_gemv(unsigned long long* d_buf) { cudaMemcpyToSymbol(c_zg_trace, &d_buf, sizeof(d_buf)); }
+
 namespace {
 
 constexpr int kMaxWarps = 8;
@@ -147,6 +150,7 @@ qgemv_kernel(const QGemvParams p) {
     // Programmatic dependent launch: the next kernel in the stream may begin (and prefetch ITS weights, which
     // nobody writes) as soon as SM resources free up.  Everything mutable (x, out, partials, counters) is
     // only touched after griddepcontrol.wait, i.e. after the previous kernel has fully completed.
+    ZG_TRACE_BEGIN(10)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ── per-warp ring of NS slots in shared memory, filled by TMA bulk copies (one per chunk of <= G
@@ -178,6 +182,7 @@ qgemv_kernel(const QGemvParams p) {
     float sm_next = __ldg(p.smax + nb_begin);      // power of two >= every scale of the column group
 
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
 
     // ── stage x'[m, k] = x[m, k] * 0.499 / (max|x| * smax) of this warp's k-range in shared memory (so that
     //    |s * x'| <= 0.499).  Non-finite activations poison the partial sums (NaN out, like the reference);
@@ -404,6 +409,7 @@ qgemv_kernel(const QGemvParams p) {
         }
         buf ^= 1;
     }
+    ZG_TRACE_MARK(2)
 }
 
 // Generic block size / ragged N: one thread per output column, exact scale lookup

@@ -101,6 +101,7 @@ struct ZgCudaCtx {
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
+    bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
     void* peer_mem = nullptr;    // this rank's slots + flags + seq (cudaMalloc, exported by cudaIpc)
@@ -135,13 +136,42 @@ size_t zg_qgemm_scratch_elems(const ZgCudaQWeight* w, uint32_t M);
 bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out, uint32_t M, uint32_t in_rs,
                      uint32_t out_rs, float* scratch, cudaStream_t st);
 
+// In-kernel timeline (debug aid, ZG tracing off by default): block 0 / thread 0 of every program kernel stamps
+// %globaltimer at entry (after the PDL wait) and exit into a device buffer: [0] = slot counter, then per slot
+// {kind << 56 | t_entry_before_wait, t_after_wait, t_exit}.  Each translation unit keeps its own __constant__ pointer.
+#define ZG_TRACE_DECL static __constant__ unsigned long long* c_zg_trace = nullptr;
+#define ZG_TRACE_BEGIN(kind)                                                                                          \
+    unsigned long long* zt_slot = nullptr;                                                                            \
+    if (c_zg_trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {                                       \
+        unsigned long long t;                                                                                         \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));                                                         \
+        const unsigned long long s = atomicAdd(c_zg_trace, 1ull);                                                     \
+        if (s < 16000) { zt_slot = c_zg_trace + 1 + 3 * s; zt_slot[0] = ((unsigned long long)(kind) << 56) | (t & 0xFFFFFFFFFFFFFFull); } \
+    }
+#define ZG_TRACE_MARK(idx)                                                                                            \
+    if (zt_slot) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); zt_slot[idx] = t; }
+void zg_trace_set_ops(unsigned long long* d_buf);
+void zg_trace_set_gemv(unsigned long long* d_buf);
+extern bool g_zg_pdl;   // ops.cu: launch op kernels with the programmatic-dependent-launch attribute
 // ops.cu : one launcher per DeviceOp tag (buffers = device pointer table)
 struct ZgDevStep { uint32_t op, is_swapped; const float* sec; };
 // one op's parameters in the device table of the batched per-head kernels (rope, slice_assign, attention)
-struct ZgBatchEntry { float* dst; const float* s0; const float* s1; const float* s2; const float* s3; uint32_t u[18]; float f; uint32_t dyn; };
+// dst2 != null (attention only): the output is ALSO stored at dst2[d2_off + r * d2_rs + qi * d2_cs] — the slice_assign that
+// copies a head's output into the concatenated buffer (device_inference.zig:695-701), absorbed into the attention launch.
+struct ZgBatchEntry { float* dst; const float* s0; const float* s1; const float* s2; const float* s3; uint32_t u[18]; float f; uint32_t dyn;
+                      float* dst2; uint32_t d2_off, d2_rs, d2_cs, _pad; };
 // one op of a chained run of small ops (ops.cu k_chain): executed by a single CTA in table order
 struct ZgChainOp { float* dst; const float* s0; const float* s1; const ZgDevStep* steps; uint32_t u[18]; float f; uint32_t dyn, kind, sync, group, _pad; };
-constexpr uint32_t kZgChainMaxOps = 256;   // ops per chain launch (the table lives in shared memory)
+constexpr uint32_t kZgChainMaxOps = 160;
+// macro ops of a chain (several consecutive DeviceOps evaluated in registers, every op's output still written):
+//   FUSED_NORM: [elementwise add] -> rmsnorm -> repeat(gamma over rows) -> elementwise mul      (llama_transformer.zig:118-125)
+//   EW_MUL:     fused_elementwise -> elementwise mul by another vector                          (SiLU(gate) * up, nn.zig:38-44)
+constexpr uint32_t kZgChainFusedNorm = 100, kZgChainEwMul = 101;
+struct ZgNormMacro { const float* a; const float* b; float* sum; float* bare; const float* gamma; float* gamma_rep; float* norm; uint32_t rows, cols; float eps; };
+struct ZgEwMulMacro { const float* src; float* mid; const float* other; float* dst; const ZgDevStep* steps; uint32_t n_steps, n; };
+bool zg_fill_chain_norm(const ZgNormMacro& m, bool sync, ZgChainOp* c);
+bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c);
+bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st);   // the same pair as one multi-CTA launch   // ops per chain launch (the table lives in shared memory)
 size_t zg_chain_work(const ZgOp& op);
 bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
 bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st);
