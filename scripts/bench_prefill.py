@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Prefill GEMM throughput on the tcgen05 path: M x K x N quantized matmul, CUDA-event timed, weights rotating
-over > L2 worth of copies.  Prints one JSON line per case (TFLOP/s = 2 M N K / t; 3xTF32 issues 3x that in MMAs)."""
+over > L2 worth of copies.  Prints one JSON line per case (TFLOP/s = 2 M N K / t; 3xBF16 issues 3x that in MMAs)."""
 import argparse, json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -41,7 +41,7 @@ for shp in args.shapes.split(","):
     flops = 2.0 * args.M * N * K
     print(json.dumps({"metric": "prefill_qgemm", "M": args.M, "K": K, "N": N, "kind": args.kind, "ms": round(ms, 4),
                       "tflops": round(flops / ms / 1e9, 1), "tok_per_s_this_linear": round(args.M / ms * 1e3),
-                      "mode": "tf32x1" if os.environ.get("ZG_GEMM_TF32X1") == "1" else "3xTF32"}))
+                      "mode": "bf16x1" if os.environ.get("ZG_GEMM_X1") == "1" else "3xBF16"}))
     for w in ws:
         w.free()
 be.close()

@@ -280,7 +280,7 @@ def test_program_rejects_bad_descriptors(cuda_backend):  # reference src/backend
     assert cuda_backend.compile_program(bad_buf) is None
 
 
-# ── prefill path: M > 8 on the tcgen05 tensor cores (3xTF32 operands, fp32 accumulate) ──────────
+# ── prefill path: M > 8 on the tcgen05 tensor cores (3xBF16 operand terms, fp32 accumulate) ──────
 @pytest.mark.parametrize("K,N", [(64, 64), (100, 160), (576, 1536), (1536, 576), (2048, 2048)])
 @pytest.mark.parametrize("M", [9, 64, 128, 200, 257])
 @pytest.mark.parametrize("kind", ["i8_f32", "q8_0", "q4_0"])
@@ -303,12 +303,12 @@ def test_qmatmul_prefill_tensor_core_path_vs_oracle(cuda_backend, K, N, M, kind)
     want = o.matmul(x, M, threads=8)
     e = rel_err(got, want)
     assert e < REL_TOL, e          # north-star tolerance
-    assert e < 5e-5, e             # 3xTF32 (hi/lo split of both operands) is fp32-class (tensor-core fp32 accumulation order)
+    assert e < 5e-5, e             # 3xBF16 (hi/lo split of both operands, 16 significant bits each; fp32 accumulation in TMEM)
     w.free()
 
 
 def test_prefill_rows_match_decode_rows(cuda_backend):
-    """Row i of an M = 40 tensor-core matmul equals the exact M = 1 matvec of that row within the TF32 envelope."""
+    """Row i of an M = 40 tensor-core matmul equals the exact M = 1 matvec of that row within the 3xBF16 envelope."""
     K, N = 576, 1536
     raw = make_q8_0_raw(K, N, 77)
     w = QuantizedWeight.from_gguf_blocks(cuda_backend, raw, 8, K, N)

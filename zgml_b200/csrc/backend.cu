@@ -80,7 +80,7 @@ struct ZgCudaProgram {
         std::vector<uint32_t> entry_ops;   // batched: the ops that own a table entry (absorbed slice_assigns do not)
         std::map<uint32_t, uint32_t> store_of;   // batched attention op -> the slice_assign absorbed into it
         uint32_t first_entry = 0, n_entries = 0;
-        bool batched = false, chain = false, ewmul = false;
+        bool batched = false, chain = false, ewmul = false, gemv_batch = false;
         ZgEwMulMacro em = {};
     };
     std::vector<Unit> units;
@@ -109,6 +109,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
     g_zg_pdl = ctx->pdl;
+    if (const char* e = getenv("ZG_CUDA_GEMV_BATCH")) { ctx->gemv_batch = atoi(e); if (ctx->gemv_batch < 1) ctx->gemv_batch = 1; if (ctx->gemv_batch > (int)kZgGemvBatch) ctx->gemv_batch = kZgGemvBatch; }
     if (const char* e = getenv("ZG_CUDA_FUSE")) ctx->fuse = (e[0] != '0');   // 0: no macro patterns (one chain / batch entry per DeviceOp)
     if (const char* e = getenv("ZG_CUDA_CHAIN")) ctx->chain_max = (size_t)atol(e);   // 0: one launch per small op
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -690,10 +691,31 @@ static bool build_schedule(ZgCudaProgram* p) {
         }
         if (has_big && !close_chain()) return false;
         std::vector<std::pair<uint64_t, size_t>> open;   // batch signature -> unit index (within this level)
+        std::vector<std::pair<const ZgCudaQWeight*, size_t>> open_mv;   // representative weight -> open matvec batch
         for (size_t k = pos; k < end; k++) {
             const ZgItem& it = items[order[k]];
             if (in_chain(it)) continue;   // chained above
             const ZgOp& op = p->ops[it.first];
+            if (it.kind == ITEM_OP && op.tag == ZG_OP_QMATMUL && op.u.qmatmul.M >= 1 && op.u.qmatmul.M <= 8 && p->ctx->gemv_batch > 1 &&
+                p->qweights[op.u.qmatmul.weight_idx]->fmt != ZG_QFMT_GENERIC) {
+                // independent matvecs of one shape / format / row count share a launch (q|k|v, gate|up)
+                const ZgCudaQWeight* w = p->qweights[op.u.qmatmul.weight_idx];
+                size_t ui = (size_t)-1;
+                for (auto& o : open_mv) {
+                    const ZgCudaQWeight* r = o.first;
+                    const ZgCudaProgram::Unit& u = p->units[o.second];
+                    if (r->fmt == w->fmt && r->K == w->K && r->N == w->N && p->ops[u.ops[0]].u.qmatmul.M == op.u.qmatmul.M &&
+                        u.ops.size() < (size_t)p->ctx->gemv_batch) { ui = o.second; break; }
+                }
+                if (ui == (size_t)-1) {
+                    ZgCudaProgram::Unit u; u.gemv_batch = true;
+                    p->units.push_back(u);
+                    ui = p->units.size() - 1;
+                    open_mv.push_back({w, ui});
+                }
+                p->units[ui].ops.push_back(it.first);
+                continue;
+            }
             if (it.kind == ITEM_EWMUL) {   // fused_elementwise + mul as one multi-CTA launch
                 ZgCudaProgram::Unit u; u.ops.push_back(it.first); u.ops.push_back(it.first + 1);
                 u.ewmul = true; u.em = ewmul_of[order[k]];
@@ -777,6 +799,22 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, p->ctx->peer, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
+    if (u.gemv_batch && u.ops.size() > 1) {
+        const ZgCudaQWeight* w[kZgGemvBatch]; const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];
+        uint32_t irs[kZgGemvBatch], ors[kZgGemvBatch]; ZgGemvWs view[kZgGemvBatch];
+        const uint32_t cnt = (uint32_t)u.ops.size();
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t i = u.ops[k];
+            const auto& q = p->ops[i].u.qmatmul;
+            w[k] = p->qweights[q.weight_idx];
+            xin[k] = p->buffers[q.input] + q.input_offset; xout[k] = p->buffers[q.dst] + q.dst_offset;
+            irs[k] = q.input_row_stride; ors[k] = q.dst_row_stride;
+            view[k] = p->ws;
+            if (view[k].partials) { view[k].partials += p->ws_part_off[i]; view[k].partials_elems -= p->ws_part_off[i]; }
+            if (view[k].counters) { view[k].counters += p->ws_cnt_off[i]; view[k].counters_n -= p->ws_cnt_off[i]; }
+        }
+        return zg_qgemv_launch_batch(p->ctx, cnt, w, xin, xout, p->ops[u.ops[0]].u.qmatmul.M, irs, ors, view, st);
+    }
     if (!u.batched) return launch_one(p, u.ops[0], st);
     return zg_launch_batch(p->ops[u.entry_ops[0]], p->d_batch + u.first_entry, u.n_entries, p->d_dyn, st);
 }

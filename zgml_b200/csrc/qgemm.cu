@@ -3,22 +3,22 @@
 // zgml's W8·f32 algorithm (QuantizedWeight.matmul, src/quant.zig:475-578; DeviceOp.qmatmul,
 // src/backend/reference.zig:499-566) as a dense contraction on the 5th-generation tensor cores:
 //
-//   * tcgen05.mma.cta_group::1.kind::tf32, 128 x 256 output tile per CTA, fp32 accumulators in TMEM
-//     (128 lanes x 256 columns), issued by one thread; K advances 32 per pipeline stage (4 MMAs of K = 8).
-//   * A = activations: split once into TF32 terms x = x_hi + x_lo (each round-to-nearest, so the tensor core's
-//     operand truncation is exact) in a dense scratch, then TMA (cp.async.bulk.tensor.2d, 128B swizzle)
-//     straight into the canonical K-major shared-memory layout.
+//   * tcgen05.mma.cta_group::1.kind::f16 on BF16 operands, 128 x 256 output tile per CTA, fp32 accumulators in TMEM
+//     (128 lanes x 256 columns), issued by one thread; K advances 64 per pipeline stage (4 MMAs of K = 16 per term).
+//   * A = activations: split once into two BF16 terms x = x_hi + x_lo (each round-to-nearest) in a dense scratch,
+//     then TMA (cp.async.bulk.tensor.2d, 128B swizzle) straight into the canonical K-major shared-memory layout.
 //   * B = weights: eight dequantize warps read the packed records (zg_internal.cuh) with 128-bit loads, form
-//     w = f32(q) * s exactly like dequantizeTo (src/quant.zig:594-618), round to TF32 and store 16-byte
-//     chunks into the same swizzled K-major layout (a record's 16 bytes per lane are four k-runs of four
-//     weights = four chunks).  Weights are dequantized once per 128 activation rows, in shared memory only.
-//   * 4-stage mbarrier pipeline: TMA warp / dequant warps -> MMA warp -> (tcgen05.commit) -> stage free;
-//     the dequant warps turn into the epilogue (tcgen05.ld 32x32b -> global stores) at the end.
+//     w = f32(q) * s exactly like dequantizeTo (src/quant.zig:594-618), split w = w_hi + w_lo in BF16 and store
+//     8-byte runs (four consecutive k) into the same swizzled K-major layout, two records (2 x 32 k) per stage.
+//     Weights are dequantized once per 128 activation rows, in shared memory only.
+//   * 2-stage mbarrier pipeline (96 KB per stage: hi and lo tiles of A and B): TMA warp / dequant warps -> MMA warp
+//     -> (tcgen05.commit) -> stage free; the dequant warps turn into the epilogue (tcgen05.ld 32x32b -> global stores).
 //
-// Numerics: "3xTF32" — both operands are split hi + lo (22 significant bits), D += hi*hi + hi*lo + lo*hi with
-// fp32 accumulation in TMEM: ~1e-6 relative on outputs (fp32-class; a single rounded term would give ~4e-4 and
-// does not survive 200+ chained linears inside the 1e-3 logit budget).  ZG_GEMM_TF32X1=1 selects the single-term
-// mode (3x fewer MMAs) for throughput experiments.  The exact fixed-point matvec (qgemv.cu) stays the path for M <= 8.
+// Numerics: "3xBF16" — both operands are split hi + lo (16 significant bits, residual 2^-18), D += hi*hi + hi*lo +
+// lo*hi with fp32 accumulation in TMEM: ~5e-6 relative on outputs (the dropped lo*lo and the residuals are 2^-17 per
+// product and average out over K), far inside the 1e-3 budget and twice the tensor throughput of the TF32 form
+// (BF16 MMAs run at the full dense rate).  A single BF16 term (4e-3) would not survive 200+ chained linears.
+// The exact fixed-point matvec (qgemv.cu) stays the path for M <= 8.
 #include "zg_internal.cuh"
 
 #include <cuda.h>
@@ -26,12 +26,13 @@
 
 namespace {
 
-constexpr uint32_t BM = 128, BN = 256, BK = 32;
-constexpr uint32_t kTileA = BM * BK * 4, kTileB = BN * BK * 4;      // one TF32 operand tile: 16 KB (A), 32 KB (B)
-constexpr uint32_t kGemmThreads = 320;                             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: dequant + epilogue
+constexpr uint32_t BM = 128, BN = 256, BK = 64;                     // BK bf16 = one 128-byte swizzle row = two records of 32 k
+constexpr uint32_t kTileA = BM * BK * 2, kTileB = BN * BK * 2;      // one BF16 operand tile: 16 KB (A), 32 KB (B)
+constexpr uint32_t kDqWarps = 16;                                  // dequantize warps: enough resident warps to hide ALU latency (8 left the MMA waiting)
+constexpr uint32_t kGemmThreads = 64 + 32 * kDqWarps;              // warp 0: TMA, warp 1: MMA + TMEM, warps 2-17: dequant + epilogue
 constexpr uint32_t kTmemCols = 256;
-// NT = TF32 terms per operand.  NT = 2 (default): x = x_hi + x_lo, w = w_hi + w_lo, D += hi*hi + hi*lo + lo*hi
-// ("3xTF32": ~1e-6 relative, fp32-class); NT = 1: one rounded term each (~4e-4 relative, 3x fewer MMAs).
+// NT = BF16 terms per operand.  NT = 2 (default): x = x_hi + x_lo, w = w_hi + w_lo, D += hi*hi + hi*lo + lo*hi
+// ("3xBF16": ~5e-6 relative); NT = 1: one rounded term each (~4e-3 relative, 3x fewer MMAs; throughput experiments only).
 __host__ __device__ constexpr uint32_t stages_of(int NT) { return NT == 1 ? 4u : 2u; }
 __host__ __device__ constexpr uint32_t smem_of(int NT) { return stages_of(NT) * NT * (kTileA + kTileB) + 1024 /* alignment slack */ + 256 /* barriers */; }
 
@@ -66,11 +67,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float v) {
+// {lo16, hi16} = {bf16_rn(a), bf16_rn(b)}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+__device__ __forceinline__ float bf16_lo_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_f32(uint32_t packed) { return __uint_as_float(packed & 0xFFFF0000u); }
 // K-major, 128-byte swizzle, 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major layouts.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -82,21 +86,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     return d;
 }
 
-// hi = rn_tf32(x), lo = rn_tf32(x - hi) into dense [Mp][Kp] planes (plane 1 only when NT == 2); zero padding
-__global__ void k_round_tf32(const float* __restrict__ x, uint32_t x_rs, float* __restrict__ xr, uint32_t xr_rs,
-                             uint32_t M, uint32_t K, size_t plane_elems, int NT) {
+// hi = bf16_rn(x), lo = bf16_rn(x - hi) into dense [Mp][Kp] bf16 planes (plane 1 only when NT == 2); zero padding.
+// Two k per thread (one packed 32-bit store per plane).
+__global__ void k_split_bf16(const float* __restrict__ x, uint32_t x_rs, uint32_t* __restrict__ xr, uint32_t kp2,
+                             uint32_t M, uint32_t K, size_t plane_words, int NT) {
     const uint32_t m = blockIdx.y;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < xr_rs; k += gridDim.x * blockDim.x) {
-        const float v = (m < M && k < K) ? x[(size_t)m * x_rs + k] : 0.0f;
-        const float hi = __uint_as_float(to_tf32(v));
-        xr[(size_t)m * xr_rs + k] = hi;
-        if (NT == 2) xr[plane_elems + (size_t)m * xr_rs + k] = __uint_as_float(to_tf32(v - hi));
+    for (uint32_t k2 = blockIdx.x * blockDim.x + threadIdx.x; k2 < kp2; k2 += gridDim.x * blockDim.x) {
+        const uint32_t k = 2 * k2;
+        const float a = (m < M && k < K) ? x[(size_t)m * x_rs + k] : 0.0f;
+        const float b = (m < M && k + 1 < K) ? x[(size_t)m * x_rs + k + 1] : 0.0f;
+        const uint32_t hi = pack_bf16x2(a, b);
+        xr[(size_t)m * kp2 + k2] = hi;
+        if (NT == 2) xr[plane_words + (size_t)m * kp2 + k2] = pack_bf16x2(a - bf16_lo_f32(hi), b - bf16_hi_f32(hi));
     }
 }
 
 template <int FMT, int NT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo, const QGemmParams p) {
+qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo, const QGemmParams p) {
     constexpr uint32_t kStages = stages_of(NT);
     constexpr uint32_t kStageA = NT * kTileA, kStageB = NT * kTileB;   // [hi | lo] tiles
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
@@ -114,12 +121,13 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_n = blockIdx.x, tile_m = blockIdx.y;
-    const uint32_t n_k = p.n_kc;
+    const uint32_t n_rec = p.n_kc;                 // records (32 k each) per column group
+    const uint32_t n_k = (n_rec + 1) / 2;          // pipeline stages of 64 k
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kStages; s++) {
             mbar_init(full_a + 8 * s, 1);
-            mbar_init(full_b + 8 * s, 8);      // one arrive per dequant warp
+            mbar_init(full_b + 8 * s, kDqWarps);   // one arrive per dequant warp
             mbar_init(empty + 8 * s, 1);       // tcgen05.commit
         }
         mbar_init(tmem_full, 1);
@@ -148,8 +156,8 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else if (warp == 1) {
         // ── MMA issuer ──
-        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+        // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
         for (uint32_t kt = 0; kt < n_k; kt++) {
             const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
             mbar_wait(full_a + 8 * s, ph);
@@ -157,7 +165,7 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
 #pragma unroll
-                for (uint32_t k = 0; k < BK / 8; k++) {
+                for (uint32_t k = 0; k < BK / 16; k++) {   // one MMA = 16 bf16 of k = 32 bytes along the swizzled row
                     // term 0: hi*hi; NT == 2 adds hi*lo and lo*hi (lo*lo is below fp32 resolution)
 #pragma unroll
                     for (int term = 0; term < (NT == 2 ? 3 : 1); term++) {
@@ -167,7 +175,7 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t"
                             "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                             ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
                     }
                 }
@@ -179,19 +187,22 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
         }
     } else {
-        // ── dequantize warps: warp dw owns column group dw (one record = 32 columns x 32 k) of the CTA tile per k-step ──
-        const uint32_t dw = warp - 2;                    // 0..7
+        // ── dequantize warps: warp (dw, h) owns column group dw (32 columns) and record half h of every stage
+        //    (one record = 32 columns x 32 k; a stage = 64 k = records 2 kt and 2 kt + 1) ──
+        const uint32_t dwi = warp - 2;                   // 0..15
+        const uint32_t dw = dwi & 7, h = dwi >> 3;
         const uint32_t g = lane >> 2, t = lane & 3;
         const uint32_t nb = tile_n * (BN / 32) + dw;
         const bool nb_ok = nb < p.n_nb;
         const uint8_t* rec = p.recs + (size_t)(nb_ok ? nb : 0) * p.n_kc * RB;
-        // register ring: the records of the next kPf k-steps are in flight while the current one is converted
-        constexpr int kPf = 3;
+        // register ring: the records of the next kPf stages are in flight while the current one is converted
+        constexpr int kPf = 2;
         uint4 rq[kPf], rq1[kPf], rs0[kPf], rs1[kPf];
-        auto load_rec = [&](int slot, uint32_t kt) {
+        auto load_rec = [&](int slot, uint32_t kt) {   // record 2 kt + h; past the end (odd record count): zeros
+            const uint32_t ri = 2 * kt + h;
             rq[slot] = make_uint4(0, 0, 0, 0); rq1[slot] = rq[slot]; rs0[slot] = rq[slot]; rs1[slot] = rq[slot];
-            if (nb_ok && kt < n_k) {
-                const uint8_t* r = rec + (size_t)kt * RB;
+            if (nb_ok && ri < n_rec) {
+                const uint8_t* r = rec + (size_t)ri * RB;
                 rq[slot] = __ldg(reinterpret_cast<const uint4*>(r + lane * 16));
                 if constexpr (!kI4) rq1[slot] = __ldg(reinterpret_cast<const uint4*>(r + 512 + lane * 16));
                 rs0[slot] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB));
@@ -245,19 +256,18 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     for (int b = 0; b < 4; b++) qf[b] = __uint_as_float(__byte_perm(nib, 0x4B000000u, 0x7650 + b)) - 8388616.0f;
                 }
                 const uint32_t n = row_lo + 8 * (r & 1);
-                const uint32_t chunk = t + 4 * (r >> 1);                        // 16-byte chunk = four consecutive k
+                // four consecutive k starting at 32 h + 16 (r >> 1) + 4 t  ->  8 bytes at byte 2 k of the 128-byte row
+                const uint32_t chunk = 4 * h + 2 * (r >> 1) + (t >> 1);          // 16-byte chunk = eight consecutive k
                 float wv[4];
 #pragma unroll
                 for (int b = 0; b < 4; b++) wv[b] = qf[b] * sc[4 * (r >> 1) + b];   // f32(q) * scale, src/quant.zig:612-615
-                uint4 o;
-                o.x = to_tf32(wv[0]); o.y = to_tf32(wv[1]); o.z = to_tf32(wv[2]); o.w = to_tf32(wv[3]);
-                const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+                const uint32_t h0 = pack_bf16x2(wv[0], wv[1]), h1 = pack_bf16x2(wv[2], wv[3]);
+                const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4) + ((t & 1) << 3);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(h0), "r"(h1) : "memory");
                 if constexpr (NT == 2) {
-                    uint4 l;
-                    l.x = to_tf32(wv[0] - __uint_as_float(o.x)); l.y = to_tf32(wv[1] - __uint_as_float(o.y));
-                    l.z = to_tf32(wv[2] - __uint_as_float(o.z)); l.w = to_tf32(wv[3] - __uint_as_float(o.w));
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr + kTileB), "r"(l.x), "r"(l.y), "r"(l.z), "r"(l.w) : "memory");
+                    const uint32_t l0 = pack_bf16x2(wv[0] - bf16_lo_f32(h0), wv[1] - bf16_hi_f32(h0));
+                    const uint32_t l1 = pack_bf16x2(wv[2] - bf16_lo_f32(h1), wv[3] - bf16_hi_f32(h1));
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + kTileB), "r"(l0), "r"(l1) : "memory");
                 }
             }
             }
@@ -271,9 +281,9 @@ qgemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t quarter = warp & 3;
         const uint32_t m = tile_m * BM + quarter * 32 + lane;
-        const uint32_t c_begin = (dw >> 2) * (BN / 2);   // the two warps of a TMEM lane quarter split the columns
+        const uint32_t c_begin = (dwi >> 2) * (BN / 4);  // the four warps of a TMEM lane quarter split the columns
 #pragma unroll 1
-        for (uint32_t c0 = c_begin; c0 < c_begin + BN / 2; c0 += 32) {
+        for (uint32_t c0 = c_begin; c0 < c_begin + BN / 4; c0 += 32) {
             uint32_t v[32];
             const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + c0;
             asm volatile(
@@ -319,7 +329,7 @@ bool get_encode() {
 template <int FMT, int NT>
 bool launch_gemm(const CUtensorMap& map, const CUtensorMap& map_lo, const QGemmParams& p, cudaStream_t st) {
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    qgemm_tf32_kernel<FMT, NT><<<grid, kGemmThreads, smem_of(NT), st>>>(map, map_lo, p);
+    qgemm_bf16_kernel<FMT, NT><<<grid, kGemmThreads, smem_of(NT), st>>>(map, map_lo, p);
     ZG_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { zg_set_error("qgemm launch failed: %s", cudaGetErrorString(e)); return false; }
@@ -328,43 +338,45 @@ bool launch_gemm(const CUtensorMap& map, const CUtensorMap& map_lo, const QGemmP
 
 template <int FMT, int NT>
 bool set_attr() {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_tf32_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(NT));
+    cudaError_t e = cudaFuncSetAttribute(qgemm_bf16_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(NT));
     if (e != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemm) failed: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 
-int g_terms = 2;   // ZG_GEMM_TF32X1=1 selects the single-term (fast, ~4e-4) mode
+int g_terms = 2;   // ZG_GEMM_X1=1 selects the single-term mode (throughput experiments only: 4e-3 relative)
 
 } // namespace
 
 bool zg_qgemm_init(ZgCudaCtx*) {
-    if (const char* e = getenv("ZG_GEMM_TF32X1")) g_terms = (e[0] == '1') ? 1 : 2;
+    if (const char* e = getenv("ZG_GEMM_X1")) g_terms = (e[0] == '1') ? 1 : 2;
     return set_attr<ZG_QFMT_I8_F32, 1>() && set_attr<ZG_QFMT_I8_F16, 1>() && set_attr<ZG_QFMT_I4_F16, 1>() &&
            set_attr<ZG_QFMT_I8_F32, 2>() && set_attr<ZG_QFMT_I8_F16, 2>() && set_attr<ZG_QFMT_I4_F16, 2>() && get_encode();
 }
 
-// TF32 hi (and lo) planes of the activations the GEMM's TMA reads: 2 x [round_up(M, 128)][n_kc * 32] floats.
+// BF16 hi and lo planes of the activations the GEMM's TMA reads: 2 x [round_up(M, 128)][round_up(K, 64)] bf16,
+// counted in f32 elements (the workspace unit).
 size_t zg_qgemm_scratch_elems(const ZgCudaQWeight* w, uint32_t M) {
     if (w->fmt == ZG_QFMT_GENERIC || M <= 8) return 0;
-    return 2 * (size_t)((M + BM - 1) / BM * BM) * ((size_t)w->n_kc * ZG_KR);
+    return (size_t)((M + BM - 1) / BM * BM) * ((size_t)(w->n_kc + 1) / 2 * BK);
 }
 
 bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out, uint32_t M, uint32_t in_rs,
                      uint32_t out_rs, float* scratch, cudaStream_t st) {
     (void)ctx;
     if (!get_encode()) return false;
-    const uint32_t Kp = w->n_kc * ZG_KR, Mp = (M + BM - 1) / BM * BM;
-    const size_t plane = (size_t)Mp * Kp;
+    const uint32_t Kp = (w->n_kc + 1) / 2 * BK, Mp = (M + BM - 1) / BM * BM;
+    const size_t plane_words = (size_t)Mp * (Kp / 2);   // one bf16 plane in 32-bit words
     const int NT = g_terms;
-    k_round_tf32<<<dim3((Kp + 255) / 256, Mp), 256, 0, st>>>(d_in, in_rs, scratch, Kp, M, (uint32_t)w->K, plane, NT);
+    uint32_t* planes = reinterpret_cast<uint32_t*>(scratch);
+    k_split_bf16<<<dim3((Kp / 2 + 255) / 256, Mp), 256, 0, st>>>(d_in, in_rs, planes, Kp / 2, M, (uint32_t)w->K, plane_words, NT);
     ZG_COUNT_LAUNCH();
     CUtensorMap map[2];
     const cuuint64_t gdim[2] = {Kp, Mp};
-    const cuuint64_t gstride[1] = {(cuuint64_t)Kp * 4};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
     const cuuint32_t box[2] = {BK, BM};
     const cuuint32_t estr[2] = {1, 1};
     for (int i = 0; i < 2; i++) {
-        CUresult r = g_encode(&map[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, scratch + (size_t)i * plane, gdim, gstride, box, estr,
+        CUresult r = g_encode(&map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes + (size_t)i * plane_words, gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { zg_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }

@@ -32,6 +32,7 @@
 #include "zg_internal.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 
 ZG_TRACE_DECL
@@ -57,6 +58,10 @@ struct QGemvParams {
     float* partials;
     uint32_t* counters;
 };
+
+// Up to kZgGemvBatch independent matvecs of one shape / format share a launch (blockIdx.y selects the op): q|k|v,
+// gate|up, or the copies of a microbenchmark.  The parameter block stays in the constant bank.
+struct QGemvBatch { QGemvParams p[kZgGemvBatch]; };
 
 // D(16x8, s32) += A(16x32: weights) * B(32x8, u8: digits of x*s)
 __device__ __forceinline__ void imma_s8u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -110,7 +115,8 @@ constexpr uint32_t kPlaneRow = 144;   // bytes per (record, activation row) digi
 // XR: activation rows staged per warp (1 for the decode matvec M == 1, else 2*MP).
 template <int FMT, int MP, int XR>
 __global__ void __launch_bounds__(kThreads, MP == 1 ? 3 : (MP == 2 ? 2 : 1))
-qgemv_kernel(const QGemvParams p) {
+qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
+    const QGemvParams& p = bt.p[blockIdx.y];
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
     constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
     constexpr int MR = 2 * MP;
@@ -432,9 +438,9 @@ __global__ void qmatmul_generic_kernel(const int8_t* __restrict__ data, const fl
 }
 
 template <int FMT, int MP, int XR>
-bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
+bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan.grid);
+    cfg.gridDim = dim3(plan.grid, count);
     cfg.blockDim = dim3(plan.threads);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = st;
@@ -453,11 +459,11 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, 
 }
 
 template <int FMT>
-bool launch_fmt(const ZgGemvPlan& plan, const QGemvParams& p, cudaStream_t st, bool pdl) {
+bool launch_fmt(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cudaStream_t st, bool pdl) {
     switch (plan.mp) {
-        case 1: return p.M == 1 ? launch_fast<FMT, 1, 1>(plan, p, st, pdl) : launch_fast<FMT, 1, 2>(plan, p, st, pdl);
-        case 2: return launch_fast<FMT, 2, 4>(plan, p, st, pdl);
-        case 4: return launch_fast<FMT, 4, 8>(plan, p, st, pdl);
+        case 1: return p.p[0].M == 1 ? launch_fast<FMT, 1, 1>(plan, p, count, st, pdl) : launch_fast<FMT, 1, 2>(plan, p, count, st, pdl);
+        case 2: return launch_fast<FMT, 2, 4>(plan, p, count, st, pdl);
+        case 4: return launch_fast<FMT, 4, 8>(plan, p, count, st, pdl);
         default: zg_set_error("qmatmul: bad plan (row pairs %u)", plan.mp); return false;
     }
 }
@@ -495,10 +501,12 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     pl.P = P; pl.S = S;
     const uint32_t len_max = (w->n_kc + S - 1) / S;
     pl.lcap = (len_max + warps - 1) / warps;
-    // weight ring per warp: NS slots of G records (one TMA bulk copy each), ~6.5 KB per warp
+    // weight ring per warp: NS slots of G records (one TMA bulk copy each), ~4.5 KB per warp
     const uint32_t rb = w->rec_bytes;
     pl.G = w->fmt == ZG_QFMT_I4_F16 ? 4 : 2;   // compile-time constant of the kernel
-    pl.NS = ctx->tune_u ? (uint32_t)ctx->tune_u : 3;
+    // 2 slots keep a decode CTA under 70 KB of shared memory: THREE CTAs per SM stay resident (the limit the 80 registers
+    // allow), which is worth more than a deeper ring - short-lived CTAs are latency-bound, bytes in flight come from CTA count
+    pl.NS = ctx->tune_u ? (uint32_t)ctx->tune_u : 2;
     pl.xs_stride = pl.lcap * ZG_KR;
     const uint32_t xrows = rows == 1 ? 1 : 2 * pl.mp;
     const uint32_t chunks = ((pl.lcap + pl.G - 1) / pl.G) * P;   // chunks a warp ever requests
@@ -561,32 +569,52 @@ bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in
         if (!ws || ws->gemm_scratch_elems < need) { zg_set_error("internal: GEMM scratch too small (%zu needed)", need); return false; }
         return zg_qgemm_launch(ctx, w, d_in, d_out, M, in_rs, out_rs, ws->gemm_scratch, st);
     }
-    size_t pe = 0, nc = 0;
-    zg_qgemv_ws_need(ctx, w, M, &pe, &nc);
-    if (pe && (!ws || ws->partials_elems < pe || ws->counters_n < nc)) {
-        zg_set_error("internal: split workspace too small (%zu/%zu needed)", pe, nc);
-        return false;
-    }
-    for (uint32_t m0 = 0; m0 < M; m0 += 8) {  // larger batches: 8 rows per pass (prefill uses the GEMM path)
+    if (M <= 8) return zg_qgemv_launch_batch(ctx, 1, &w, &d_in, &d_out, M, &in_rs, &out_rs, ws, st);
+    // M > 8 in the generic-format-free matvec path never happens (the GEMM takes it); kept for direct callers
+    for (uint32_t m0 = 0; m0 < M; m0 += 8) {
         const uint32_t rows = (M - m0) > 8 ? 8 : (M - m0);
-        ZgGemvPlan plan = zg_qgemv_plan(ctx, w, rows);
-        QGemvParams p;
-        p.recs = w->recs; p.smax = w->smax;
-        p.n_kc = w->n_kc; p.n_nb = w->n_nb;
-        p.K = (uint32_t)w->K; p.N = (uint32_t)w->N; p.M = rows;
-        p.x = d_in + (size_t)m0 * in_rs; p.x_rs = in_rs;
-        p.xs_stride = plan.xs_stride;
-        p.out = d_out + (size_t)m0 * out_rs; p.out_rs = out_rs;
-        p.P = plan.P; p.S = plan.S; p.NS = plan.NS;
-        p.partials = ws ? ws->partials : nullptr; p.counters = ws ? ws->counters : nullptr;
-        bool ok;
-        switch (w->fmt) {
-            case ZG_QFMT_I8_F32: ok = launch_fmt<ZG_QFMT_I8_F32>(plan, p, st, ctx->pdl); break;
-            case ZG_QFMT_I8_F16: ok = launch_fmt<ZG_QFMT_I8_F16>(plan, p, st, ctx->pdl); break;
-            case ZG_QFMT_I4_F16: ok = launch_fmt<ZG_QFMT_I4_F16>(plan, p, st, ctx->pdl); break;
-            default: zg_set_error("qmatmul: unknown weight format %d", w->fmt); ok = false;
-        }
-        if (!ok) return false;
+        const float* xin = d_in + (size_t)m0 * in_rs;
+        float* xout = d_out + (size_t)m0 * out_rs;
+        if (!zg_qgemv_launch_batch(ctx, 1, &w, &xin, &xout, rows, &in_rs, &out_rs, ws, st)) return false;
     }
     return true;
+}
+
+// `count` (<= kZgGemvBatch) matvecs with identical weight shape, format and row count M <= 8 in one launch.
+bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
+                           float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
+                           const ZgGemvWs* ws, cudaStream_t st) {
+    if (count == 0 || M == 0) return true;
+    if (count > kZgGemvBatch || M > 8) { zg_set_error("internal: bad matvec batch (%u ops, %u rows)", count, M); return false; }
+    const ZgCudaQWeight* w0 = ws_w[0];
+    const ZgGemvWs none[kZgGemvBatch] = {};
+    if (!ws) ws = none;
+    ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M);
+    QGemvBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    for (uint32_t i = 0; i < count; i++) {
+        const ZgCudaQWeight* w = ws_w[i];
+        if (w->fmt != w0->fmt || w->K != w0->K || w->N != w0->N || w->fmt == ZG_QFMT_GENERIC) { zg_set_error("internal: mixed matvec batch"); return false; }
+        size_t pe = 0, nc = 0;
+        zg_qgemv_ws_need(ctx, w, M, &pe, &nc);
+        if (pe && (ws[i].partials_elems < pe || ws[i].counters_n < nc)) {
+            zg_set_error("internal: split workspace too small (%zu/%zu needed)", pe, nc);
+            return false;
+        }
+        QGemvParams& p = bt.p[i];
+        p.recs = w->recs; p.smax = w->smax;
+        p.n_kc = w->n_kc; p.n_nb = w->n_nb;
+        p.K = (uint32_t)w->K; p.N = (uint32_t)w->N; p.M = M;
+        p.x = d_in[i]; p.x_rs = in_rs[i] ? in_rs[i] : (uint32_t)w->K;
+        p.xs_stride = plan.xs_stride;
+        p.out = d_out[i]; p.out_rs = out_rs[i] ? out_rs[i] : (uint32_t)w->N;
+        p.P = plan.P; p.S = plan.S; p.NS = plan.NS;
+        p.partials = ws[i].partials; p.counters = ws[i].counters;
+    }
+    switch (w0->fmt) {
+        case ZG_QFMT_I8_F32: return launch_fmt<ZG_QFMT_I8_F32>(plan, bt, count, st, ctx->pdl);
+        case ZG_QFMT_I8_F16: return launch_fmt<ZG_QFMT_I8_F16>(plan, bt, count, st, ctx->pdl);
+        case ZG_QFMT_I4_F16: return launch_fmt<ZG_QFMT_I4_F16>(plan, bt, count, st, ctx->pdl);
+        default: zg_set_error("qmatmul: unknown weight format %d", w0->fmt); return false;
+    }
 }

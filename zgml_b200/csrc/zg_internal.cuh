@@ -101,6 +101,7 @@ struct ZgCudaCtx {
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
+    int gemv_batch = 8;          // independent same-shape matvecs of a dependency level per launch (ZG_CUDA_GEMV_BATCH, 1 = off)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
@@ -129,6 +130,10 @@ void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, 
                       size_t* counters);
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
                        uint32_t M, uint32_t in_rs, uint32_t out_rs, const ZgGemvWs* ws, cudaStream_t st);
+constexpr uint32_t kZgGemvBatch = 8;   // independent same-shape matvecs of one dependency level per launch
+bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* w, const float* const* d_in,
+                           float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
+                           const ZgGemvWs* ws, cudaStream_t st);   // ws: one workspace view per op
 bool zg_qgemv_init(ZgCudaCtx* ctx);
 // qgemm.cu : M > 8 on tcgen05 tensor cores
 bool zg_qgemm_init(ZgCudaCtx* ctx);
