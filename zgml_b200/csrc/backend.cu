@@ -81,6 +81,7 @@ struct ZgCudaProgram {
         std::map<uint32_t, uint32_t> store_of;   // batched attention op -> the slice_assign absorbed into it
         uint32_t first_entry = 0, n_entries = 0;
         bool batched = false, chain = false, ewmul = false, gemv_batch = false;
+        uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
         ZgEwMulMacro em = {};
     };
     std::vector<Unit> units;
@@ -89,6 +90,8 @@ struct ZgCudaProgram {
     std::vector<uint32_t> peer_entry;    // index into d_chain of a peer-memory all-reduce's standalone entry (UINT32_MAX: NCCL)
     ZgBatchEntry* d_batch = nullptr;
     ZgChainOp* d_chain = nullptr;
+    float* d_attn_part = nullptr;      // split-KV partial states, one slice per attention unit
+    uint32_t* d_attn_cnt = nullptr;    // arrival counters (self re-arming)
     bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
 };
 
@@ -110,6 +113,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
     g_zg_pdl = ctx->pdl;
     if (const char* e = getenv("ZG_CUDA_GEMV_BATCH")) { ctx->gemv_batch = atoi(e); if (ctx->gemv_batch < 1) ctx->gemv_batch = 1; if (ctx->gemv_batch > (int)kZgGemvBatch) ctx->gemv_batch = kZgGemvBatch; }
+    if (const char* e = getenv("ZG_CUDA_ATTN_SPLIT")) ctx->attn_split = (e[0] != '0');
     if (const char* e = getenv("ZG_CUDA_FUSE")) ctx->fuse = (e[0] != '0');   // 0: no macro patterns (one chain / batch entry per DeviceOp)
     if (const char* e = getenv("ZG_CUDA_CHAIN")) ctx->chain_max = (size_t)atol(e);   // 0: one launch per small op
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -206,7 +210,7 @@ static void free_program(ZgCudaProgram* p) {
     for (float* b : p->buffers) cudaFree(b);
     for (size_t i = 0; i < p->qweights.size(); i++)
         if (p->qweight_owned[i]) zg_cuda_qweight_free(p->ctx, p->qweights[i]);
-    cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch); cudaFree(p->d_chain);
+    cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch); cudaFree(p->d_chain); cudaFree(p->d_attn_part); cudaFree(p->d_attn_cnt);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -754,6 +758,26 @@ static bool build_schedule(ZgCudaProgram* p) {
             entries.push_back(e);
         }
     }
+    // split-KV scratch of the decode attention units
+    size_t part_total = 0, cnt_total = 0;
+    for (auto& u : p->units) {
+        if (!u.batched || u.entry_ops.empty() || p->ops[u.entry_ops[0]].tag != ZG_OP_ATTENTION || !p->ctx->attn_split) continue;
+        const ZgOp& a0 = p->ops[u.entry_ops[0]];
+        size_t kmin = (size_t)-1;
+        for (uint32_t i : u.entry_ops) kmin = std::min(kmin, p->buffer_elems[p->ops[i].u.attention.k] - std::min<size_t>(p->buffer_elems[p->ops[i].u.attention.k], p->ops[i].u.attention.k_off) + a0.u.attention.k_off);
+        u.attn_splits = zg_attention_splits(a0, kmin, u.n_entries, p->ctx->sm_count);
+        if (u.attn_splits <= 1) { u.attn_splits = 1; continue; }
+        u.attn_part_off = part_total; u.attn_cnt_off = cnt_total;
+        part_total += zg_attention_part_elems(a0, u.n_entries, u.attn_splits);
+        cnt_total += (size_t)u.n_entries * a0.u.attention.seq_q;
+    }
+    cudaFree(p->d_attn_part); p->d_attn_part = nullptr;
+    cudaFree(p->d_attn_cnt); p->d_attn_cnt = nullptr;
+    if (part_total) {
+        ZG_CUDA_OK(cudaMalloc(&p->d_attn_part, part_total * sizeof(float)));
+        ZG_CUDA_OK(cudaMalloc(&p->d_attn_cnt, cnt_total * sizeof(uint32_t)));
+        ZG_CUDA_OK(cudaMemset(p->d_attn_cnt, 0, cnt_total * sizeof(uint32_t)));
+    }
     // single-op launches (profiling / eager per-op mode) of batched kinds need their own plain entries
     p->single_entry.assign(n, 0);
     for (size_t i = 0; i < n; i++) {
@@ -816,6 +840,9 @@ static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStre
         return zg_qgemv_launch_batch(p->ctx, cnt, w, xin, xout, p->ops[u.ops[0]].u.qmatmul.M, irs, ors, view, st);
     }
     if (!u.batched) return launch_one(p, u.ops[0], st);
+    if (u.attn_splits > 1)
+        return zg_launch_batch(p->ops[u.entry_ops[0]], p->d_batch + u.first_entry, u.n_entries, p->d_dyn, st,
+                               p->d_attn_part + u.attn_part_off, p->d_attn_cnt + u.attn_cnt_off, u.attn_splits);
     return zg_launch_batch(p->ops[u.entry_ops[0]], p->d_batch + u.first_entry, u.n_entries, p->d_dyn, st);
 }
 

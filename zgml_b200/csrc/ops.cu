@@ -385,18 +385,24 @@ k_attention(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d
 constexpr int kAttnFastWarps = 16;
 template <int NI>
 __global__ void __launch_bounds__(kAttnFastWarps * 32)
-k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn, float* __restrict__ part,
+                 uint32_t* __restrict__ cnt, const uint32_t max_splits) {
     ZG_TRACE_BEGIN(7)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const ZgBatchEntry e = tab[blockIdx.y];
+    // the launch provides max_splits CTAs per head; a short context uses fewer (>= 128 positions each), the rest leave
+    const uint32_t splits = min(max_splits, max(1u, (d_dyn[e.dyn] + 127u) / 128u));
+    if (blockIdx.z >= splits) return;
     {   // While the producer kernels still run: pull this head's K and V rows into L2 (one 128-byte line per prefetch).
         // The op table and seq_kv are fixed before the step starts; the cache rows are only read after the wait (the
         // row written by this step just gets prefetched a little early — L2 is the point of coherence).
         const uint32_t seq_kv0 = d_dyn[e.dyn], dhb = e.u[1] * 4;
         const char* kb = reinterpret_cast<const char*>(e.s1 + e.u[4]);
         const char* vb0 = reinterpret_cast<const char*>(e.s2 + e.u[5]);
+        const uint32_t ch0 = ((seq_kv0 + splits - 1) / splits + 31) & ~31u;
+        const uint32_t p_lo = blockIdx.z * ch0, p_hi = min(p_lo + ch0, seq_kv0);
         if (blockIdx.x == 0)
-            for (uint32_t s = threadIdx.x; s < seq_kv0; s += blockDim.x)
+            for (uint32_t s = p_lo + threadIdx.x; s < p_hi; s += blockDim.x)
                 for (uint32_t b = 0; b < dhb; b += 128) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (size_t)s * e.u[11] * 4 + b));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(vb0 + (size_t)s * e.u[13] * 4 + b));
@@ -427,10 +433,14 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
 #pragma unroll
     for (int i = 0; i < NI; i++) acc[i] = 0.0f;
     float m_val = -INFINITY, l = 0.0f;
-    for (uint32_t s0 = warp * 32; s0 < seq_kv; s0 += kAttnFastWarps * 32) {
+    // split-KV: this CTA covers positions [kv_lo, kv_hi) (32-aligned chunks); one head's cache is then streamed by
+    // `splits` SMs instead of one (a single SM's L2 bandwidth, not HBM, bounds a 512 KB head otherwise)
+    const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
+    const uint32_t kv_lo = blockIdx.z * chunk, kv_hi = min(kv_lo + chunk, seq_kv);
+    for (uint32_t s0 = kv_lo + warp * 32; s0 < kv_hi; s0 += kAttnFastWarps * 32) {
         const uint32_t s = s0 + lane;
         float mask_add = -INFINITY;
-        if (s < seq_kv) mask_add = has_mask ? mask[m_base + (size_t)s * mask_rs] : 0.0f;
+        if (s < kv_hi) mask_add = has_mask ? mask[m_base + (size_t)s * mask_rs] : 0.0f;
         bool ok = isfinite(mask_add);
         float score = -INFINITY;
         if (ok) {
@@ -470,7 +480,7 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
         m_val = new_m;
 #pragma unroll
         for (int i = 0; i < NI; i++) acc[i] *= alpha;
-        const uint32_t nj = min(32u, seq_kv - s0);
+        const uint32_t nj = min(32u, kv_hi - s0);
         const float* vb = v + (size_t)v_off + (size_t)s0 * v_cs + lane;
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < nj; j0 += 8) {
@@ -501,6 +511,51 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
     for (int w = 0; w < kAttnFastWarps; w++) {
         wscale[w] = (sh_m[w] == -INFINITY) ? 0.0f : expf(sh_m[w] - gm);
         gl += sh_l[w] * wscale[w];
+    }
+    if (splits > 1) {
+        // partial state (max, sum, unnormalised accumulator) of this split -> scratch; the last split to arrive merges
+        // all of them in split order (deterministic) and writes the output
+        __shared__ uint32_t s_last;
+        const uint32_t row = blockIdx.y * gridDim.x + qi;
+        float* mine = part + ((size_t)row * max_splits + blockIdx.z) * (NI * 32 + 2);
+        for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
+            float a = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
+            mine[2 + r] = a;
+        }
+        if (threadIdx.x == 0) { mine[0] = gm; mine[1] = gl; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt + row) : "memory");
+            const uint32_t last = (old == splits - 1) ? 1u : 0u;
+            if (last) cnt[row] = 0u;   // re-arm for the next launch
+            s_last = last;
+        }
+        __syncthreads();
+        if (s_last) {
+            const float* all = part + (size_t)row * max_splits * (NI * 32 + 2);
+            float G = -INFINITY;
+            for (uint32_t sp = 0; sp < splits; sp++) G = fmaxf(G, __ldcg(all + (size_t)sp * (NI * 32 + 2)));
+            float L = 0.0f;
+            for (uint32_t sp = 0; sp < splits; sp++) {
+                const float ms = __ldcg(all + (size_t)sp * (NI * 32 + 2));
+                L += (ms == -INFINITY) ? 0.0f : __ldcg(all + (size_t)sp * (NI * 32 + 2) + 1) * expf(ms - G);
+            }
+            const float inv_L = L > 0.0f ? 1.0f / L : 0.0f;
+            for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
+                float a = 0.0f;
+                for (uint32_t sp = 0; sp < splits; sp++) {
+                    const float ms = __ldcg(all + (size_t)sp * (NI * 32 + 2));
+                    if (ms != -INFINITY) a += __ldcg(all + (size_t)sp * (NI * 32 + 2) + 2 + r) * expf(ms - G);
+                }
+                dst[(size_t)dst_off + (size_t)qi * dst_cs + r] = a * inv_L;
+                if (e.dst2) e.dst2[(size_t)e.d2_off + (size_t)r * e.d2_rs + (size_t)qi * e.d2_cs] = a * inv_L;
+            }
+        }
+        ZG_TRACE_MARK(2)
+        return;
     }
     const float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
     for (uint32_t r = threadIdx.x; r < dh; r += blockDim.x) {
@@ -1185,7 +1240,23 @@ bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, 
 }
 
 // `first` = any op of the batch (all share the work shape); `d_entries` = `count` consecutive table entries.
-bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st) {
+// Decode attention: how many CTAs share one head's kv range (1 = no split).  `count` ops x seq_q rows are in the launch.
+uint32_t zg_attention_splits(const ZgOp& op, size_t k_buffer_elems, uint32_t count, int sm_count) {
+    const auto& a = op.u.attention;
+    if (!attn_fast_ok(op) || a.seq_q == 0 || a.seq_q > 8 || a.k_cs == 0) return 1;
+    const size_t max_kv = (k_buffer_elems > a.k_off ? k_buffer_elems - a.k_off : 0) / a.k_cs;   // the cache cannot hold more rows
+    uint32_t s = (uint32_t)((max_kv + 127) / 128);
+    const uint32_t rows = count * a.seq_q;
+    while (s > 1 && rows * s > (uint32_t)sm_count) s--;   // at most one wave of CTAs
+    return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+size_t zg_attention_part_elems(const ZgOp& op, uint32_t count, uint32_t splits) {
+    const uint32_t ni = op.u.attention.d_head <= 64 ? 2 : (op.u.attention.d_head <= 128 ? 4 : 8);
+    return splits > 1 ? (size_t)count * op.u.attention.seq_q * splits * (ni * 32 + 2) : 0;
+}
+
+bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st,
+                     float* attn_part, uint32_t* attn_cnt, uint32_t attn_splits) {
     if (count == 0) return true;
     switch (first.tag) {
         case ZG_OP_SLICE_ASSIGN: {
@@ -1204,10 +1275,11 @@ bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t 
             const auto& a = first.u.attention;
             if (a.seq_q == 0 || a.d_head == 0) return true;
             if (attn_fast_ok(first)) {
-                const dim3 grid(a.seq_q, count);
-                if (a.d_head <= 64) launch_k(k_attention_fast<2>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
-                else if (a.d_head <= 128) launch_k(k_attention_fast<4>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
-                else launch_k(k_attention_fast<8>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn);
+                const uint32_t sp = (attn_part && attn_cnt && attn_splits > 1) ? attn_splits : 1u;
+                const dim3 grid(a.seq_q, count, sp);
+                if (a.d_head <= 64) launch_k(k_attention_fast<2>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn, attn_part, attn_cnt, sp);
+                else if (a.d_head <= 128) launch_k(k_attention_fast<4>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn, attn_part, attn_cnt, sp);
+                else launch_k(k_attention_fast<8>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn, attn_part, attn_cnt, sp);
             } else launch_k(k_attention, dim3(dim3(a.seq_q, count)), dim3(kAttnWarps * 32), st, d_entries, d_dyn);
             break;
         }

@@ -102,6 +102,7 @@ struct ZgCudaCtx {
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
     int gemv_batch = 8;          // independent same-shape matvecs of a dependency level per launch (ZG_CUDA_GEMV_BATCH, 1 = off)
+    bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
@@ -184,7 +185,10 @@ bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n);   // comm.cu: the pee
 bool zg_op_is_batched(uint32_t tag);
 uint64_t zg_batch_signature(const ZgOp& op);
 bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, ZgBatchEntry* e);
-bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
+bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t count, const uint32_t* d_dyn, cudaStream_t st,
+                     float* attn_part = nullptr, uint32_t* attn_cnt = nullptr, uint32_t attn_splits = 1);
+uint32_t zg_attention_splits(const ZgOp& op, size_t k_buffer_elems, uint32_t count, int sm_count);
+size_t zg_attention_part_elems(const ZgOp& op, uint32_t count, uint32_t splits);
 bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
                   uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st);
 
