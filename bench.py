@@ -306,17 +306,26 @@ def run_b200(args):
                          "share_of_step": round(ms / sum(case_ms), 4)})
     dom_i = max(range(len(cases)), key=lambda i: case_ms[i])
     dom, domc = case_out[dom_i], cases[dom_i]
-    traffic = None
+    # one launch carries up to 8 same-level same-shape matvecs (csrc/backend.cu gemv_batch): per-launch figures below
+    per_launch = min(8, domc["R"])
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(f"{domc['K']}x{domc['N']}_{domc['format']}")
+            t = json.load(open(tp)).get(f"{domc['K']}x{domc['N']}_{domc['format']}")
+            if isinstance(t, dict):
+                traffic = t["dram_bytes_per_launch"] if t.get("gemvs_per_launch") == per_launch else int(t["dram_bytes_per_launch"] / max(t.get("gemvs_per_launch", 1), 1) * per_launch)
+                traffic_note = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of {t.get('gemvs_per_launch')} matvecs (profiles/traffic.json)"
+            elif t is not None:
+                traffic = int(t) * per_launch
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"qgemv_kernel<{domc['format']}> {domc['K']}x{domc['N']} batch 1",
+    roofline = {"bound": "hbm", "kernel": f"qgemv_kernel<{domc['format']}> {domc['K']}x{domc['N']} batch 1, {per_launch} matvecs per launch",
                 "achieved": dom["gbps"], "peak": peak, "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "unit": "GB/s", "frac": round(dom["gbps"] / peak, 4), "frac_all_cases": round(value / world / peak, 4),
-                "algorithmic_bytes_per_launch": alg_bytes(domc["K"], domc["N"], domc["blk"]), "traffic": traffic}
+                "algorithmic_bytes_per_launch": alg_bytes(domc["K"], domc["N"], domc["blk"]) * per_launch,
+                "launch_us": round(dom["us_per_gemv"] * per_launch, 3), "matvecs_per_launch": per_launch,
+                "traffic": traffic, "traffic_note": traffic_note}
 
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zgml_b200 import CudaBackend  # noqa: E402
 from zgml_b200.host import llama  # noqa: E402
 
-KINDS = {1: "elementwise", 2: "fused_ew", 3: "rmsnorm", 4: "repeat", 5: "slice_assign", 6: "rope", 7: "attention", 8: "chain", 9: "matmul", 10: "qgemv"}
+KINDS = {1: "elementwise", 2: "fused_ew", 3: "rmsnorm", 4: "repeat", 5: "slice_assign", 6: "rope", 7: "attention", 8: "chain", 9: "matmul", 10: "qgemv", 11: "allreduce"}
 MODELS = {"smollm-135m": llama.SMOLLM_135M, "smollm-1.7b": llama.SMOLLM_1_7B, "llama3-8b": llama.LLAMA3_8B, "llama3-70b": llama.LLAMA3_70B}
 
 
@@ -25,19 +25,20 @@ def main():
     ap.add_argument("--context", type=int, default=512)
     ap.add_argument("--emulate-world", type=int, default=1)
     ap.add_argument("--show", type=int, default=40)
+    ap.add_argument("--batch", type=int, default=1)
     args = ap.parse_args()
     cfg = MODELS[args.model]
     if args.layers:
         cfg = llama.LlamaConfig(**{**cfg.__dict__, "n_layers": args.layers})
     be = CudaBackend(0)
     w, handles = llama.synthetic_resident_shard(be, cfg, args.kind, 0, 0, args.emulate_world)
-    sess = llama.DeviceLlamaSession(be, cfg, w, 1)
-    sess.pos = args.context
-    tok = 1
-    for _ in range(4):
-        tok = int(np.argmax(sess.step(tok)))
+    T = args.batch
+    sess = llama.DeviceLlamaSession(be, cfg, w, T)
+    toks = list(range(1, T + 1))
+    for i in range(4):
+        sess.execute_at(toks, args.context + i * T)
     be.lib.zg_cuda_trace(be.ctx, 1)
-    sess.step(tok)
+    sess.execute_at(toks, args.context + 4 * T)
     buf = (C.c_uint64 * (3 * 16000))()
     n = be.lib.zg_cuda_trace_read(be.ctx, buf, 16000)
     be.lib.zg_cuda_trace(be.ctx, 0)

@@ -87,7 +87,6 @@ struct ZgCudaProgram {
     std::vector<Unit> units;
     std::vector<uint32_t> entry_of_op;   // index into d_batch for batched op kinds
     std::vector<uint32_t> single_entry;  // index into d_batch of a batched-kind op's own plain entry (per-op launches)
-    std::vector<uint32_t> peer_entry;    // index into d_chain of a peer-memory all-reduce's standalone entry (UINT32_MAX: NCCL)
     ZgBatchEntry* d_batch = nullptr;
     ZgChainOp* d_chain = nullptr;
     float* d_attn_part = nullptr;      // split-KV partial states, one slice per attention unit
@@ -289,7 +288,8 @@ static bool reserve_workspace(ZgCudaProgram* p) {
 // ── op dependencies (element ranges per buffer) for concurrent graph branches ─────────────────
 // dyn != 0: the range is shifted at run time by pos * dyn (slice_assign with patch_stride, i.e. KV-cache writes);
 // all such ops of a program share one pos (src/device_inference.zig:240-247), checked in zg_cuda_refresh.
-struct ZgRange { uint32_t buf; size_t lo, hi; bool write; uint32_t dyn; };
+// stride != 0: only the windows [lo + j * stride, + width) inside [lo, hi) are touched (a head's rows of a [T, D] matrix)
+struct ZgRange { uint32_t buf; size_t lo, hi; bool write; uint32_t dyn; uint32_t stride = 0, width = 0; };
 
 static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRange>& out) {
     out.clear();
@@ -325,7 +325,11 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
             if (sa.rows == 0 || sa.cols == 0) break;
             const size_t dext = (size_t)(sa.rows - 1) * sa.dst_row_stride + (size_t)(sa.cols - 1) * sa.dst_col_stride + 1;
             const size_t sext = (size_t)(sa.rows - 1) * sa.src_row_stride + (size_t)(sa.cols - 1) * sa.src_col_stride + 1;
-            if (sa.patch_stride == 0) span(sa.dst, sa.dst_offset, dext, true);
+            if (sa.patch_stride == 0 && sa.dst_row_stride == 1 && sa.cols > 1 && sa.dst_col_stride >= sa.rows) {
+                ZgRange r{sa.dst, sa.dst_offset, sa.dst_offset + dext, true, 0};
+                r.stride = sa.dst_col_stride; r.width = sa.rows;   // per-head column window: heads do not overlap
+                out.push_back(r);
+            } else if (sa.patch_stride == 0) span(sa.dst, sa.dst_offset, dext, true);
             else if (p->uniform_pos) out.push_back({sa.dst, sa.dst_base_offset, sa.dst_base_offset + dext, true, sa.patch_stride});
             else whole(sa.dst, true);
             span(sa.src, sa.src_offset, sext, false);
@@ -361,6 +365,10 @@ static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRang
 static inline bool range_conflict(const ZgRange& x, const ZgRange& y) {
     if (x.buf != y.buf || !(x.write || y.write)) return false;
     if (x.dyn && x.dyn == y.dyn) return x.lo < y.hi && y.lo < x.hi;   // same run-time shift: compare the bases
+    if (x.stride && x.stride == y.stride && !x.dyn && !y.dyn) {       // same row pitch: disjoint column windows never meet
+        const size_t ax = x.lo % x.stride, ay = y.lo % y.stride;
+        if (ax + x.width <= x.stride && ay + y.width <= y.stride && (ax + x.width <= ay || ay + y.width <= ax)) return false;
+    }
     const size_t xhi = x.dyn ? (size_t)-1 : x.hi, yhi = y.dyn ? (size_t)-1 : y.hi;   // shifted range: anywhere above its base
     return x.lo < yhi && y.lo < xhi;
 }
@@ -596,7 +604,7 @@ static bool build_schedule(ZgCudaProgram* p) {
         level[k] = lvl;
         for (const ZgRange& r : rng) {
             // a write covering the whole buffer orders everything after it: older accesses need not be kept
-            if (r.write && !r.dyn && r.buf < p->buffer_elems.size() && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
+            if (r.write && !r.dyn && !r.stride && r.buf < p->buffer_elems.size() && r.lo == 0 && r.hi >= p->buffer_elems[r.buf]) acc[r.buf].clear();
             acc[r.buf].push_back({r, lvl});
         }
     }
@@ -616,25 +624,16 @@ static bool build_schedule(ZgCudaProgram* p) {
         if (it.kind == ITEM_EWMUL) return ewmul_of[&it - items.data()].n <= 1024 ? 1 : 0;   // transcendental chains: one CTA only when tiny
         if (it.kind != ITEM_OP) return 0;
         const ZgOp& op = p->ops[it.first];
-        if (op.tag == ZG_OP_ALLREDUCE)   // peer-memory all-reduce runs inside the chain kernel; NCCL ones are "big" ops
-            return zg_peer_allreduce_ok(p->ctx, op.u.allreduce.n) ? 1 : 0;
+        if (op.tag == ZG_OP_ALLREDUCE) return 0;   // its own multi-CTA kernel (peer memory) or NCCL
         const size_t wk = zg_chain_work(op);
         return wk <= chain_max ? wk : 0;
     };
-    p->peer_entry.assign(n, UINT32_MAX);
-    for (size_t i = 0; i < n; i++) {   // standalone single-op entries: eager / profiling launches and chaining switched off
-        if (p->ops[i].tag != ZG_OP_ALLREDUCE || !zg_peer_allreduce_ok(p->ctx, p->ops[i].u.allreduce.n)) continue;
-        ZgChainOp c;
-        if (!zg_fill_chain_op(p->ops[i], p->buffers.data(), (uint32_t)i, nullptr, false, &c)) return false;
-        p->peer_entry[i] = (uint32_t)chain_ops.size();
-        chain_ops.push_back(c);
-    }
     std::vector<uint32_t> chain_items;
     std::vector<char> chain_sync, chain_tiny;
     auto close_chain = [&]() {
         if (chain_items.empty()) return true;
         const ZgItem& only = items[chain_items[0]];
-        if (chain_items.size() == 1 && only.kind == ITEM_OP && !zg_op_is_batched(p->ops[only.first].tag) && p->ops[only.first].tag != ZG_OP_ALLREDUCE) {
+        if (chain_items.size() == 1 && only.kind == ITEM_OP && !zg_op_is_batched(p->ops[only.first].tag) && true) {
             ZgCudaProgram::Unit u; u.ops.push_back(only.first); p->units.push_back(u);   // a lone op: its own (wider) kernel is as good
         } else {
             ZgCudaProgram::Unit chain; chain.chain = true;
@@ -811,7 +810,8 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
         return zg_qmatmul_launch(ctx, p->qweights[q.weight_idx], p->buffers[q.input] + q.input_offset,
                                  p->buffers[q.dst] + q.dst_offset, q.M, q.input_row_stride, q.dst_row_stride, &view, st);
     }
-    if (op.tag == ZG_OP_ALLREDUCE && p->peer_entry[i] != UINT32_MAX) return zg_launch_chain(p->d_chain + p->peer_entry[i], 1, p->d_dyn, ctx->peer, st);
+    if (op.tag == ZG_OP_ALLREDUCE && zg_peer_allreduce_ok(ctx, op.u.allreduce.n) && (((size_t)(p->buffers[op.u.allreduce.buf] + op.u.allreduce.offset)) & 15) == 0)
+        return zg_launch_peer_allreduce(p->buffers[op.u.allreduce.buf] + op.u.allreduce.offset, op.u.allreduce.n, ctx->peer, st);
     if (op.tag == ZG_OP_ALLREDUCE) return zg_comm_allreduce(ctx, p->buffers[op.u.allreduce.buf] + op.u.allreduce.offset, op.u.allreduce.n, st);
     if (op.tag == ZG_OP_ALLGATHER)
         return zg_comm_allgather(ctx, p->buffers[op.u.allgather.src] + op.u.allgather.src_offset,
@@ -821,7 +821,7 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 }
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
-    if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, p->ctx->peer, st);
+    if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
     if (u.gemv_batch && u.ops.size() > 1) {
         const ZgCudaQWeight* w[kZgGemvBatch]; const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];

@@ -4,8 +4,8 @@
 //
 // Small all-reduces (the d_model partial sums after the o / down projections: 32 KB at Llama-3-70B, 160 per token)
 // are latency-bound, so they do not go through NCCL: every rank exports one cudaMalloc region (slots + flags) with
-// cudaIpc, maps its peers' regions, and the all-reduce becomes peer stores + a flag inside the single-CTA chain
-// kernel (ops.cu, ZG_OP_ALLREDUCE case) — one NVLink store latency instead of a ring.  NCCL carries the handle
+// cudaIpc, maps its peers' regions, and the all-reduce becomes peer stores + a flag in a 16-CTA one-shot
+// all-reduce kernel (ops.cu k_allreduce_peer) — one NVLink store latency instead of a ring.  NCCL carries the handle
 // exchange, the all-gathers, and any all-reduce larger than a slot.  ZG_CUDA_PEER=0 keeps everything on NCCL.
 #include "zg_internal.cuh"
 
@@ -96,8 +96,8 @@ static bool peer_setup(ZgCudaCtx* ctx) {
     if (world > kZgMaxRanks) return false;
     if (const char* e = getenv("ZG_CUDA_PEER")) if (e[0] == '0') return false;
     const size_t slot_bytes = (size_t)kZgPeerSets * world * kPeerSlotFloats * sizeof(float);
-    const size_t flag_bytes = (size_t)kZgPeerSets * kZgMaxRanks * sizeof(uint32_t);
-    const size_t total = slot_bytes + flag_bytes + 64;
+    const size_t flag_bytes = (size_t)kZgPeerSets * kZgMaxRanks * kZgPeerCtas * sizeof(uint32_t);
+    const size_t total = slot_bytes + flag_bytes + (2 + kZgPeerCtas) * sizeof(uint32_t) + 64;
     if (cudaMalloc(&ctx->peer_mem, total) != cudaSuccess) { cudaGetLastError(); return false; }
     cudaMemset(ctx->peer_mem, 0, total);
     cudaIpcMemHandle_t mine;
@@ -143,7 +143,7 @@ static bool peer_setup(ZgCudaCtx* ctx) {
 }
 
 bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n) {
-    return ctx->world > 1 && ctx->peer.max_n != 0 && n != 0 && n <= ctx->peer.max_n;
+    return ctx->world > 1 && ctx->peer.max_n != 0 && n != 0 && (n & 3) == 0 && n <= ctx->peer.max_n;
 }
 
 extern "C" int zg_cuda_comm_mode(const ZgCudaCtx* ctx) {   // 0 none, 1 NCCL only, 2 NVLink peer-memory all-reduce + NCCL

@@ -134,6 +134,62 @@ __global__ void k_fused_ew_mul(const ZgDevStep* __restrict__ steps, uint32_t n_s
     ZG_TRACE_MARK(2)
 }
 
+// One-shot all-reduce over NVLink peer memory (ZG_OP_ALLREDUCE; state set up in comm.cu).  kZgPeerCtas CTAs each own a
+// contiguous slice of the vector: push the slice into every peer's slot [set][this rank], raise a release flag there,
+// wait for the peers' flags here, then sum the slots in RANK ORDER (bit-identical results on every rank) back into
+// the buffer.  Slot sets alternate per all-reduce: a rank can only get two all-reduces ahead of a peer after that peer
+// has finished reading the older set (it must have sent its flag for the one in between, from a later kernel).
+// Every CTA keeps its own sequence counter; all ranks run the same all-reduces with the same grid, so they agree.
+__global__ void __launch_bounds__(256)
+k_allreduce_peer(float* __restrict__ buf, uint32_t n4, const ZgPeerComm pc) {
+    ZG_TRACE_BEGIN(11)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tid = threadIdx.x, c = blockIdx.x;
+    uint32_t* my_seq = pc.seq + 2 + c;
+    const uint32_t chunk = (n4 + gridDim.x - 1) / gridDim.x, lo = c * chunk, hi = min(lo + chunk, n4);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
+    // the counter is written by the previous all-reduce kernel, which may still be running while this one is already
+    // resident (programmatic dependent launch chains several kernels deep): read it only after the wait
+    const uint32_t seq = *(volatile uint32_t*)my_seq, set = seq % kZgPeerSets, epoch = seq + 1;
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    const size_t my_slot4 = (((size_t)set * pc.world + pc.rank) * pc.max_n) >> 2;
+    for (int pr = 0; pr < pc.world; pr++) {
+        if (pr == pc.rank) continue;
+        float4* p4 = reinterpret_cast<float4*>(pc.slots[pr]) + my_slot4;
+        for (uint32_t j = lo + tid; j < hi; j += 256) p4[j] = b4[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < (uint32_t)pc.world && tid != (uint32_t)pc.rank) {
+        uint32_t* f = pc.flags[tid] + (set * kZgMaxRanks + pc.rank) * kZgPeerCtas + c;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+        const uint32_t* mine = pc.flags[pc.rank] + (set * kZgMaxRanks + tid) * kZgPeerCtas + c;
+        uint32_t got = 0;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
+            if (got != epoch && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
+        } while (got != epoch);
+    }
+    __syncthreads();
+    const float4* base4 = reinterpret_cast<const float4*>(pc.slots[pc.rank] + (size_t)set * pc.world * pc.max_n);
+    const size_t stride4 = pc.max_n >> 2;
+    for (uint32_t j = lo + tid; j < hi; j += 256) {
+        float4 v[kZgMaxRanks];   // every rank's value is requested before the first add (L2-coherent loads)
+#pragma unroll
+        for (int r = 0; r < kZgMaxRanks; r++)
+            if (r < pc.world) v[r] = (r == pc.rank) ? b4[j] : __ldcg(base4 + (size_t)r * stride4 + j);
+        float4 acc = v[0];
+#pragma unroll
+        for (int r = 1; r < kZgMaxRanks; r++)
+            if (r < pc.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        b4[j] = acc;
+    }
+    if (tid == 0) *(volatile uint32_t*)my_seq = epoch;
+    ZG_TRACE_MARK(2)
+}
+
 // one block per row
 __global__ void k_softmax(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols) {
     pdl_enter();
@@ -746,9 +802,8 @@ __device__ __forceinline__ void chain_small_op(const ZgChainOp* o, uint32_t t, u
 }
 
 __global__ void __launch_bounds__(kChainThreads, 4)
-k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __restrict__ d_dyn, const ZgPeerComm pc) {
+k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __restrict__ d_dyn) {
     __shared__ float sh[32];
-    __shared__ uint32_t s_seq;
     __shared__ ZgDevStep s_steps[16];
     __shared__ __align__(16) ZgChainOp s_tab[kZgChainMaxOps];   // the whole op table: one coalesced read instead of a dependent load per op
     const uint32_t tid = threadIdx.x;
@@ -911,70 +966,6 @@ k_chain(const ZgChainOp* __restrict__ tab, uint32_t count, const uint32_t* __res
                         if (j < n) { mid[j] = v[u]; dst[j] = v[u] * other[j]; }
                     }
                 }
-                break;
-            }
-            case ZG_OP_ALLREDUCE: {
-                // One-shot all-reduce over NVLink peer memory: push this rank's vector into every peer's slot, raise a
-                // release flag there, wait for the peers' flags here, then sum the slots in RANK ORDER (every rank gets
-                // bit-identical sums).  Slot sets alternate per all-reduce: a rank can only be two all-reduces ahead of a
-                // peer after that peer finished reading the older set (it has to send its flag for the one in between).
-                const uint32_t n = o->u[0], n4 = (n & 3u) == 0 && ((size_t)dst & 15u) == 0 ? n >> 2 : 0;
-                if (tid == 0) s_seq = *(volatile uint32_t*)pc.seq;
-                __syncthreads();
-                const uint32_t seq = s_seq, set = seq % kZgPeerSets, epoch = seq + 1;
-                const size_t my_slot = ((size_t)set * pc.world + pc.rank) * pc.max_n;
-                for (int pr = 0; pr < pc.world; pr++) {
-                    if (pr == pc.rank) continue;
-                    float* ps = pc.slots[pr] + my_slot;
-                    if (n4) {
-                        float4* p4 = reinterpret_cast<float4*>(ps);
-                        const float4* i4 = reinterpret_cast<const float4*>(dst);
-                        for (uint32_t j = tid; j < n4; j += kChainThreads) p4[j] = i4[j];
-                    } else {
-                        for (uint32_t j = tid; j < n; j += kChainThreads) ps[j] = dst[j];
-                    }
-                }
-                __threadfence_system();
-                __syncthreads();
-                if (tid < (uint32_t)pc.world && tid != (uint32_t)pc.rank) {
-                    uint32_t* f = pc.flags[tid] + set * kZgMaxRanks + pc.rank;
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-                    const uint32_t* mine = pc.flags[pc.rank] + set * kZgMaxRanks + tid;
-                    uint32_t got = 0;
-                    const long long t0 = clock64();
-                    do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-                        if (got != epoch && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
-                    } while (got != epoch);
-                }
-                __syncthreads();
-                const float* base = pc.slots[pc.rank] + (size_t)set * pc.world * pc.max_n;
-                if (n4) {
-                    // all ranks' values of an element are requested before the first add (L2-coherent loads: peers wrote
-                    // them over NVLink; the acquire above ordered them), then summed in rank order
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-                    for (uint32_t j = tid; j < n4; j += kChainThreads) {
-                        float4 v[kZgMaxRanks];
-#pragma unroll
-                        for (int r = 0; r < kZgMaxRanks; r++)
-                            if (r < pc.world) v[r] = (r == pc.rank) ? d4[j] : __ldcg(reinterpret_cast<const float4*>(base + (size_t)r * pc.max_n) + j);
-                        float4 acc = v[0];
-#pragma unroll
-                        for (int r = 1; r < kZgMaxRanks; r++)
-                            if (r < pc.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-                        d4[j] = acc;
-                    }
-                } else {
-                    for (uint32_t j = tid; j < n; j += kChainThreads) {
-                        float acc = 0.f;
-                        for (int r = 0; r < pc.world; r++) {
-                            const float v = (r == pc.rank) ? dst[j] : __ldcg(base + (size_t)r * pc.max_n + j);
-                            acc = (r == 0) ? v : acc + v;
-                        }
-                        dst[j] = acc;
-                    }
-                }
-                if (tid == 0) *(volatile uint32_t*)pc.seq = epoch;
                 break;
             }
             default: chain_small_op(o, tid, kChainThreads, d_dyn); break;
@@ -1148,11 +1139,6 @@ bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, con
             c->u[5] = r.src_rs; c->u[6] = r.src_cs; c->u[7] = r.cs_cs;
             return true;
         }
-        case ZG_OP_ALLREDUCE: {
-            const auto& a = op.u.allreduce;
-            c->dst = bufs[a.buf] + a.offset; c->u[0] = a.n;
-            return true;
-        }
         default: zg_set_error("internal: op kind %u cannot be chained", op.tag); return false;
     }
 }
@@ -1179,6 +1165,13 @@ bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c) {
     return true;
 }
 
+bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st) {
+    if (n == 0) return true;
+    launch_k(k_allreduce_peer, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 2), pc);
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
 bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st) {
     if (m.n == 0) return true;
     launch_k(k_fused_ew_mul, dim3(blocks_for(m.n, 128)), dim3(128), st, m.steps, m.n_steps, m.mid, m.src, m.n, m.other, m.dst);
@@ -1186,9 +1179,9 @@ bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st) {
     return true;
 }
 
-bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st) {
+bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, cudaStream_t st) {
     if (count == 0) return true;
-    launch_k(k_chain, dim3(1), dim3(kChainThreads), st, d_ops, count, d_dyn, pc);
+    launch_k(k_chain, dim3(1), dim3(kChainThreads), st, d_ops, count, d_dyn);
     ZG_COUNT_LAUNCH();
     return true;
 }

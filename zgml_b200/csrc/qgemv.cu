@@ -31,6 +31,7 @@
 //    scratch and the last-arriving CTA sums them in split order -> deterministic.
 #include "zg_internal.cuh"
 
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
@@ -535,6 +536,7 @@ bool zg_qgemv_init(ZgCudaCtx* ctx) {
     if (const char* e = getenv("ZG_GEMV_SMAX")) ctx->tune_smax = atoi(e);
     if (const char* e = getenv("ZG_GEMV_NS")) ctx->tune_u = atoi(e);
     if (const char* e = getenv("ZG_GEMV_G")) ctx->tune_g = atoi(e);
+    if (const char* e = getenv("ZG_GEMV_ROWS")) { ctx->tune_rows = atoi(e); if (ctx->tune_rows < 1 || ctx->tune_rows > 8) ctx->tune_rows = 0; }
     if (ctx->tune_u < 2 || ctx->tune_u > 16) ctx->tune_u = 0;
     if (ctx->tune_g < 1 || ctx->tune_g > 16) ctx->tune_g = 0;
     // opt every instantiation into its dynamic shared memory once per context, outside any stream capture
@@ -580,15 +582,13 @@ bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in
     return true;
 }
 
-// `count` (<= kZgGemvBatch) matvecs with identical weight shape, format and row count M <= 8 in one launch.
-bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
-                           float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
-                           const ZgGemvWs* ws, cudaStream_t st) {
-    if (count == 0 || M == 0) return true;
-    if (count > kZgGemvBatch || M > 8) { zg_set_error("internal: bad matvec batch (%u ops, %u rows)", count, M); return false; }
+// `count` (<= kZgGemvBatch) matvecs with identical weight shape, format and row count M <= 8 in one launch per pass of
+// `rows_per_pass` activation rows (ZG_GEMV_ROWS: the wide 8-row variant keeps one CTA per SM and short k-ranges; fewer
+// rows per pass re-stream the weights but run the well-occupied narrow variants).
+static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
+                              float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
+                              const ZgGemvWs* ws, cudaStream_t st) {
     const ZgCudaQWeight* w0 = ws_w[0];
-    const ZgGemvWs none[kZgGemvBatch] = {};
-    if (!ws) ws = none;
     ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M);
     QGemvBatch bt;
     memset(&bt, 0, sizeof(bt));
@@ -617,4 +617,24 @@ bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* 
         case ZG_QFMT_I4_F16: return launch_fmt<ZG_QFMT_I4_F16>(plan, bt, count, st, ctx->pdl);
         default: zg_set_error("qmatmul: unknown weight format %d", w0->fmt); return false;
     }
+}
+
+bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
+                           float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
+                           const ZgGemvWs* ws, cudaStream_t st) {
+    if (count == 0 || M == 0) return true;
+    if (count > kZgGemvBatch || M > 8) { zg_set_error("internal: bad matvec batch (%u ops, %u rows)", count, M); return false; }
+    const ZgGemvWs none[kZgGemvBatch] = {};
+    if (!ws) ws = none;
+    const uint32_t rpp = ctx->tune_rows ? (uint32_t)ctx->tune_rows : 4u;   // measured: two 4-row passes beat one 8-row pass (ZG_GEMV_ROWS)
+    if (M <= rpp) return launch_batch_rows(ctx, count, ws_w, d_in, d_out, M, in_rs, out_rs, ws, st);
+    for (uint32_t m0 = 0; m0 < M; m0 += rpp) {
+        const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];
+        for (uint32_t i = 0; i < count; i++) {
+            xin[i] = d_in[i] + (size_t)m0 * (in_rs[i] ? in_rs[i] : (uint32_t)ws_w[i]->K);
+            xout[i] = d_out[i] + (size_t)m0 * (out_rs[i] ? out_rs[i] : (uint32_t)ws_w[i]->N);
+        }
+        if (!launch_batch_rows(ctx, count, ws_w, xin, xout, std::min(rpp, M - m0), in_rs, out_rs, ws, st)) return false;
+    }
+    return true;
 }

@@ -83,12 +83,13 @@ struct ZgGemvWs {
 // `flags[set][src_rank]`; peers store their vector + a release flag straight into them.  Passed to k_chain by value.
 constexpr int kZgMaxRanks = 8;
 constexpr uint32_t kZgPeerSets = 2;
+constexpr uint32_t kZgPeerCtas = 16;   // CTAs of one all-reduce (each owns a slice of the vector, its own flags and counter)
 struct ZgPeerComm {
     int rank = 0, world = 1;
     uint32_t max_n = 0;                 // floats per slot; 0 = peer path unavailable (NCCL is used instead)
     float* slots[kZgMaxRanks] = {};     // slot base of every rank (own entry = local pointer)
     uint32_t* flags[kZgMaxRanks] = {};  // flag base of every rank
-    uint32_t* seq = nullptr;            // local: number of all-reduces this rank has completed; [1] = timeout marker
+    uint32_t* seq = nullptr;            // local: [1] = timeout marker, [2 + c] = all-reduces CTA c has completed
 };
 
 struct ZgCudaCtx {
@@ -99,7 +100,7 @@ struct ZgCudaCtx {
     bool graph_mode = true;
     bool profiling = false;
     bool pdl = true; // programmatic dependent launch between consecutive qgemv kernels (ZG_CUDA_PDL=0 disables)
-    int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
+    int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0, tune_rows = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
     int gemv_batch = 8;          // independent same-shape matvecs of a dependency level per launch (ZG_CUDA_GEMV_BATCH, 1 = off)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
@@ -180,7 +181,8 @@ bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c);
 bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st);   // the same pair as one multi-CTA launch   // ops per chain launch (the table lives in shared memory)
 size_t zg_chain_work(const ZgOp& op);
 bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
-bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, const ZgPeerComm& pc, cudaStream_t st);
+bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
+bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st);
 bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n);   // comm.cu: the peer path can take an n-float all-reduce
 bool zg_op_is_batched(uint32_t tag);
 uint64_t zg_batch_signature(const ZgOp& op);
