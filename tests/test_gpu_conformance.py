@@ -123,7 +123,8 @@ def test_random_rope_and_slice_assign(cuda_backend):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("d_head,seq_q,seq_kv", [(64, 1, 1), (64, 1, 37), (64, 1, 513), (128, 5, 64), (40, 3, 9), (512, 2, 17)])
+@pytest.mark.parametrize("d_head,seq_q,seq_kv", [(64, 1, 1), (64, 1, 37), (64, 1, 513), (128, 5, 64), (40, 3, 9), (512, 2, 17),
+                                                  (128, 1, 1000), (64, 4, 700), (32, 1, 2048), (256, 2, 300)])
 def test_random_attention(cuda_backend, d_head, seq_q, seq_kv):
     q = r32(1, d_head * seq_q)
     k = r32(2, d_head * seq_kv)
@@ -189,6 +190,42 @@ def test_refresh_patches_slice_offset_and_seq_kv(cuda_backend):
             cuda_backend.execute_program(h, [ProgramIO(0, x)], [ProgramIO(4, got)])
             np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-6)
         cuda_backend.free_program(h)
+    st.close()
+    cuda_backend.set_graph_mode(True)
+
+
+@pytest.mark.parametrize("graph", [True, False], ids=["graph", "eager"])
+def test_split_kv_decode_attention_over_a_growing_context(cuda_backend, graph):
+    """Three heads of one layer (batched launch, split over the kv range, head output also stored into the concatenated
+    buffer by the absorbed slice_assign) against a 1024-row cache whose valid length is patched per step."""
+    d, cap, heads = 64, 1024, 3
+    bufs = [d * heads, d * cap * heads, d * cap * heads, cap] + [d] * heads + [d * heads]   # q | k | v | mask | out_h.. | concat
+    concat = 4 + heads
+
+    def ops_for(skv):
+        ops = []
+        for h in range(heads):
+            ops.append(DeviceOp.attention(4 + h, 0, 1, 2, 3, True, d, 1, skv, 0.125, h * d, h * d * cap, h * d * cap, 0, 0,
+                                          1, d, 1, d, 1, d, 1, cap, 1, d))
+            ops.append(DeviceOp.slice_assign(concat, 4 + h, d, 1, 0, h * d, 1, d * heads, 0, 1, d, 0))
+        return ops
+
+    prog = DeviceProgram(ops_for(1), bufs, [ProgramIO(0, r32(1, d * heads)), ProgramIO(1, r32(2, d * cap * heads)),
+                                            ProgramIO(2, r32(3, d * cap * heads)), ProgramIO(3, np.zeros(cap, np.float32))])
+    cuda_backend.set_graph_mode(graph)
+    h = cuda_backend.compile_program(prog)
+    st = oracle.ProgramState(prog)
+    for skv in (1, 127, 128, 129, 400, 1023, 1024, 5):
+        ops = ops_for(skv)
+        arr = (type(ops[0]) * len(ops))(*ops)
+        want, got = np.zeros(d * heads, np.float32), np.zeros(d * heads, np.float32)
+        want1, got1 = np.zeros(d, np.float32), np.zeros(d, np.float32)
+        st.execute(arr, len(ops), [], [ProgramIO(concat, want), ProgramIO(5, want1)])
+        cuda_backend.refresh_program(h, ops)
+        cuda_backend.execute_program(h, [], [ProgramIO(concat, got), ProgramIO(5, got1)])
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(got1, want1, rtol=1e-4, atol=2e-6)
+    cuda_backend.free_program(h)
     st.close()
     cuda_backend.set_graph_mode(True)
 

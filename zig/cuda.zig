@@ -41,6 +41,9 @@ const ZgOp = extern struct {
             q_rs: u32, q_cs: u32, k_rs: u32, k_cs: u32, v_rs: u32, v_cs: u32, mask_rs: u32, mask_cs: u32, dst_rs: u32, dst_cs: u32,
         },
         fused_elementwise: extern struct { steps: ?[*]const ZgFusedEwStep, n_steps: usize, n: u32, dst: u32, src: u32, dst_offset: u32, src_offset: u32 },
+        // extensions (tags 12 / 13): collectives of a row-sharded program; zgml's DeviceOp has no such variants yet
+        allreduce: extern struct { buf: u32, offset: u32, n: u32 },
+        allgather: extern struct { dst: u32, src: u32, n: u32, dst_offset: u32, src_offset: u32 },
     },
 };
 const ZgIO = extern struct { buf_idx: u32, offset: u32, host_ptr: ?*anyopaque, size: u32, _pad: u32 = 0 };
@@ -59,6 +62,13 @@ extern fn zg_cuda_execute(ctx: *anyopaque, prog: *anyopaque, inputs: [*]const Zg
 extern fn zg_cuda_free(ctx: *anyopaque, prog: *anyopaque) void;
 extern fn zg_cuda_profile(ctx: *anyopaque, prog: *anyopaque) ?*const ZgProfile;
 extern fn zg_cuda_last_error() [*:0]const u8;
+// extensions: multi-GPU communicator (one process per GPU) and weights packed in HBM ahead of compile
+extern fn zg_cuda_comm_unique_id(id128: *[128]u8) c_int;
+extern fn zg_cuda_comm_init(ctx: *anyopaque, id128: *const [128]u8, rank: c_int, world: c_int) c_int;
+extern fn zg_cuda_comm_destroy(ctx: *anyopaque) void;
+extern fn zg_cuda_qweight_upload_gguf(ctx: *anyopaque, raw: [*]const u8, raw_bytes: usize, ggml_type: u32, rows: usize, cols: usize) ?*anyopaque;
+extern fn zg_cuda_qweight_free(ctx: *anyopaque, w: *anyopaque) void;
+pub const ZG_QWEIGHT_RESIDENT: usize = std.math.maxInt(usize); // ZgQWeight.block_size marker: `data` is a handle from zg_cuda_qweight_upload*
 
 // ── flattening ──────────────────────────────────────────────────────────────
 const Flat = struct {
