@@ -264,6 +264,16 @@ int zg_cuda_qmatmul_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* 
 int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input,
                          float* h_dst, uint32_t M);
 
+/* QuantizedWeight.fromSlice / fromTensor — reference src/quant.zig:216-264 — on device: quantizes a host f32 [rows=K, cols=N]
+ * row-major matrix per flat block of `block_size` (scale = max_abs / 127, q = trunc(clamp(v * 127 / max_abs))) and packs it.
+ * h_data_out [rows*cols] / h_scales_out [ceil(rows*cols / block_size)] (either may be NULL) receive the reference's flat
+ * form, bit-identical to the CPU result.  NULL on failure. */
+ZgCudaQWeight* zg_cuda_qweight_from_f32(ZgCudaCtx* ctx, const float* h_weights, size_t rows, size_t cols, size_t block_size,
+                                        int8_t* h_data_out, float* h_scales_out);
+/* QuantizedWeight.matmulBias — reference src/quant.zig:581-589: matmul, then dst[m, n] += bias[n] (host buffers). */
+int zg_cuda_qmatmul_bias_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, const float* h_bias,
+                              float* h_dst, uint32_t M);
+
 /* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
  * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */
 int zg_cuda_comm_unique_id(void* id128);

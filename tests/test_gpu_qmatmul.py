@@ -318,3 +318,32 @@ def test_prefill_rows_match_decode_rows(cuda_backend):
         one = w.matmul(x[i:i + 1], 1)
         assert rel_err(big[i], one[0]) < 5e-5
     w.free()
+
+
+# ── QuantizedWeight.fromSlice / matmulBias on device ────────────────
+@pytest.mark.parametrize("K,N,bs", [(64, 64, 32), (100, 37, 32), (576, 1536, 32), (128, 96, 64), (33, 7, 16), (4096, 512, 128)])
+def test_from_slice_on_device_is_bit_identical_to_reference(cuda_backend, K, N, bs):
+    r = rng(K * 7 + N + bs)
+    w = r.uniform(-2, 2, K * N).astype(np.float32)
+    w[:bs] = 0.0                      # an all-zero block: scale 1.0, q 0 (src/quant.zig:236)
+    w[bs + 3] = 1e-30                 # a tiny block maximum
+    o = oracle.QuantizedWeight.from_slice(w, K, N, bs)
+    qw, data, scales = QuantizedWeight.from_slice(cuda_backend, w, K, N, bs, return_flat=True)
+    assert np.array_equal(data, o.data)
+    assert np.array_equal(scales.view(np.uint32), o.scales.view(np.uint32))
+    assert np.array_equal(qw.dequantize_to().view(np.uint32), o.dequantize_to().view(np.uint32))
+    x = r.standard_normal((1, K)).astype(np.float32)
+    assert rel_err(qw.matmul(x, 1), oracle_out(o, x, 1)) < 2e-5
+    qw.free()
+
+
+@pytest.mark.parametrize("M", [1, 3, 20])
+def test_matmul_bias_matches_reference(cuda_backend, M):   # reference test: src/quant.zig:1211-1247 (tolerance 0.1 vs float)
+    K, N = 96, 160
+    r = rng(M)
+    o = oracle.QuantizedWeight.from_slice(r.uniform(-1, 1, K * N).astype(np.float32), K, N, 32)
+    w = QuantizedWeight.upload(cuda_backend, o.data, o.scales, K, N, 32)
+    x = r.standard_normal((M, K)).astype(np.float32)
+    b = r.standard_normal(N).astype(np.float32)
+    assert rel_err(w.matmul_bias(x, b, M), o.matmul_bias(x, b, M)) < 5e-5
+    w.free()

@@ -467,6 +467,21 @@ class QuantizedWeight:
         return cls(be, ptr, rows, cols, block_size)
 
     @classmethod
+    def from_slice(cls, be: CudaBackend, weights: np.ndarray, rows: int, cols: int, block_size: int = 32, return_flat: bool = False):
+        """QuantizedWeight.fromSlice (src/quant.zig:216-256) on device.  `return_flat`: also the reference's flat
+        (data i8, scales f32) form, for bit-exact comparison."""
+        w = np.ascontiguousarray(weights, dtype=np.float32).ravel()
+        assert w.size == rows * cols
+        data = np.zeros(w.size, np.int8) if return_flat else None
+        scales = np.zeros((w.size + block_size - 1) // block_size, np.float32) if return_flat else None
+        ptr = be.lib.zg_cuda_qweight_from_f32(be.ctx, w.ctypes.data, rows, cols, block_size,
+                                              data.ctypes.data if return_flat else None, scales.ctypes.data if return_flat else None)
+        if not ptr:
+            raise BackendError(f"qweight from_slice failed: {last_error()}")
+        qw = cls(be, ptr, rows, cols, block_size)
+        return (qw, data, scales) if return_flat else qw
+
+    @classmethod
     def from_gguf_blocks(cls, be: CudaBackend, raw: np.ndarray, ggml_type: int, rows: int, cols: int) -> "QuantizedWeight":
         """quantizedWeightFromInfo (src/models/gguf_loader.zig:99-154) on device."""
         raw = np.ascontiguousarray(raw, dtype=np.uint8)
@@ -494,6 +509,15 @@ class QuantizedWeight:
         out = np.empty((M, self.cols), dtype=np.float32)
         if self.be.lib.zg_cuda_qmatmul_host(self.be.ctx, self.ptr, x.ctypes.data, out.ctypes.data, M) != 0:
             raise BackendError(f"qmatmul failed: {last_error()}")
+        return out
+
+    def matmul_bias(self, input: np.ndarray, bias: np.ndarray, M: int) -> np.ndarray:  # src/quant.zig:581-589
+        x = np.ascontiguousarray(input, dtype=np.float32).reshape(M, self.rows)
+        b = np.ascontiguousarray(bias, dtype=np.float32).ravel()
+        assert b.size == self.cols
+        out = np.empty((M, self.cols), dtype=np.float32)
+        if self.be.lib.zg_cuda_qmatmul_bias_host(self.be.ctx, self.ptr, x.ctypes.data, b.ctypes.data, out.ctypes.data, M) != 0:
+            raise BackendError(f"qmatmul_bias failed: {last_error()}")
         return out
 
     def matmul_device(self, d_input: int, d_dst: int, M: int, input_row_stride: int = 0, dst_row_stride: int = 0):

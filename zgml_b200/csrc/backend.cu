@@ -1054,6 +1054,34 @@ extern "C" int zg_cuda_qmatmul_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, cons
     return rc;
 }
 
+// QuantizedWeight.matmulBias (src/quant.zig:581-589): matmul, then dst[m, n] += bias[n]
+__global__ void k_add_bias(float* __restrict__ dst, const float* __restrict__ bias, uint32_t M, uint32_t N) {
+    const size_t total = (size_t)M * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) dst[i] += bias[i % N];
+}
+extern "C" int zg_cuda_qmatmul_bias_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, const float* h_bias, float* h_dst, uint32_t M) {
+    if (!ctx || !w || !h_bias) { zg_set_error("qmatmul_bias_host: null argument"); return -1; }
+    cudaSetDevice(ctx->device);
+    float *d_in = nullptr, *d_out = nullptr, *d_b = nullptr;
+    const size_t in_b = (size_t)M * w->K * 4, out_b = (size_t)M * w->N * 4, b_b = w->N * 4;
+    if (cudaMalloc(&d_in, in_b ? in_b : 4) != cudaSuccess || cudaMalloc(&d_out, out_b ? out_b : 4) != cudaSuccess || cudaMalloc(&d_b, b_b ? b_b : 4) != cudaSuccess) {
+        zg_set_error("qmatmul_bias_host: cudaMalloc failed"); cudaFree(d_in); cudaFree(d_out); cudaFree(d_b); return -1;
+    }
+    cudaMemcpyAsync(d_in, h_input, in_b, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_b, h_bias, b_b, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = zg_cuda_qmatmul_device(ctx, w, d_in, d_out, M, 0, 0);
+    if (rc == 0 && M && w->N) {
+        const size_t total = (size_t)M * w->N;
+        k_add_bias<<<(unsigned)std::min<size_t>((total + 255) / 256, 4096), 256, 0, ctx->stream>>>(d_out, d_b, M, (uint32_t)w->N);
+        ZG_COUNT_LAUNCH();
+    }
+    cudaMemcpyAsync(h_dst, d_out, out_b, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_b);
+    if (e != cudaSuccess) { zg_set_error("qmatmul_bias_host: %s", cudaGetErrorString(e)); return -1; }
+    return rc;
+}
+
 // ── raw device memory helpers for tests / bench ──────────────────────────────
 extern "C" void* zg_cuda_malloc(ZgCudaCtx* ctx, size_t bytes) {
     if (!ctx) return nullptr;

@@ -305,6 +305,53 @@ extern "C" ZgCudaQWeight* zg_cuda_qweight_upload(ZgCudaCtx* ctx, const ZgQWeight
     return w;
 }
 
+// QuantizedWeight.fromSlice (src/quant.zig:216-256) on device: one warp per flat block of `bs` weights:
+// max_abs -> scale = max_abs / 127 (1 when the block is all zero), q = trunc(clamp(v * (127 / max_abs), +-127)).
+// Separate IEEE operations, no contraction: data and scales are bit-identical to the reference's.
+__global__ void k_from_slice(const float* __restrict__ w, size_t n_elems, uint32_t bs, int8_t* __restrict__ data, float* __restrict__ scales) {
+    const size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t start = b * bs;
+    if (start >= n_elems) return;
+    const size_t end = start + bs < n_elems ? start + bs : n_elems;
+    float mx = 0.0f;
+    for (size_t j = start + lane; j < end; j += 32) { const float a = fabsf(w[j]); if (a > mx) mx = a; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float scale = mx > 0.0f ? __fdiv_rn(mx, 127.0f) : 1.0f;
+    const float inv = mx > 0.0f ? __fdiv_rn(127.0f, mx) : 0.0f;
+    if (lane == 0) scales[b] = scale;
+    for (size_t j = start + lane; j < end; j += 32) {
+        float q = __fmul_rn(w[j], inv);
+        q = q < -127.0f ? -127.0f : (q > 127.0f ? 127.0f : q);
+        data[j] = (int8_t)(int)q;   // float -> int conversion truncates toward zero, like @intFromFloat
+    }
+}
+
+extern "C" ZgCudaQWeight* zg_cuda_qweight_from_f32(ZgCudaCtx* ctx, const float* h_weights, size_t rows, size_t cols, size_t block_size,
+                                                   int8_t* h_data_out, float* h_scales_out) {
+    if (!ctx || !h_weights || block_size == 0 || block_size > 0xFFFFFFFFull) { zg_set_error("qweight_from_f32: bad arguments"); return nullptr; }
+    const size_t n_elems = rows * cols, n_blocks = (n_elems + block_size - 1) / block_size;
+    cudaSetDevice(ctx->device);
+    float* d_w = nullptr; int8_t* d_data = nullptr; float* d_scales = nullptr;
+    if (cudaMalloc(&d_w, (n_elems ? n_elems : 1) * sizeof(float)) != cudaSuccess || cudaMalloc(&d_data, n_elems ? n_elems : 1) != cudaSuccess ||
+        cudaMalloc(&d_scales, (n_blocks ? n_blocks : 1) * sizeof(float)) != cudaSuccess) {
+        zg_set_error("qweight_from_f32: staging cudaMalloc failed");
+        cudaFree(d_w); cudaFree(d_data); cudaFree(d_scales); return nullptr;
+    }
+    cudaMemcpyAsync(d_w, h_weights, n_elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (n_blocks) {
+        k_from_slice<<<grid_for(n_blocks * 32, 256), 256, 0, ctx->stream>>>(d_w, n_elems, (uint32_t)block_size, d_data, d_scales);
+        ZG_COUNT_LAUNCH();
+    }
+    if (h_data_out) cudaMemcpyAsync(h_data_out, d_data, n_elems, cudaMemcpyDeviceToHost, ctx->stream);
+    if (h_scales_out) cudaMemcpyAsync(h_scales_out, d_scales, n_blocks * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    ZgCudaQWeight* w = zg_qweight_from_device_flat(ctx, d_data, d_scales, rows, cols, block_size, ZG_QFMT_AUTO);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_w); cudaFree(d_data); cudaFree(d_scales);
+    return w;
+}
+
 extern "C" ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void* raw, size_t raw_bytes,
                                                       uint32_t ggml_type, size_t rows, size_t cols) {
     if (!ctx || !raw) { zg_set_error("qweight_upload_gguf: bad arguments"); return nullptr; }
