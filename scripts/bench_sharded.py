@@ -25,7 +25,7 @@ from zgml_b200.host import llama  # noqa: E402
 MODELS = {"smollm-135m": llama.SMOLLM_135M, "smollm-1.7b": llama.SMOLLM_1_7B, "llama3-8b": llama.LLAMA3_8B, "llama3-70b": llama.LLAMA3_70B}
 
 
-def run_sharded_decode(be, cfg, kind, rank, world, dist, tokens=32, batches=(1,), context=0, model_name=""):
+def run_sharded_decode(be, cfg, kind, rank, world, dist, tokens=32, batches=(1,), context=0, model_name="", trace=False):
     """Load this rank's shard once, then time one session per batch size.  Returns the result dicts (every rank)."""
     import torch
     t0 = time.perf_counter()
@@ -69,6 +69,32 @@ def run_sharded_decode(be, cfg, kind, rank, world, dist, tokens=32, batches=(1,)
                     "hbm_floor_ms_per_step": round(dev_bytes / 6540.8e6, 3),
                     "load_s": round(t_load, 1), "comm": be.comm_mode(), "collectives_per_step": 2 * cfg.n_layers + 1 if world > 1 else 0,
                     "data": "synthetic random-init GGUF blocks, streamed per shard", "last_token": int(np.argmax(lg))})
+        if trace and rank == 0:
+            import collections
+            import ctypes as C
+            kinds = {1: "elementwise", 2: "fused_ew", 3: "rmsnorm", 4: "repeat", 5: "slice_assign", 6: "rope", 7: "attention", 8: "chain", 9: "matmul", 10: "qgemv", 11: "allreduce"}
+            be.lib.zg_cuda_trace(be.ctx, 1)
+        if trace:
+            sess.execute_at(toks, pos)
+        if trace and rank == 0:
+            buf = (C.c_uint64 * (3 * 16000))()
+            n = be.lib.zg_cuda_trace_read(be.ctx, buf, 16000)
+            be.lib.zg_cuda_trace(be.ctx, 0)
+            rec = np.frombuffer(buf, dtype=np.uint64)[:3 * n].reshape(n, 3).astype(np.int64)
+            kind = rec[:, 0] >> 56
+            t_in, t_go, t_out = rec[:, 0] & ((1 << 56) - 1), rec[:, 1] & ((1 << 56) - 1), rec[:, 2] & ((1 << 56) - 1)
+            order = np.argsort(t_go)
+            kind, t_in, t_go, t_out = kind[order], t_in[order], t_go[order], t_out[order]
+            agg = collections.defaultdict(lambda: [0, 0])
+            for k, b, c in zip(kind, t_go, t_out):
+                if c > b:
+                    agg[int(k)][0] += 1; agg[int(k)][1] += int(c - b)
+            print(f"trace batch {T}: {n} records, span {(t_out.max() - t_in.min()) / 1e3:.1f} us", file=sys.stderr)
+            for k, (cnt, work) in sorted(agg.items(), key=lambda x: -x[1][1]):
+                print(f"  {kinds.get(k, k):12s} n={cnt:5d} work total {work / 1e3:9.1f} us avg {work / cnt / 1e3:6.2f} us", file=sys.stderr)
+            mid = n // 2
+            for i in range(mid, min(mid + 40, n)):
+                print(f"    {kinds.get(int(kind[i]), kind[i]):12s} {(t_in[i] - t_in.min()) / 1e3:9.2f} {(t_go[i] - t_in.min()) / 1e3:9.2f} {(t_out[i] - t_in.min()) / 1e3:9.2f} {(t_out[i] - t_go[i]) / 1e3:7.2f}", file=sys.stderr)
         sess.close()
     for h in handles:
         h.free()
@@ -84,6 +110,7 @@ def main():
     ap.add_argument("--context", type=int, default=0)
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--max-seq", type=int, default=0)
+    ap.add_argument("--trace", action="store_true", help="rank 0 prints an in-graph kernel timeline of one more step to stderr")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="single process: run rank 0's shard of an N-way split with the collectives as identity (per-rank compute profile)")
     args = ap.parse_args()
@@ -108,7 +135,7 @@ def main():
         world_shape = args.emulate_world
         orig = llama.synthetic_resident_shard
         llama.synthetic_resident_shard = lambda be_, cfg_, kind_, seed=0, rank=0, world=1, **kw: orig(be_, cfg_, kind_, seed, 0, world_shape, **kw)
-    res = run_sharded_decode(be, cfg, args.kind, rank, world, dist, args.tokens, [int(b) for b in args.batch.split(",")], args.context, args.model)
+    res = run_sharded_decode(be, cfg, args.kind, rank, world, dist, args.tokens, [int(b) for b in args.batch.split(",")], args.context, args.model, trace=args.trace)
     be.close()
     if world > 1:
         dist.destroy_process_group()

@@ -134,58 +134,70 @@ __global__ void k_fused_ew_mul(const ZgDevStep* __restrict__ steps, uint32_t n_s
     ZG_TRACE_MARK(2)
 }
 
-// One-shot all-reduce over NVLink peer memory (ZG_OP_ALLREDUCE; state set up in comm.cu).  kZgPeerCtas CTAs each own a
-// contiguous slice of the vector: push the slice into every peer's slot [set][this rank], raise a release flag there,
-// wait for the peers' flags here, then sum the slots in RANK ORDER (bit-identical results on every rank) back into
-// the buffer.  Slot sets alternate per all-reduce: a rank can only get two all-reduces ahead of a peer after that peer
-// has finished reading the older set (it must have sent its flag for the one in between, from a later kernel).
-// Every CTA keeps its own sequence counter; all ranks run the same all-reduces with the same grid, so they agree.
+// One-shot all-reduce over NVLink peer memory (ZG_OP_ALLREDUCE; state set up in comm.cu), low-latency protocol: every
+// 16-byte store carries two floats AND the all-reduce's epoch twice ({x, epoch, y, epoch}), so data and "ready" flag
+// arrive together — no fence, no separate flag round trip; the receiver polls the words of its own slot until both
+// epochs match (a torn 16-byte transaction simply fails the check and is re-read).  kZgPeerCtas CTAs each own a
+// contiguous slice: push it into every peer's slot [set][this rank], poll the peers' slices here, sum in RANK ORDER
+// (bit-identical results on every rank), write back.  Slot sets alternate per all-reduce: a rank can only get two
+// all-reduces ahead of a peer after that peer has finished reading the older set (it must have sent its data for
+// the one in between, from a later kernel).  Every CTA keeps its own sequence counter; all ranks run the same
+// all-reduces with the same grid, so the epochs agree.
 __global__ void __launch_bounds__(256)
-k_allreduce_peer(float* __restrict__ buf, uint32_t n4, const ZgPeerComm pc) {
+k_allreduce_peer(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc) {
     ZG_TRACE_BEGIN(11)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t tid = threadIdx.x, c = blockIdx.x;
     uint32_t* my_seq = pc.seq + 2 + c;
-    const uint32_t chunk = (n4 + gridDim.x - 1) / gridDim.x, lo = c * chunk, hi = min(lo + chunk, n4);
+    const uint32_t chunk = (n2 + gridDim.x - 1) / gridDim.x, lo = c * chunk, hi = min(lo + chunk, n2);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     ZG_TRACE_MARK(1)
     // the counter is written by the previous all-reduce kernel, which may still be running while this one is already
     // resident (programmatic dependent launch chains several kernels deep): read it only after the wait
     const uint32_t seq = *(volatile uint32_t*)my_seq, set = seq % kZgPeerSets, epoch = seq + 1;
-    float4* b4 = reinterpret_cast<float4*>(buf);
-    const size_t my_slot4 = (((size_t)set * pc.world + pc.rank) * pc.max_n) >> 2;
-    for (int pr = 0; pr < pc.world; pr++) {
-        if (pr == pc.rank) continue;
-        float4* p4 = reinterpret_cast<float4*>(pc.slots[pr]) + my_slot4;
-        for (uint32_t j = lo + tid; j < hi; j += 256) p4[j] = b4[j];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < (uint32_t)pc.world && tid != (uint32_t)pc.rank) {
-        uint32_t* f = pc.flags[tid] + (set * kZgMaxRanks + pc.rank) * kZgPeerCtas + c;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
-        const uint32_t* mine = pc.flags[pc.rank] + (set * kZgMaxRanks + tid) * kZgPeerCtas + c;
-        uint32_t got = 0;
-        const long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-            if (got != epoch && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
-        } while (got != epoch);
-    }
-    __syncthreads();
-    const float4* base4 = reinterpret_cast<const float4*>(pc.slots[pc.rank] + (size_t)set * pc.world * pc.max_n);
-    const size_t stride4 = pc.max_n >> 2;
+    float2* b2 = reinterpret_cast<float2*>(buf);
+    const size_t slot_pairs = pc.max_n >> 1;                                  // 16-byte cells per (set, rank) slot
+    const size_t my_cell = ((size_t)set * pc.world + pc.rank) * slot_pairs;
     for (uint32_t j = lo + tid; j < hi; j += 256) {
-        float4 v[kZgMaxRanks];   // every rank's value is requested before the first add (L2-coherent loads)
+        const float2 v = b2[j];
+        for (int pr = 0; pr < pc.world; pr++) {
+            if (pr == pc.rank) continue;
+            uint4* cell = reinterpret_cast<uint4*>(pc.slots[pr]) + my_cell + j;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(__float_as_uint(v.x)), "r"(epoch),
+                         "r"(__float_as_uint(v.y)), "r"(epoch) : "memory");
+        }
+    }
+    const uint4* mine = reinterpret_cast<const uint4*>(pc.slots[pc.rank]) + (size_t)set * pc.world * slot_pairs;
+    const long long t0 = clock64();
+    for (uint32_t j = lo + tid; j < hi; j += 256) {
+        uint4 got[kZgMaxRanks];
+        uint32_t pending = 0;
 #pragma unroll
         for (int r = 0; r < kZgMaxRanks; r++)
-            if (r < pc.world) v[r] = (r == pc.rank) ? b4[j] : __ldcg(base4 + (size_t)r * stride4 + j);
-        float4 acc = v[0];
+            if (r < pc.world && r != pc.rank) pending |= 1u << r;
+        while (pending) {   // every peer's cell is requested before any is checked; only the late ones are re-read
 #pragma unroll
-        for (int r = 1; r < kZgMaxRanks; r++)
-            if (r < pc.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
-        b4[j] = acc;
+            for (int r = 0; r < kZgMaxRanks; r++)
+                if (pending & (1u << r)) {
+                    const uint4* cell = mine + (size_t)r * slot_pairs + j;
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(got[r].x), "=r"(got[r].y), "=r"(got[r].z), "=r"(got[r].w) : "l"(cell) : "memory");
+                }
+#pragma unroll
+            for (int r = 0; r < kZgMaxRanks; r++)
+                if ((pending & (1u << r)) && got[r].y == epoch && got[r].w == epoch) pending &= ~(1u << r);
+            if (pending && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
+        }
+        const float2 own = b2[j];
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kZgMaxRanks; r++)
+            if (r < pc.world) {
+                const float2 v = (r == pc.rank) ? own : make_float2(__uint_as_float(got[r].x), __uint_as_float(got[r].z));
+                acc = (r == 0) ? v : make_float2(acc.x + v.x, acc.y + v.y);
+            }
+        b2[j] = acc;
     }
+    __syncthreads();
     if (tid == 0) *(volatile uint32_t*)my_seq = epoch;
     ZG_TRACE_MARK(2)
 }
@@ -1167,7 +1179,7 @@ bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c) {
 
 bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st) {
     if (n == 0) return true;
-    launch_k(k_allreduce_peer, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 2), pc);
+    launch_k(k_allreduce_peer, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 1), pc);
     ZG_COUNT_LAUNCH();
     return true;
 }
