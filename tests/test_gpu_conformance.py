@@ -230,6 +230,31 @@ def test_split_kv_decode_attention_over_a_growing_context(cuda_backend, graph):
     cuda_backend.set_graph_mode(True)
 
 
+@pytest.mark.parametrize("rows,cols,with_add", [(1, 64, True), (3, 2048, True), (1, 4096, False), (1, 4100, True), (1, 8192, True), (1, 8192, False), (2, 4096, True)])
+def test_norm_pattern_writes_every_buffer(cuda_backend, rows, cols, with_add):
+    """[add,] rmsnorm, repeat(gamma over rows), mul — the lowering's norm block (llama_transformer.zig:118-125) is evaluated
+    in one pass (chain macro up to 4096 columns, a 1024-thread kernel per row above); sum, bare, gamma_rep and the
+    result must all equal op-by-op execution."""
+    n = rows * cols
+    a, b, gamma = r32(1, n), r32(2, n), r32(3, cols)
+    ops = []
+    if with_add:
+        ops.append(DeviceOp.elementwise("add", 3, 0, 1, n))
+    src = 3 if with_add else 0
+    ops += [DeviceOp.rmsnorm(4, src, rows, cols, 1e-5),
+            DeviceOp.repeat(5, 2, n, (cols, 1, 1, 1), (cols, rows, 1, 1), (1, cols, cols, cols), (1, cols, n, n)),
+            DeviceOp.elementwise("mul", 6, 4, 5, n)]
+    prog = DeviceProgram(ops, [n, n, cols, n, n, n, n], [ProgramIO(0, a), ProgramIO(1, b), ProgramIO(2, gamma)])
+    h = cuda_backend.compile_program(prog)
+    outs_g = [np.zeros(n, np.float32) for _ in range(4)]
+    outs_w = [np.zeros(n, np.float32) for _ in range(4)]
+    cuda_backend.execute_program(h, [], [ProgramIO(3 + i, outs_g[i]) for i in range(4)])
+    cuda_backend.free_program(h)
+    oracle.run_program(prog, [], [ProgramIO(3 + i, outs_w[i]) for i in range(4)])
+    for g, w in zip(outs_g, outs_w):
+        np.testing.assert_allclose(g, w, rtol=2e-5, atol=1e-6)
+
+
 def test_runtime_profile_slot(cuda_backend):  # reference src/backend.zig:351, src/profile.zig:819-842
     name, program, out_idx, out_len, _ = core_cases()[1]
     h = cuda_backend.compile_program(program)

@@ -80,7 +80,8 @@ struct ZgCudaProgram {
         std::vector<uint32_t> entry_ops;   // batched: the ops that own a table entry (absorbed slice_assigns do not)
         std::map<uint32_t, uint32_t> store_of;   // batched attention op -> the slice_assign absorbed into it
         uint32_t first_entry = 0, n_entries = 0;
-        bool batched = false, chain = false, ewmul = false, gemv_batch = false;
+        bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false;
+        ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
         ZgEwMulMacro em = {};
     };
@@ -620,7 +621,7 @@ static bool build_schedule(ZgCudaProgram* p) {
     // them: they may consume the chain's earlier levels, and nothing in the chain depends on them (same level = no
     // conflict; later levels start a new chain).  The unit order stays a topological order of the dependency DAG.
     auto chain_work = [&](const ZgItem& it) -> size_t {
-        if (it.kind == ITEM_NORM) return 1;   // size-checked by the matcher
+        if (it.kind == ITEM_NORM) return norm_of[&it - items.data()].cols <= 4096 ? 1 : 0;   // longer rows: their own 1024-thread kernel
         if (it.kind == ITEM_EWMUL) return ewmul_of[&it - items.data()].n <= 1024 ? 1 : 0;   // transcendental chains: one CTA only when tiny
         if (it.kind != ITEM_OP) return 0;
         const ZgOp& op = p->ops[it.first];
@@ -718,6 +719,12 @@ static bool build_schedule(ZgCudaProgram* p) {
                 }
                 p->units[ui].ops.push_back(it.first);
                 continue;
+            }
+            if (it.kind == ITEM_NORM) {    // long rows: one wide CTA per row instead of the 256-thread chain
+                ZgCudaProgram::Unit u;
+                for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
+                u.norm = true; u.nm = norm_of[order[k]];
+                p->units.push_back(u); continue;
             }
             if (it.kind == ITEM_EWMUL) {   // fused_elementwise + mul as one multi-CTA launch
                 ZgCudaProgram::Unit u; u.ops.push_back(it.first); u.ops.push_back(it.first + 1);
@@ -823,6 +830,7 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
+    if (u.norm) return zg_launch_norm_macro(u.nm, st);
     if (u.gemv_batch && u.ops.size() > 1) {
         const ZgCudaQWeight* w[kZgGemvBatch]; const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];
         uint32_t irs[kZgGemvBatch], ors[kZgGemvBatch]; ZgGemvWs view[kZgGemvBatch];

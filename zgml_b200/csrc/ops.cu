@@ -113,6 +113,54 @@ __global__ void k_fused_elementwise(const ZgDevStep* __restrict__ steps, uint32_
     ZG_TRACE_MARK(2)
 }
 
+// [a + b ->] sum ; rmsnorm(sum) -> bare ; gamma broadcast -> gamma_rep ; bare * gamma_rep -> norm for LONG rows (4096 < cols <=
+// 8192): one CTA of 1024 threads per row, the row held in registers (2 float4 per thread), one load round, one
+// block reduction, one store round.  Shorter rows run inside the chain kernel (kZgChainFusedNorm).
+__global__ void __launch_bounds__(1024)
+k_norm_macro(const ZgNormMacro m) {
+    ZG_TRACE_BEGIN(3)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
+    __shared__ float sh[32];
+    const uint32_t tid = threadIdx.x, r = blockIdx.x, c4 = m.cols >> 2;
+    const size_t ro = (size_t)r * c4;
+    const float4* a4 = reinterpret_cast<const float4*>(m.a);
+    const float4* b4 = reinterpret_cast<const float4*>(m.b);
+    const float4* g4 = reinterpret_cast<const float4*>(m.gamma);
+    float4 x[2], g[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const uint32_t j = tid + u * 1024;
+        x[u] = j < c4 ? a4[ro + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        g[u] = j < c4 ? g4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (b4) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t j = tid + u * 1024;
+            if (j >= c4) continue;
+            const float4 t = b4[ro + j];
+            x[u] = make_float4(x[u].x + t.x, x[u].y + t.y, x[u].z + t.z, x[u].w + t.w);
+            reinterpret_cast<float4*>(m.sum)[ro + j] = x[u];
+        }
+    }
+    float ss = 0.0f;
+#pragma unroll
+    for (int u = 0; u < 2; u++) ss += (x[u].x * x[u].x + x[u].y * x[u].y) + (x[u].z * x[u].z + x[u].w * x[u].w);
+    ss = block_reduce<false>(ss, sh);
+    const float inv_rms = 1.0f / sqrtf(ss / (float)m.cols + m.eps);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const uint32_t j = tid + u * 1024;
+        if (j >= c4) continue;
+        const float4 bz = make_float4(x[u].x * inv_rms, x[u].y * inv_rms, x[u].z * inv_rms, x[u].w * inv_rms);
+        reinterpret_cast<float4*>(m.bare)[ro + j] = bz;
+        reinterpret_cast<float4*>(m.gamma_rep)[ro + j] = g[u];
+        reinterpret_cast<float4*>(m.norm)[ro + j] = make_float4(bz.x * g[u].x, bz.y * g[u].y, bz.z * g[u].z, bz.w * g[u].w);
+    }
+    ZG_TRACE_MARK(2)
+}
+
 // fused_elementwise chain -> mid, then mid * other -> dst (SiLU(gate) * up): one launch for the two ops
 __global__ void k_fused_ew_mul(const ZgDevStep* __restrict__ steps, uint32_t n_steps, float* __restrict__ mid,
                                const float* __restrict__ src, uint32_t n, const float* __restrict__ other, float* __restrict__ dst) {
@@ -1180,6 +1228,13 @@ bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c) {
 bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st) {
     if (n == 0) return true;
     launch_k(k_allreduce_peer, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 1), pc);
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
+bool zg_launch_norm_macro(const ZgNormMacro& m, cudaStream_t st) {
+    if (m.rows == 0) return true;
+    launch_k(k_norm_macro, dim3(m.rows), dim3(1024), st, m);
     ZG_COUNT_LAUNCH();
     return true;
 }

@@ -178,7 +178,8 @@ struct ZgNormMacro { const float* a; const float* b; float* sum; float* bare; co
 struct ZgEwMulMacro { const float* src; float* mid; const float* other; float* dst; const ZgDevStep* steps; uint32_t n_steps, n; };
 bool zg_fill_chain_norm(const ZgNormMacro& m, bool sync, ZgChainOp* c);
 bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c);
-bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st);   // the same pair as one multi-CTA launch   // ops per chain launch (the table lives in shared memory)
+bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st);
+bool zg_launch_norm_macro(const ZgNormMacro& m, cudaStream_t st);   // rows longer than 4096: one 1024-thread CTA per row   // the same pair as one multi-CTA launch   // ops per chain launch (the table lives in shared memory)
 size_t zg_chain_work(const ZgOp& op);
 bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
 bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
