@@ -553,37 +553,64 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
     // `splits` SMs instead of one (a single SM's L2 bandwidth, not HBM, bounds a 512 KB head otherwise)
     const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
     const uint32_t kv_lo = blockIdx.z * chunk, kv_hi = min(kv_lo + chunk, seq_kv);
-    for (uint32_t s0 = kv_lo + warp * 32; s0 < kv_hi; s0 += kAttnFastWarps * 32) {
-        const uint32_t s = s0 + lane;
+    // Lanes per position: a short range is spread over all 16 warps (PW = 32 / LPP positions per warp step) and each
+    // K row is read by LPP lanes (dh / LPP contiguous floats each, then a shuffle reduction), so a step is one round of
+    // independent loads for K and one for V instead of four each when only a few warps had work.
+    uint32_t lpp = 1;
+    {
+        const uint32_t len = kv_hi > kv_lo ? kv_hi - kv_lo : 0;
+        while (lpp < 8 && len <= (kAttnFastWarps * 32u) / (2 * lpp) && (dh4 % (2 * lpp)) == 0) lpp *= 2;
+    }
+    const uint32_t pw = 32 / lpp, seg = lane & (lpp - 1), pos_in_warp = lane / lpp;
+    const uint32_t f4 = dh4 / lpp;   // float4 per lane of a K row
+    for (uint32_t s0 = kv_lo + warp * pw; s0 < kv_hi; s0 += kAttnFastWarps * pw) {
+        const uint32_t s = s0 + pos_in_warp;
         float mask_add = -INFINITY;
         if (s < kv_hi) mask_add = has_mask ? mask[m_base + (size_t)s * mask_rs] : 0.0f;
         bool ok = isfinite(mask_add);
         float score = -INFINITY;
-        if (ok) {
-            const float4* kr = reinterpret_cast<const float4*>(k + (size_t)k_off + (size_t)s * k_cs);
-            const float4* q4 = reinterpret_cast<const float4*>(sq);
+        {
             float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
-            uint32_t d = 0;
-            for (; d + 8 <= dh4; d += 8) {   // 8 independent 128-bit loads in flight per lane
-                float4 kk[8];
+            if (ok) {
+                const float4* kr = reinterpret_cast<const float4*>(k + (size_t)k_off + (size_t)s * k_cs) + seg * f4;
+                const float4* q4 = reinterpret_cast<const float4*>(sq) + seg * f4;
+                uint32_t d = 0;
+                for (; d + 8 <= f4; d += 8) {   // 8 independent 128-bit loads in flight per lane
+                    float4 kk[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) kk[u] = kr[d + u];
+                    for (int u = 0; u < 8; u++) kk[u] = kr[d + u];
 #pragma unroll
-                for (int u = 0; u < 8; u += 4) {
-                    const float4 qa = q4[d + u], qb = q4[d + u + 1], qc = q4[d + u + 2], qf = q4[d + u + 3];
-                    d0 = fmaf(qa.x, kk[u].x, d0); d0 = fmaf(qa.y, kk[u].y, d0); d0 = fmaf(qa.z, kk[u].z, d0); d0 = fmaf(qa.w, kk[u].w, d0);
-                    d1 = fmaf(qb.x, kk[u + 1].x, d1); d1 = fmaf(qb.y, kk[u + 1].y, d1); d1 = fmaf(qb.z, kk[u + 1].z, d1); d1 = fmaf(qb.w, kk[u + 1].w, d1);
-                    d2 = fmaf(qc.x, kk[u + 2].x, d2); d2 = fmaf(qc.y, kk[u + 2].y, d2); d2 = fmaf(qc.z, kk[u + 2].z, d2); d2 = fmaf(qc.w, kk[u + 2].w, d2);
-                    d3 = fmaf(qf.x, kk[u + 3].x, d3); d3 = fmaf(qf.y, kk[u + 3].y, d3); d3 = fmaf(qf.z, kk[u + 3].z, d3); d3 = fmaf(qf.w, kk[u + 3].w, d3);
+                    for (int u = 0; u < 8; u += 4) {
+                        const float4 qa = q4[d + u], qb = q4[d + u + 1], qc = q4[d + u + 2], qf = q4[d + u + 3];
+                        d0 = fmaf(qa.x, kk[u].x, d0); d0 = fmaf(qa.y, kk[u].y, d0); d0 = fmaf(qa.z, kk[u].z, d0); d0 = fmaf(qa.w, kk[u].w, d0);
+                        d1 = fmaf(qb.x, kk[u + 1].x, d1); d1 = fmaf(qb.y, kk[u + 1].y, d1); d1 = fmaf(qb.z, kk[u + 1].z, d1); d1 = fmaf(qb.w, kk[u + 1].w, d1);
+                        d2 = fmaf(qc.x, kk[u + 2].x, d2); d2 = fmaf(qc.y, kk[u + 2].y, d2); d2 = fmaf(qc.z, kk[u + 2].z, d2); d2 = fmaf(qc.w, kk[u + 2].w, d2);
+                        d3 = fmaf(qf.x, kk[u + 3].x, d3); d3 = fmaf(qf.y, kk[u + 3].y, d3); d3 = fmaf(qf.z, kk[u + 3].z, d3); d3 = fmaf(qf.w, kk[u + 3].w, d3);
+                    }
+                }
+                if (d + 4 <= f4) {
+                    float4 kk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) kk[u] = kr[d + u];
+                    const float4 qa = q4[d], qb = q4[d + 1], qc = q4[d + 2], qf = q4[d + 3];
+                    d0 = fmaf(qa.x, kk[0].x, d0); d0 = fmaf(qa.y, kk[0].y, d0); d0 = fmaf(qa.z, kk[0].z, d0); d0 = fmaf(qa.w, kk[0].w, d0);
+                    d1 = fmaf(qb.x, kk[1].x, d1); d1 = fmaf(qb.y, kk[1].y, d1); d1 = fmaf(qb.z, kk[1].z, d1); d1 = fmaf(qb.w, kk[1].w, d1);
+                    d2 = fmaf(qc.x, kk[2].x, d2); d2 = fmaf(qc.y, kk[2].y, d2); d2 = fmaf(qc.z, kk[2].z, d2); d2 = fmaf(qc.w, kk[2].w, d2);
+                    d3 = fmaf(qf.x, kk[3].x, d3); d3 = fmaf(qf.y, kk[3].y, d3); d3 = fmaf(qf.z, kk[3].z, d3); d3 = fmaf(qf.w, kk[3].w, d3);
+                    d += 4;
+                }
+                for (; d < f4; d++) {
+                    const float4 a = kr[d], qa = q4[d];
+                    d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
                 }
             }
-            for (; d < dh4; d++) {
-                const float4 a = kr[d], qa = q4[d];
-                d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
+            float dot = (d0 + d1) + (d2 + d3);
+            for (uint32_t o = 1; o < lpp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);   // the lanes of a position share ok
+            if (ok) {
+                score = dot * scale + mask_add;
+                ok = isfinite(score);
+                if (!ok) score = -INFINITY;
             }
-            score = ((d0 + d1) + (d2 + d3)) * scale + mask_add;
-            ok = isfinite(score);
-            if (!ok) score = -INFINITY;
         }
         float bm = score;
 #pragma unroll
@@ -591,12 +618,12 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
         if (bm == -INFINITY) continue;   // warp-uniform: nothing attendable in this block
         const float new_m = fmaxf(m_val, bm);
         const float alpha = (m_val == -INFINITY) ? 0.0f : expf(m_val - new_m);
-        const float wgt = ok ? expf(score - new_m) : 0.0f;   // lanes past seq_kv and skipped entries weigh 0
-        l = l * alpha + warp_sum(wgt);
+        const float wgt = ok ? expf(score - new_m) : 0.0f;   // lanes past the range and skipped entries weigh 0
+        l = l * alpha + warp_sum(seg == 0 ? wgt : 0.0f);     // one lane per position counts
         m_val = new_m;
 #pragma unroll
         for (int i = 0; i < NI; i++) acc[i] *= alpha;
-        const uint32_t nj = min(32u, kv_hi - s0);
+        const uint32_t nj = min(pw, kv_hi - s0);
         const float* vb = v + (size_t)v_off + (size_t)s0 * v_cs + lane;
 #pragma unroll 1
         for (uint32_t j0 = 0; j0 < nj; j0 += 8) {
@@ -609,7 +636,7 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
             }
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
-                const float wj = __shfl_sync(0xffffffffu, wgt, (j0 + jj) & 31);
+                const float wj = __shfl_sync(0xffffffffu, wgt, ((j0 + jj) * lpp) & 31);
 #pragma unroll
                 for (int i = 0; i < NI; i++) acc[i] = fmaf(wj, vv[jj][i], acc[i]);
             }
