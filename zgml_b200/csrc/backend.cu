@@ -90,6 +90,12 @@ struct ZgCudaProgram {
     std::vector<uint32_t> single_entry;  // index into d_batch of a batched-kind op's own plain entry (per-op launches)
     ZgBatchEntry* d_batch = nullptr;
     ZgChainOp* d_chain = nullptr;
+    // input staging: the per-step inputs of a decode program are many small host buffers (one RoPE leaf per layer);
+    // they are packed into ONE pinned buffer, copied once and scattered by a kernel instead of one pageable copy each
+    uint8_t* h_in_stage = nullptr; uint8_t* d_in_stage = nullptr; size_t in_stage_bytes = 0;
+    struct InSeg { float* dst; uint32_t src_off, words; };
+    InSeg* d_in_tab = nullptr; size_t in_tab_cap = 0;
+    std::vector<InSeg> in_tab_host;   // what d_in_tab holds
     float* d_attn_part = nullptr;      // split-KV partial states, one slice per attention unit
     uint32_t* d_attn_cnt = nullptr;    // arrival counters (self re-arming)
     bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
@@ -211,6 +217,8 @@ static void free_program(ZgCudaProgram* p) {
     for (size_t i = 0; i < p->qweights.size(); i++)
         if (p->qweight_owned[i]) zg_cuda_qweight_free(p->ctx, p->qweights[i]);
     cudaFree(p->d_steps); cudaFree(p->d_dyn); cudaFree(p->d_batch); cudaFree(p->d_chain); cudaFree(p->d_attn_part); cudaFree(p->d_attn_cnt);
+    cudaFree(p->d_in_stage); cudaFree(p->d_in_tab);
+    if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -969,6 +977,59 @@ static bool run_ops(ZgCudaProgram* p) {
     return true;
 }
 
+__global__ void k_scatter_inputs(const ZgCudaProgram::InSeg* __restrict__ tab, const uint8_t* __restrict__ stage) {
+    const ZgCudaProgram::InSeg s = tab[blockIdx.x];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(stage + s.src_off);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s.dst);
+    for (uint32_t i = threadIdx.x; i < s.words; i += blockDim.x) dst[i] = src[i];
+}
+
+// Many small inputs: pack -> one pinned H2D copy -> scatter kernel.  Returns false when the inputs do not qualify (the
+// caller then copies them one by one).
+static bool upload_inputs_staged(ZgCudaProgram* p, const ZgIO* in, size_t n_in, cudaStream_t st) {
+    if (n_in < 3) return false;
+    size_t total = 0;
+    for (size_t i = 0; i < n_in; i++) {
+        if ((in[i].offset | in[i].size) & 3u) return false;
+        total += (in[i].size + 15u) & ~15u;
+    }
+    if (total == 0 || total > (4u << 20) || n_in > 512) return false;
+    for (size_t i = 0; i < n_in; i++)   // overlapping destinations must keep "later input wins": leave them to ordered copies
+        for (size_t j = 0; j < i; j++)
+            if (in[i].buf_idx == in[j].buf_idx && in[i].offset < in[j].offset + in[j].size && in[j].offset < in[i].offset + in[i].size) return false;
+    if (total > p->in_stage_bytes) {
+        if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
+        cudaFree(p->d_in_stage);
+        p->h_in_stage = nullptr; p->d_in_stage = nullptr; p->in_stage_bytes = 0;
+        if (cudaMallocHost(&p->h_in_stage, total) != cudaSuccess || cudaMalloc(&p->d_in_stage, total) != cudaSuccess) { cudaGetLastError(); return false; }
+        p->in_stage_bytes = total;
+    }
+    std::vector<ZgCudaProgram::InSeg> tab(n_in);
+    size_t off = 0;
+    for (size_t i = 0; i < n_in; i++) {
+        memcpy(p->h_in_stage + off, in[i].host_ptr, in[i].size);
+        tab[i] = {reinterpret_cast<float*>((uint8_t*)p->buffers[in[i].buf_idx] + in[i].offset), (uint32_t)off, in[i].size / 4};
+        off += (in[i].size + 15u) & ~15u;
+    }
+    bool same = tab.size() == p->in_tab_host.size();
+    for (size_t i = 0; same && i < tab.size(); i++)
+        same = tab[i].dst == p->in_tab_host[i].dst && tab[i].src_off == p->in_tab_host[i].src_off && tab[i].words == p->in_tab_host[i].words;
+    if (!same) {
+        if (n_in > p->in_tab_cap) {
+            cudaFree(p->d_in_tab); p->d_in_tab = nullptr; p->in_tab_cap = 0;
+            if (cudaMalloc(&p->d_in_tab, n_in * sizeof(ZgCudaProgram::InSeg)) != cudaSuccess) { cudaGetLastError(); return false; }
+            p->in_tab_cap = n_in;
+        }
+        if (cudaMemcpyAsync(p->d_in_tab, tab.data(), n_in * sizeof(ZgCudaProgram::InSeg), cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+        cudaStreamSynchronize(st);   // `tab` is a local
+        p->in_tab_host = tab;
+    }
+    if (cudaMemcpyAsync(p->d_in_stage, p->h_in_stage, total, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    k_scatter_inputs<<<(unsigned)n_in, 128, 0, st>>>(p->d_in_tab, p->d_in_stage);
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
 extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in, size_t n_in, const ZgIO* out, size_t n_out) {
     if (!ctx || !p) return;
     cudaSetDevice(ctx->device);
@@ -978,8 +1039,10 @@ extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in
         if (io.buf_idx >= p->buffers.size() || (size_t)io.offset + io.size > p->buffer_elems[io.buf_idx] * sizeof(float)) {
             zg_set_error("execute: input %zu out of range", i); return; // reference asserts (reference.zig:116)
         }
-        cudaMemcpyAsync((uint8_t*)p->buffers[io.buf_idx] + io.offset, io.host_ptr, io.size, cudaMemcpyHostToDevice, st);
     }
+    if (!upload_inputs_staged(p, in, n_in, st))
+        for (size_t i = 0; i < n_in; i++)
+            cudaMemcpyAsync((uint8_t*)p->buffers[in[i].buf_idx] + in[i].offset, in[i].host_ptr, in[i].size, cudaMemcpyHostToDevice, st);
     if (!run_ops(p)) { cudaStreamSynchronize(st); return; }
     for (size_t i = 0; i < n_out; i++) {
         const ZgIO& io = out[i];

@@ -3,7 +3,7 @@
 // libnccl is resolved with dlopen at first use, so single-GPU users need no NCCL at all.
 //
 // Small all-reduces (the d_model partial sums after the o / down projections: 32 KB at Llama-3-70B, 160 per token)
-// are latency-bound, so they do not go through NCCL: every rank exports one cudaMalloc region (slots + flags) with
+// are latency-bound, so they do not go through NCCL: every rank exports one cudaMalloc region of slots with
 // cudaIpc, maps its peers' regions, and the all-reduce becomes peer stores + a flag in a 16-CTA one-shot
 // all-reduce kernel (ops.cu k_allreduce_peer, data + epoch in every 16-byte store) — one NVLink store latency instead of a ring.  NCCL carries the handle
 // exchange, the all-gathers, and any all-reduce larger than a slot.  ZG_CUDA_PEER=0 keeps everything on NCCL.
@@ -96,7 +96,7 @@ static bool peer_setup(ZgCudaCtx* ctx) {
     if (world > kZgMaxRanks) return false;
     if (const char* e = getenv("ZG_CUDA_PEER")) if (e[0] == '0') return false;
     const size_t slot_bytes = (size_t)kZgPeerSets * world * kPeerSlotFloats * 2 * sizeof(float);   // every float travels with its epoch
-    const size_t flag_bytes = (size_t)kZgPeerSets * kZgMaxRanks * kZgPeerCtas * sizeof(uint32_t);
+    const size_t flag_bytes = 0;   // readiness travels inside the data cells (epoch words)
     const size_t total = slot_bytes + flag_bytes + (2 + kZgPeerCtas) * sizeof(uint32_t) + 64;
     if (cudaMalloc(&ctx->peer_mem, total) != cudaSuccess) { cudaGetLastError(); return false; }
     cudaMemset(ctx->peer_mem, 0, total);
@@ -136,7 +136,6 @@ static bool peer_setup(ZgCudaCtx* ctx) {
     for (int r = 0; r < world; r++) {
         char* base = (char*)(r == rank ? ctx->peer_mem : ctx->peer_mapped[r]);
         pc.slots[r] = (float*)base;
-        pc.flags[r] = (uint32_t*)(base + slot_bytes);
     }
     pc.seq = (uint32_t*)((char*)ctx->peer_mem + slot_bytes + flag_bytes);
     return true;

@@ -79,16 +79,16 @@ struct ZgGemvWs {
     size_t gemm_scratch_elems = 0;
 };
 
-// One-shot all-reduce over NVLink peer memory (comm.cu): every rank owns `slots[set][src_rank][max_n]` floats and
-// `flags[set][src_rank]`; peers store their vector + a release flag straight into them.  Passed to k_chain by value.
+// One-shot all-reduce over NVLink peer memory (comm.cu, ops.cu k_allreduce_peer): every rank owns
+// `slots[set][src_rank][max_n / 2]` 16-byte cells {x, epoch, y, epoch}; peers store their vector straight into them.
+// Passed to the kernel by value.
 constexpr int kZgMaxRanks = 8;
 constexpr uint32_t kZgPeerSets = 2;
-constexpr uint32_t kZgPeerCtas = 16;   // CTAs of one all-reduce (each owns a slice of the vector, its own flags and counter)
+constexpr uint32_t kZgPeerCtas = 16;   // CTAs of one all-reduce (each owns a slice of the vector and its own counter)
 struct ZgPeerComm {
     int rank = 0, world = 1;
     uint32_t max_n = 0;                 // floats per slot; 0 = peer path unavailable (NCCL is used instead)
     float* slots[kZgMaxRanks] = {};     // slot base of every rank (own entry = local pointer)
-    uint32_t* flags[kZgMaxRanks] = {};  // flag base of every rank
     uint32_t* seq = nullptr;            // local: [1] = timeout marker, [2 + c] = all-reduces CTA c has completed
 };
 
@@ -107,7 +107,7 @@ struct ZgCudaCtx {
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
-    void* peer_mem = nullptr;    // this rank's slots + flags + seq (cudaMalloc, exported by cudaIpc)
+    void* peer_mem = nullptr;    // this rank's slots + counters (cudaMalloc, exported by cudaIpc)
     void* peer_mapped[kZgMaxRanks] = {};   // cudaIpcOpenMemHandle mappings to close
     void* nccl_comm = nullptr;   // ncclComm_t (comm.cu), null unless zg_cuda_comm_init ran
     int rank = 0, world = 1;
