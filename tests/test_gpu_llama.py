@@ -109,3 +109,42 @@ def test_every_program_buffer_matches_oracle_with_fused_patterns(cuda_backend, t
             assert np.array_equal(np.isfinite(g), fin), f"buffer {i}"
             assert np.max(np.abs(g[fin] - wv[fin]), initial=0.0) <= 1e-4 * scale + 1e-6, f"buffer {i} at pos {pos}"
     dev.close(); ref.close()
+
+
+@pytest.mark.parametrize("knobs", [{"ZG_CUDA_GEMV_FUSE": "3"}, {"ZG_CUDA_CHAIN": "0", "ZG_CUDA_FUSE": "0", "ZG_CUDA_GEMV_BATCH": "1", "ZG_CUDA_ATTN_SPLIT": "0", "ZG_CUDA_PDL": "0"}],
+                         ids=["matvec-prologue-fusion", "every-scheduling-feature-off"])
+def test_scheduling_knobs_do_not_change_results(knobs):
+    """The scheduling features are switches read at context creation: the optional matvec-prologue fusion
+    (off by default, measured slower) and the plain one-launch-per-op configuration must give the same program buffers."""
+    import os
+    from zgml_b200 import CudaBackend, ProgramIO
+    old = {k: os.environ.get(k) for k in knobs}
+    os.environ.update(knobs)
+    try:
+        be = CudaBackend(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        cfg = TINY_UNTIED
+        w = synthetic_weights(cfg, "q4_0", seed=31, embed_scale=1.0)
+        dev, ref = DeviceLlamaSession(be, cfg, w, 1), DeviceLlamaSession(OracleBackend(), cfg, w, 1)
+        sizes = dev.lp.program.buffer_sizes
+        got = [np.zeros(n, np.float32) for n in sizes]
+        want = [np.zeros(n, np.float32) for n in sizes]
+        dev.outputs = [ProgramIO(i, got[i]) for i in range(len(sizes))]
+        ref.outputs = [ProgramIO(i, want[i]) for i in range(len(sizes))]
+        for pos, tok in enumerate([9, 200, 31]):
+            dev.execute_at([tok], pos)
+            ref.execute_at([tok], pos)
+            for i, (g, wv) in enumerate(zip(got, want)):
+                fin = np.isfinite(wv)
+                scale = float(np.max(np.abs(wv[fin]))) if fin.any() else 0.0
+                assert np.array_equal(np.isfinite(g), fin), f"buffer {i}"
+                assert np.max(np.abs(g[fin] - wv[fin]), initial=0.0) <= 1e-4 * scale + 1e-6, f"buffer {i} at pos {pos}"
+        dev.close(); ref.close()
+    finally:
+        be.close()

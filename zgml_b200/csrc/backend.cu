@@ -49,6 +49,8 @@ void zg_gemv_ws_free(ZgGemvWs* ws) {
     *ws = ZgGemvWs();
 }
 
+// stride != 0: only the windows [lo + j * stride, + width) inside [lo, hi) are touched (a head's rows of a [T, D] matrix)
+struct ZgRange { uint32_t buf; size_t lo, hi; bool write; uint32_t dyn; uint32_t stride = 0, width = 0; };
 struct ZgCudaProgram {
     ZgCudaCtx* ctx = nullptr;
     std::vector<ZgOp> ops;
@@ -80,6 +82,8 @@ struct ZgCudaProgram {
         std::vector<uint32_t> entry_ops;   // batched: the ops that own a table entry (absorbed slice_assigns do not)
         std::map<uint32_t, uint32_t> store_of;   // batched attention op -> the slice_assign absorbed into it
         uint32_t first_entry = 0, n_entries = 0;
+        std::vector<ZgGemvPrologue> pros;  // matvec batch: how each op obtains its activations
+        std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
         bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false;
         ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
@@ -119,6 +123,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (const char* e = getenv("ZG_CUDA_PDL")) ctx->pdl = (e[0] != '0');
     g_zg_pdl = ctx->pdl;
     if (const char* e = getenv("ZG_CUDA_GEMV_BATCH")) { ctx->gemv_batch = atoi(e); if (ctx->gemv_batch < 1) ctx->gemv_batch = 1; if (ctx->gemv_batch > (int)kZgGemvBatch) ctx->gemv_batch = kZgGemvBatch; }
+    if (const char* e = getenv("ZG_CUDA_GEMV_FUSE")) ctx->gemv_fuse = atoi(e);   // bit 0: norm block, bit 1: SiLU*up pair
     if (const char* e = getenv("ZG_CUDA_ATTN_SPLIT")) ctx->attn_split = (e[0] != '0');
     if (const char* e = getenv("ZG_CUDA_FUSE")) ctx->fuse = (e[0] != '0');   // 0: no macro patterns (one chain / batch entry per DeviceOp)
     if (const char* e = getenv("ZG_CUDA_CHAIN")) ctx->chain_max = (size_t)atol(e);   // 0: one launch per small op
@@ -297,8 +302,7 @@ static bool reserve_workspace(ZgCudaProgram* p) {
 // ── op dependencies (element ranges per buffer) for concurrent graph branches ─────────────────
 // dyn != 0: the range is shifted at run time by pos * dyn (slice_assign with patch_stride, i.e. KV-cache writes);
 // all such ops of a program share one pos (src/device_inference.zig:240-247), checked in zg_cuda_refresh.
-// stride != 0: only the windows [lo + j * stride, + width) inside [lo, hi) are touched (a head's rows of a [T, D] matrix)
-struct ZgRange { uint32_t buf; size_t lo, hi; bool write; uint32_t dyn; uint32_t stride = 0, width = 0; };
+
 
 static void op_ranges(const ZgCudaProgram* p, const ZgOp& op, std::vector<ZgRange>& out) {
     out.clear();
@@ -599,13 +603,92 @@ static bool build_schedule(ZgCudaProgram* p) {
         i += c;
     }
     const size_t ni = items.size();
+    // ── matvec prologue fusion: a norm block / SiLU*up pair whose result is consumed by the matvecs that follow it
+    //    directly (q|k|v, gate|up, down) is evaluated inside those matvecs' prologues (ZgGemvPrologue); the first consumer
+    //    also stores the absorbed ops' buffers.  Decode rows only (M <= 2). ──
+    std::vector<ZgGemvPrologue> pro_of(ni);      // per consumer item
+    std::vector<int> absorbed_by(ni, -1);        // macro item -> first consumer item
+    std::vector<int> macro_of(ni, -1);           // consumer item -> macro item
+    if (p->ctx->fuse && p->ctx->gemv_fuse) {
+        for (size_t k = 0; k + 1 < ni; k++) {
+            const ZgItem& it = items[k];
+            if (it.kind != ITEM_NORM && it.kind != ITEM_EWMUL) continue;
+            if (!(p->ctx->gemv_fuse & (it.kind == ITEM_NORM ? 1 : 2))) continue;
+            const ZgOp& last = p->ops[it.first + it.count - 1];           // the closing elementwise mul: its dst is the matvec input
+            const uint32_t out_buf = last.u.elementwise.dst;
+            ZgGemvPrologue pr;
+            uint32_t rows, cols;
+            std::vector<uint32_t> touched;                                  // buffers the recipe reads or writes
+            if (it.kind == ITEM_NORM) {
+                const ZgNormMacro& m = norm_of[k];
+                if (m.rows > 2) continue;
+                rows = m.rows; cols = m.cols;
+                pr.kind = 1; pr.eps = m.eps; pr.a = m.a; pr.b = m.b; pr.gamma = m.gamma;
+                pr.o_sum = m.sum; pr.o_mid = m.bare; pr.o_grep = m.gamma_rep; pr.o_x = m.norm;
+            } else {
+                const ZgEwMulMacro& m = ewmul_of[k];
+                if (m.n_steps > 6) continue;
+                rows = 0; cols = m.n;                                       // rows fixed by the consumer: n = M * K
+                pr.kind = 2; pr.n_steps = m.n_steps; pr.a = m.src; pr.b = m.other; pr.o_mid = m.mid; pr.o_x = m.dst;
+                const auto& st = p->steps[it.first];
+                for (uint32_t q = 0; q < m.n_steps; q++) {
+                    pr.steps[q].op = st[q].op; pr.steps[q].is_swapped = st[q].is_swapped;
+                    pr.steps[q].sec = (st[q].op == ZG_EW_ADD || st[q].op == ZG_EW_MUL) ? p->buffers[st[q].secondary_buf] + st[q].secondary_offset : nullptr;
+                }
+            }
+            for (uint32_t j = 0; j < it.count; j++) {
+                std::vector<ZgRange> rr; op_ranges(p, p->ops[it.first + j], rr);
+                for (const ZgRange& r : rr) touched.push_back(r.buf);
+            }
+            size_t j = k + 1;
+            for (; j < ni; j++) {
+                const ZgItem& c = items[j];
+                if (c.kind != ITEM_OP || p->ops[c.first].tag != ZG_OP_QMATMUL) break;
+                const auto& q = p->ops[c.first].u.qmatmul;
+                const ZgCudaQWeight* w = p->qweights[q.weight_idx];
+                if (q.input != out_buf || q.input_offset != 0 || (q.input_row_stride != 0 && q.input_row_stride != q.K) || q.M == 0 || q.M > 2 ||
+                    w->fmt == ZG_QFMT_GENERIC) break;
+                if (it.kind == ITEM_NORM ? (q.M != rows || q.K != cols) : ((size_t)q.M * q.K != cols)) break;
+                if (std::find(touched.begin(), touched.end(), q.dst) != touched.end()) break;   // the matvec must not overwrite a recipe buffer
+                pro_of[j] = pr;
+                pro_of[j].write = (absorbed_by[k] < 0) ? 1u : 0u;
+                macro_of[j] = (int)k;
+                if (absorbed_by[k] < 0) absorbed_by[k] = (int)j;
+            }
+        }
+    }
+    // element ranges of every item (absorbed macro: none of its own; first consumer: macro + matvec; other consumers:
+    // the matvec with its activation read replaced by reads of the recipe's inputs, so they do not wait for the writer)
+    std::vector<std::vector<ZgRange>> item_rng(ni);
+    {
+        std::vector<ZgRange> tmp;
+        for (size_t k = 0; k < ni; k++) {
+            if (absorbed_by[k] >= 0) continue;
+            for (uint32_t j = 0; j < items[k].count; j++) { op_ranges(p, p->ops[items[k].first + j], tmp); item_rng[k].insert(item_rng[k].end(), tmp.begin(), tmp.end()); }
+            if (macro_of[k] < 0) continue;
+            const ZgItem& mi = items[macro_of[k]];
+            const uint32_t in_buf = p->ops[items[k].first].u.qmatmul.input;
+            std::vector<ZgRange> mr;
+            for (uint32_t j = 0; j < mi.count; j++) { op_ranges(p, p->ops[mi.first + j], tmp); mr.insert(mr.end(), tmp.begin(), tmp.end()); }
+            if (pro_of[k].write) {
+                item_rng[k].insert(item_rng[k].end(), mr.begin(), mr.end());
+            } else {
+                std::vector<ZgRange> keep;
+                for (const ZgRange& r : item_rng[k]) if (r.write || r.buf != in_buf) keep.push_back(r);
+                std::vector<uint32_t> written;
+                for (const ZgRange& r : mr) if (r.write) written.push_back(r.buf);
+                for (const ZgRange& r : mr)   // the macro's external inputs: read ranges of buffers the macro does not itself produce
+                    if (!r.write && std::find(written.begin(), written.end(), r.buf) == written.end()) keep.push_back(r);
+                item_rng[k] = keep;
+            }
+        }
+    }
     struct Access { ZgRange r; int level; };
     std::vector<std::vector<Access>> acc(p->buffers.size() + 2);   // + the virtual GEMM-scratch and communicator buffers
     std::vector<int> level(ni, 0);
-    std::vector<ZgRange> rng, tmp;
     for (size_t k = 0; k < ni; k++) {
-        rng.clear();
-        for (uint32_t j = 0; j < items[k].count; j++) { op_ranges(p, p->ops[items[k].first + j], tmp); rng.insert(rng.end(), tmp.begin(), tmp.end()); }
+        if (absorbed_by[k] >= 0) { level[k] = -1; continue; }
+        const std::vector<ZgRange>& rng = item_rng[k];
         int lvl = 0;
         for (const ZgRange& r : rng)
             for (const Access& a : acc[r.buf])
@@ -617,9 +700,10 @@ static bool build_schedule(ZgCudaProgram* p) {
             acc[r.buf].push_back({r, lvl});
         }
     }
-    std::vector<uint32_t> order(ni);
-    for (size_t k = 0; k < ni; k++) order[k] = (uint32_t)k;
+    std::vector<uint32_t> order;
+    for (size_t k = 0; k < ni; k++) if (absorbed_by[k] < 0) order.push_back((uint32_t)k);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
+    const size_t no = order.size();
     p->units.clear();
     p->entry_of_op.assign(n, 0);
     std::vector<ZgBatchEntry> entries;
@@ -678,9 +762,9 @@ static bool build_schedule(ZgCudaProgram* p) {
         return op.tag != ZG_OP_RMSNORM && op.tag != ZG_OP_ALLREDUCE && zg_chain_work(op) <= 512;
     };
     size_t pos = 0;
-    while (pos < ni) {
+    while (pos < no) {
         size_t end = pos;
-        while (end < ni && level[order[end]] == level[order[pos]]) end++;
+        while (end < no && level[order[end]] == level[order[pos]]) end++;
         bool first_small = true, has_big = false;
         // per-head ops (rope, cache stores): one warp each inside a chain is only a win for a handful of heads; a wide
         // level (32 heads x 4 ops) is better served by the batched multi-CTA kernels
@@ -708,16 +792,17 @@ static bool build_schedule(ZgCudaProgram* p) {
             const ZgItem& it = items[order[k]];
             if (in_chain(it)) continue;   // chained above
             const ZgOp& op = p->ops[it.first];
-            if (it.kind == ITEM_OP && op.tag == ZG_OP_QMATMUL && op.u.qmatmul.M >= 1 && op.u.qmatmul.M <= 8 && p->ctx->gemv_batch > 1 &&
-                p->qweights[op.u.qmatmul.weight_idx]->fmt != ZG_QFMT_GENERIC) {
-                // independent matvecs of one shape / format / row count share a launch (q|k|v, gate|up)
+            if (it.kind == ITEM_OP && op.tag == ZG_OP_QMATMUL && op.u.qmatmul.M >= 1 && op.u.qmatmul.M <= 8 &&
+                (p->ctx->gemv_batch > 1 || pro_of[order[k]].kind != 0) && p->qweights[op.u.qmatmul.weight_idx]->fmt != ZG_QFMT_GENERIC) {
+                // independent matvecs of one shape / format / row count (and prologue kind) share a launch (q|k|v, gate|up)
                 const ZgCudaQWeight* w = p->qweights[op.u.qmatmul.weight_idx];
+                const uint32_t pk = pro_of[order[k]].kind;
                 size_t ui = (size_t)-1;
                 for (auto& o : open_mv) {
                     const ZgCudaQWeight* r = o.first;
                     const ZgCudaProgram::Unit& u = p->units[o.second];
-                    if (r->fmt == w->fmt && r->K == w->K && r->N == w->N && p->ops[u.ops[0]].u.qmatmul.M == op.u.qmatmul.M &&
-                        u.ops.size() < (size_t)p->ctx->gemv_batch) { ui = o.second; break; }
+                    if (r->fmt == w->fmt && r->K == w->K && r->N == w->N && p->ops[u.entry_ops[0]].u.qmatmul.M == op.u.qmatmul.M &&
+                        u.pros[0].kind == pk && u.entry_ops.size() < (size_t)std::max(p->ctx->gemv_batch, 1)) { ui = o.second; break; }
                 }
                 if (ui == (size_t)-1) {
                     ZgCudaProgram::Unit u; u.gemv_batch = true;
@@ -725,7 +810,15 @@ static bool build_schedule(ZgCudaProgram* p) {
                     ui = p->units.size() - 1;
                     open_mv.push_back({w, ui});
                 }
-                p->units[ui].ops.push_back(it.first);
+                ZgCudaProgram::Unit& u = p->units[ui];
+                u.entry_ops.push_back(it.first);
+                u.ops.push_back(it.first);
+                u.pros.push_back(pro_of[order[k]]);
+                if (pk && pro_of[order[k]].write) {   // the absorbed ops belong to this launch
+                    const ZgItem& mi = items[macro_of[order[k]]];
+                    for (uint32_t j = 0; j < mi.count; j++) u.ops.push_back(mi.first + j);
+                }
+                u.ranges.insert(u.ranges.end(), item_rng[order[k]].begin(), item_rng[order[k]].end());
                 continue;
             }
             if (it.kind == ITEM_NORM) {    // long rows: one wide CTA per row instead of the 256-thread chain
@@ -839,12 +932,12 @@ static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStre
     if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
     if (u.norm) return zg_launch_norm_macro(u.nm, st);
-    if (u.gemv_batch && u.ops.size() > 1) {
+    if (u.gemv_batch && (u.entry_ops.size() > 1 || u.pros[0].kind != 0)) {
         const ZgCudaQWeight* w[kZgGemvBatch]; const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];
         uint32_t irs[kZgGemvBatch], ors[kZgGemvBatch]; ZgGemvWs view[kZgGemvBatch];
-        const uint32_t cnt = (uint32_t)u.ops.size();
+        const uint32_t cnt = (uint32_t)u.entry_ops.size();
         for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t i = u.ops[k];
+            const uint32_t i = u.entry_ops[k];
             const auto& q = p->ops[i].u.qmatmul;
             w[k] = p->qweights[q.weight_idx];
             xin[k] = p->buffers[q.input] + q.input_offset; xout[k] = p->buffers[q.dst] + q.dst_offset;
@@ -853,7 +946,7 @@ static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStre
             if (view[k].partials) { view[k].partials += p->ws_part_off[i]; view[k].partials_elems -= p->ws_part_off[i]; }
             if (view[k].counters) { view[k].counters += p->ws_cnt_off[i]; view[k].counters_n -= p->ws_cnt_off[i]; }
         }
-        return zg_qgemv_launch_batch(p->ctx, cnt, w, xin, xout, p->ops[u.ops[0]].u.qmatmul.M, irs, ors, view, st);
+        return zg_qgemv_launch_batch(p->ctx, cnt, w, xin, xout, p->ops[u.entry_ops[0]].u.qmatmul.M, irs, ors, view, st, u.pros.data());
     }
     if (!u.batched) return launch_one(p, u.ops[0], st);
     if (u.attn_splits > 1)
@@ -905,10 +998,12 @@ static bool launch_all_branched(ZgCudaProgram* p, cudaStream_t origin) {
     int rr = 0;
     bool ok = true;
     for (size_t i = 0; i < n && ok; i++) {
-        for (uint32_t oi : p->units[i].ops) {   // a unit reads / writes the union of its ops' ranges
-            op_ranges(p, p->ops[oi], tmp);
-            rng[i].insert(rng[i].end(), tmp.begin(), tmp.end());
-        }
+        if (!p->units[i].ranges.empty()) rng[i] = p->units[i].ranges;
+        else
+            for (uint32_t oi : p->units[i].ops) {   // a unit reads / writes the union of its ops' ranges
+                op_ranges(p, p->ops[oi], tmp);
+                rng[i].insert(rng[i].end(), tmp.begin(), tmp.end());
+            }
         std::fill(dep.begin(), dep.end(), -1L);
         int found = 0;
         for (long k = (long)i - 1; k >= 0 && found < ns; k--) {   // latest conflicting unit of every stream

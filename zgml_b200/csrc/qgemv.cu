@@ -58,6 +58,7 @@ struct QGemvParams {
     uint32_t P, S, NS;
     float* partials;
     uint32_t* counters;
+    ZgGemvPrologue pro;
 };
 
 // Up to kZgGemvBatch independent matvecs of one shape / format share a launch (blockIdx.y selects the op): q|k|v,
@@ -114,7 +115,8 @@ constexpr uint32_t kPlaneRow = 144;   // bytes per (record, activation row) digi
 
 // FMT: ZG_QFMT_I8_F32 / ZG_QFMT_I8_F16 / ZG_QFMT_I4_F16.  MP: pairs of activation rows (M <= 2*MP).
 // XR: activation rows staged per warp (1 for the decode matvec M == 1, else 2*MP).
-template <int FMT, int MP, int XR>
+// PRO: 0 = activations are read; 1 / 2 = produced in the prologue (ZgGemvPrologue; M <= 2 only)
+template <int FMT, int MP, int XR, int PRO = 0>
 __global__ void __launch_bounds__(kThreads, MP == 1 ? 3 : (MP == 2 ? 2 : 1))
 qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
     const QGemvParams& p = bt.p[blockIdx.y];
@@ -194,6 +196,79 @@ qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
     // ── stage x'[m, k] = x[m, k] * 0.499 / (max|x| * smax) of this warp's k-range in shared memory (so that
     //    |s * x'| <= 0.499).  Non-finite activations poison the partial sums (NaN out, like the reference);
     //    k >= K reads as zero; only rows < M are staged (the other B columns alias row M - 1). ──
+    float inv_rms[XR];
+#pragma unroll
+    for (int m = 0; m < XR; m++) inv_rms[m] = 0.0f;
+    if constexpr (PRO == 1) {
+        // rmsnorm scale of every staged row: all 256 threads walk the whole row (K floats, L2-resident), fixed reduction
+        // order -> every CTA of every consumer matvec computes the identical value
+        __shared__ float s_red[kMaxWarps][XR];
+#pragma unroll
+        for (int m = 0; m < XR; m++) {
+            float ss = 0.0f;
+            if (XR == 1 || (uint32_t)m < p.M) {
+                const float* ar = p.pro.a + (size_t)m * p.K;
+                const float* br = p.pro.b ? p.pro.b + (size_t)m * p.K : nullptr;
+                if ((p.K & 3u) == 0) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+                    for (uint32_t jq = tid; jq < (p.K >> 2); jq += kThreads) {
+                        float4 v = reinterpret_cast<const float4*>(ar)[jq];
+                        if (br) { const float4 t = reinterpret_cast<const float4*>(br)[jq]; v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w); }
+                        s0 += v.x * v.x; s1 += v.y * v.y; s2 += v.z * v.z; s3 += v.w * v.w;
+                    }
+                    ss = (s0 + s1) + (s2 + s3);
+                } else {
+                    for (uint32_t jq = tid; jq < p.K; jq += kThreads) { float v = ar[jq]; if (br) v = __fadd_rn(v, br[jq]); ss += v * v; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) s_red[warp][m] = ss;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < XR; m++) {
+            float tot = 0.0f;
+            for (uint32_t w2 = 0; w2 < W; w2++) tot += s_red[w2][m];
+            inv_rms[m] = 1.0f / sqrtf(tot / (float)p.K + p.pro.eps);
+        }
+    }
+    const bool pro_write = PRO != 0 && p.pro.write != 0 && grp == 0;   // column-group block 0: its S splits x 8 warps cover every k once
+    // activation k of row m: read (PRO 0) or produced by the absorbed ops, whose outputs the writer CTAs also store
+    auto load_x = [&](uint32_t m, uint32_t kidx) -> float {
+        if constexpr (PRO == 0) {
+            return p.x[(size_t)m * p.x_rs + kidx];
+        } else if constexpr (PRO == 1) {
+            const size_t f = (size_t)m * p.K + kidx;
+            float sv = p.pro.a[f];
+            if (p.pro.b) sv = __fadd_rn(sv, p.pro.b[f]);
+            const float bare = __fmul_rn(sv, inv_rms[m]), gm = p.pro.gamma[kidx], xv = __fmul_rn(bare, gm);
+            if (pro_write) {
+                if (p.pro.o_sum) p.pro.o_sum[f] = sv;
+                p.pro.o_mid[f] = bare; p.pro.o_grep[f] = gm; p.pro.o_x[f] = xv;
+            }
+            return xv;
+        } else {
+            const size_t f = (size_t)m * p.K + kidx;
+            float v = p.pro.a[f];
+            for (uint32_t st = 0; st < p.pro.n_steps; st++) {
+                const uint32_t sop = p.pro.steps[st].op, sw = p.pro.steps[st].is_swapped;
+                if (sop == ZG_EW_ADD) { const float t2 = p.pro.steps[st].sec[f]; v = sw ? __fadd_rn(t2, v) : __fadd_rn(v, t2); }
+                else if (sop == ZG_EW_MUL) { const float t2 = p.pro.steps[st].sec[f]; v = sw ? __fmul_rn(t2, v) : __fmul_rn(v, t2); }
+                else if (sop == ZG_EW_NEG) v = -v;
+                else if (sop == ZG_EW_EXP) v = expf(v);
+                else if (sop == ZG_EW_RECIP) v = 1.0f / v;
+                else if (sop == ZG_EW_ABS) v = fabsf(v);
+                else if (sop == ZG_EW_RELU) v = fmaxf(v, 0.0f);
+                else if (sop == ZG_EW_SQRT) v = sqrtf(v);
+                else if (sop == ZG_EW_LOG) v = logf(v);
+            }
+            const float xv = __fmul_rn(v, p.pro.b[f]);
+            if (pro_write) { p.pro.o_mid[f] = v; p.pro.o_x[f] = xv; }
+            return xv;
+        }
+    };
     float xm[MR];
     {
         const uint32_t kb = k0 * ZG_KR;
@@ -203,13 +278,12 @@ qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
 #pragma unroll
         for (int m = 0; m < XR; m++) {
             if (XR == 1 || (uint32_t)m < p.M) {
-                const float* xr = p.x + (size_t)m * p.x_rs + kb + lane;
                 float* xd = xs_w + (size_t)m * p.xs_stride + lane;
                 float v[kLcap];
                 float mx = 0.0f;
 #pragma unroll
                 for (int i = 0; i < (int)kLcap; i++) {
-                    v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? xr[32 * i] : 0.0f;
+                    v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? load_x((uint32_t)m, kb + lane + 32 * i) : 0.0f;
                     const float aa = fabsf(v[i]);
                     mx = (aa <= 3.0e38f) ? fmaxf(mx, aa) : INFINITY;
                 }
@@ -438,7 +512,7 @@ __global__ void qmatmul_generic_kernel(const int8_t* __restrict__ data, const fl
     out[(size_t)m * out_rs + n] = acc;
 }
 
-template <int FMT, int MP, int XR>
+template <int FMT, int MP, int XR, int PRO = 0>
 bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid, count);
@@ -450,7 +524,7 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cu
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR, PRO>, p);
     ZG_COUNT_LAUNCH();
     if (e != cudaSuccess) {
         zg_set_error("qgemv launch failed: %s (grid %u, %u B shared)", cudaGetErrorString(e), plan.grid, plan.smem_bytes);
@@ -461,6 +535,12 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cu
 
 template <int FMT>
 bool launch_fmt(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cudaStream_t st, bool pdl) {
+    const uint32_t pk = p.p[0].pro.kind;
+    if (pk != 0) {   // prologue recipes exist for the decode variants only (M <= 2)
+        if (plan.mp != 1) { zg_set_error("internal: matvec prologue with more than 2 rows"); return false; }
+        if (pk == 1) return p.p[0].M == 1 ? launch_fast<FMT, 1, 1, 1>(plan, p, count, st, pdl) : launch_fast<FMT, 1, 2, 1>(plan, p, count, st, pdl);
+        return p.p[0].M == 1 ? launch_fast<FMT, 1, 1, 2>(plan, p, count, st, pdl) : launch_fast<FMT, 1, 2, 2>(plan, p, count, st, pdl);
+    }
     switch (plan.mp) {
         case 1: return p.p[0].M == 1 ? launch_fast<FMT, 1, 1>(plan, p, count, st, pdl) : launch_fast<FMT, 1, 2>(plan, p, count, st, pdl);
         case 2: return launch_fast<FMT, 2, 4>(plan, p, count, st, pdl);
@@ -521,14 +601,17 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     return pl;
 }
 
-template <int FMT, int MP, int XR>
+template <int FMT, int MP, int XR, int PRO = 0>
 bool set_smem_attr() {
-    cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<FMT, MP, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(qgemv_kernel<FMT, MP, XR, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemv) failed: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 template <int FMT>
-bool set_smem_attrs() { return set_smem_attr<FMT, 1, 1>() && set_smem_attr<FMT, 1, 2>() && set_smem_attr<FMT, 2, 4>() && set_smem_attr<FMT, 4, 8>(); }
+bool set_smem_attrs() {
+    return set_smem_attr<FMT, 1, 1>() && set_smem_attr<FMT, 1, 2>() && set_smem_attr<FMT, 2, 4>() && set_smem_attr<FMT, 4, 8>() &&
+           set_smem_attr<FMT, 1, 1, 1>() && set_smem_attr<FMT, 1, 2, 1>() && set_smem_attr<FMT, 1, 1, 2>() && set_smem_attr<FMT, 1, 2, 2>();
+}
 
 bool zg_qgemv_init(ZgCudaCtx* ctx) {
     if (const char* e = getenv("ZG_GEMV_S")) ctx->tune_s = atoi(e);
@@ -587,7 +670,7 @@ bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in
 // rows per pass re-stream the weights but run the well-occupied narrow variants).
 static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
                               float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
-                              const ZgGemvWs* ws, cudaStream_t st) {
+                              const ZgGemvWs* ws, cudaStream_t st, const ZgGemvPrologue* pro) {
     const ZgCudaQWeight* w0 = ws_w[0];
     ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M);
     QGemvBatch bt;
@@ -610,6 +693,10 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
         p.out = d_out[i]; p.out_rs = out_rs[i] ? out_rs[i] : (uint32_t)w->N;
         p.P = plan.P; p.S = plan.S; p.NS = plan.NS;
         p.partials = ws[i].partials; p.counters = ws[i].counters;
+        if (pro) {
+            if (pro[i].kind != pro[0].kind || (pro[i].kind && (M > 2 || p.x_rs != p.K))) { zg_set_error("internal: mixed or unsupported matvec prologue"); return false; }
+            p.pro = pro[i];
+        }
     }
     switch (w0->fmt) {
         case ZG_QFMT_I8_F32: return launch_fmt<ZG_QFMT_I8_F32>(plan, bt, count, st, ctx->pdl);
@@ -621,20 +708,21 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
 
 bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* ws_w, const float* const* d_in,
                            float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
-                           const ZgGemvWs* ws, cudaStream_t st) {
+                           const ZgGemvWs* ws, cudaStream_t st, const ZgGemvPrologue* pro) {
     if (count == 0 || M == 0) return true;
     if (count > kZgGemvBatch || M > 8) { zg_set_error("internal: bad matvec batch (%u ops, %u rows)", count, M); return false; }
     const ZgGemvWs none[kZgGemvBatch] = {};
     if (!ws) ws = none;
     const uint32_t rpp = ctx->tune_rows ? (uint32_t)ctx->tune_rows : 4u;   // measured: two 4-row passes beat one 8-row pass (ZG_GEMV_ROWS)
-    if (M <= rpp) return launch_batch_rows(ctx, count, ws_w, d_in, d_out, M, in_rs, out_rs, ws, st);
+    if (M <= rpp) return launch_batch_rows(ctx, count, ws_w, d_in, d_out, M, in_rs, out_rs, ws, st, pro);
+    if (pro && pro[0].kind) { zg_set_error("internal: matvec prologue on a multi-pass launch"); return false; }
     for (uint32_t m0 = 0; m0 < M; m0 += rpp) {
         const float* xin[kZgGemvBatch]; float* xout[kZgGemvBatch];
         for (uint32_t i = 0; i < count; i++) {
             xin[i] = d_in[i] + (size_t)m0 * (in_rs[i] ? in_rs[i] : (uint32_t)ws_w[i]->K);
             xout[i] = d_out[i] + (size_t)m0 * (out_rs[i] ? out_rs[i] : (uint32_t)ws_w[i]->N);
         }
-        if (!launch_batch_rows(ctx, count, ws_w, xin, xout, std::min(rpp, M - m0), in_rs, out_rs, ws, st)) return false;
+        if (!launch_batch_rows(ctx, count, ws_w, xin, xout, std::min(rpp, M - m0), in_rs, out_rs, ws, st, nullptr)) return false;
     }
     return true;
 }

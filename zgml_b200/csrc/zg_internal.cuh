@@ -103,6 +103,8 @@ struct ZgCudaCtx {
     int tune_s = 0, tune_p = 0, tune_u = 0, tune_g = 0, tune_smax = 0, tune_rows = 0; // ZG_GEMV_S / _P / _NS / _G overrides (kernel tuning only)
     ZgGemvWs ws; // split-K workspace for the direct zg_cuda_qmatmul_* calls
     int gemv_batch = 8;          // independent same-shape matvecs of a dependency level per launch (ZG_CUDA_GEMV_BATCH, 1 = off)
+    int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
+                                 // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
@@ -132,10 +134,25 @@ void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, 
                       size_t* counters);
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
                        uint32_t M, uint32_t in_rs, uint32_t out_rs, const ZgGemvWs* ws, cudaStream_t st);
+// How a decode matvec obtains its activation vector.  kind 0: read x.  Otherwise the small ops that PRODUCE x in the
+// program (the lowering's norm block, or the SiLU chain times `up`) are evaluated in the matvec's own prologue, every
+// CTA redundantly on its k-range, and the CTAs of column-group block 0 of the op flagged `write` also store the absorbed
+// ops' output buffers (every DeviceOp result stays observable).  One kernel less per block on the decode critical path.
+struct ZgDevStepC { uint32_t op, is_swapped; const float* sec; };
+struct ZgGemvPrologue {
+    uint32_t kind = 0;      // 1: [a + b ->] sum ; rmsnorm(sum) -> bare ; gamma -> gamma_rep ; bare * gamma_rep -> x
+                            // 2: steps(a) -> mid ; mid * b -> x
+    uint32_t write = 0;
+    uint32_t n_steps = 0;
+    float eps = 0.0f;
+    const float* a = nullptr; const float* b = nullptr; const float* gamma = nullptr;
+    float* o_sum = nullptr; float* o_mid = nullptr; float* o_grep = nullptr; float* o_x = nullptr;   // o_mid: bare (1) / mid (2)
+    ZgDevStepC steps[6] = {};
+};
 constexpr uint32_t kZgGemvBatch = 8;   // independent same-shape matvecs of one dependency level per launch
 bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* w, const float* const* d_in,
                            float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
-                           const ZgGemvWs* ws, cudaStream_t st);   // ws: one workspace view per op
+                           const ZgGemvWs* ws, cudaStream_t st, const ZgGemvPrologue* pro = nullptr);   // ws, pro: one per op
 bool zg_qgemv_init(ZgCudaCtx* ctx);
 // qgemm.cu : M > 8 on tcgen05 tensor cores
 bool zg_qgemm_init(ZgCudaCtx* ctx);
