@@ -58,12 +58,14 @@ struct QGemvParams {
     uint32_t P, S, NS;
     float* partials;
     uint32_t* counters;
-    ZgGemvPrologue pro;
 };
+struct QGemvParamsPro : QGemvParams { ZgGemvPrologue pro; };   // only the prologue-fusion instantiations carry the recipe
 
 // Up to kZgGemvBatch independent matvecs of one shape / format share a launch (blockIdx.y selects the op): q|k|v,
 // gate|up, or the copies of a microbenchmark.  The parameter block stays in the constant bank.
-struct QGemvBatch { QGemvParams p[kZgGemvBatch]; };
+template <bool HAS_PRO>
+struct QGemvBatchT { std::conditional_t<HAS_PRO, QGemvParamsPro, QGemvParams> p[kZgGemvBatch]; };
+using QGemvBatch = QGemvBatchT<true>;   // host-side form; narrowed to QGemvBatchT<false> for the plain kernels
 
 // D(16x8, s32) += A(16x32: weights) * B(32x8, u8: digits of x*s)
 __device__ __forceinline__ void imma_s8u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -118,8 +120,8 @@ constexpr uint32_t kPlaneRow = 144;   // bytes per (record, activation row) digi
 // PRO: 0 = activations are read; 1 / 2 = produced in the prologue (ZgGemvPrologue; M <= 2 only)
 template <int FMT, int MP, int XR, int PRO = 0>
 __global__ void __launch_bounds__(kThreads, MP == 1 ? 3 : (MP == 2 ? 2 : 1))
-qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
-    const QGemvParams& p = bt.p[blockIdx.y];
+qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
+    const auto& p = bt.p[blockIdx.y];
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
     constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
     constexpr int MR = 2 * MP;
@@ -197,8 +199,10 @@ qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
     //    |s * x'| <= 0.499).  Non-finite activations poison the partial sums (NaN out, like the reference);
     //    k >= K reads as zero; only rows < M are staged (the other B columns alias row M - 1). ──
     float inv_rms[XR];
+    if constexpr (PRO != 0) {
 #pragma unroll
-    for (int m = 0; m < XR; m++) inv_rms[m] = 0.0f;
+        for (int m = 0; m < XR; m++) inv_rms[m] = 0.0f;
+    }
     if constexpr (PRO == 1) {
         // rmsnorm scale of every staged row: all 256 threads walk the whole row (K floats, L2-resident), fixed reduction
         // order -> every CTA of every consumer matvec computes the identical value
@@ -234,7 +238,8 @@ qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
             inv_rms[m] = 1.0f / sqrtf(tot / (float)p.K + p.pro.eps);
         }
     }
-    const bool pro_write = PRO != 0 && p.pro.write != 0 && grp == 0;   // column-group block 0: its S splits x 8 warps cover every k once
+    bool pro_write = false;   // column-group block 0: its S splits x 8 warps cover every k once
+    if constexpr (PRO != 0) pro_write = p.pro.write != 0 && grp == 0;
     // activation k of row m: read (PRO 0) or produced by the absorbed ops, whose outputs the writer CTAs also store
     auto load_x = [&](uint32_t m, uint32_t kidx) -> float {
         if constexpr (PRO == 0) {
@@ -278,12 +283,14 @@ qgemv_kernel(const __grid_constant__ QGemvBatch bt) {
 #pragma unroll
         for (int m = 0; m < XR; m++) {
             if (XR == 1 || (uint32_t)m < p.M) {
+                const float* xr = p.x + (size_t)m * p.x_rs + kb + lane;
                 float* xd = xs_w + (size_t)m * p.xs_stride + lane;
                 float v[kLcap];
                 float mx = 0.0f;
 #pragma unroll
                 for (int i = 0; i < (int)kLcap; i++) {
-                    v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? load_x((uint32_t)m, kb + lane + 32 * i) : 0.0f;
+                    if constexpr (PRO == 0) v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? xr[32 * i] : 0.0f;
+                    else v[i] = ((uint32_t)i < L && kb + lane + 32 * i < p.K) ? load_x((uint32_t)m, kb + lane + 32 * i) : 0.0f;
                     const float aa = fabsf(v[i]);
                     mx = (aa <= 3.0e38f) ? fmaxf(mx, aa) : INFINITY;
                 }
@@ -524,7 +531,14 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cu
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR, PRO>, p);
+    cudaError_t e;
+    if constexpr (PRO != 0) {
+        e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR, PRO>, p);
+    } else {
+        QGemvBatchT<false> plain;
+        for (uint32_t i = 0; i < kZgGemvBatch; i++) plain.p[i] = static_cast<const QGemvParams&>(p.p[i]);
+        e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR, 0>, plain);
+    }
     ZG_COUNT_LAUNCH();
     if (e != cudaSuccess) {
         zg_set_error("qgemv launch failed: %s (grid %u, %u B shared)", cudaGetErrorString(e), plan.grid, plan.smem_bytes);
@@ -684,7 +698,7 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
             zg_set_error("internal: split workspace too small (%zu/%zu needed)", pe, nc);
             return false;
         }
-        QGemvParams& p = bt.p[i];
+        QGemvParamsPro& p = bt.p[i];
         p.recs = w->recs; p.smax = w->smax;
         p.n_kc = w->n_kc; p.n_nb = w->n_nb;
         p.K = (uint32_t)w->K; p.N = (uint32_t)w->N; p.M = M;
