@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu > gpurun_out/pytest_sharded.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_sharded.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
+timeout 400 $TR scripts/bench_sharded.py --model llama3-70b --layers 16 --kind q4_0 --tokens 32 --batch 1,8 --context 512 > gpurun_out/sharded_70b_l16_g2_peer.log 2>&1
+tail -n 3 gpurun_out/pytest_sharded.log; grep -h '^{' gpurun_out/sharded_70b_l16_g2_peer.log | cut -c90-330
