@@ -726,7 +726,7 @@ static bool build_schedule(ZgCudaProgram* p) {
     auto close_chain = [&]() {
         if (chain_items.empty()) return true;
         const ZgItem& only = items[chain_items[0]];
-        if (chain_items.size() == 1 && only.kind == ITEM_OP && !zg_op_is_batched(p->ops[only.first].tag) && true) {
+        if (chain_items.size() == 1 && only.kind == ITEM_OP && !zg_op_is_batched(p->ops[only.first].tag)) {
             ZgCudaProgram::Unit u; u.ops.push_back(only.first); p->units.push_back(u);   // a lone op: its own (wider) kernel is as good
         } else {
             ZgCudaProgram::Unit chain; chain.chain = true;
