@@ -12,6 +12,7 @@ ap.add_argument("--M", type=int, default=2048)
 ap.add_argument("--shapes", default="4096x4096,4096x14336,14336x4096")
 ap.add_argument("--kind", default="q8_0")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--check", action="store_true", help="compare 64 sampled rows with a torch fp64 product of the dequantized weight")
 args = ap.parse_args()
 be = CudaBackend(0)
 stream = torch.cuda.Stream()
@@ -38,10 +39,20 @@ for shp in args.shapes.split(","):
         e1.record(stream)
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
+    err = None
+    if args.check:   # floating-point kernel: torch reference of the same product, fp64 accumulate (tolerance: north star's 1e-3)
+        ws[(args.iters - 1) % 3].matmul_device(x.data_ptr(), y.data_ptr(), args.M)
+        torch.cuda.synchronize()
+        wd = (torch.from_numpy(data.astype(np.float32)).view(K * N // 32, 32) * torch.from_numpy(scales)[:, None]).view(K, N).cuda()
+        rows = torch.linspace(0, args.M - 1, 64).long().cuda()
+        ref = x[rows].double() @ wd.double()
+        err = float((y[rows].double() - ref).abs().max() / ref.abs().max())
+        del wd, ref
     flops = 2.0 * args.M * N * K
     print(json.dumps({"metric": "prefill_qgemm", "M": args.M, "K": K, "N": N, "kind": args.kind, "ms": round(ms, 4),
                       "tflops": round(flops / ms / 1e9, 1), "tok_per_s_this_linear": round(args.M / ms * 1e3),
-                      "mode": "bf16x1" if os.environ.get("ZG_GEMM_X1") == "1" else "3xBF16"}))
+                      "mode": "bf16x1" if os.environ.get("ZG_GEMM_X1") == "1" else "3xBF16",
+                      "tile": os.environ.get("ZG_GEMM_MH", "auto"), "max_rel_err": err}))
     for w in ws:
         w.free()
 be.close()

@@ -307,6 +307,32 @@ def test_qmatmul_prefill_tensor_core_path_vs_oracle(cuda_backend, K, N, M, kind)
     w.free()
 
 
+@pytest.mark.parametrize("M,out_pad,out_off", [(40, 3, 2), (300, 3, 2), (300, 4, 4), (130, 0, 0)])
+def test_program_prefill_qmatmul_strides_and_untouched_cells(cuda_backend, M, out_pad, out_off):
+    """DeviceOp.qmatmul with M > 8 (tensor-core path): input / dst offsets and row strides (reference.zig:499-566);
+    unaligned destinations take the epilogue's scalar row stores, 16-byte aligned ones the 128-bit stores; cells
+    outside the dst rows keep their previous contents in both."""
+    K, N = 96, 160
+    r = rng(40 + M)
+    o = oracle.QuantizedWeight.from_slice(r.uniform(-1, 1, K * N).astype(np.float32), K, N, 32)
+    in_rs, out_rs, in_off = K + 5, N + out_pad, 7
+    inp = r.standard_normal(in_off + M * in_rs).astype(np.float32)
+    dst0 = np.full(out_off + M * out_rs + 4, -7, np.float32)
+    qw = QuantizedWeightUpload(o.data, o.scales, K, N, 32)
+    prog = DeviceProgram([DeviceOp.qmatmul(1, 0, 0, M, N, K, in_off, in_rs, out_off, out_rs)],
+                         [inp.size, dst0.size], [ProgramIO(0, inp), ProgramIO(1, dst0)], [qw])
+    want = np.zeros_like(dst0)
+    oracle.run_program(prog, [], [ProgramIO(1, want)])
+    h = cuda_backend.compile_program(prog)
+    assert h is not None
+    got = np.zeros_like(dst0)
+    cuda_backend.execute_program(h, [], [ProgramIO(1, got)])
+    cuda_backend.free_program(h)
+    touched = want != -7
+    assert np.array_equal(got[~touched], want[~touched])
+    assert rel_err(got[touched], want[touched]) < 5e-5
+
+
 def test_prefill_rows_match_decode_rows(cuda_backend):
     """Row i of an M = 40 tensor-core matmul equals the exact M = 1 matvec of that row within the 3xBF16 envelope."""
     K, N = 576, 1536

@@ -26,15 +26,21 @@
 
 namespace {
 
-constexpr uint32_t BM = 128, BN = 256, BK = 64;                     // BK bf16 = one 128-byte swizzle row = two records of 32 k
-constexpr uint32_t kTileA = BM * BK * 2, kTileB = BN * BK * 2;      // one BF16 operand tile: 16 KB (A), 32 KB (B)
+constexpr uint32_t BK = 64;                                        // BK bf16 = one 128-byte swizzle row = two records of 32 k
+// MH = accumulator halves along M.  MH = 1: 128 x 256 tile (few activation rows).  MH = 2: 256 x 128 tile, two 128-row
+// accumulators in TMEM fed from ONE dequantized weight tile: the dequantize work per flop halves, and that — not the
+// tensor pipe — is what bounds this kernel (a single-term run was only 1.3x faster than the three-term one).
+__host__ __device__ constexpr uint32_t tbm(int MH) { return 128u * MH; }
+__host__ __device__ constexpr uint32_t tbn(int MH) { return MH == 1 ? 256u : 128u; }
+__host__ __device__ constexpr uint32_t tile_a(int MH) { return tbm(MH) * BK * 2; }   // one BF16 A tile: 16 / 32 KB
+__host__ __device__ constexpr uint32_t tile_b(int MH) { return tbn(MH) * BK * 2; }   // one BF16 B tile: 32 / 16 KB
 constexpr uint32_t kDqWarps = 16;                                  // dequantize warps: enough resident warps to hide ALU latency (8 left the MMA waiting)
 constexpr uint32_t kGemmThreads = 64 + 32 * kDqWarps;              // warp 0: TMA, warp 1: MMA + TMEM, warps 2-17: dequant + epilogue
 constexpr uint32_t kTmemCols = 256;
 // NT = BF16 terms per operand.  NT = 2 (default): x = x_hi + x_lo, w = w_hi + w_lo, D += hi*hi + hi*lo + lo*hi
 // ("3xBF16": ~5e-6 relative); NT = 1: one rounded term each (~4e-3 relative, 3x fewer MMAs; throughput experiments only).
 __host__ __device__ constexpr uint32_t stages_of(int NT) { return NT == 1 ? 4u : 2u; }
-__host__ __device__ constexpr uint32_t smem_of(int NT) { return stages_of(NT) * NT * (kTileA + kTileB) + 1024 /* alignment slack */ + 256 /* barriers */; }
+__host__ __device__ constexpr uint32_t smem_of(int NT) { return stages_of(NT) * NT * (tile_a(1) + tile_b(1)) + 1024 /* alignment slack */ + 256 /* barriers */; }   // same for MH = 2
 
 struct QGemmParams {
     const uint8_t* recs;
@@ -42,6 +48,7 @@ struct QGemmParams {
     uint32_t M, N;
     float* out;
     uint32_t out_rs;
+    uint32_t out_vec4;   // destination rows are 16-byte aligned: the epilogue may use 128-bit stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -101,11 +108,14 @@ __global__ void k_split_bf16(const float* __restrict__ x, uint32_t x_rs, uint32_
     }
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, int MH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a_lo, const QGemmParams p) {
     constexpr uint32_t kStages = stages_of(NT);
+    constexpr uint32_t BM = tbm(MH), BN = tbn(MH), kTileA = tile_a(MH), kTileB = tile_b(MH);
     constexpr uint32_t kStageA = NT * kTileA, kStageB = NT * kTileB;   // [hi | lo] tiles
+    constexpr uint32_t kDqPerStage = MH == 1 ? kDqWarps : kDqWarps / 2;   // MH = 2: the two halves of the dequant warps alternate stages
+    static_assert(NT != 1 || MH == 1, "the single-term experiment keeps the 128 x 256 tile");
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
     constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
     constexpr uint32_t QB = kI4 ? 512u : 1024u;
@@ -127,7 +137,7 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kStages; s++) {
             mbar_init(full_a + 8 * s, 1);
-            mbar_init(full_b + 8 * s, kDqWarps);   // one arrive per dequant warp
+            mbar_init(full_b + 8 * s, kDqPerStage);   // one arrive per dequant warp working on the stage
             mbar_init(empty + 8 * s, 1);       // tcgen05.commit
         }
         mbar_init(tmem_full, 1);
@@ -156,8 +166,8 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else if (warp == 1) {
         // ── MMA issuer ──
-        // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+        // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = BN, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((128u >> 4) << 24);
         for (uint32_t kt = 0; kt < n_k; kt++) {
             const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
             mbar_wait(full_a + 8 * s, ph);
@@ -170,13 +180,17 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int term = 0; term < (NT == 2 ? 3 : 1); term++) {
                         const uint32_t a_off = (term == 2) ? kTileA : 0u, b_off = (term == 1) ? kTileB : 0u;
-                        const uint64_t da = make_desc(sA + s * kStageA + a_off + k * 32), db = make_desc(sB + s * kStageB + b_off + k * 32);
+                        const uint64_t db = make_desc(sB + s * kStageB + b_off + k * 32);
                         const uint32_t accumulate = (kt | k | (uint32_t)term) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                            ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+#pragma unroll
+                        for (int mh = 0; mh < MH; mh++) {   // 128-row halves of the A tile -> their own TMEM accumulator (BN columns apart)
+                            const uint64_t da = make_desc(sA + s * kStageA + a_off + (uint32_t)mh * (128u * 128u) + k * 32);
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                ::"r"(tmem_base + (uint32_t)mh * BN), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+                        }
                     }
                 }
                 // frees the stage when the MMAs that read it have completed
@@ -190,7 +204,9 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ── dequantize warps: warp (dw, h) owns column group dw (32 columns) and record half h of every stage
         //    (one record = 32 columns x 32 k; a stage = 64 k = records 2 kt and 2 kt + 1) ──
         const uint32_t dwi = warp - 2;                   // 0..15
-        const uint32_t dw = dwi & 7, h = dwi >> 3;
+        // MH = 1: 8 column groups x 2 record halves, every stage.  MH = 2: 4 column groups x 2 halves x 2 stage parities.
+        const uint32_t dw = MH == 1 ? (dwi & 7) : (dwi & 3), h = MH == 1 ? (dwi >> 3) : ((dwi >> 2) & 1);
+        const uint32_t par = MH == 1 ? 0u : (dwi >> 3), kstep = MH == 1 ? 1u : 2u;   // this warp's stages: par, par + kstep, ...
         const uint32_t g = lane >> 2, t = lane & 3;
         const uint32_t nb = tile_n * (BN / 32) + dw;
         const bool nb_ok = nb < p.n_nb;
@@ -198,10 +214,11 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // register ring: the records of the next kPf stages are in flight while the current one is converted
         constexpr int kPf = 2;
         uint4 rq[kPf], rq1[kPf], rs0[kPf], rs1[kPf];
-        auto load_rec = [&](int slot, uint32_t kt) {   // record 2 kt + h; past the end (odd record count): zeros
+        auto load_rec = [&](int slot, uint32_t j) {   // this warp's j-th stage: record 2 kt + h; past the end: zeros
+            const uint32_t kt = par + j * kstep;
             const uint32_t ri = 2 * kt + h;
             rq[slot] = make_uint4(0, 0, 0, 0); rq1[slot] = rq[slot]; rs0[slot] = rq[slot]; rs1[slot] = rq[slot];
-            if (nb_ok && ri < n_rec) {
+            if (nb_ok && kt < n_k && ri < n_rec) {
                 const uint8_t* r = rec + (size_t)ri * RB;
                 rq[slot] = __ldg(reinterpret_cast<const uint4*>(r + lane * 16));
                 if constexpr (!kI4) rq1[slot] = __ldg(reinterpret_cast<const uint4*>(r + 512 + lane * 16));
@@ -211,14 +228,14 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         };
 #pragma unroll
         for (int i = 0; i < kPf; i++) load_rec(i, i);
-        for (uint32_t kt0 = 0; kt0 < n_k; kt0 += kPf) {
+        for (uint32_t j0 = 0; par + j0 * kstep < n_k; j0 += kPf) {
 #pragma unroll
           for (int slot = 0; slot < kPf; slot++) {
-            const uint32_t kt = kt0 + slot;
+            const uint32_t kt = par + (j0 + slot) * kstep;
             if (kt >= n_k) break;
             const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
             const uint4 qa = rq[slot], qb = rq1[slot], s0 = rs0[slot], s1 = rs1[slot];
-            load_rec(slot, kt + kPf);
+            load_rec(slot, j0 + slot + kPf);
             float sc[8];   // scales of rows k = 4t + i (i < 4) and 16 + 4t + (i - 4)
             if constexpr (kF32) {
                 sc[0] = __uint_as_float(s0.x); sc[1] = __uint_as_float(s0.y); sc[2] = __uint_as_float(s0.z); sc[3] = __uint_as_float(s0.w);
@@ -231,11 +248,12 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     sc[2 * i] = f.x; sc[2 * i + 1] = f.y;
                 }
             }
-            mbar_wait(empty + 8 * s, ph ^ 1);
-            const uint32_t stage = sB + s * kStageB;
+            // Convert into registers FIRST: nothing here needs the stage to be free, so the only work left between the
+            // MMA releasing the stage and this warp's arrive is the stores (ncu: the convert chain, ~2900 cycles of
+            // dependent ALU latency per record half, used to sit on that critical path).
+            uint32_t pk[2][4][2 * NT];   // [column tile][unit] -> {hi k0k1, hi k2k3, lo k0k1, lo k2k3}
 #pragma unroll
             for (int ct = 0; ct < 2; ct++) {
-            const uint32_t row_lo = dw * 32 + ct * 16 + g;   // B-tile rows of this lane in column tile ct: row_lo and row_lo + 8
             uint4 q;
             if constexpr (kI4) { q.x = ct ? qa.z : qa.x; q.y = ct ? qa.w : qa.y; q.z = 0; q.w = 0; }
             else q = ct ? qb : qa;
@@ -255,20 +273,41 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                     for (int b = 0; b < 4; b++) qf[b] = __uint_as_float(__byte_perm(nib, 0x4B000000u, 0x7650 + b)) - 8388616.0f;
                 }
-                const uint32_t n = row_lo + 8 * (r & 1);
-                // four consecutive k starting at 32 h + 16 (r >> 1) + 4 t  ->  8 bytes at byte 2 k of the 128-byte row
-                const uint32_t chunk = 4 * h + 2 * (r >> 1) + (t >> 1);          // 16-byte chunk = eight consecutive k
                 float wv[4];
 #pragma unroll
                 for (int b = 0; b < 4; b++) wv[b] = qf[b] * sc[4 * (r >> 1) + b];   // f32(q) * scale, src/quant.zig:612-615
                 const uint32_t h0 = pack_bf16x2(wv[0], wv[1]), h1 = pack_bf16x2(wv[2], wv[3]);
-                const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4) + ((t & 1) << 3);
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(h0), "r"(h1) : "memory");
+                pk[ct][r][0] = h0; pk[ct][r][1] = h1;
                 if constexpr (NT == 2) {
-                    const uint32_t l0 = pack_bf16x2(wv[0] - bf16_lo_f32(h0), wv[1] - bf16_hi_f32(h0));
-                    const uint32_t l1 = pack_bf16x2(wv[2] - bf16_lo_f32(h1), wv[3] - bf16_hi_f32(h1));
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + kTileB), "r"(l0), "r"(l1) : "memory");
+                    pk[ct][r][2] = pack_bf16x2(wv[0] - bf16_lo_f32(h0), wv[1] - bf16_hi_f32(h0));
+                    pk[ct][r][3] = pack_bf16x2(wv[2] - bf16_lo_f32(h1), wv[3] - bf16_hi_f32(h1));
                 }
+            }
+            }
+            // Keep the packed values live ACROSS the wait: ptxas otherwise sinks the packs below the wait loop (seen in the
+            // SASS).  A fold of all of them feeds a store that never executes (M is never 2^32 - 1), which pins them here.
+            uint32_t fold = 0;
+#pragma unroll
+            for (int ct = 0; ct < 2; ct++)
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int i = 0; i < 2 * NT; i++) fold ^= pk[ct][r][i];
+            if (p.M == 0xFFFFFFFFu) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_slot), "r"(fold) : "memory");
+            mbar_wait(empty + 8 * s, ph ^ 1);
+            const uint32_t stage = sB + s * kStageB;
+#pragma unroll
+            for (int ct = 0; ct < 2; ct++) {
+            const uint32_t row_lo = dw * 32 + ct * 16 + g;   // B-tile rows of this lane in column tile ct: row_lo and row_lo + 8
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t n = row_lo + 8 * (r & 1);
+                // four consecutive k starting at 32 h + 16 (r >> 1) + 4 t  ->  8 bytes at byte 2 k of the 128-byte row
+                const uint32_t chunk = 4 * h + 2 * (r >> 1) + (t >> 1);          // 16-byte chunk = eight consecutive k
+                const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4) + ((t & 1) << 3);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(pk[ct][r][0]), "r"(pk[ct][r][1]) : "memory");
+                if constexpr (NT == 2)
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + kTileB), "r"(pk[ct][r][2]), "r"(pk[ct][r][3]) : "memory");
             }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -280,12 +319,15 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t quarter = warp & 3;
-        const uint32_t m = tile_m * BM + quarter * 32 + lane;
-        const uint32_t c_begin = (dwi >> 2) * (BN / 4);  // the four warps of a TMEM lane quarter split the columns
+        // the four warps of a TMEM lane quarter split the work: MH = 1: 4 x 64 columns; MH = 2: accumulator half x 64 columns
+        const uint32_t e_mh = MH == 1 ? 0u : ((dwi >> 2) & 1u);
+        const uint32_t m_base = tile_m * BM + e_mh * 128 + quarter * 32;   // first of this warp's 32 output rows
+        uint4* tb = reinterpret_cast<uint4*>(dsm_raw + (base - smem_u32(dsm_raw)) + dwi * (32 * 36 * 4));
+        const uint32_t c_begin = MH == 1 ? (dwi >> 2) * 64u : (dwi >> 3) * 64u;
 #pragma unroll 1
-        for (uint32_t c0 = c_begin; c0 < c_begin + BN / 4; c0 += 32) {
+        for (uint32_t c0 = c_begin; c0 < c_begin + 64; c0 += 32) {
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + c0;
+            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + e_mh * BN + c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -296,12 +338,30 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const uint32_t n0 = tile_n * BN + c0;
-            if (m < p.M && n0 < p.N) {
-                float* dstp = p.out + (size_t)m * p.out_rs + n0;
+            // lane = output row here; a direct store would touch 32 rows (32 sectors) per instruction — ncu: 19 % of all
+            // warp samples stalled on those.  Transpose the 32 x 32 block through this warp's patch of the (now idle)
+            // stage memory (row pitch 36 words: conflict-free both ways) and write whole 128-byte row segments.
 #pragma unroll
-                for (int i = 0; i < 32; i++) dstp[i] = __uint_as_float(v[i]);   // N % 32 == 0: whole column groups only
+            for (int i = 0; i < 8; i++)
+                tb[lane * 9 + i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            __syncwarp();
+            const uint32_t n0 = tile_n * BN + c0;
+            if (n0 < p.N) {                                  // N % 32 == 0: whole column groups only
+                if (p.out_vec4) {
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {         // four rows x eight 16-byte pieces per instruction
+                        const uint32_t rr = it * 4 + (lane >> 3), mm = m_base + rr;
+                        const uint4 o = tb[rr * 9 + (lane & 7)];
+                        if (mm < p.M) *reinterpret_cast<uint4*>(p.out + (size_t)mm * p.out_rs + n0 + 4 * (lane & 7)) = o;
+                    }
+                } else {
+                    const uint32_t* tw = reinterpret_cast<const uint32_t*>(tb);
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; rr++)          // unaligned destination: one row segment per instruction
+                        if (m_base + rr < p.M) p.out[(size_t)(m_base + rr) * p.out_rs + n0 + lane] = __uint_as_float(tw[rr * 36 + lane]);
+                }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -326,54 +386,70 @@ bool get_encode() {
     return true;
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, int MH>
 bool launch_gemm(const CUtensorMap& map, const CUtensorMap& map_lo, const QGemmParams& p, cudaStream_t st) {
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
-    qgemm_bf16_kernel<FMT, NT><<<grid, kGemmThreads, smem_of(NT), st>>>(map, map_lo, p);
+    dim3 grid((p.N + tbn(MH) - 1) / tbn(MH), (p.M + tbm(MH) - 1) / tbm(MH));
+    qgemm_bf16_kernel<FMT, NT, MH><<<grid, kGemmThreads, smem_of(NT), st>>>(map, map_lo, p);
     ZG_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { zg_set_error("qgemm launch failed: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 
-template <int FMT, int NT>
+template <int FMT, int NT, int MH>
 bool set_attr() {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_bf16_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(NT));
+    cudaError_t e = cudaFuncSetAttribute(qgemm_bf16_kernel<FMT, NT, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(NT));
     if (e != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemm) failed: %s", cudaGetErrorString(e)); return false; }
     return true;
 }
 
+template <int FMT>
+bool launch_fmt(int NT, int MH, const CUtensorMap& map, const CUtensorMap& map_lo, const QGemmParams& p, cudaStream_t st) {
+    if (NT == 1) return launch_gemm<FMT, 1, 1>(map, map_lo, p, st);
+    return MH == 2 ? launch_gemm<FMT, 2, 2>(map, map_lo, p, st) : launch_gemm<FMT, 2, 1>(map, map_lo, p, st);
+}
+
 int g_terms = 2;   // ZG_GEMM_X1=1 selects the single-term mode (throughput experiments only: 4e-3 relative)
+int g_mh = 0;      // ZG_GEMM_MH: 1 / 2 force the 128 x 256 / 256 x 128 tile; 0 (default): 256 x 128 whenever it wastes no extra rows
+
+// Tile choice for M activation rows: two accumulator halves when that pads M no further than 128-row tiles would.
+int pick_mh(uint32_t M) {
+    if (g_terms == 1 || g_mh == 1) return 1;
+    if (g_mh == 2) return 2;
+    return (M > 128 && (M + 255) / 256 * 256 == (M + 127) / 128 * 128) ? 2 : 1;
+}
 
 } // namespace
 
 bool zg_qgemm_init(ZgCudaCtx*) {
     if (const char* e = getenv("ZG_GEMM_X1")) g_terms = (e[0] == '1') ? 1 : 2;
-    return set_attr<ZG_QFMT_I8_F32, 1>() && set_attr<ZG_QFMT_I8_F16, 1>() && set_attr<ZG_QFMT_I4_F16, 1>() &&
-           set_attr<ZG_QFMT_I8_F32, 2>() && set_attr<ZG_QFMT_I8_F16, 2>() && set_attr<ZG_QFMT_I4_F16, 2>() && get_encode();
+    if (const char* e = getenv("ZG_GEMM_MH")) g_mh = (e[0] == '1') ? 1 : (e[0] == '2' ? 2 : 0);
+    return set_attr<ZG_QFMT_I8_F32, 1, 1>() && set_attr<ZG_QFMT_I8_F16, 1, 1>() && set_attr<ZG_QFMT_I4_F16, 1, 1>() &&
+           set_attr<ZG_QFMT_I8_F32, 2, 1>() && set_attr<ZG_QFMT_I8_F16, 2, 1>() && set_attr<ZG_QFMT_I4_F16, 2, 1>() &&
+           set_attr<ZG_QFMT_I8_F32, 2, 2>() && set_attr<ZG_QFMT_I8_F16, 2, 2>() && set_attr<ZG_QFMT_I4_F16, 2, 2>() && get_encode();
 }
 
-// BF16 hi and lo planes of the activations the GEMM's TMA reads: 2 x [round_up(M, 128)][round_up(K, 64)] bf16,
-// counted in f32 elements (the workspace unit).
+// BF16 hi and lo planes of the activations the GEMM's TMA reads: 2 x [round_up(M, 256)][round_up(K, 64)] bf16,
+// counted in f32 elements (the workspace unit).  256 rows: whole TMA boxes for either tile shape.
 size_t zg_qgemm_scratch_elems(const ZgCudaQWeight* w, uint32_t M) {
     if (w->fmt == ZG_QFMT_GENERIC || M <= 8) return 0;
-    return (size_t)((M + BM - 1) / BM * BM) * ((size_t)(w->n_kc + 1) / 2 * BK);
+    return (size_t)((M + 255) / 256 * 256) * ((size_t)(w->n_kc + 1) / 2 * BK);
 }
 
 bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out, uint32_t M, uint32_t in_rs,
                      uint32_t out_rs, float* scratch, cudaStream_t st) {
     (void)ctx;
     if (!get_encode()) return false;
-    const uint32_t Kp = (w->n_kc + 1) / 2 * BK, Mp = (M + BM - 1) / BM * BM;
+    const uint32_t Kp = (w->n_kc + 1) / 2 * BK, Mp = (M + 255) / 256 * 256;
     const size_t plane_words = (size_t)Mp * (Kp / 2);   // one bf16 plane in 32-bit words
-    const int NT = g_terms;
+    const int NT = g_terms, MH = pick_mh(M);
     uint32_t* planes = reinterpret_cast<uint32_t*>(scratch);
     k_split_bf16<<<dim3((Kp / 2 + 255) / 256, Mp), 256, 0, st>>>(d_in, in_rs, planes, Kp / 2, M, (uint32_t)w->K, plane_words, NT);
     ZG_COUNT_LAUNCH();
     CUtensorMap map[2];
     const cuuint64_t gdim[2] = {Kp, Mp};
     const cuuint64_t gstride[1] = {(cuuint64_t)Kp * 2};
-    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t box[2] = {BK, tbm(MH)};
     const cuuint32_t estr[2] = {1, 1};
     for (int i = 0; i < 2; i++) {
         CUresult r = g_encode(&map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, planes + (size_t)i * plane_words, gdim, gstride, box, estr,
@@ -383,20 +459,12 @@ bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, 
     }
     QGemmParams p;
     p.recs = w->recs; p.n_kc = w->n_kc; p.n_nb = w->n_nb; p.M = M; p.N = (uint32_t)w->N; p.out = d_out; p.out_rs = out_rs;
-    if (NT == 1) {
-        switch (w->fmt) {
-            case ZG_QFMT_I8_F32: return launch_gemm<ZG_QFMT_I8_F32, 1>(map[0], map[1], p, st);
-            case ZG_QFMT_I8_F16: return launch_gemm<ZG_QFMT_I8_F16, 1>(map[0], map[1], p, st);
-            case ZG_QFMT_I4_F16: return launch_gemm<ZG_QFMT_I4_F16, 1>(map[0], map[1], p, st);
-            default: break;
-        }
-    } else {
-        switch (w->fmt) {
-            case ZG_QFMT_I8_F32: return launch_gemm<ZG_QFMT_I8_F32, 2>(map[0], map[1], p, st);
-            case ZG_QFMT_I8_F16: return launch_gemm<ZG_QFMT_I8_F16, 2>(map[0], map[1], p, st);
-            case ZG_QFMT_I4_F16: return launch_gemm<ZG_QFMT_I4_F16, 2>(map[0], map[1], p, st);
-            default: break;
-        }
+    p.out_vec4 = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (out_rs & 3) == 0) ? 1u : 0u;
+    switch (w->fmt) {
+        case ZG_QFMT_I8_F32: return launch_fmt<ZG_QFMT_I8_F32>(NT, MH, map[0], map[1], p, st);
+        case ZG_QFMT_I8_F16: return launch_fmt<ZG_QFMT_I8_F16>(NT, MH, map[0], map[1], p, st);
+        case ZG_QFMT_I4_F16: return launch_fmt<ZG_QFMT_I4_F16>(NT, MH, map[0], map[1], p, st);
+        default: break;
     }
     zg_set_error("qgemm: unknown weight format %d", w->fmt);
     return false;
