@@ -7,12 +7,14 @@
 //     (128 lanes x 256 columns), issued by one thread; K advances 64 per pipeline stage (4 MMAs of K = 16 per term).
 //   * A = activations: split once into two BF16 terms x = x_hi + x_lo (each round-to-nearest) in a dense scratch,
 //     then TMA (cp.async.bulk.tensor.2d, 128B swizzle) straight into the canonical K-major shared-memory layout.
-//   * B = weights: eight dequantize warps read the packed records (zg_internal.cuh) with 128-bit loads, form
-//     w = f32(q) * s exactly like dequantizeTo (src/quant.zig:594-618), split w = w_hi + w_lo in BF16 and store
-//     8-byte runs (four consecutive k) into the same swizzled K-major layout, two records (2 x 32 k) per stage.
+//   * B = weights: sixteen dequantize warps read the packed records (zg_internal.cuh) with 128-bit loads, form
+//     w = f32(q) * s exactly like dequantizeTo (src/quant.zig:594-618), split w = w_hi + w_lo in BF16 — all in
+//     registers, before waiting for the stage — then store 8-byte runs (four consecutive k) into the same swizzled
+//     K-major layout with a lane / record assignment that makes the 64-bit stores bank-conflict free.
 //     Weights are dequantized once per 128 activation rows, in shared memory only.
 //   * 2-stage mbarrier pipeline (96 KB per stage: hi and lo tiles of A and B): TMA warp / dequant warps -> MMA warp
-//     -> (tcgen05.commit) -> stage free; the dequant warps turn into the epilogue (tcgen05.ld 32x32b -> global stores).
+//     -> (tcgen05.commit) -> stage free; the dequant warps turn into the epilogue: tcgen05.ld 32x32b, a 32 x 32
+//     transpose through the idle stage memory, 128-byte row-segment stores.
 //
 // Numerics: "3xBF16" — both operands are split hi + lo (16 significant bits, residual 2^-18), D += hi*hi + hi*lo +
 // lo*hi with fp32 accumulation in TMEM: ~5e-6 relative on outputs (the dropped lo*lo and the residuals are 2^-17 per
@@ -27,9 +29,10 @@
 namespace {
 
 constexpr uint32_t BK = 64;                                        // BK bf16 = one 128-byte swizzle row = two records of 32 k
-// MH = accumulator halves along M.  MH = 1: 128 x 256 tile (few activation rows).  MH = 2: 256 x 128 tile, two 128-row
-// accumulators in TMEM fed from ONE dequantized weight tile: the dequantize work per flop halves, and that — not the
-// tensor pipe — is what bounds this kernel (a single-term run was only 1.3x faster than the three-term one).
+// MH = accumulator halves along M.  MH = 1 (default): 128 x 256 tile.  MH = 2 (ZG_GEMM_MH=2, experiment): 256 x 128 tile,
+// two 128-row accumulators in TMEM fed from ONE dequantized weight tile — the dequantize instructions per flop halve
+// (ncu: 84 M -> 47 M warp instructions at 2048 x 4096 x 4096) but the time does not change (0-4 % slower): the dequantize
+// warps are not the limiter.  Kept because it is parity-tested and the right B-side shape for a future cta_group::2 tile.
 __host__ __device__ constexpr uint32_t tbm(int MH) { return 128u * MH; }
 __host__ __device__ constexpr uint32_t tbn(int MH) { return MH == 1 ? 256u : 128u; }
 __host__ __device__ constexpr uint32_t tile_a(int MH) { return tbm(MH) * BK * 2; }   // one BF16 A tile: 16 / 32 KB
@@ -39,6 +42,8 @@ constexpr uint32_t kGemmThreads = 64 + 32 * kDqWarps;              // warp 0: TM
 constexpr uint32_t kTmemCols = 256;
 // NT = BF16 terms per operand.  NT = 2 (default): x = x_hi + x_lo, w = w_hi + w_lo, D += hi*hi + hi*lo + lo*hi
 // ("3xBF16": ~5e-6 relative); NT = 1: one rounded term each (~4e-3 relative, 3x fewer MMAs; throughput experiments only).
+// Ring slots: 2 of 96 KB (NT = 2), 4 of 48 KB (NT = 1).  Measured and rejected: separate rings with a third slot for the
+// TMA-fed activation tile (3 x 32 KB + 2 x 64 KB, own empty barriers): 3-5 % slower — the kernel is not waiting on TMA.
 __host__ __device__ constexpr uint32_t stages_of(int NT) { return NT == 1 ? 4u : 2u; }
 __host__ __device__ constexpr uint32_t smem_of(int NT) { return stages_of(NT) * NT * (tile_a(1) + tile_b(1)) + 1024 /* alignment slack */ + 256 /* barriers */; }   // same for MH = 2
 
@@ -201,29 +206,42 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
         }
     } else {
-        // ── dequantize warps: warp (dw, h) owns column group dw (32 columns) and record half h of every stage
-        //    (one record = 32 columns x 32 k; a stage = 64 k = records 2 kt and 2 kt + 1) ──
+        // ── dequantize warps: warp (dw, ct) owns 16 columns (column tile ct of column group dw) of BOTH records of a
+        //    stage (one record = 32 columns x 32 k; a stage = 64 k = records 2 kt and 2 kt + 1).
+        //    Lanes with odd g take the two records in swapped order (slot s holds record 2 kt + (s ^ (g & 1))): one
+        //    64-bit store instruction then spreads a half-warp's four rows g over four different 8-bank groups of the
+        //    128B-swizzled tile.  With one record per warp (the first version) rows 2j and 2j + 1 always shared a bank
+        //    group — ncu: 57 % excess store wavefronts, and shared-memory bandwidth (operand reads of the MMAs + these
+        //    stores + the TMA writes) is what bounds this kernel. ──
         const uint32_t dwi = warp - 2;                   // 0..15
-        // MH = 1: 8 column groups x 2 record halves, every stage.  MH = 2: 4 column groups x 2 halves x 2 stage parities.
-        const uint32_t dw = MH == 1 ? (dwi & 7) : (dwi & 3), h = MH == 1 ? (dwi >> 3) : ((dwi >> 2) & 1);
+        // MH = 1: 8 column groups x 2 column tiles, every stage.  MH = 2: 4 column groups x 2 column tiles x 2 stage parities.
+        const uint32_t dw = MH == 1 ? (dwi & 7) : (dwi & 3), ct = MH == 1 ? (dwi >> 3) : ((dwi >> 2) & 1);
         const uint32_t par = MH == 1 ? 0u : (dwi >> 3), kstep = MH == 1 ? 1u : 2u;   // this warp's stages: par, par + kstep, ...
-        const uint32_t g = lane >> 2, t = lane & 3;
+        const uint32_t g = lane >> 2, t = lane & 3, gx = g & 1;
         const uint32_t nb = tile_n * (BN / 32) + dw;
         const bool nb_ok = nb < p.n_nb;
         const uint8_t* rec = p.recs + (size_t)(nb_ok ? nb : 0) * p.n_kc * RB;
         // register ring: the records of the next kPf stages are in flight while the current one is converted
-        constexpr int kPf = 2;
-        uint4 rq[kPf], rq1[kPf], rs0[kPf], rs1[kPf];
-        auto load_rec = [&](int slot, uint32_t j) {   // this warp's j-th stage: record 2 kt + h; past the end: zeros
+        // (f32 scales take twice the registers: one stage ahead — a full MMA stage time — still covers an L2 hit)
+        constexpr int kPf = kF32 ? 1 : 2;
+        uint4 rq[kPf][2], rs0[kPf][2], rs1[kPf][2];
+        auto load_rec = [&](int slot, uint32_t j) {   // this warp's j-th stage; records past the end: zeros
             const uint32_t kt = par + j * kstep;
-            const uint32_t ri = 2 * kt + h;
-            rq[slot] = make_uint4(0, 0, 0, 0); rq1[slot] = rq[slot]; rs0[slot] = rq[slot]; rs1[slot] = rq[slot];
-            if (nb_ok && kt < n_k && ri < n_rec) {
-                const uint8_t* r = rec + (size_t)ri * RB;
-                rq[slot] = __ldg(reinterpret_cast<const uint4*>(r + lane * 16));
-                if constexpr (!kI4) rq1[slot] = __ldg(reinterpret_cast<const uint4*>(r + 512 + lane * 16));
-                rs0[slot] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB));
-                if constexpr (kF32) rs1[slot] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB + 16));
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const uint32_t ri = 2 * kt + ((uint32_t)sl ^ gx);
+                rq[slot][sl] = make_uint4(0, 0, 0, 0); rs0[slot][sl] = rq[slot][sl]; rs1[slot][sl] = rq[slot][sl];
+                if (nb_ok && kt < n_k && ri < n_rec) {
+                    const uint8_t* r = rec + (size_t)ri * RB;
+                    if constexpr (kI4) {
+                        const uint2 v = __ldg(reinterpret_cast<const uint2*>(r + lane * 16 + ct * 8));
+                        rq[slot][sl].x = v.x; rq[slot][sl].y = v.y;
+                    } else {
+                        rq[slot][sl] = __ldg(reinterpret_cast<const uint4*>(r + ct * 512 + lane * 16));
+                    }
+                    rs0[slot][sl] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB));
+                    if constexpr (kF32) rs1[slot][sl] = __ldg(reinterpret_cast<const uint4*>(r + QB + t * SB + 16));
+                }
             }
         };
 #pragma unroll
@@ -234,8 +252,12 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t kt = par + (j0 + slot) * kstep;
             if (kt >= n_k) break;
             const uint32_t s = kt % kStages, ph = (kt / kStages) & 1;
-            const uint4 qa = rq[slot], qb = rq1[slot], s0 = rs0[slot], s1 = rs1[slot];
-            load_rec(slot, j0 + slot + kPf);
+            // Convert into registers FIRST: nothing here needs the stage to be free, so the only work left between the
+            // MMA releasing the stage and this warp's arrive is the stores.
+            uint32_t pk[2][4][2 * NT];   // [record slot][unit] -> {hi k0k1, hi k2k3, lo k0k1, lo k2k3}
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+            const uint4 q = rq[slot][sl], s0 = rs0[slot][sl], s1 = rs1[slot][sl];
             float sc[8];   // scales of rows k = 4t + i (i < 4) and 16 + 4t + (i - 4)
             if constexpr (kF32) {
                 sc[0] = __uint_as_float(s0.x); sc[1] = __uint_as_float(s0.y); sc[2] = __uint_as_float(s0.z); sc[3] = __uint_as_float(s0.w);
@@ -248,18 +270,9 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     sc[2 * i] = f.x; sc[2 * i + 1] = f.y;
                 }
             }
-            // Convert into registers FIRST: nothing here needs the stage to be free, so the only work left between the
-            // MMA releasing the stage and this warp's arrive is the stores (ncu: the convert chain, ~2900 cycles of
-            // dependent ALU latency per record half, used to sit on that critical path).
-            uint32_t pk[2][4][2 * NT];   // [column tile][unit] -> {hi k0k1, hi k2k3, lo k0k1, lo k2k3}
-#pragma unroll
-            for (int ct = 0; ct < 2; ct++) {
-            uint4 q;
-            if constexpr (kI4) { q.x = ct ? qa.z : qa.x; q.y = ct ? qa.w : qa.y; q.z = 0; q.w = 0; }
-            else q = ct ? qb : qa;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                // unit r: column n = row_lo + 8 (r & 1), rows k = 4 t + b + 16 (r >> 1), b = 0..3.
+                // unit r: column n = 16 ct + g + 8 (r & 1), rows k = 4 t + b + 16 (r >> 1), b = 0..3.
                 // int -> float through the mantissa: bits 0x4B000000 | u are the float 2^23 + u exactly.
                 float qf[4];
                 if constexpr (!kI4) {
@@ -277,37 +290,38 @@ qgemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                 for (int b = 0; b < 4; b++) wv[b] = qf[b] * sc[4 * (r >> 1) + b];   // f32(q) * scale, src/quant.zig:612-615
                 const uint32_t h0 = pack_bf16x2(wv[0], wv[1]), h1 = pack_bf16x2(wv[2], wv[3]);
-                pk[ct][r][0] = h0; pk[ct][r][1] = h1;
+                pk[sl][r][0] = h0; pk[sl][r][1] = h1;
                 if constexpr (NT == 2) {
-                    pk[ct][r][2] = pack_bf16x2(wv[0] - bf16_lo_f32(h0), wv[1] - bf16_hi_f32(h0));
-                    pk[ct][r][3] = pack_bf16x2(wv[2] - bf16_lo_f32(h1), wv[3] - bf16_hi_f32(h1));
+                    pk[sl][r][2] = pack_bf16x2(wv[0] - bf16_lo_f32(h0), wv[1] - bf16_hi_f32(h0));
+                    pk[sl][r][3] = pack_bf16x2(wv[2] - bf16_lo_f32(h1), wv[3] - bf16_hi_f32(h1));
                 }
             }
             }
+            load_rec(slot, j0 + slot + kPf);
             // Keep the packed values live ACROSS the wait: ptxas otherwise sinks the packs below the wait loop (seen in the
             // SASS).  A fold of all of them feeds a store that never executes (M is never 2^32 - 1), which pins them here.
             uint32_t fold = 0;
 #pragma unroll
-            for (int ct = 0; ct < 2; ct++)
+            for (int sl = 0; sl < 2; sl++)
 #pragma unroll
                 for (int r = 0; r < 4; r++)
 #pragma unroll
-                    for (int i = 0; i < 2 * NT; i++) fold ^= pk[ct][r][i];
+                    for (int i = 0; i < 2 * NT; i++) fold ^= pk[sl][r][i];
             if (p.M == 0xFFFFFFFFu) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tmem_slot), "r"(fold) : "memory");
             mbar_wait(empty + 8 * s, ph ^ 1);
             const uint32_t stage = sB + s * kStageB;
 #pragma unroll
-            for (int ct = 0; ct < 2; ct++) {
-            const uint32_t row_lo = dw * 32 + ct * 16 + g;   // B-tile rows of this lane in column tile ct: row_lo and row_lo + 8
+            for (int sl = 0; sl < 2; sl++) {
+            const uint32_t hh = (uint32_t)sl ^ gx;               // which record (k half of the stage) this slot holds
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const uint32_t n = row_lo + 8 * (r & 1);
-                // four consecutive k starting at 32 h + 16 (r >> 1) + 4 t  ->  8 bytes at byte 2 k of the 128-byte row
-                const uint32_t chunk = 4 * h + 2 * (r >> 1) + (t >> 1);          // 16-byte chunk = eight consecutive k
+                const uint32_t n = dw * 32 + ct * 16 + g + 8 * (r & 1);   // B-tile row (output column)
+                // four consecutive k starting at 32 hh + 16 (r >> 1) + 4 t  ->  8 bytes at byte 2 k of the 128-byte row
+                const uint32_t chunk = 4 * hh + 2 * (r >> 1) + (t >> 1);         // 16-byte chunk = eight consecutive k
                 const uint32_t addr = stage + n * 128 + ((chunk ^ (n & 7)) << 4) + ((t & 1) << 3);
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(pk[ct][r][0]), "r"(pk[ct][r][1]) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(pk[sl][r][0]), "r"(pk[sl][r][1]) : "memory");
                 if constexpr (NT == 2)
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + kTileB), "r"(pk[ct][r][2]), "r"(pk[ct][r][3]) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr + kTileB), "r"(pk[sl][r][2]), "r"(pk[sl][r][3]) : "memory");
             }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -410,20 +424,15 @@ bool launch_fmt(int NT, int MH, const CUtensorMap& map, const CUtensorMap& map_l
 }
 
 int g_terms = 2;   // ZG_GEMM_X1=1 selects the single-term mode (throughput experiments only: 4e-3 relative)
-int g_mh = 0;      // ZG_GEMM_MH: 1 / 2 force the 128 x 256 / 256 x 128 tile; 0 (default): 256 x 128 whenever it wastes no extra rows
+int g_mh = 1;      // ZG_GEMM_MH=2 selects the 256 x 128 two-accumulator tile (experiment, see above); default 128 x 256
 
-// Tile choice for M activation rows: two accumulator halves when that pads M no further than 128-row tiles would.
-int pick_mh(uint32_t M) {
-    if (g_terms == 1 || g_mh == 1) return 1;
-    if (g_mh == 2) return 2;
-    return (M > 128 && (M + 255) / 256 * 256 == (M + 127) / 128 * 128) ? 2 : 1;
-}
+int pick_mh(uint32_t) { return (g_terms == 2 && g_mh == 2) ? 2 : 1; }
 
 } // namespace
 
 bool zg_qgemm_init(ZgCudaCtx*) {
     if (const char* e = getenv("ZG_GEMM_X1")) g_terms = (e[0] == '1') ? 1 : 2;
-    if (const char* e = getenv("ZG_GEMM_MH")) g_mh = (e[0] == '1') ? 1 : (e[0] == '2' ? 2 : 0);
+    if (const char* e = getenv("ZG_GEMM_MH")) g_mh = (e[0] == '2') ? 2 : 1;
     return set_attr<ZG_QFMT_I8_F32, 1, 1>() && set_attr<ZG_QFMT_I8_F16, 1, 1>() && set_attr<ZG_QFMT_I4_F16, 1, 1>() &&
            set_attr<ZG_QFMT_I8_F32, 2, 1>() && set_attr<ZG_QFMT_I8_F16, 2, 1>() && set_attr<ZG_QFMT_I4_F16, 2, 1>() &&
            set_attr<ZG_QFMT_I8_F32, 2, 2>() && set_attr<ZG_QFMT_I8_F16, 2, 2>() && set_attr<ZG_QFMT_I4_F16, 2, 2>() && get_encode();
