@@ -274,6 +274,22 @@ ZgCudaQWeight* zg_cuda_qweight_from_f32(ZgCudaCtx* ctx, const float* h_weights, 
 int zg_cuda_qmatmul_bias_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, const float* h_bias,
                               float* h_dst, uint32_t M);
 
+/* W8A8 decode path (what `session.quantize()` models run per linear on the reference's aarch64 builds).  All three are
+ * integer / IEEE-exact work and bit-identical to the reference.
+ * prepareTransposed — reference src/quant.zig:274-317 (twin src/backend/reference.zig:26-70): dequantize [K, N], re-quantize
+ * into [N, K] int8 with K-aligned blocks + [N, ceil(K / block_size)] f32 scales; both stay resident with the weight.
+ * h_t_data / h_t_scales (either may be NULL) receive copies.  Idempotent.  Returns 0 on success. */
+int zg_cuda_qweight_prepare_transposed(ZgCudaCtx* ctx, ZgCudaQWeight* w, int8_t* h_t_data, float* h_t_scales);
+/* quantizeInput — reference src/quant.zig:320-341: per K-block scale = max_abs / 127 (1 if zero),
+ * q = trunc(clamp(v * (127 / max_abs), +-127)).  Host buffers: h_q [K], h_scales [ceil(K / block_size)].
+ * Limits as the reference's stack buffers (src/quant.zig:452-453): K <= 16384, <= 512 blocks. */
+int zg_cuda_quantize_input_host(ZgCudaCtx* ctx, const float* h_input, size_t K, size_t block_size, int8_t* h_q, float* h_scales);
+/* gemv — reference src/quant.zig:443-459 = quantizeInput + gemvRange (:358-440) over all N outputs, M = 1:
+ * dst[n] = sum over K-blocks ascending of f32(int32 dot) * (s_x[b] * s_w[n, b]).  Needs prepare_transposed.
+ * _device: device pointers, async on the ctx stream; _host: host buffers, synchronous. */
+int zg_cuda_gemv_w8a8_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_input, float* d_dst);
+int zg_cuda_gemv_w8a8_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, float* h_dst);
+
 /* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
  * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */
 int zg_cuda_comm_unique_id(void* id128);

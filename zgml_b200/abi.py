@@ -171,6 +171,10 @@ SYMBOLS = [
     ("zg_cuda_qmatmul_host", C.c_int, [vp, vp, vp, vp, u32]),
     ("zg_cuda_qweight_from_f32", vp, [vp, vp, sz, sz, sz, vp, vp]),
     ("zg_cuda_qmatmul_bias_host", C.c_int, [vp, vp, vp, vp, vp, u32]),
+    ("zg_cuda_qweight_prepare_transposed", C.c_int, [vp, vp, vp, vp]),
+    ("zg_cuda_quantize_input_host", C.c_int, [vp, vp, sz, sz, vp, vp]),
+    ("zg_cuda_gemv_w8a8_device", C.c_int, [vp, vp, vp, vp]),
+    ("zg_cuda_gemv_w8a8_host", C.c_int, [vp, vp, vp, vp]),
     ("zg_cuda_comm_unique_id", C.c_int, [vp]),
     ("zg_cuda_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("zg_cuda_comm_destroy", None, [vp]),

@@ -520,6 +520,29 @@ class QuantizedWeight:
             raise BackendError(f"qmatmul_bias failed: {last_error()}")
         return out
 
+    def prepare_transposed(self, return_host: bool = False):  # src/quant.zig:274-317
+        """Build the W8A8 form on device ([N, K] int8, K-aligned blocks).  `return_host`: also (t_data, t_scales) copies,
+        bit-identical to the reference's."""
+        bpr = (self.rows + self.block_size - 1) // self.block_size
+        t_data = np.empty(self.cols * self.rows, np.int8) if return_host else None
+        t_scales = np.empty(self.cols * bpr, np.float32) if return_host else None
+        if self.be.lib.zg_cuda_qweight_prepare_transposed(self.be.ctx, self.ptr, t_data.ctypes.data if return_host else None,
+                                                          t_scales.ctypes.data if return_host else None) != 0:
+            raise BackendError(f"prepare_transposed failed: {last_error()}")
+        return (t_data, t_scales) if return_host else None
+
+    def gemv(self, input: np.ndarray) -> np.ndarray:  # src/quant.zig:443-459 (quantizeInput + gemvRange), M = 1
+        x = np.ascontiguousarray(input, dtype=np.float32).ravel()
+        assert x.size == self.rows
+        out = np.empty(self.cols, dtype=np.float32)
+        if self.be.lib.zg_cuda_gemv_w8a8_host(self.be.ctx, self.ptr, x.ctypes.data, out.ctypes.data) != 0:
+            raise BackendError(f"gemv failed: {last_error()}")
+        return out
+
+    def gemv_device(self, d_input: int, d_dst: int):
+        if self.be.lib.zg_cuda_gemv_w8a8_device(self.be.ctx, self.ptr, d_input, d_dst) != 0:
+            raise BackendError(f"gemv_device failed: {last_error()}")
+
     def matmul_device(self, d_input: int, d_dst: int, M: int, input_row_stride: int = 0, dst_row_stride: int = 0):
         if self.be.lib.zg_cuda_qmatmul_device(self.be.ctx, self.ptr, d_input, d_dst, M, input_row_stride, dst_row_stride) != 0:
             raise BackendError(f"qmatmul_device failed: {last_error()}")
@@ -528,3 +551,13 @@ class QuantizedWeight:
         if self.ptr:
             self.be.lib.zg_cuda_qweight_free(self.be.ctx, self.ptr)
             self.ptr = None
+
+
+def quantize_input(be: CudaBackend, input: np.ndarray, block_size: int = 32):  # src/quant.zig:320-341
+    """quantizeInput on device: (int8 [K], f32 scales [ceil(K / block_size)]), bit-identical to the reference's."""
+    x = np.ascontiguousarray(input, dtype=np.float32).ravel()
+    q = np.empty(x.size, np.int8)
+    scales = np.empty((x.size + block_size - 1) // block_size, np.float32)
+    if be.lib.zg_cuda_quantize_input_host(be.ctx, x.ctypes.data, x.size, block_size, q.ctypes.data, scales.ctypes.data) != 0:
+        raise BackendError(f"quantize_input failed: {last_error()}")
+    return q, scales

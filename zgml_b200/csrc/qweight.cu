@@ -385,11 +385,23 @@ extern "C" void zg_cuda_qweight_free(ZgCudaCtx* ctx, ZgCudaQWeight* w) {
     if (!w) return;
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(w->recs); cudaFree(w->smax); cudaFree(w->g_data); cudaFree(w->g_scales);
+    cudaFree(w->t_data); cudaFree(w->t_scales); cudaFree(w->x_q); cudaFree(w->x_s);
     delete w;
 }
 
 extern "C" int zg_cuda_qweight_format(const ZgCudaQWeight* w) { return w ? w->fmt : -1; }
 extern "C" size_t zg_cuda_qweight_device_bytes(const ZgCudaQWeight* w) { return w ? w->device_bytes : 0; }
+
+bool zg_qweight_dequant_to_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, float* d_out) {
+    const size_t n = w->K * w->N;
+    if (n == 0) return true;
+    if (w->fmt == ZG_QFMT_GENERIC)
+        k_dequant_flat<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->g_data, w->g_scales, n, w->bs, d_out);
+    else
+        k_dequant_packed<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->recs, w->fmt, w->rec_bytes, w->q_bytes, w->n_kc, w->K, w->N, d_out);
+    ZG_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess;
+}
 
 extern "C" int zg_cuda_qweight_dequantize(ZgCudaCtx* ctx, const ZgCudaQWeight* w, float* host_dst) {
     if (!ctx || !w || !host_dst) { zg_set_error("qweight_dequantize: bad arguments"); return -1; }
@@ -398,11 +410,7 @@ extern "C" int zg_cuda_qweight_dequantize(ZgCudaCtx* ctx, const ZgCudaQWeight* w
     if (n == 0) return 0;
     float* d_out = nullptr;
     if (cudaMalloc(&d_out, n * sizeof(float)) != cudaSuccess) { zg_set_error("qweight_dequantize: cudaMalloc failed"); return -1; }
-    if (w->fmt == ZG_QFMT_GENERIC)
-        k_dequant_flat<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->g_data, w->g_scales, n, w->bs, d_out);
-    else
-        k_dequant_packed<<<grid_for(n, 256), 256, 0, ctx->stream>>>(w->recs, w->fmt, w->rec_bytes, w->q_bytes, w->n_kc, w->K, w->N, d_out);
-    ZG_COUNT_LAUNCH();
+    zg_qweight_dequant_to_device(ctx, w, d_out);
     cudaMemcpyAsync(host_dst, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_out);

@@ -63,6 +63,12 @@ struct ZgCudaQWeight {
     // generic format: flat copies
     int8_t* g_data = nullptr;
     float* g_scales = nullptr;
+    // W8A8 form (prepareTransposed, src/quant.zig:274-317): [N, K] int8 + [N, ceil(K / bs)] f32, plus the quantized
+    // activation scratch of gemv (qw8a8.cu); null until zg_cuda_qweight_prepare_transposed
+    int8_t* t_data = nullptr;
+    float* t_scales = nullptr;
+    int8_t* x_q = nullptr;
+    float* x_s = nullptr;
     size_t device_bytes = 0;
 };
 
@@ -122,6 +128,7 @@ bool zg_gemv_ws_reserve(ZgGemvWs* ws, size_t partial_elems, size_t counters, cud
 void zg_gemv_ws_free(ZgGemvWs* ws);
 
 // qweight.cu
+bool zg_qweight_dequant_to_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, float* d_out);   // dequantizeTo into K * N device floats (async)
 ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data, const float* d_scales,
                                            size_t K, size_t N, size_t bs, int fmt_hint);
 // qgemv.cu
