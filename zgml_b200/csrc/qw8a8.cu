@@ -32,6 +32,9 @@ __device__ __forceinline__ int8_t quant_one(float v, float inv) {
 
 // One warp per K-block of the activation vector.
 __global__ void k_quantize_input(const float* __restrict__ x, uint32_t K, uint32_t bs, int8_t* __restrict__ xq, float* __restrict__ xs) {
+    // the gemv that follows is launched programmatically dependent: it may become resident now and stream its weight
+    // rows while this kernel runs; it reads xq / xs only after its griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const uint32_t start = b * bs;
     if (start >= K) return;
@@ -73,7 +76,7 @@ __device__ __forceinline__ int dot16(const uint4& a, const uint4& b) {
 
 // Fast path: K % 16 == 0, bs = 16 * GS with GS a power of two <= 32.  GS consecutive lanes hold one block.
 template <int GS>
-__global__ void __launch_bounds__(32 * kGemvWarps)
+__global__ void __launch_bounds__(32 * kGemvWarps, 4)
 k_gemv_w8a8(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const int8_t* __restrict__ xq,
             const float* __restrict__ xs, float* __restrict__ dst, uint32_t N, uint32_t K, uint32_t bpr) {
     extern __shared__ float terms[];                                         // [warp][bpr]
@@ -85,28 +88,29 @@ k_gemv_w8a8(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const
     const uint4* row = reinterpret_cast<const uint4*>(t_d + (size_t)n * K);
     const uint4* x4 = reinterpret_cast<const uint4*>(xq);
     const float* srow = t_s + (size_t)n * bpr;
-    constexpr int U = 8;                                                     // 128-bit loads in flight per lane
+    const bool leader = (lane & (GS - 1)) == 0;
+    constexpr int U = 8;                                                     // 128-bit weight loads in flight per lane
     for (uint32_t c0 = 0; c0 < chunks; c0 += 32 * U) {
-        uint4 w[U], xv[U];
+        uint4 w[U];
+        float sw[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
+        for (int u = 0; u < U; u++) {                                        // immutable weights + their scales first
             const uint32_t c = c0 + u * 32 + lane;
             w[u] = c < chunks ? __ldg(row + c) : make_uint4(0, 0, 0, 0);
+            sw[u] = (c < chunks && leader) ? __ldg(srow + c / GS) : 0.0f;
         }
+        // quantized activations: written by the kernel before this one — complete and visible only after the wait
+        if (c0 == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t c = c0 + u * 32 + lane;
-            xv[u] = c < chunks ? __ldg(x4 + c) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t c = c0 + u * 32 + lane;
-            int d = dot16(w[u], xv[u]);
+            const uint4 xv = c < chunks ? __ldg(x4 + c) : make_uint4(0, 0, 0, 0);
+            int d = dot16(w[u], xv);
 #pragma unroll
             for (int o = 1; o < GS; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            if (c < chunks && (lane & (GS - 1)) == 0) {
+            if (c < chunks && leader) {
                 const uint32_t b = c / GS;
-                my_terms[b] = __fmul_rn((float)d, __fmul_rn(__ldg(xs + b), __ldg(srow + b)));   // f32(int) * (s_x[b] * s_w[n, b])
+                my_terms[b] = __fmul_rn((float)d, __fmul_rn(__ldg(xs + b), sw[u]));   // f32(int) * (s_x[b] * s_w[n, b])
             }
         }
     }
@@ -122,6 +126,7 @@ k_gemv_w8a8(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const
 __global__ void k_gemv_w8a8_generic(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const int8_t* __restrict__ xq,
                                     const float* __restrict__ xs, float* __restrict__ dst, uint32_t N, uint32_t K, uint32_t bs,
                                     uint32_t bpr) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float acc = 0.0f;
@@ -150,12 +155,26 @@ bool launch_quantize(const float* d_x, size_t K, size_t bs, int8_t* d_q, float* 
     return cudaGetLastError() == cudaSuccess;
 }
 
+// Programmatically dependent on the quantizeInput kernel launched just before it on the same stream.
+template <typename... KArgs>
+bool launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, KArgs... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    ZG_COUNT_LAUNCH();
+    return e == cudaSuccess;
+}
+
 template <int GS>
 bool launch_fast(const ZgCudaQWeight* w, float* d_dst, uint32_t bpr, size_t smem, cudaStream_t st) {
-    k_gemv_w8a8<GS><<<(unsigned)((w->N + kGemvWarps - 1) / kGemvWarps), 32 * kGemvWarps, smem, st>>>(
-        w->t_data, w->t_scales, w->x_q, w->x_s, d_dst, (uint32_t)w->N, (uint32_t)w->K, bpr);
-    ZG_COUNT_LAUNCH();
-    return true;
+    return launch_pdl(k_gemv_w8a8<GS>, (unsigned)((w->N + kGemvWarps - 1) / kGemvWarps), 32 * kGemvWarps, smem, st,
+                      (const int8_t*)w->t_data, (const float*)w->t_scales, (const int8_t*)w->x_q, (const float*)w->x_s, d_dst,
+                      (uint32_t)w->N, (uint32_t)w->K, bpr);
 }
 
 } // namespace
@@ -241,9 +260,9 @@ extern "C" int zg_cuda_gemv_w8a8_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, 
             default: ok = launch_fast<32>(w, d_dst, bpr, smem, ctx->stream); break;
         }
     } else {
-        k_gemv_w8a8_generic<<<(unsigned)((w->N + 127) / 128), 128, 0, ctx->stream>>>(w->t_data, w->t_scales, w->x_q, w->x_s, d_dst,
-                                                                                   (uint32_t)w->N, (uint32_t)K, (uint32_t)bs, bpr);
-        ZG_COUNT_LAUNCH();
+        ok = launch_pdl(k_gemv_w8a8_generic, (unsigned)((w->N + 127) / 128), 128u, (size_t)0, ctx->stream, (const int8_t*)w->t_data,
+                        (const float*)w->t_scales, (const int8_t*)w->x_q, (const float*)w->x_s, d_dst, (uint32_t)w->N, (uint32_t)K,
+                        (uint32_t)bs, bpr);
     }
     cudaError_t e = cudaGetLastError();
     if (!ok || e != cudaSuccess) { zg_set_error("gemv_w8a8: launch failed: %s", cudaGetErrorString(e)); return -1; }
