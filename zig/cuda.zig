@@ -68,6 +68,11 @@ extern fn zg_cuda_comm_init(ctx: *anyopaque, id128: *const [128]u8, rank: c_int,
 extern fn zg_cuda_comm_destroy(ctx: *anyopaque) void;
 extern fn zg_cuda_qweight_upload_gguf(ctx: *anyopaque, raw: [*]const u8, raw_bytes: usize, ggml_type: u32, rows: usize, cols: usize) ?*anyopaque;
 extern fn zg_cuda_qweight_free(ctx: *anyopaque, w: *anyopaque) void;
+// W8A8 decode path (src/quant.zig:274-459): transposed re-quantization at load, then quantizeInput + gemvRange per call
+extern fn zg_cuda_qweight_prepare_transposed(ctx: *anyopaque, w: *anyopaque, h_t_data: ?[*]i8, h_t_scales: ?[*]f32) c_int;
+extern fn zg_cuda_quantize_input_host(ctx: *anyopaque, h_input: [*]const f32, K: usize, block_size: usize, h_q: [*]i8, h_scales: [*]f32) c_int;
+extern fn zg_cuda_gemv_w8a8_device(ctx: *anyopaque, w: *const anyopaque, d_input: *const anyopaque, d_dst: *anyopaque) c_int;
+extern fn zg_cuda_gemv_w8a8_host(ctx: *anyopaque, w: *const anyopaque, h_input: [*]const f32, h_dst: [*]f32) c_int;
 pub const ZG_QWEIGHT_RESIDENT: usize = std.math.maxInt(usize); // ZgQWeight.block_size marker: `data` is a handle from zg_cuda_qweight_upload*
 
 // ── flattening ──────────────────────────────────────────────────────────────
