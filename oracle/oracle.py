@@ -41,6 +41,10 @@ def lib(native: bool = False):
         "zo_from_slice": (None, [vp, sz, sz, sz, vp, vp]),
         "zo_prepare_transposed": (None, [vp, vp, sz, sz, sz, vp, vp]),
         "zo_quantize_input": (None, [vp, sz, sz, vp, vp]),
+        "zo_kv_store_column": (None, [vp, vp, sz, sz, sz, vp]),
+        "zo_kv_dequant_column": (None, [vp, vp, sz, sz, sz, vp]),
+        "zo_attention_quantized": (C.c_int, [vp, sz, vp, sz, sz, sz, vp, vp, sz, vp, vp, sz, sz, sz, vp, sz, sz,
+                                             C.c_float, C.c_int]),
         "zo_gemv_range": (None, [vp, vp, vp, vp, vp, sz, sz, sz, sz]),
         "zo_gemv": (C.c_int, [vp, vp, vp, vp, sz, sz, sz]),
         "zo_gemv_pool": (C.c_int, [vp, vp, vp, vp, sz, sz, sz, sz]),
@@ -162,6 +166,45 @@ def quantize_input(x, bs):  # src/quant.zig:320-341
     s = np.zeros((K + bs - 1) // bs, np.float32)
     lib().zo_quantize_input(_p(x), K, bs, _p(q), _p(s))
     return q, s
+
+
+class QuantizedKVCache:
+    """QuantizedKVCache (src/quant.zig:646-761): column-major Q8 cache, column = d_head int8 + d_head/bs scales."""
+
+    def __init__(self, d_head, n_cols, block_size):  # init, src/quant.zig:658-678
+        assert d_head % block_size == 0
+        self.d_head, self.n_cols, self.block_size = d_head, n_cols, block_size
+        self.blocks_per_col = d_head // block_size
+        self.q_data = np.zeros(d_head * n_cols, np.int8)
+        self.scales = np.zeros(self.blocks_per_col * n_cols, np.float32)
+
+    def store_column(self, col, src):  # src/quant.zig:689-701
+        src = f32(src).ravel()
+        assert src.size == self.d_head and col < self.n_cols
+        lib().zo_kv_store_column(_p(self.q_data), _p(self.scales), self.d_head, self.block_size, col, _p(src))
+
+    def dequant_column(self, col):  # src/quant.zig:704-716
+        out = np.zeros(self.d_head, np.float32)
+        lib().zo_kv_dequant_column(_p(self.q_data), _p(self.scales), self.d_head, self.block_size, col, _p(out))
+        return out
+
+
+def attention_quantized(q, seq_q, k_cache, k_col_start, v_cache, v_col_start, seq_kv, scale, mask=None, mask_row_stride=0,
+                        mask_col_stride=0, use_sdot=True, q_col_stride=None, dst_col_stride=None):
+    """attentionQuantized (src/quant.zig:924-1091).  q: [d_head, seq_q] column-major.  use_sdot: the aarch64 branch
+    (int8 query); False: the portable f32-query branch.  Returns dst [seq_q, d_head] rows = query columns."""
+    d = k_cache.d_head
+    q_cs = d if q_col_stride is None else q_col_stride
+    d_cs = d if dst_col_stride is None else dst_col_stride
+    q = f32(q).ravel()
+    dst = np.zeros(max(1, (seq_q - 1) * d_cs + d), np.float32)
+    m = None if mask is None else f32(mask).ravel()
+    rc = lib().zo_attention_quantized(_p(dst), d_cs, _p(q), q_cs, d, seq_q, _p(k_cache.q_data), _p(k_cache.scales), k_col_start,
+                                      _p(v_cache.q_data), _p(v_cache.scales), v_col_start, k_cache.block_size, seq_kv,
+                                      None if m is None else _p(m), mask_row_stride, mask_col_stride, scale, 1 if use_sdot else 0)
+    if rc != 0:
+        raise ValueError("attentionQuantized: d_head > 512 or d_head % block_size != 0")
+    return dst
 
 
 def dequant_q4_0(raw, n):

@@ -207,6 +207,160 @@ ZO_API int zo_gemv_pool(const int8_t* t_d, const float* t_s, const float* input,
     return (int)(n_disp + 1);
 }
 
+/* ── QuantizedKVCache + attentionQuantized — src/quant.zig:633-1091 ─────────
+ * Column-major Q8 cache: column c = d_head int8 at q_data[c*d_head], d_head/bs scales at
+ * scales[c*bpc].  storeColumn = quantizeInput on the column (src/quant.zig:689-701). */
+ZO_API void zo_kv_store_column(int8_t* q_data, float* scales, size_t d_head, size_t bs, size_t col,
+                               const float* src) {
+    size_t bpc = d_head / bs;
+    zo_quantize_input(src, d_head, bs, q_data + col * d_head, scales + col * bpc);
+}
+
+/* dequantColumn — src/quant.zig:704-716 */
+ZO_API void zo_kv_dequant_column(const int8_t* q_data, const float* scales, size_t d_head, size_t bs,
+                                 size_t col, float* dst) {
+    size_t bpc = d_head / bs;
+    for (size_t b = 0; b < bpc; b++)
+        for (size_t i = 0; i < bs; i++)
+            dst[b * bs + i] = (float)q_data[col * d_head + b * bs + i] * scales[col * bpc + b];
+}
+
+/* dotI8I8 — src/quant.zig:764-798: per block an exact int32 dot, total += f32(int) * q_s[b] * k_s[b]
+ * (left to right), blocks ascending. */
+static float zo_dot_i8i8(const int8_t* q_i8, const float* q_s, const int8_t* k_i8, const float* k_s,
+                         size_t bs, size_t nb) {
+    float total = 0;
+    for (size_t b = 0; b < nb; b++) {
+        int32_t acc = 0;
+        for (size_t j = 0; j < bs; j++) acc += (int32_t)q_i8[b * bs + j] * (int32_t)k_i8[b * bs + j];
+        total += (float)acc * q_s[b] * k_s[b];
+    }
+    return total;
+}
+
+/* dotI8F32 — src/quant.zig:800-830: 8 vector lanes of partial sums per block, @reduce(.Add) taken as
+ * lanes 0..7 in order (strict float mode), scalar tail, total += sub * scale[b]. */
+static float zo_dot_i8f32(const float* f, const int8_t* q, const float* sc, size_t bs, size_t nb) {
+    float total = 0;
+    for (size_t b = 0; b < nb; b++) {
+        float lane[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        size_t i = 0;
+        for (; i + 8 <= bs; i += 8)
+            for (size_t v = 0; v < 8; v++) lane[v] += f[b * bs + i + v] * (float)q[b * bs + i + v];
+        float sub = lane[0];
+        for (size_t v = 1; v < 8; v++) sub += lane[v];
+        for (; i < bs; i++) sub += f[b * bs + i] * (float)q[b * bs + i];
+        total += sub * sc[b];
+    }
+    return total;
+}
+
+/* accumI8F32 — src/quant.zig:832-860: acc[i] = acc[i] + (w * scale[b]) * f32(q[i]) */
+static void zo_accum_i8f32(float* acc, float w, const int8_t* q, const float* sc, size_t bs, size_t nb) {
+    for (size_t b = 0; b < nb; b++) {
+        float ws = w * sc[b];
+        for (size_t i = 0; i < bs; i++) acc[b * bs + i] = acc[b * bs + i] + ws * (float)q[b * bs + i];
+    }
+}
+
+/* accumBatchI8F32 — src/quant.zig:865-908 with Bs = 8: per block ws_scaled[c] = ws[c] * scale of column
+ * col_start + c; per element sum = acc, then += ws_scaled[c] * f32(q) for c = 0..7 in order. */
+static void zo_accum_batch8(float* acc, const float* ws, const int8_t* q_data, const float* scales,
+                            size_t col_start, size_t d_head, size_t bs, size_t nb) {
+    for (size_t bl = 0; bl < nb; bl++) {
+        float wsc[8];
+        for (size_t c = 0; c < 8; c++) wsc[c] = ws[c] * scales[(col_start + c) * nb + bl];
+        for (size_t i = 0; i < bs; i++) {
+            float sum = acc[bl * bs + i];
+            for (size_t c = 0; c < 8; c++) sum = sum + wsc[c] * (float)q_data[(col_start + c) * d_head + bl * bs + i];
+            acc[bl * bs + i] = sum;
+        }
+    }
+}
+
+/* attentionQuantized — src/quant.zig:924-1091.  use_sdot = the aarch64 branch (query quantized per column with
+ * the cache's block size, int8 x int8 scores); 0 = the portable branch (f32 query x int8 keys).  Tiles of 8
+ * kv positions with one rescale per tile, then a one-at-a-time tail; non-finite mask entries skip the
+ * position, a fully masked query column gives zeros.  Returns -1 when d_head > 512 (the reference's stack
+ * buffers) or d_head % bs != 0. */
+ZO_API int zo_attention_quantized(float* dst, size_t dst_cs, const float* q, size_t q_cs, size_t d_head, size_t seq_q,
+                                  const int8_t* k_q, const float* k_s, size_t k_col_start, const int8_t* v_q,
+                                  const float* v_s, size_t v_col_start, size_t bs, size_t seq_kv, const float* mask,
+                                  size_t mask_rs, size_t mask_cs, float scale, int use_sdot) {
+    if (d_head > 512 || bs == 0 || d_head % bs != 0) return -1;
+    size_t nb = d_head / bs;
+    if (use_sdot && nb > 32) return -1; /* q_scales_buf holds 512 / 16 entries */
+    float acc[512];
+    int8_t q_i8[512];
+    float q_sc[512];
+    const float neg_inf = -INFINITY;
+    for (size_t qi = 0; qi < seq_q; qi++) {
+        const float* q_col = q + qi * q_cs;
+        size_t mask_base = qi * mask_cs;
+        if (use_sdot) zo_quantize_input(q_col, d_head, bs, q_i8, q_sc);
+        float m_val = neg_inf, l = 0;
+        memset(acc, 0, d_head * sizeof(float));
+        size_t s = 0;
+        for (; s + 8 <= seq_kv; s += 8) {
+            if (mask) {
+                int any_valid = 0;
+                for (size_t b = 0; b < 8; b++)
+                    if (isfinite(mask[mask_base + (s + b) * mask_rs])) any_valid = 1;
+                if (!any_valid) continue;
+            }
+            float scores[8], ws[8], tile_max = neg_inf;
+            for (size_t b = 0; b < 8; b++) {
+                float mask_add = mask ? mask[mask_base + (s + b) * mask_rs] : 0.0f;
+                if (isfinite(mask_add)) {
+                    size_t c = k_col_start + s + b;
+                    float dot = use_sdot ? zo_dot_i8i8(q_i8, q_sc, k_q + c * d_head, k_s + c * nb, bs, nb)
+                                         : zo_dot_i8f32(q_col, k_q + c * d_head, k_s + c * nb, bs, nb);
+                    float score = dot * scale + mask_add;
+                    scores[b] = score;
+                    if (score > tile_max) tile_max = score;
+                } else {
+                    scores[b] = neg_inf;
+                }
+            }
+            if (tile_max == neg_inf) continue;
+            float new_m = (m_val == neg_inf) ? tile_max : (m_val > tile_max ? m_val : tile_max);
+            float alpha = (m_val == neg_inf) ? 0.0f : expf(m_val - new_m);
+            float tile_l = 0;
+            for (size_t b = 0; b < 8; b++) {
+                float w = expf(scores[b] - new_m);
+                ws[b] = w;
+                tile_l += w;
+            }
+            if (m_val != neg_inf && alpha != 1.0f)
+                for (size_t r = 0; r < d_head; r++) acc[r] = acc[r] * alpha;
+            zo_accum_batch8(acc, ws, v_q, v_s, v_col_start + s, d_head, bs, nb);
+            l = l * alpha + tile_l;
+            m_val = new_m;
+        }
+        for (; s < seq_kv; s++) {
+            float mask_add = mask ? mask[mask_base + s * mask_rs] : 0.0f;
+            if (!isfinite(mask_add)) continue;
+            size_t c = k_col_start + s;
+            float dot = use_sdot ? zo_dot_i8i8(q_i8, q_sc, k_q + c * d_head, k_s + c * nb, bs, nb)
+                                 : zo_dot_i8f32(q_col, k_q + c * d_head, k_s + c * nb, bs, nb);
+            float score = dot * scale + mask_add;
+            if (!isfinite(score)) continue;
+            float new_m = m_val > score ? m_val : score;
+            float alpha = (m_val == neg_inf) ? 0.0f : expf(m_val - new_m);
+            float w = expf(score - new_m);
+            if (m_val != neg_inf && alpha != 1.0f)
+                for (size_t r = 0; r < d_head; r++) acc[r] = acc[r] * alpha;
+            size_t vc = v_col_start + s;
+            zo_accum_i8f32(acc, w, v_q + vc * d_head, v_s + vc * nb, bs, nb);
+            l = l * alpha + w;
+            m_val = new_m;
+        }
+        float inv_l = l > 0 ? 1.0f / l : 0.0f;
+        for (size_t r = 0; r < d_head; r++) dst[qi * dst_cs + r] = acc[r] * inv_l;
+    }
+    return 0;
+}
+
 /* ── QuantizedWeight.matmul (W8·f32) — src/quant.zig:475-578 ─────────────────
  * dst zeroed; loop M -> K (unrolled x4) -> N in chunks cut at the FIRST row's
  * block boundary.  Vector path (8 lanes): d += f32(q) * (scale*x), one k after
