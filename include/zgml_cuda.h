@@ -290,6 +290,37 @@ int zg_cuda_quantize_input_host(ZgCudaCtx* ctx, const float* h_input, size_t K, 
 int zg_cuda_gemv_w8a8_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_input, float* d_dst);
 int zg_cuda_gemv_w8a8_host(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* h_input, float* h_dst);
 
+/* Quantized KV cache + attention over it — reference src/quant.zig:633-1091, callers
+ * src/llama_inference.zig:330-377.  Column-major Q8 cache: column c = d_head int8 + d_head / block_size f32 scales; one
+ * column per kv position inside a head's slab.  d_head <= 512 and d_head % block_size == 0 as in the reference; this
+ * implementation additionally needs d_head % 4 == 0 and block_size % 4 == 0. */
+typedef struct ZgCudaKVCache ZgCudaKVCache;
+/* QuantizedKVCache.init / deinit / clear — src/quant.zig:658-686 (zero-filled). NULL on failure. */
+ZgCudaKVCache* zg_cuda_kvcache_create(ZgCudaCtx* ctx, size_t d_head, size_t n_cols, size_t block_size);
+void zg_cuda_kvcache_free(ZgCudaCtx* ctx, ZgCudaKVCache* cache);
+int zg_cuda_kvcache_clear(ZgCudaCtx* ctx, ZgCudaKVCache* cache);
+/* storeColumn — src/quant.zig:689-701 — for n_write consecutive columns from src [n_write][d_head] (the slice_assign
+ * routing of src/llama_inference.zig:336-348): quantizeInput per column, bit-identical data and scales.
+ * _device: device pointer, async on the ctx stream; _host: host buffer, synchronous. */
+int zg_cuda_kvcache_store_device(ZgCudaCtx* ctx, ZgCudaKVCache* cache, size_t col_start, size_t n_write, const float* d_src);
+int zg_cuda_kvcache_store_host(ZgCudaCtx* ctx, ZgCudaKVCache* cache, size_t col_start, size_t n_write, const float* h_src);
+/* whole cache to the host: h_q [d_head * n_cols], h_scales [d_head / block_size * n_cols] (either may be NULL) */
+int zg_cuda_kvcache_download(ZgCudaCtx* ctx, const ZgCudaKVCache* cache, int8_t* h_q, float* h_scales);
+/* attentionQuantized — src/quant.zig:924-1091, same argument meaning: q / dst column-major [d_head, seq_q] with column
+ * strides, kv columns [col_start, col_start + seq_kv) of each cache, optional additive mask [seq_kv, seq_q or 1] with
+ * (row, column) strides (column stride 0 broadcasts one column; non-finite entries skip the position; a fully masked
+ * query column yields zeros).  int8_query != 0: the aarch64 branch (query quantized per block, int8 x int8 scores);
+ * 0: the portable branch (f32 query x int8 keys).  Scores are bit-identical to the reference's; the softmax groups
+ * positions differently, so outputs agree to float rounding. */
+int zg_cuda_attention_quantized_device(ZgCudaCtx* ctx, float* d_dst, size_t dst_col_stride, const float* d_q, size_t q_col_stride,
+                                       size_t d_head, size_t seq_q, const ZgCudaKVCache* k_cache, size_t k_col_start,
+                                       const ZgCudaKVCache* v_cache, size_t v_col_start, size_t seq_kv, const float* d_mask,
+                                       size_t mask_row_stride, size_t mask_col_stride, float scale, int int8_query);
+int zg_cuda_attention_quantized_host(ZgCudaCtx* ctx, float* h_dst, size_t dst_col_stride, const float* h_q, size_t q_col_stride,
+                                     size_t d_head, size_t seq_q, const ZgCudaKVCache* k_cache, size_t k_col_start,
+                                     const ZgCudaKVCache* v_cache, size_t v_col_start, size_t seq_kv, const float* h_mask,
+                                     size_t mask_row_stride, size_t mask_col_stride, float scale, int int8_query);
+
 /* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
  * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */
 int zg_cuda_comm_unique_id(void* id128);

@@ -175,6 +175,14 @@ SYMBOLS = [
     ("zg_cuda_quantize_input_host", C.c_int, [vp, vp, sz, sz, vp, vp]),
     ("zg_cuda_gemv_w8a8_device", C.c_int, [vp, vp, vp, vp]),
     ("zg_cuda_gemv_w8a8_host", C.c_int, [vp, vp, vp, vp]),
+    ("zg_cuda_kvcache_create", vp, [vp, sz, sz, sz]),
+    ("zg_cuda_kvcache_free", None, [vp, vp]),
+    ("zg_cuda_kvcache_clear", C.c_int, [vp, vp]),
+    ("zg_cuda_kvcache_store_device", C.c_int, [vp, vp, sz, sz, vp]),
+    ("zg_cuda_kvcache_store_host", C.c_int, [vp, vp, sz, sz, vp]),
+    ("zg_cuda_kvcache_download", C.c_int, [vp, vp, vp, vp]),
+    ("zg_cuda_attention_quantized_device", C.c_int, [vp, vp, sz, vp, sz, sz, sz, vp, sz, vp, sz, sz, vp, sz, sz, C.c_float, C.c_int]),
+    ("zg_cuda_attention_quantized_host", C.c_int, [vp, vp, sz, vp, sz, sz, sz, vp, sz, vp, sz, sz, vp, sz, sz, C.c_float, C.c_int]),
     ("zg_cuda_comm_unique_id", C.c_int, [vp]),
     ("zg_cuda_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("zg_cuda_comm_destroy", None, [vp]),

@@ -561,3 +561,62 @@ def quantize_input(be: CudaBackend, input: np.ndarray, block_size: int = 32):  #
     if be.lib.zg_cuda_quantize_input_host(be.ctx, x.ctypes.data, x.size, block_size, q.ctypes.data, scales.ctypes.data) != 0:
         raise BackendError(f"quantize_input failed: {last_error()}")
     return q, scales
+
+
+class QuantizedKVCache:
+    """GPU-resident QuantizedKVCache (src/quant.zig:646-761): column-major Q8, one column per kv position."""
+
+    def __init__(self, be: CudaBackend, d_head: int, n_cols: int, block_size: int = 32):  # init, src/quant.zig:658-678
+        self.be, self.d_head, self.n_cols, self.block_size = be, d_head, n_cols, block_size
+        self.blocks_per_col = d_head // block_size if block_size else 0
+        self.ptr = be.lib.zg_cuda_kvcache_create(be.ctx, d_head, n_cols, block_size)
+        if not self.ptr:
+            raise BackendError(f"kvcache create failed: {last_error()}")
+
+    def clear(self):  # src/quant.zig:683-686
+        if self.be.lib.zg_cuda_kvcache_clear(self.be.ctx, self.ptr) != 0:
+            raise BackendError(f"kvcache clear failed: {last_error()}")
+
+    def store_column(self, col_idx: int, src: np.ndarray):  # src/quant.zig:689-701
+        self.store_columns(col_idx, np.ascontiguousarray(src, dtype=np.float32).reshape(1, self.d_head))
+
+    def store_columns(self, col_start: int, src: np.ndarray):  # n_write consecutive columns, src/llama_inference.zig:336-348
+        x = np.ascontiguousarray(src, dtype=np.float32).reshape(-1, self.d_head)
+        if self.be.lib.zg_cuda_kvcache_store_host(self.be.ctx, self.ptr, col_start, x.shape[0], x.ctypes.data) != 0:
+            raise BackendError(f"kvcache store failed: {last_error()}")
+
+    def download(self):
+        q = np.empty(self.d_head * self.n_cols, np.int8)
+        s = np.empty(self.blocks_per_col * self.n_cols, np.float32)
+        if self.be.lib.zg_cuda_kvcache_download(self.be.ctx, self.ptr, q.ctypes.data, s.ctypes.data) != 0:
+            raise BackendError(f"kvcache download failed: {last_error()}")
+        return q, s
+
+    def dequant_column(self, col_idx: int) -> np.ndarray:  # src/quant.zig:704-716 (host arithmetic on the downloaded column)
+        q, s = self.download()
+        d, bs = self.d_head, self.block_size
+        col = q[col_idx * d:(col_idx + 1) * d].astype(np.float32).reshape(-1, bs)
+        return (col * s[col_idx * self.blocks_per_col:(col_idx + 1) * self.blocks_per_col, None]).ravel()
+
+    def free(self):
+        if self.ptr:
+            self.be.lib.zg_cuda_kvcache_free(self.be.ctx, self.ptr)
+            self.ptr = None
+
+
+def attention_quantized(be: CudaBackend, q: np.ndarray, seq_q: int, k_cache: QuantizedKVCache, k_col_start: int,
+                        v_cache: QuantizedKVCache, v_col_start: int, seq_kv: int, scale: float, mask=None, mask_row_stride: int = 0,
+                        mask_col_stride: int = 0, int8_query: bool = True, q_col_stride=None, dst_col_stride=None) -> np.ndarray:
+    """attentionQuantized (src/quant.zig:924-1091) through host buffers; same argument meaning as the reference."""
+    d = k_cache.d_head
+    q_cs = d if q_col_stride is None else q_col_stride
+    d_cs = d if dst_col_stride is None else dst_col_stride
+    qh = np.ascontiguousarray(q, dtype=np.float32).ravel()
+    dst = np.zeros(max(1, (seq_q - 1) * d_cs + d), np.float32)
+    m = None if mask is None else np.ascontiguousarray(mask, dtype=np.float32).ravel()
+    rc = be.lib.zg_cuda_attention_quantized_host(be.ctx, dst.ctypes.data, d_cs, qh.ctypes.data, q_cs, d, seq_q, k_cache.ptr, k_col_start,
+                                                 v_cache.ptr, v_col_start, seq_kv, None if m is None else m.ctypes.data,
+                                                 mask_row_stride, mask_col_stride, float(scale), 1 if int8_query else 0)
+    if rc != 0:
+        raise BackendError(f"attention_quantized failed: {last_error()}")
+    return dst
