@@ -72,6 +72,12 @@ extern fn zg_cuda_qweight_free(ctx: *anyopaque, w: *anyopaque) void;
 extern fn zg_cuda_qweight_prepare_transposed(ctx: *anyopaque, w: *anyopaque, h_t_data: ?[*]i8, h_t_scales: ?[*]f32) c_int;
 extern fn zg_cuda_quantize_input_host(ctx: *anyopaque, h_input: [*]const f32, K: usize, block_size: usize, h_q: [*]i8, h_scales: [*]f32) c_int;
 extern fn zg_cuda_gemv_w8a8_device(ctx: *anyopaque, w: *const anyopaque, d_input: *const anyopaque, d_dst: *anyopaque) c_int;
+// quantized KV cache (src/quant.zig:633-1091)
+extern fn zg_cuda_kvcache_create(ctx: *anyopaque, d_head: usize, n_cols: usize, block_size: usize) ?*anyopaque;
+extern fn zg_cuda_kvcache_free(ctx: *anyopaque, cache: *anyopaque) void;
+extern fn zg_cuda_kvcache_clear(ctx: *anyopaque, cache: *anyopaque) c_int;
+extern fn zg_cuda_kvcache_store_device(ctx: *anyopaque, cache: *anyopaque, col_start: usize, n_write: usize, d_src: *const anyopaque) c_int;
+extern fn zg_cuda_attention_quantized_device(ctx: *anyopaque, d_dst: *anyopaque, dst_col_stride: usize, d_q: *const anyopaque, q_col_stride: usize, d_head: usize, seq_q: usize, k_cache: *const anyopaque, k_col_start: usize, v_cache: *const anyopaque, v_col_start: usize, seq_kv: usize, d_mask: ?*const anyopaque, mask_row_stride: usize, mask_col_stride: usize, scale: f32, int8_query: c_int) c_int;
 extern fn zg_cuda_gemv_w8a8_host(ctx: *anyopaque, w: *const anyopaque, h_input: [*]const f32, h_dst: [*]f32) c_int;
 pub const ZG_QWEIGHT_RESIDENT: usize = std.math.maxInt(usize); // ZgQWeight.block_size marker: `data` is a handle from zg_cuda_qweight_upload*
 
