@@ -52,7 +52,8 @@ for shp in args.shapes.split(","):
     print(json.dumps({"metric": "prefill_qgemm", "M": args.M, "K": K, "N": N, "kind": args.kind, "ms": round(ms, 4),
                       "tflops": round(flops / ms / 1e9, 1), "tok_per_s_this_linear": round(args.M / ms * 1e3),
                       "mode": "bf16x1" if os.environ.get("ZG_GEMM_X1") == "1" else "3xBF16",
-                      "tile": os.environ.get("ZG_GEMM_MH", "auto"), "max_rel_err": err}))
+                      "tile": "cta_pair 256x256" if os.environ.get("ZG_GEMM_CTA2") == "1" else "128x256" if os.environ.get("ZG_GEMM_MH", "1") != "2" else "256x128",
+                      "max_rel_err": err}))
     for w in ws:
         w.free()
 be.close()

@@ -427,12 +427,17 @@ int g_terms = 2;   // ZG_GEMM_X1=1 selects the single-term mode (throughput expe
 int g_mh = 1;      // ZG_GEMM_MH=2 selects the 256 x 128 two-accumulator tile (experiment, see above); default 128 x 256
 
 int pick_mh(uint32_t) { return (g_terms == 2 && g_mh == 2) ? 2 : 1; }
+int g_cta2 = 0;    // ZG_GEMM_CTA2=1: the CTA-pair kernel of qgemm_cta2.cu for M > 128 (experimental, not yet run on hardware)
 
 } // namespace
+
+bool zg_qgemm_cta2_launch(const CUtensorMap& map, const CUtensorMap& map_lo, const ZgCudaQWeight* w, uint32_t M, float* d_out,
+                          uint32_t out_rs, cudaStream_t st);   // qgemm_cta2.cu
 
 bool zg_qgemm_init(ZgCudaCtx*) {
     if (const char* e = getenv("ZG_GEMM_X1")) g_terms = (e[0] == '1') ? 1 : 2;
     if (const char* e = getenv("ZG_GEMM_MH")) g_mh = (e[0] == '2') ? 2 : 1;
+    if (const char* e = getenv("ZG_GEMM_CTA2")) g_cta2 = (e[0] == '1') ? 1 : 0;
     return set_attr<ZG_QFMT_I8_F32, 1, 1>() && set_attr<ZG_QFMT_I8_F16, 1, 1>() && set_attr<ZG_QFMT_I4_F16, 1, 1>() &&
            set_attr<ZG_QFMT_I8_F32, 2, 1>() && set_attr<ZG_QFMT_I8_F16, 2, 1>() && set_attr<ZG_QFMT_I4_F16, 2, 1>() &&
            set_attr<ZG_QFMT_I8_F32, 2, 2>() && set_attr<ZG_QFMT_I8_F16, 2, 2>() && set_attr<ZG_QFMT_I4_F16, 2, 2>() && get_encode();
@@ -451,7 +456,8 @@ bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, 
     if (!get_encode()) return false;
     const uint32_t Kp = (w->n_kc + 1) / 2 * BK, Mp = (M + 255) / 256 * 256;
     const size_t plane_words = (size_t)Mp * (Kp / 2);   // one bf16 plane in 32-bit words
-    const int NT = g_terms, MH = pick_mh(M);
+    const bool cta2 = g_cta2 && g_terms == 2 && M > 128;
+    const int NT = g_terms, MH = cta2 ? 1 : pick_mh(M);   // the pair kernel loads 128-row boxes like the 128 x 256 tile
     uint32_t* planes = reinterpret_cast<uint32_t*>(scratch);
     k_split_bf16<<<dim3((Kp / 2 + 255) / 256, Mp), 256, 0, st>>>(d_in, in_rs, planes, Kp / 2, M, (uint32_t)w->K, plane_words, NT);
     ZG_COUNT_LAUNCH();
@@ -466,6 +472,7 @@ bool zg_qgemm_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, 
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { zg_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return false; }
     }
+    if (cta2) return zg_qgemm_cta2_launch(map[0], map[1], w, M, d_out, out_rs, st);
     QGemmParams p;
     p.recs = w->recs; p.n_kc = w->n_kc; p.n_nb = w->n_nb; p.M = M; p.N = (uint32_t)w->N; p.out = d_out; p.out_rs = out_rs;
     p.out_vec4 = ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0 && (out_rs & 3) == 0) ? 1u : 0u;
