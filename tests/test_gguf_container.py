@@ -203,3 +203,34 @@ def test_llama_gguf_file_round_trip_through_the_reference_executor(tmp_path, kin
     assert np.array_equal(logits[0][1], logits[1][1])
     with pytest.raises(GGUFError, match="TensorNotFound"):
         gguf.load_tensor_f32(gf, "blk.9.attn_norm.weight")
+
+
+@pytest.mark.parametrize("kind,tied", [("q8_0", True), ("q4_0", False)])
+def test_block_level_shards_equal_sharding_the_expanded_weights(tmp_path, kind, tied):
+    """`shard_blocks` (raw GGUF bytes, what each rank uploads) decodes to exactly the slabs `llama.shard_weights` cuts
+    from the host-expanded model: column slabs for q / k / v / gate / up / head, row slabs for o / down."""
+    from zgml_b200.host.llama import shard_weights
+    cfg = LlamaConfig(vocab_size=128, d_model=128, n_layers=1, n_heads=4, n_kv_heads=2, d_ff=192, max_seq_len=16, tied_lm_head=tied)
+    path = str(tmp_path / "m.gguf")
+    gguf.write_llama_gguf(path, cfg, kind, seed=9)
+    gf = GGUFFile.open(path)
+    whole = gguf.load_direct_quantized(gf)
+    world = 2
+    for rank in range(world):
+        want = shard_weights(whole, rank, world)
+        names = dict(gguf._LINEAR_NAMES)
+        for key, tname in names.items():
+            info = gf.get_tensor_info(f"blk.0.{tname}")
+            raw, K, N = gguf.shard_blocks(info, gf.get_tensor_data(info), key, rank, world)
+            got = gguf.quantized_weight_from_info(TensorInfo(tname, 2, (K, N, 1, 1), info.type_, 0), raw)
+            ref = want.layers[0][key]
+            assert (got.rows, got.cols) == (ref.rows, ref.cols)
+            assert np.array_equal(got.data, ref.data) and np.array_equal(got.scales.view(np.uint32), ref.scales.view(np.uint32))
+        if not tied:
+            info = gf.get_tensor_info("output.weight")
+            raw, K, N = gguf.shard_blocks(info, gf.get_tensor_data(info), "out_proj", rank, world)
+            got = gguf.quantized_weight_from_info(TensorInfo("o", 2, (K, N, 1, 1), info.type_, 0), raw)
+            assert np.array_equal(got.data, want.out_proj.data) and np.array_equal(got.scales, want.out_proj.scales)
+    info = gf.get_tensor_info("blk.0.attn_q.weight")
+    raw, K, N = gguf.shard_blocks(info, gf.get_tensor_data(info), "wq", 0, 1)
+    assert (K, N) == (128, 128) and raw.size == info.data_size()

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from ..backend import QuantizedWeightUpload, ResidentQuantizedWeight
-from .llama import LINEARS, LlamaConfig, LlamaWeights, linear_shapes
+from .llama import LINEARS, LlamaConfig, LlamaWeights, check_shardable, linear_shapes
 
 GGUF_MAGIC = 0x46554747  # "GGUF" little-endian, src/gguf.zig:191
 DEFAULT_ALIGNMENT = 32   # src/gguf.zig:192
@@ -421,8 +421,30 @@ def load_direct_quantized(gf: GGUFFile, cfg: Optional[LlamaConfig] = None) -> Ll
     return LlamaWeights(cfg, emb, layers, n1, n2, nf, out_proj)
 
 
-def upload_quantized_tensor(be, gf: GGUFFile, name: str):
-    """One Q8_0 / Q4_0 tensor, raw block bytes -> packed device weight (`zg_cuda_qweight_upload_gguf`)."""
+_COLUMN_SHARDED = ("wq", "wk", "wv", "w_gate", "w_up", "out_proj")   # this rank's output columns; wo / w_down: its input rows
+
+
+def shard_blocks(info: TensorInfo, raw: np.ndarray, key: str, rank: int, world: int):
+    """This rank's slab of a Q8_0 / Q4_0 [K, N] tensor, cut at BLOCK level from the raw GGUF bytes (no int8 expansion).
+    Blocks run along n inside one k row (flat index k * N + n), so a column slab [n0, n1) with n0, n1 multiples of 32 is
+    the block range [n0 / 32, n1 / 32) of every row, and a row slab is one contiguous run.
+    Returns (bytes, K_local, N_local); the same slabs as `llama.shard_weights` makes from the expanded form."""
+    K, N = info.dims[0], info.dims[1]
+    bb = info.type_.type_size
+    blk = np.asarray(raw).reshape(K, N // 32, bb)
+    if world == 1:
+        return blk.reshape(-1), K, N
+    if key in _COLUMN_SHARDED:
+        w = N // world
+        assert w % 32 == 0
+        return np.ascontiguousarray(blk[:, rank * w // 32:(rank + 1) * w // 32]).reshape(-1), K, w
+    r = K // world
+    return np.ascontiguousarray(blk[rank * r:(rank + 1) * r]).reshape(-1), r, N
+
+
+def upload_quantized_tensor(be, gf: GGUFFile, name: str, key: str = "", rank: int = 0, world: int = 1):
+    """One Q8_0 / Q4_0 tensor (or this rank's slab of it), raw block bytes -> packed device weight
+    (`zg_cuda_qweight_upload_gguf`)."""
     from ..backend import QuantizedWeight
     info = gf.get_tensor_info(name)
     if info is None:
@@ -431,27 +453,34 @@ def upload_quantized_tensor(be, gf: GGUFFile, name: str):
         raise GGUFError("UnsupportedShape")
     if not is_direct_quantized_matmul_type(info.type_):
         raise GGUFError("UnsupportedType")
-    return QuantizedWeight.from_gguf_blocks(be, np.asarray(gf.get_tensor_data(info)), int(info.type_), info.dims[0], info.dims[1])
+    raw, K, N = shard_blocks(info, gf.get_tensor_data(info), key, rank, world)
+    return QuantizedWeight.from_gguf_blocks(be, raw, int(info.type_), K, N)
 
 
-def load_resident(be, gf: GGUFFile, cfg: Optional[LlamaConfig] = None):
+def load_resident(be, gf: GGUFFile, cfg: Optional[LlamaConfig] = None, rank: int = 0, world: int = 1):
     """The device form of loadDirectQuantized: linears go tensor by tensor from the (memory-mapped) file into HBM and
-    the program borrows them (`ZG_QWEIGHT_RESIDENT`).  Returns (LlamaWeights, handles to free after the session)."""
+    the program borrows them (`ZG_QWEIGHT_RESIDENT`).  With world > 1 every rank reads only its own slabs of the file
+    (row-sharded model).  Returns (LlamaWeights, handles to free after the session)."""
     cfg = cfg or config_from_gguf(gf)
+    check_shardable(cfg, world)
     shapes = linear_shapes(cfg)
     handles, layers = [], []
 
-    def up(name, K, N):
+    def up(name, key, K, N):
         _check_linear(gf, name, K, N)
-        h = upload_quantized_tensor(be, gf, name)
+        h = upload_quantized_tensor(be, gf, name, key, rank, world)
         handles.append(h)
         return ResidentQuantizedWeight(h)
 
     for i in range(cfg.n_layers):
-        layers.append({key: up(f"blk.{i}.{_LINEAR_NAMES[key]}", *shapes[key]) for key in LINEARS})
+        layers.append({key: up(f"blk.{i}.{_LINEAR_NAMES[key]}", key, *shapes[key]) for key in LINEARS})
     emb, n1, n2, nf = _f32_params(gf, cfg)
-    out_proj = None if cfg.tied_lm_head else up("output.weight", cfg.d_model, cfg.vocab_size)
-    return LlamaWeights(cfg, emb, layers, n1, n2, nf, out_proj), handles
+    out_proj = None if cfg.tied_lm_head else up("output.weight", "out_proj", cfg.d_model, cfg.vocab_size)
+    if world == 1:
+        return LlamaWeights(cfg, emb, layers, n1, n2, nf, out_proj), handles
+    V = cfg.vocab_size // world
+    head_rows = np.ascontiguousarray(emb[rank * V:(rank + 1) * V]) if cfg.tied_lm_head else None
+    return LlamaWeights(cfg, emb, layers, n1, n2, nf, out_proj, (rank, world), head_rows), handles
 
 
 def write_llama_gguf(path: str, cfg: LlamaConfig, kind: str = "q8_0", seed: int = 0, embed_scale: float = 0.05, version: int = 3):
