@@ -31,14 +31,28 @@ def main():
     ap.add_argument("--cpu-tokens", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="per-DeviceOp-tag device time (one launch per op, program order)")
     ap.add_argument("--layers", type=int, default=0, help="override n_layers (memory-bounded experiments only)")
+    ap.add_argument("--gguf", default="", help="decode a GGUF file (Q8_0 / Q4_0 linears) instead of in-memory synthetic weights: memory-mapped, "
+                    "raw blocks go tensor by tensor to HBM (host/gguf.py::load_resident)")
+    ap.add_argument("--write-gguf", default="", help="first write the synthetic model of --model / --kind to this path, then decode it from the file")
     args = ap.parse_args()
     cfg = MODELS[args.model]
     if args.layers:
         cfg = llama.LlamaConfig(**{**cfg.__dict__, "n_layers": args.layers})
-    t0 = time.perf_counter()
-    w = llama.synthetic_weights(cfg, args.kind, seed=0)
-    t_gen = time.perf_counter() - t0
     be = CudaBackend(0)
+    handles = []
+    t0 = time.perf_counter()
+    if args.gguf or args.write_gguf:
+        from zgml_b200.host import gguf
+        if args.write_gguf:
+            gguf.write_llama_gguf(args.write_gguf, cfg, args.kind, seed=0)
+        gf = gguf.GGUFFile.open(args.gguf or args.write_gguf)
+        cfg = gguf.config_from_gguf(gf)
+        w, handles = gguf.load_resident(be, gf, cfg)
+        t = gf.get_tensor_info("blk.0.attn_q.weight").type_
+        args.kind = "q8_0" if t == gguf.GGMLType.q8_0 else "q4_0"
+    else:
+        w = llama.synthetic_weights(cfg, args.kind, seed=0)
+    t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     sess = llama.DeviceLlamaSession(be, cfg, w, 1)
     t_compile = time.perf_counter() - t0
@@ -80,7 +94,11 @@ def main():
         be.set_profiling(False)
     if args.cpu_tokens:
         from llama_reference import OracleBackend
-        ref = llama.DeviceLlamaSession(OracleBackend(native=True), cfg, w, 1)
+        w_cpu = w
+        if handles:   # resident descriptors only exist on the device: the CPU arm reads the same file in the reference's host form
+            from zgml_b200.host import gguf
+            w_cpu = gguf.load_direct_quantized(gguf.GGUFFile.open(args.gguf or args.write_gguf), cfg)
+        ref = llama.DeviceLlamaSession(OracleBackend(native=True), cfg, w_cpu, 1)
         ref.pos = args.context
         t = 1
         lg = ref.step(t)
@@ -97,7 +115,11 @@ def main():
         line["greedy_tokens_match_cpu"] = ctoks == toks[:args.cpu_tokens]
         ref.close()
     sess.close()
+    for h in handles:
+        h.free()
     be.close()
+    if args.gguf or args.write_gguf:
+        line["data"] = f"GGUF file {args.gguf or args.write_gguf} (memory-mapped, raw blocks -> HBM)"
     print(json.dumps(line))
 
 
