@@ -427,7 +427,7 @@ int g_terms = 2;   // ZG_GEMM_X1=1 selects the single-term mode (throughput expe
 int g_mh = 1;      // ZG_GEMM_MH=2 selects the 256 x 128 two-accumulator tile (experiment, see above); default 128 x 256
 
 int pick_mh(uint32_t) { return (g_terms == 2 && g_mh == 2) ? 2 : 1; }
-int g_cta2 = 0;    // ZG_GEMM_CTA2=1: the CTA-pair kernel of qgemm_cta2.cu for M > 128 (experimental, not yet run on hardware)
+int g_cta2 = 1;    // the CTA-pair kernel of qgemm_cta2.cu for M > 128 (validated round 2: parity green, +11 % over the 1-CTA tile); ZG_GEMM_CTA2=0 selects the 1-CTA tile
 
 } // namespace
 

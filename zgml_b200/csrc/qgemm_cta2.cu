@@ -1,6 +1,6 @@
-// EXPERIMENTAL, NOT YET RUN ON HARDWARE (written after this round's GPU budget ended; off unless ZG_GEMM_CTA2=1, no default
-// path reaches it).  The prefill quantized matmul of qgemm.cu as a CTA-PAIR kernel: tcgen05.mma.cta_group::2, one
-// 256 x 256 output tile per cluster of two CTAs.
+// The prefill quantized matmul of qgemm.cu as a CTA-PAIR kernel: tcgen05.mma.cta_group::2, one 256 x 256 output tile per
+// cluster of two CTAs.  Default for M > 128 since round 2 (parity tests green with it, 427 / 458 / 457 TFLOP/s against
+// 384 / 404 / 411 for the 1-CTA tile at M = 2048 on the Llama-3-8B linears); ZG_GEMM_CTA2=0 falls back to the 1-CTA tile.
 //
 // Why (profiles/r01_qgemm_ncu_full_stall_summary.txt): the 1-CTA 128 x 256 tile is bound by shared-memory
 // bandwidth — every 128 x 256 x 16 MMA reads 12 KB of operands in its 128 cycles, and the dequantized weight tile has to be
@@ -353,7 +353,7 @@ bool launch(const CUtensorMap& map, const CUtensorMap& map_lo, const Params& p, 
 
 } // namespace
 
-// Called by zg_qgemm_launch (qgemm.cu) when ZG_GEMM_CTA2=1; `map` / `map_lo` are the 64 x 128-row boxes of the hi / lo planes.
+// Called by zg_qgemm_launch (qgemm.cu) for M > 128 (unless ZG_GEMM_CTA2=0); `map` / `map_lo` are the 64 x 128-row boxes of the hi / lo planes.
 bool zg_qgemm_cta2_launch(const CUtensorMap& map, const CUtensorMap& map_lo, const ZgCudaQWeight* w, uint32_t M, float* d_out,
                           uint32_t out_rs, cudaStream_t st) {
     Params p;

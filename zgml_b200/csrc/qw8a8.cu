@@ -124,82 +124,9 @@ k_gemv_w8a8(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const
     }
 }
 
-// EXPERIMENTAL (ZG_W8A8_FUSED=1, bs == 32 only; written after this round's GPU budget ended — NOT YET RUN): one kernel per
-// gemv.  A first fused version (a warp per K-block, one dependent load -> reduce -> store round per block: 16 rounds per
-// CTA) measured 1.0 TB/s against 2.25 for the two-kernel form.  Here every warp first issues ALL its activation loads (16
-// independent coalesced loads per lane at K = 4096, eight at a time: lane = element of the block, blocks warp, warp + 8, ...), so the
-// prologue costs one L2 round trip that overlaps the weight rows already in flight.
-__global__ void __launch_bounds__(32 * kGemvWarps, 3)
-k_gemv_w8a8_fused32(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const float* __restrict__ x,
-                    float* __restrict__ dst, uint32_t N, uint32_t K, uint32_t bpr) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    int8_t* xq_s = reinterpret_cast<int8_t*>(sm);                            // K bytes
-    float* xs_s = reinterpret_cast<float*>(sm + K);                          // bpr
-    float* terms = xs_s + bpr;                                               // [warp][bpr]
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n = blockIdx.x * kGemvWarps + warp;
-    const uint32_t nc = min(n, N - 1);                                       // rows past N: computed on row N - 1, not stored
-    const uint32_t chunks = K / 16;
-    float* my_terms = terms + (size_t)warp * bpr;
-    const uint4* row = reinterpret_cast<const uint4*>(t_d + (size_t)nc * K);
-    const float* srow = t_s + (size_t)nc * bpr;
-    const bool leader = (lane & 1) == 0;
-    constexpr int U = 8, XB = 8;
-    uint4 w[U];
-    float sw[U];
-    auto load_group = [&](uint32_t c0) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t c = c0 + u * 32 + lane;
-            w[u] = c < chunks ? __ldg(row + c) : make_uint4(0, 0, 0, 0);
-            sw[u] = (c < chunks && leader) ? __ldg(srow + c / 2) : 0.0f;
-        }
-    };
-    load_group(0);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");                       // x may come from the previous kernel
-    // quantizeInput (src/quant.zig:320-341), block size 32 = one warp-wide element per lane
-    for (uint32_t b0 = warp; b0 < bpr; b0 += kGemvWarps * XB) {
-        float v[XB];
-#pragma unroll
-        for (int i = 0; i < XB; i++) {
-            const uint32_t b = b0 + i * kGemvWarps;
-            v[i] = b < bpr ? x[(size_t)b * 32 + lane] : 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < XB; i++) {
-            const uint32_t b = b0 + i * kGemvWarps;
-            float mx = fabsf(v[i]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float scale, inv;
-            block_scale(mx, &scale, &inv);
-            if (b < bpr) {
-                if (lane == 0) xs_s[b] = scale;
-                xq_s[(size_t)b * 32 + lane] = quant_one(v[i], inv);
-            }
-        }
-    }
-    __syncthreads();
-    const uint4* x4 = reinterpret_cast<const uint4*>(xq_s);
-    for (uint32_t c0 = 0; c0 < chunks; c0 += 32 * U) {
-        if (c0 != 0) load_group(c0);
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t c = c0 + u * 32 + lane;
-            const uint4 xv = c < chunks ? x4[c] : make_uint4(0, 0, 0, 0);
-            int d = dot16(w[u], xv);
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            if (c < chunks && leader) my_terms[c / 2] = __fmul_rn((float)d, __fmul_rn(xs_s[c / 2], sw[u]));
-        }
-    }
-    __syncwarp();
-    if (lane == 0 && n < N) {
-        float acc = 0.0f;
-        for (uint32_t b = 0; b < bpr; b++) acc = __fadd_rn(acc, my_terms[b]);   // blocks ascending, like gemvRange
-        dst[n] = acc;
-    }
-}
+// Measured and removed (round 2): a single-kernel form that quantizes x inside every CTA (ZG_W8A8_FUSED) was bit-identical
+// but ran at 1.39 / 1.88 TB/s against 2.23 / 3.61 TB/s for the two-kernel form below (every CTA repeats the activation
+// quantization, and its 16 dependent rounds sit in front of the first weight byte).
 
 // Any block size / K: one thread per output, the reference loop as written.
 __global__ void k_gemv_w8a8_generic(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const int8_t* __restrict__ xq,
@@ -324,16 +251,7 @@ extern "C" int zg_cuda_gemv_w8a8_device(ZgCudaCtx* ctx, const ZgCudaQWeight* w, 
     cudaSetDevice(ctx->device);
     const size_t K = w->K, bs = w->bs;
     const uint32_t bpr = (uint32_t)((K + bs - 1) / bs);
-    static const bool fused = [] { const char* e = getenv("ZG_W8A8_FUSED"); return e && e[0] == '1'; }();
     bool ok = true;
-    if (fused && bs == 32 && K % 32 == 0) {   // experimental single-kernel form (never run on hardware yet): quantizes x itself
-        const size_t smem = K + (size_t)bpr * sizeof(float) * (1 + kGemvWarps);
-        ok = launch_pdl(k_gemv_w8a8_fused32, (unsigned)((w->N + kGemvWarps - 1) / kGemvWarps), 32 * kGemvWarps, smem, ctx->stream,
-                        (const int8_t*)w->t_data, (const float*)w->t_scales, d_input, d_dst, (uint32_t)w->N, (uint32_t)K, bpr);
-        cudaError_t e = cudaGetLastError();
-        if (!ok || e != cudaSuccess) { zg_set_error("gemv_w8a8 (fused): launch failed: %s", cudaGetErrorString(e)); return -1; }
-        return 0;
-    }
     if (!launch_quantize(d_input, K, bs, w->x_q, w->x_s, ctx->stream)) { zg_set_error("gemv_w8a8: quantize launch failed"); return -1; }
     const size_t gs = bs / 16;
     const bool fast = K % 16 == 0 && bs % 16 == 0 && gs <= 32 && (gs & (gs - 1)) == 0;
