@@ -230,6 +230,10 @@ uint64_t zg_cuda_launch_count(void);
 void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int enabled);
 /* Device pointer of program buffer `buf_idx` (for device-resident benches). */
 void* zg_cuda_program_buffer(ZgCudaProgram* prog, uint32_t buf_idx);
+/* Schedule introspection (tests / benches assert that the fast paths are the ones that run): what == 0: kernels one
+ * execution launches (graph nodes); 1: DeviceOps covered by the fused single-token decode kernel (0: general schedule);
+ * 2: layers inside that kernel. */
+uint64_t zg_cuda_program_stats(const ZgCudaProgram* prog, int what);
 /* Run the program's ops with no host<->device copies (inputs already resident);
  * asynchronous on the ctx stream. */
 void zg_cuda_execute_device(ZgCudaCtx* ctx, ZgCudaProgram* prog);

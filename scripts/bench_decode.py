@@ -81,7 +81,7 @@ def main():
     line = {"metric": "llama_decode_tok_s", "model": args.model, "kind": args.kind, "n_layers": cfg.n_layers, "value": round(args.tokens / dt, 1),
             "unit": "tok/s", "ms_per_token": round(1e3 * dt / args.tokens, 3), "device_ms_per_token": round(1e3 * dt_dev / args.tokens, 3),
             "device_tok_s": round(args.tokens / dt_dev, 1), "tokens": args.tokens, "context": args.context,
-            "ops_per_token": sess.n_ops, "kernels_per_token": launches // args.tokens,
+            "ops_per_token": sess.n_ops, "kernels_per_token": launches // args.tokens, "schedule": be.program_stats(sess.handle),
             "weight_bytes_per_token": qbytes + head_bytes, "hbm_gbps_on_weights": round((qbytes + head_bytes) / (dt / args.tokens) / 1e9, 1),
             "gen_s": round(t_gen, 1), "compile_s": round(t_compile, 1), "data": "synthetic random-init GGUF-direct weights"}
     if args.profile:

@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from zgml_b200 import CudaBackend  # noqa: E402
 from zgml_b200.host import llama  # noqa: E402
 
-KINDS = {1: "elementwise", 2: "fused_ew", 3: "rmsnorm", 4: "repeat", 5: "slice_assign", 6: "rope", 7: "attention", 8: "chain", 9: "matmul", 10: "qgemv", 11: "allreduce"}
+KINDS = {1: "elementwise", 2: "fused_ew", 3: "rmsnorm", 4: "repeat", 5: "slice_assign", 6: "rope", 7: "attention", 8: "chain", 9: "matmul", 10: "qgemv", 11: "allreduce",
+         32: "F:norm+qkv", 33: "F:attention", 34: "F:merge+o", 35: "F:norm+gate|up", 36: "F:act+down", 37: "F:allreduce", 40: "F:item"}
 MODELS = {"smollm-135m": llama.SMOLLM_135M, "smollm-1.7b": llama.SMOLLM_1_7B, "llama3-8b": llama.LLAMA3_8B, "llama3-70b": llama.LLAMA3_70B}
 
 
@@ -47,9 +48,31 @@ def main():
     t_in = (rec[:, 0] & np.uint64((1 << 56) - 1)).astype(np.int64)
     t_go = (rec[:, 1] & np.uint64((1 << 56) - 1)).astype(np.int64)
     t_out = (rec[:, 2] & np.uint64((1 << 56) - 1)).astype(np.int64)
+    live = kind != 0
+    kind, t_in, t_go, t_out = kind[live], t_in[live], t_go[live], t_out[live]
     order = np.argsort(t_go)
     kind, t_in, t_go, t_out = kind[order], t_in[order], t_go[order], t_out[order]
     t0 = t_in.min()
+    pts = kind >= 64
+    if pts.any():   # fused decode kernel: named points of CTA 0 (kind = 64 + 16 * phase + point)
+        PH = ["qkv", "o", "gate|up", "down"]
+        PT = {0: "begin", 1: "issued", 2: "prologue", 3: "synced", 4: "filled", 5: "staged", 6: "chunks", 7: "reduced", 8: "attn-begin", 9: "attn-end",
+              10: "end", 11: "barrier", 12: "allreduce", 13: "barrier2"}
+        tk, tt = kind[pts], t_in[pts]
+        o2 = np.argsort(tt)
+        tk, tt = tk[o2], tt[o2]
+        print(f"fused decode kernel: {len(tk)} trace points; showing the middle layer (us since the previous point)")
+        begins = [i for i, k in enumerate(tk) if k == 64]
+        if begins:
+            b = begins[len(begins) // 2]
+            e = begins[len(begins) // 2 + 1] if len(begins) // 2 + 1 < len(begins) else len(tk)
+            for i in range(b, e):
+                k = int(tk[i]) - 64
+                print(f"    {PH[k // 16]:8s} {PT.get(k % 16, k % 16):10s} +{(tt[i] - tt[i - 1]) / 1e3 if i else 0:6.2f}")
+            print(f"    layer total {(tt[e - 1] - tt[b]) / 1e3:.2f} us")
+        keep = ~pts
+        kind, t_in, t_go, t_out = kind[keep], t_in[keep], t_go[keep], t_out[keep]
+        n = len(kind)
     print(f"{n} kernels, step span {(t_out.max() - t0) / 1e3:.1f} us")
     agg = collections.defaultdict(lambda: [0, 0, 0])
     for k, a, b, c in zip(kind, t_in, t_go, t_out):

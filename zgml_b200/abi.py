@@ -160,6 +160,7 @@ SYMBOLS = [
     ("zg_cuda_launch_count", C.c_uint64, []),
     ("zg_cuda_set_graph_mode", None, [vp, C.c_int]),
     ("zg_cuda_program_buffer", vp, [vp, u32]),
+    ("zg_cuda_program_stats", C.c_uint64, [vp, C.c_int]),
     ("zg_cuda_execute_device", None, [vp, vp]),
     ("zg_cuda_qweight_upload", vp, [vp, C.POINTER(ZgQWeight), C.c_int]),
     ("zg_cuda_qweight_upload_gguf", vp, [vp, vp, sz, u32, sz, sz]),

@@ -448,6 +448,11 @@ class CudaBackend:
     def launch_count(self) -> int:
         return int(self.lib.zg_cuda_launch_count())
 
+    def program_stats(self, handle: CompiledHandle) -> dict:
+        """Schedule facts of a compiled program: kernels per execution, DeviceOps / layers inside the fused decode kernel."""
+        f = self.lib.zg_cuda_program_stats
+        return {"kernels": int(f(handle.ptr, 0)), "fused_decode_ops": int(f(handle.ptr, 1)), "fused_decode_layers": int(f(handle.ptr, 2))}
+
 
 class QuantizedWeight:
     """GPU-resident packed QuantizedWeight (src/quant.zig:200-212): rows = K, cols = N."""

@@ -84,7 +84,7 @@ struct ZgCudaProgram {
         uint32_t first_entry = 0, n_entries = 0;
         std::vector<ZgGemvPrologue> pros;  // matvec batch: how each op obtains its activations
         std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
-        bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false;
+        bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false, decode = false;
         ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
         ZgEwMulMacro em = {};
@@ -103,6 +103,8 @@ struct ZgCudaProgram {
     float* d_attn_part = nullptr;      // split-KV partial states, one slice per attention unit
     uint32_t* d_attn_cnt = nullptr;    // arrival counters (self re-arming)
     bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
+    ZgDecodeHost dec;          // fused decode kernel (decode.cu) when the program's layers match the single-token LLaMA pattern
+    uint32_t dec_first = 0, dec_count = 0;   // the ops it covers
 };
 
 // ── context ──────────────────────────────────────────────────────────────────
@@ -130,7 +132,8 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
-    if (!zg_qgemv_init(ctx) || !zg_qgemm_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
+    if (const char* e = getenv("ZG_CUDA_DECODE")) ctx->decode_fused = (e[0] != '0');   // 0: never use the fused decode kernel
+    if (!zg_qgemv_init(ctx) || !zg_qgemm_init(ctx) || !zg_decode_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
     int n_branch = 7; // capture streams for independent ops of a program (ZG_CUDA_BRANCH=0: strictly serial graphs)
     if (const char* e = getenv("ZG_CUDA_BRANCH")) n_branch = atoi(e);
     for (int i = 0; i < n_branch && i < 31; i++) {
@@ -226,6 +229,7 @@ static void free_program(ZgCudaProgram* p) {
     if (p->h_in_stage) cudaFreeHost(p->h_in_stage);
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
+    zg_decode_free(&p->dec);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->dep_events) cudaEventDestroy(e);
     delete p;
@@ -512,7 +516,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 // every op is what the op-by-op execution gives.  Matching is deliberately strict: consecutive in program order, whole
 // contiguous vectors, all buffers distinct.
 struct ZgItem { uint32_t first = 0, count = 1, kind = 0; };   // kind 0: one op; 1: [add,] rmsnorm, repeat, mul; 2: fused_elementwise, mul; 3: attention, slice_assign
-enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3 };
+enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3, ITEM_DECODE = 4 };
 
 static bool distinct(std::initializer_list<uint32_t> bufs) {
     std::vector<uint32_t> v(bufs);
@@ -582,6 +586,371 @@ static uint32_t match_attn_store(const ZgCudaProgram* p, size_t i) {
     return 2;
 }
 
+// ── fused decode kernel (decode.cu): recognise the single-token layer pattern of the LLaMA lowering ───────────────
+// (src/device_inference.zig:61-238 over src/models/llama_transformer.zig:192-253; mirrored by host/llama.py build_program)
+//   [add,] rmsnorm, repeat, mul ; qmatmul q, k, v ; per KV head: rope, slice_assign(K cache), slice_assign(V cache) ;
+//   per head: rope, attention, slice_assign(concat) ; qmatmul o [; allreduce] ; add, rmsnorm, repeat, mul ;
+//   qmatmul gate, up ; fused_elementwise, mul ; qmatmul down [; allreduce]
+// Matching is strict — every offset, stride and buffer role is checked — and anything else keeps the general schedule.
+struct DecHostLayer {
+    ZgDecLayer ly; ZgDecPhase ph[4];
+    std::vector<ZgDecHead> heads; std::vector<ZgDecKv> kvs;
+    uint32_t part_elems[4];   // split-K scratch floats per phase
+};
+
+static bool plan_decode_phase(uint32_t grid, uint32_t n_kc, uint32_t n_items, bool whole_vector, uint32_t* S_out, uint32_t* slots_out) {
+    // S k-splits x (grid / S) column-group slots; cost = rounds x (records per warp + per-item overhead)
+    double best = 1e30; uint32_t bS = 0;
+    for (uint32_t S = 1; S <= n_kc && S <= grid && S <= 64; S++) {
+        const uint32_t recs = (n_kc + S - 1) / S;
+        if (!whole_vector && (size_t)recs * ZG_KR > kZgDecMaxD) continue;
+        const uint32_t slots = grid / S, rounds = (n_items + slots - 1) / slots, per_warp = (recs + 15) / 16;
+        if (rounds > kZgDecMaxItems) continue;
+        const double cost = (double)rounds * ((double)per_warp + 1.5) + 0.02 * S;
+        if (cost < best) { best = cost; bS = S; }
+    }
+    if (!bS) return false;
+    *S_out = bS; *slots_out = grid / bS;
+    return true;
+}
+
+static bool match_decode_layers(ZgCudaProgram* p, size_t i0, std::vector<DecHostLayer>& out, size_t* end_out) {
+    const size_t n = p->ops.size();
+    const uint32_t grid = zg_decode_grid(p->ctx);
+    auto bufp = [&](uint32_t b) { return p->buffers[b]; };
+    auto elems = [&](uint32_t b) { return p->buffer_elems[b]; };
+    size_t i = i0;
+    uint32_t prev_after = UINT32_MAX, prev_down = UINT32_MAX;   // buffers of the previous matched layer
+    ZgDecVec prev_down_vec = {};
+    std::vector<uint32_t> written, external;   // buffer indices: written inside the range / required to be untouched by it
+    while (i < n) {
+        DecHostLayer L; memset(&L.ly, 0, sizeof(L.ly)); memset(L.ph, 0, sizeof(L.ph)); memset(L.part_elems, 0, sizeof(L.part_elems));
+        ZgDecLayer& ly = L.ly;
+        size_t c = i;
+        std::vector<uint32_t> roles;   // role buffers of this layer that must be pairwise distinct
+        // ── norm block 1 ──
+        ZgNormMacro nm = {};
+        const uint32_t cnt1 = match_norm(p, c, &nm);
+        if (!cnt1 || nm.rows != 1 || nm.cols > kZgDecMaxD) break;
+        const bool has_add = cnt1 == 4;
+        const uint32_t D = nm.cols;
+        uint32_t x_buf;   // the layer input as later ops name it
+        {
+            const size_t r0 = c + (has_add ? 1 : 0);
+            const auto& r = p->ops[r0].u.rmsnorm; const auto& q = p->ops[r0 + 1].u.repeat; const auto& e = p->ops[r0 + 2].u.elementwise;
+            if (has_add) {
+                const auto& ad = p->ops[c].u.elementwise;
+                if (out.empty() || ad.src0 != prev_after || ad.src1 != prev_down) break;   // only the previous layer's closing add is absorbed
+                ly.x1_a = bufp(ad.src0); ly.x1_b = prev_down_vec; ly.x1_sum = bufp(ad.dst);
+                x_buf = ad.dst;
+                roles.push_back(ad.dst);   // src0 / src1 are the previous layer's after_attn / down, rewritten by this layer's phases 4 / 5
+                written.push_back(ad.dst);
+            } else {
+                if (!out.empty()) break;
+                ly.x1_a = bufp(r.src); x_buf = r.src;
+                roles.push_back(r.src);
+                external.push_back(r.src);
+            }
+            ly.gamma1 = bufp(q.src); ly.bare1 = bufp(r.dst); ly.grep1 = bufp(q.dst); ly.norm1 = bufp(e.dst); ly.eps1 = r.eps; ly.D = D;
+            roles.insert(roles.end(), {r.dst, q.src, q.dst, e.dst});
+            written.insert(written.end(), {r.dst, q.dst, e.dst});
+            external.push_back(q.src);
+            c += cnt1;
+            const uint32_t norm_buf = e.dst;
+            // ── q, k, v ──
+            if (c + 3 > n) break;
+            const ZgOp* qo[3] = {&p->ops[c], &p->ops[c + 1], &p->ops[c + 2]};
+            bool ok = true;
+            for (int k = 0; k < 3 && ok; k++) {
+                if (qo[k]->tag != ZG_OP_QMATMUL) { ok = false; break; }
+                const auto& m = qo[k]->u.qmatmul;
+                const ZgCudaQWeight* w = p->qweights[m.weight_idx];
+                ok = m.M == 1 && m.input == norm_buf && m.K == D && m.input_offset == 0 && m.dst_offset == 0 && w->fmt != ZG_QFMT_GENERIC &&
+                     w->fmt == p->qweights[qo[0]->u.qmatmul.weight_idx]->fmt && elems(m.dst) >= m.N;
+            }
+            if (!ok) break;
+            c += 3;
+        }
+        const ZgOp *op_q = &p->ops[c - 3], *op_k = &p->ops[c - 2], *op_v = &p->ops[c - 1];
+        const auto& mq = op_q->u.qmatmul; const auto& mk = op_k->u.qmatmul; const auto& mv = op_v->u.qmatmul;
+        roles.insert(roles.end(), {mq.dst, mk.dst, mv.dst});
+        written.insert(written.end(), {mq.dst, mk.dst, mv.dst});
+        // ── per KV head: rope(k) ; K store ; V store ──
+        uint32_t dh = 0, cs_buf = UINT32_MAX, kc_buf = UINT32_MAX, vc_buf = UINT32_MAX;
+        while (c + 3 <= n && p->ops[c].tag == ZG_OP_ROPE && p->ops[c].u.rope.src == mk.dst) {
+            const auto& ro = p->ops[c].u.rope;
+            const ZgOp &ks = p->ops[c + 1], &vs = p->ops[c + 2];
+            if (ks.tag != ZG_OP_SLICE_ASSIGN || vs.tag != ZG_OP_SLICE_ASSIGN) break;
+            const auto& ka = ks.u.slice_assign; const auto& va = vs.u.slice_assign;
+            const uint32_t d = 2 * ro.half_d;
+            if (dh == 0) { dh = d; cs_buf = ro.cos_sin; kc_buf = ka.dst; vc_buf = va.dst; }
+            if (d != dh || d == 0 || ro.seq_len != 1 || ro.cos_sin != cs_buf || ro.cs_off != 0 || ro.dst_off != 0 || ro.src_rs != 1 ||
+                ro.src_off + dh > mk.N || elems(ro.dst) < dh || elems(cs_buf) < dh) break;
+            if (ka.dst != kc_buf || ka.src != ro.dst || ka.rows != dh || ka.cols != 1 || ka.dst_row_stride != 1 || ka.src_offset != 0 ||
+                ka.src_row_stride != 1 || ka.patch_stride == 0) break;
+            if (va.dst != vc_buf || va.src != mv.dst || va.rows != dh || va.cols != 1 || va.dst_row_stride != 1 || va.src_row_stride != 1 ||
+                va.patch_stride == 0 || va.src_offset + dh > mv.N) break;
+            ZgDecKv kv;
+            kv.k_rot = bufp(ro.dst); kv.k_src = ro.src_off; kv.v_src = va.src_offset; kv.k_dyn = (uint32_t)(c + 1); kv.v_dyn = (uint32_t)(c + 2);
+            kv.k_base = ka.dst_base_offset; kv.v_base = va.dst_base_offset;
+            if (ka.patch_stride != va.patch_stride) break;
+            L.kvs.push_back(kv);
+            roles.push_back(ro.dst);
+            written.push_back(ro.dst);
+            c += 3;
+        }
+        if (L.kvs.empty() || kc_buf == vc_buf) break;
+        roles.insert(roles.end(), {cs_buf, kc_buf, vc_buf});
+        written.insert(written.end(), {kc_buf, vc_buf});
+        external.push_back(cs_buf);
+        const uint32_t patch_stride = p->ops[L.kvs[0].k_dyn].u.slice_assign.patch_stride;
+        // ── per head: rope(q) ; attention ; slice_assign into the concatenated buffer ──
+        uint32_t mask_buf = UINT32_MAX, cat_buf = UINT32_MAX;
+        bool heads_ok = true;
+        while (c + 3 <= n && p->ops[c].tag == ZG_OP_ROPE && p->ops[c].u.rope.src == mq.dst) {
+            const auto& ro = p->ops[c].u.rope;
+            const ZgOp &ao = p->ops[c + 1], &so = p->ops[c + 2];
+            if (ao.tag != ZG_OP_ATTENTION || so.tag != ZG_OP_SLICE_ASSIGN) { heads_ok = false; break; }
+            const auto& a = ao.u.attention; const auto& sa = so.u.slice_assign;
+            const uint32_t h = (uint32_t)L.heads.size();
+            if (2 * ro.half_d != dh || ro.seq_len != 1 || ro.cos_sin != cs_buf || ro.cs_off != 0 || ro.dst_off != 0 || ro.src_rs != 1 ||
+                ro.src_off + dh > mq.N || elems(ro.dst) < dh) { heads_ok = false; break; }
+            if (a.q != ro.dst || a.k != kc_buf || a.v != vc_buf || a.d_head != dh || a.seq_q != 1 || a.q_off != 0 || a.q_rs != 1 || a.k_rs != 1 ||
+                a.v_rs != 1 || a.dst_off != 0 || a.dst_rs != 1 || (dh % 4) != 0 || dh > 256 || (a.k_off % 4) != 0 || (a.k_cs % 4) != 0 ||
+                a.k_cs != patch_stride || a.v_cs != patch_stride || a.k_cs == 0 || elems(a.dst) < dh) { heads_ok = false; break; }
+            if (h == 0) {
+                ly.has_mask = a.has_mask; mask_buf = a.mask; ly.mask_off = a.mask_off; ly.mask_rs = a.mask_rs; ly.scale = a.scale;
+                ly.k_cs = a.k_cs; ly.v_cs = a.v_cs; cat_buf = sa.dst;
+            } else if (a.has_mask != ly.has_mask || (a.has_mask && (a.mask != mask_buf || a.mask_off != ly.mask_off || a.mask_rs != ly.mask_rs)) ||
+                       a.scale != ly.scale || a.k_cs != ly.k_cs || a.v_cs != ly.v_cs) { heads_ok = false; break; }
+            // the KV head whose cache slab this head reads
+            uint32_t kvi = UINT32_MAX;
+            for (uint32_t g = 0; g < L.kvs.size(); g++) if (L.kvs[g].k_base == a.k_off && L.kvs[g].v_base == a.v_off) kvi = g;
+            if (kvi == UINT32_MAX || (!L.heads.empty() && kvi < L.heads.back().kv)) { heads_ok = false; break; }
+            if (sa.dst != cat_buf || sa.src != a.dst || sa.patch_stride != 0 || sa.rows != dh || sa.cols != 1 || sa.dst_row_stride != 1 ||
+                sa.src_offset != 0 || sa.src_row_stride != 1 || sa.dst_offset != h * dh) { heads_ok = false; break; }
+            ZgDecHead hd;
+            hd.q_rot = bufp(ro.dst); hd.attn_out = bufp(a.dst); hd.q_src = ro.src_off; hd.k_off = a.k_off; hd.v_off = a.v_off; hd.kv = kvi;
+            hd.buf_off = sa.dst_offset; hd.dyn = (uint32_t)(c + 1);
+            L.heads.push_back(hd);
+            roles.insert(roles.end(), {ro.dst, a.dst});
+            written.insert(written.end(), {ro.dst, a.dst});
+            c += 3;
+        }
+        if (!heads_ok || L.heads.empty()) break;
+        for (uint32_t g = 0; g < L.kvs.size(); g++) {   // every KV head is read by at least one query head (its first one stores the cache rows)
+            bool used = false;
+            for (const ZgDecHead& hd : L.heads) used = used || hd.kv == g;
+            if (!used) { heads_ok = false; break; }
+        }
+        if (!heads_ok) break;
+        const uint32_t n_heads = (uint32_t)L.heads.size(), Dq = n_heads * dh;
+        if (elems(cat_buf) < Dq) break;
+        roles.push_back(cat_buf);
+        written.push_back(cat_buf);
+        if (ly.has_mask) { roles.push_back(mask_buf); external.push_back(mask_buf); }
+        // ── o projection [+ all-reduce] ──
+        if (c >= n || p->ops[c].tag != ZG_OP_QMATMUL) break;
+        const ZgOp* op_o = &p->ops[c];
+        const auto& mo = op_o->u.qmatmul;
+        {
+            const ZgCudaQWeight* w = p->qweights[mo.weight_idx];
+            if (mo.M != 1 || mo.input != cat_buf || mo.K != Dq || mo.N != D || mo.input_offset != 0 || mo.dst_offset != 0 || w->fmt == ZG_QFMT_GENERIC) break;
+        }
+        c++;
+        roles.push_back(mo.dst); written.push_back(mo.dst);
+        bool ar_o = false;
+        if (c < n && p->ops[c].tag == ZG_OP_ALLREDUCE) {
+            const auto& ar = p->ops[c].u.allreduce;
+            if (ar.buf != mo.dst || ar.offset != 0 || ar.n != D || (p->ctx->world > 1 && !zg_peer_allreduce_ok(p->ctx, D))) break;
+            ar_o = p->ctx->world > 1;
+            c++;
+        }
+        // ── norm block 2 (with the residual add) ──
+        ZgNormMacro nm2 = {};
+        if (c >= n || match_norm(p, c, &nm2) != 4 || nm2.rows != 1 || nm2.cols != D) break;
+        const auto& ad2 = p->ops[c].u.elementwise;
+        if (ad2.src0 != x_buf || ad2.src1 != mo.dst) break;
+        {
+            const auto& r = p->ops[c + 1].u.rmsnorm; const auto& q = p->ops[c + 2].u.repeat; const auto& e = p->ops[c + 3].u.elementwise;
+            ly.x2_a = bufp(ad2.src0); ly.x2_sum = bufp(ad2.dst); ly.gamma2 = bufp(q.src); ly.bare2 = bufp(r.dst); ly.grep2 = bufp(q.dst);
+            ly.norm2 = bufp(e.dst); ly.eps2 = r.eps;
+            roles.insert(roles.end(), {ad2.dst, q.src});
+            if (bufp(r.dst) != ly.bare1) roles.push_back(r.dst);
+            if (bufp(q.dst) != ly.grep1) roles.push_back(q.dst);
+            if (bufp(e.dst) != ly.norm1) roles.push_back(e.dst);
+            written.insert(written.end(), {ad2.dst, r.dst, q.dst, e.dst});
+            external.push_back(q.src);
+        }
+        const uint32_t after_buf = ad2.dst, norm2_buf = p->ops[c + 3].u.elementwise.dst;
+        c += 4;
+        // ── gate, up ──
+        if (c + 2 > n || p->ops[c].tag != ZG_OP_QMATMUL || p->ops[c + 1].tag != ZG_OP_QMATMUL) break;
+        const ZgOp *op_g = &p->ops[c], *op_u = &p->ops[c + 1];
+        const auto& mg = op_g->u.qmatmul; const auto& mu = op_u->u.qmatmul;
+        {
+            const ZgCudaQWeight *wg = p->qweights[mg.weight_idx], *wu = p->qweights[mu.weight_idx];
+            if (mg.M != 1 || mu.M != 1 || mg.input != norm2_buf || mu.input != norm2_buf || mg.K != D || mu.K != D || mg.N != mu.N ||
+                mg.input_offset || mu.input_offset || mg.dst_offset || mu.dst_offset || wg->fmt == ZG_QFMT_GENERIC || wg->fmt != wu->fmt ||
+                mg.dst == mu.dst) break;
+        }
+        const uint32_t F = mg.N;
+        c += 2;
+        roles.insert(roles.end(), {mg.dst, mu.dst}); written.insert(written.end(), {mg.dst, mu.dst});
+        // ── activation chain * up ──
+        ZgEwMulMacro em = {};
+        if (c + 2 > n || match_ewmul(p, c, &em) != 2) break;
+        const auto& fe = p->ops[c].u.fused_elementwise; const auto& me = p->ops[c + 1].u.elementwise;
+        if (fe.src != mg.dst || me.src1 != mu.dst || fe.n != F || fe.n_steps > kZgDecMaxSteps) break;
+        ly.n_steps = (uint32_t)fe.n_steps; ly.F = F; ly.silu = bufp(fe.dst); ly.hidden = bufp(me.dst);
+        for (size_t k = 0; k < fe.n_steps; k++) {
+            const ZgFusedEwStep& st = p->steps[c][k];
+            ZgDecStep& d = ly.steps[k];
+            d.op = st.op; d.is_swapped = st.is_swapped; d.sec_kind = 0; d.sec = nullptr;
+            if (st.op == ZG_EW_ADD || st.op == ZG_EW_MUL) {
+                if (st.secondary_buf == mg.dst && st.secondary_offset == 0) d.sec_kind = 1;
+                else if (st.secondary_buf == mu.dst && st.secondary_offset == 0) d.sec_kind = 2;
+                else {
+                    if ((size_t)st.secondary_offset + F > elems(st.secondary_buf)) { heads_ok = false; break; }
+                    d.sec = bufp(st.secondary_buf) + st.secondary_offset; external.push_back(st.secondary_buf);
+                }
+            }
+        }
+        if (!heads_ok) break;
+        roles.insert(roles.end(), {fe.dst, me.dst}); written.insert(written.end(), {fe.dst, me.dst});
+        const uint32_t hidden_buf = me.dst;
+        c += 2;
+        // ── down projection [+ all-reduce] ──
+        if (c >= n || p->ops[c].tag != ZG_OP_QMATMUL) break;
+        const ZgOp* op_d = &p->ops[c];
+        const auto& md = op_d->u.qmatmul;
+        {
+            const ZgCudaQWeight* w = p->qweights[md.weight_idx];
+            if (md.M != 1 || md.input != hidden_buf || md.K != F || md.N != D || md.input_offset || md.dst_offset || w->fmt == ZG_QFMT_GENERIC) break;
+        }
+        c++;
+        roles.push_back(md.dst); written.push_back(md.dst);
+        bool ar_down = false;
+        if (c < n && p->ops[c].tag == ZG_OP_ALLREDUCE) {
+            const auto& ar = p->ops[c].u.allreduce;
+            if (ar.buf != md.dst || ar.offset != 0 || ar.n != D || (p->ctx->world > 1 && !zg_peer_allreduce_ok(p->ctx, D))) break;
+            ar_down = p->ctx->world > 1;
+            c++;
+        }
+        {   // role buffers pairwise distinct (the kernel reorders the stores of a layer's small ops inside a phase)
+            std::vector<uint32_t> v(roles);
+            std::sort(v.begin(), v.end());
+            if (std::adjacent_find(v.begin(), v.end()) != v.end()) break;
+        }
+        if (D % 4 || F % 4 || (D & 1)) break;
+        // ── phases ──
+        auto fill_mv = [&](ZgDecPhase& ph, std::initializer_list<const ZgOp*> mops, uint32_t K, bool whole, uint32_t* part_elems) {
+            ph.n_mv = (uint32_t)mops.size(); ph.K = K;
+            uint32_t items = 0, k = 0;
+            for (const ZgOp* mop : mops) {
+                const auto& qm = mop->u.qmatmul;
+                const ZgCudaQWeight* w = p->qweights[qm.weight_idx];
+                ZgDecMv& m = ph.mv[k++];
+                m.recs = w->recs; m.smax = w->smax; m.out = bufp(qm.dst); m.part = nullptr; m.n_nb = w->n_nb; m.first_item = items; m.N = (uint32_t)w->N;
+                items += w->n_nb;
+                ph.fmt = (uint32_t)w->fmt; ph.n_kc = w->n_kc; ph.rec_bytes = w->rec_bytes;
+            }
+            ph.n_items = items;
+            if (!plan_decode_phase(grid, ph.n_kc, items, whole, &ph.S, &ph.n_slots)) return false;
+            *part_elems = 0;
+            if (ph.S > 1) for (uint32_t m2 = 0; m2 < ph.n_mv; m2++) *part_elems += ph.S * ph.mv[m2].N;
+            return true;
+        };
+        if (!fill_mv(L.ph[0], {op_q, op_k, op_v}, D, true, &L.part_elems[0]) || !fill_mv(L.ph[1], {op_o}, Dq, false, &L.part_elems[1]) ||
+            !fill_mv(L.ph[2], {op_g, op_u}, D, true, &L.part_elems[2]) || !fill_mv(L.ph[3], {op_d}, F, false, &L.part_elems[3])) break;
+        if (n_heads > kZgDecMaxHeads || L.kvs.size() > kZgDecMaxHeads) break;
+        if ((size_t)L.ph[0].n_kc * ZG_KR > kZgDecMaxD) break;
+        // vectors as their consumers see them (partial pointers are patched in once the scratch is allocated)
+        auto vec_of = [&](const ZgDecPhase& ph, uint32_t k) { ZgDecVec v; v.full = ph.mv[k].out; v.part = nullptr; v.S = ph.S > 1 ? ph.S : 0; v.n = ph.mv[k].N; return v; };
+        ly.q = vec_of(L.ph[0], 0); ly.k = vec_of(L.ph[0], 1); ly.v = vec_of(L.ph[0], 2);
+        ly.o_local = vec_of(L.ph[1], 0); ly.o = ly.o_local;
+        ly.gate = vec_of(L.ph[2], 0); ly.up = vec_of(L.ph[2], 1);
+        ly.down_local = vec_of(L.ph[3], 0); ly.down = ly.down_local;
+        ly.ar_o = ar_o ? 1u : 0u; ly.ar_down = ar_down ? 1u : 0u;
+        if (ar_o) { ly.o.S = 0; ly.o.part = nullptr; }
+        if (ar_down) { ly.down.S = 0; ly.down.part = nullptr; }
+        ly.cs = bufp(cs_buf); ly.mask = ly.has_mask ? bufp(mask_buf) : nullptr; ly.k_cache = bufp(kc_buf); ly.v_cache = bufp(vc_buf);
+        ly.attn_buf = bufp(cat_buf); ly.n_heads = n_heads; ly.n_kv = (uint32_t)L.kvs.size(); ly.d_head = dh;
+        out.push_back(L);
+        prev_after = after_buf; prev_down = md.dst; prev_down_vec = ly.down;
+        i = c;
+    }
+    if (out.empty()) return false;
+    // nothing the kernel treats as constant input may be written inside the range
+    std::sort(written.begin(), written.end());
+    for (uint32_t b : external) if (std::binary_search(written.begin(), written.end(), b)) { out.clear(); return false; }
+    *end_out = i;
+    return true;
+}
+
+// Allocate and upload the device tables of the fused decode kernel for the matched layers.
+static bool build_decode_plan(ZgCudaProgram* p, std::vector<DecHostLayer>& layers) {
+    ZgDecodeHost& d = p->dec;
+    zg_decode_free(&d);
+    const uint32_t grid = zg_decode_grid(p->ctx);
+    const uint32_t L = (uint32_t)layers.size();
+    uint32_t max_heads = 0, max_dh = 0; size_t part_max[4] = {0, 0, 0, 0};
+    for (DecHostLayer& h : layers) {
+        max_heads = std::max(max_heads, h.ly.n_heads); max_dh = std::max(max_dh, h.ly.d_head);
+        for (int k = 0; k < 4; k++) part_max[k] = std::max(part_max[k], (size_t)h.part_elems[k]);
+    }
+    // split-K scratch: one region per phase kind, shared by all layers (a phase's partial sums are consumed before the same
+    // phase of the next layer runs: at least two grid barriers lie in between)
+    size_t part_off[4], part_total = 0;
+    for (int k = 0; k < 4; k++) { part_off[k] = part_total; part_total += (part_max[k] + 31) & ~(size_t)31; }
+    if (part_total) ZG_CUDA_OK(cudaMalloc(&d.d_part, part_total * sizeof(float)));
+    uint32_t max_splits = grid / std::max(max_heads, 1u);
+    max_splits = std::max(1u, std::min(max_splits, 16u));
+    const uint32_t part_dh = (max_dh + 31) & ~31u;
+    ZG_CUDA_OK(cudaMalloc(&d.d_attn_part, (size_t)max_heads * max_splits * (2 + part_dh) * sizeof(float)));
+    ZG_CUDA_OK(cudaMalloc(&d.d_sync, 128 * sizeof(uint32_t)));
+    ZG_CUDA_OK(cudaMemset(d.d_sync, 0, 128 * sizeof(uint32_t)));
+    ZG_CUDA_OK(cudaMallocHost(&d.h_err, sizeof(uint32_t)));
+    *d.h_err = 0;
+    std::vector<ZgDecLayer> lys;
+    for (DecHostLayer& h : layers) {
+        for (int k = 0; k < 4; k++) {
+            ZgDecPhase& ph = h.ph[k];
+            if (ph.S > 1) {
+                float* base = d.d_part + part_off[k];
+                for (uint32_t m = 0; m < ph.n_mv; m++) { ph.mv[m].part = base; base += (size_t)ph.S * ph.mv[m].N; }
+            }
+        }
+        ZgDecLayer& ly = h.ly;
+        auto patch = [&](ZgDecVec& v, const ZgDecPhase& ph, uint32_t m) { if (v.S) v.part = ph.mv[m].part; };
+        patch(ly.q, h.ph[0], 0); patch(ly.k, h.ph[0], 1); patch(ly.v, h.ph[0], 2);
+        patch(ly.o_local, h.ph[1], 0); patch(ly.o, h.ph[1], 0);
+        patch(ly.gate, h.ph[2], 0); patch(ly.up, h.ph[2], 1);
+        patch(ly.down_local, h.ph[3], 0); patch(ly.down, h.ph[3], 0);
+        ly.head0 = 0; ly.kv0 = 0;   // head / KV tables are per layer inside its descriptor block
+        lys.push_back(ly);
+    }
+    for (uint32_t l = 1; l < L; l++) lys[l].x1_b = lys[l - 1].down;   // the previous layer's down projection, partial pointers now resolved
+    const uint32_t blk = zg_decode_block_bytes();
+    std::vector<uint8_t> blocks((size_t)L * blk);
+    uint32_t cap_heads = 0, cap_kv = 0;
+    for (uint32_t l = 0; l < L; l++) {
+        zg_decode_block_fill(blocks.data() + (size_t)l * blk, lys[l], layers[l].ph, layers[l].heads.data(), (uint32_t)layers[l].heads.size(),
+                             layers[l].kvs.data(), (uint32_t)layers[l].kvs.size());
+        cap_heads = std::max(cap_heads, (uint32_t)layers[l].heads.size()); cap_kv = std::max(cap_kv, (uint32_t)layers[l].kvs.size());
+    }
+    if (cudaMalloc(&d.d_blocks, blocks.size()) != cudaSuccess || cudaMemcpy(d.d_blocks, blocks.data(), blocks.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        zg_set_error("decode plan: device table allocation failed"); zg_decode_free(&d); return false;
+    }
+    ZgDecodePlan& P = d.plan;
+    P.blocks = (const uint8_t*)d.d_blocks; P.blk_bytes = blk; P.cap_heads = cap_heads; P.cap_kv = cap_kv; P.n_layers = L;
+    P.attn_part = d.d_attn_part; P.sync = d.d_sync; P.dyn = nullptr;   // dyn: set at launch (the table is allocated after the schedule)
+    P.max_splits = max_splits; P.part_dh = part_dh; P.grid = grid; P._pad = 0;
+    P.pc = p->ctx->peer;
+    d.valid = true;
+    return true;
+}
+
 // Dependency levels over ITEMS (level = 1 + max level of every earlier item it conflicts with), then units in (level,
 // program order); any such order is a valid topological order of the program's dependency DAG.
 static bool build_schedule(ZgCudaProgram* p) {
@@ -590,7 +959,22 @@ static bool build_schedule(ZgCudaProgram* p) {
     std::vector<ZgItem> items;
     std::vector<ZgNormMacro> norm_of;     // per item (kind ITEM_NORM)
     std::vector<ZgEwMulMacro> ewmul_of;   // per item (kind ITEM_EWMUL)
+    // single-token LLaMA layers: ONE persistent kernel for all of them (decode.cu)
+    std::vector<DecHostLayer> dec_layers;
+    size_t dec_end = 0;
+    zg_decode_free(&p->dec);
+    p->dec_first = 0; p->dec_count = 0;
+    if (p->ctx->decode_fused && p->ctx->fuse && chain_max && p->uniform_pos && match_decode_layers(p, 0, dec_layers, &dec_end)) {
+        if (!build_decode_plan(p, dec_layers)) return false;
+        p->dec_count = (uint32_t)dec_end;
+    }
     for (size_t i = 0; i < n;) {
+        if (p->dec_count && i == 0) {
+            ZgItem it; it.first = 0; it.count = p->dec_count; it.kind = ITEM_DECODE;
+            items.push_back(it); norm_of.push_back(ZgNormMacro{}); ewmul_of.push_back(ZgEwMulMacro{});
+            i = p->dec_count;
+            continue;
+        }
         ZgItem it; it.first = (uint32_t)i;
         ZgNormMacro nm = {}; ZgEwMulMacro em = {};
         uint32_t c = 0;
@@ -821,6 +1205,11 @@ static bool build_schedule(ZgCudaProgram* p) {
                 u.ranges.insert(u.ranges.end(), item_rng[order[k]].begin(), item_rng[order[k]].end());
                 continue;
             }
+            if (it.kind == ITEM_DECODE) {
+                ZgCudaProgram::Unit u; u.decode = true;
+                for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
+                p->units.push_back(u); continue;
+            }
             if (it.kind == ITEM_NORM) {    // long rows: one wide CTA per row instead of the 256-thread chain
                 ZgCudaProgram::Unit u;
                 for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
@@ -929,6 +1318,7 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 }
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
+    if (u.decode) { p->dec.plan.dyn = p->d_dyn; return zg_decode_launch(p->ctx, p->dec, st); }
     if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
     if (u.norm) return zg_launch_norm_macro(u.nm, st);
@@ -1146,8 +1536,16 @@ extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in
         }
         cudaMemcpyAsync(io.host_ptr, (uint8_t*)p->buffers[io.buf_idx] + io.offset, io.size, cudaMemcpyDeviceToHost, st);
     }
+    if (p->dec.valid) cudaMemcpyAsync(p->dec.h_err, p->dec.d_sync + 64, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) zg_set_error("execute: %s", cudaGetErrorString(e));
+    if (p->dec.valid && *p->dec.h_err) {   // a bounded wait inside the fused decode kernel gave up: results are invalid
+        static const char* what[] = {"", "grid barrier", "weight ring (TMA)", "NVLink peer all-reduce: a peer rank never arrived"};
+        zg_set_error("execute: fused decode kernel timed out in its %s wait; the step's outputs are invalid", what[*p->dec.h_err & 3]);
+        cudaMemsetAsync(p->dec.d_sync, 0, 128 * sizeof(uint32_t), st);
+        cudaStreamSynchronize(st);
+        *p->dec.h_err = 0;
+    }
 }
 
 extern "C" void zg_cuda_execute_device(ZgCudaCtx* ctx, ZgCudaProgram* p) {
@@ -1168,6 +1566,7 @@ extern "C" int zg_cuda_trace(ZgCudaCtx* ctx, int enable) {
     if (g_trace_buf) cudaMemset(g_trace_buf, 0, (1 + 3 * 16000) * 8);
     zg_trace_set_ops(enable ? g_trace_buf : nullptr);
     zg_trace_set_gemv(enable ? g_trace_buf : nullptr);
+    zg_trace_set_decode(enable ? g_trace_buf : nullptr);
     return 0;
 }
 extern "C" size_t zg_cuda_trace_read(ZgCudaCtx* ctx, unsigned long long* host, size_t max_records) {
@@ -1185,6 +1584,16 @@ extern "C" size_t zg_cuda_trace_read(ZgCudaCtx* ctx, unsigned long long* host, s
 extern "C" const ZgProfile* zg_cuda_profile(ZgCudaCtx* ctx, ZgCudaProgram* p) {
     if (!ctx || !p || !ctx->profiling) return nullptr;
     return &p->profile;
+}
+
+extern "C" uint64_t zg_cuda_program_stats(const ZgCudaProgram* p, int what) {
+    if (!p) return 0;
+    switch (what) {
+        case 0: return p->graph_kernels;
+        case 1: return p->dec.valid ? p->dec_count : 0;
+        case 2: return p->dec.valid ? p->dec.plan.n_layers : 0;
+        default: return 0;
+    }
 }
 
 extern "C" void* zg_cuda_program_buffer(ZgCudaProgram* p, uint32_t idx) {

@@ -112,6 +112,7 @@ struct ZgCudaCtx {
     int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
+    bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
@@ -218,6 +219,79 @@ uint32_t zg_attention_splits(const ZgOp& op, size_t k_buffer_elems, uint32_t cou
 size_t zg_attention_part_elems(const ZgOp& op, uint32_t count, uint32_t splits);
 bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint32_t* d_dyn,
                   uint32_t op_index, const ZgDevStep* d_steps, cudaStream_t st);
+
+// ── decode.cu : whole LLaMA layers of a single-token (T == 1) program in ONE persistent kernel ─────────────────────
+// The per-layer op pattern of the lowering (src/models/llama_transformer.zig:192-253 through src/device_inference.zig) is
+// recognised at compile time (backend.cu match_decode_layers) and executed as five phases per layer separated by grid
+// barriers: [norm + q|k|v matvecs] [rope + KV store + split-KV attention] [merge + o matvec] [residual + norm + gate|up
+// matvecs] [SiLU*up + down matvec] (+ an NVLink peer all-reduce phase after o / down when sharded).  Every DeviceOp's
+// output buffer is still written.  Weights stream through per-warp TMA rings that run AHEAD across phase and layer
+// boundaries (weights are immutable), so barrier and prologue latencies overlap with HBM traffic.
+constexpr uint32_t kZgDecMaxMv = 3;       // matvecs per phase (q|k|v, gate|up)
+constexpr uint32_t kZgDecMaxSteps = 8;    // fused_elementwise steps of the activation chain
+constexpr uint32_t kZgDecMaxD = 8192;     // floats a CTA stages per phase (norm phases: the whole d_model vector)
+struct ZgDecVec {           // a vector produced by a matvec phase: complete in `full` (S == 0) or S partial sums part[s * n + i]
+    float* full; const float* part; uint32_t S, n;
+};
+struct ZgDecMv {
+    const uint8_t* recs; const float* smax;
+    float* out;             // S == 1: results; S > 1: part[split * N + n] (the consumer phase sums the splits and stores `out`)
+    float* part;
+    uint32_t n_nb, first_item, N, _pad;
+};
+struct ZgDecPhase {
+    ZgDecMv mv[kZgDecMaxMv];
+    uint32_t n_mv, fmt, n_kc, K, S, n_slots, n_items, rec_bytes;
+};
+struct ZgDecHead { float* q_rot; float* attn_out; uint32_t q_src, k_off, v_off, kv, buf_off, dyn; };
+struct ZgDecKv { float* k_rot; uint32_t k_src, v_src, k_dyn, v_dyn, k_base, v_base; };
+struct ZgDecStep { uint32_t op, is_swapped, sec_kind, _pad; const float* sec; };   // sec_kind 0: sec[i]; 1: the gate value; 2: the up value
+struct ZgDecLayer {
+    // phase 1: x = a (+ b -> sum) ; rmsnorm -> bare ; gamma -> grep ; bare * grep -> norm ; q|k|v matvecs
+    const float* x1_a; ZgDecVec x1_b; float* x1_sum;
+    const float* gamma1; float* bare1; float* grep1; float* norm1; float eps1; uint32_t D;
+    // phase 2: rope(q), rope(k) + KV store, attention over the cache -> partial states
+    ZgDecVec q, k, v;
+    const float* cs; const float* mask; float* k_cache; float* v_cache; float* attn_buf;
+    uint32_t n_heads, n_kv, d_head, has_mask, mask_off, mask_rs, head0, kv0, k_cs, v_cs;
+    float scale;
+    // phase 3: merge -> attn_out / attn_buf ; o matvec (+ all-reduce)
+    ZgDecVec o_local, o;    // as the matvec leaves it / as phase 4 reads it (complete after an all-reduce)
+    uint32_t ar_o, ar_down;
+    // phase 4: x = a + o -> sum ; norm ; gate|up matvecs
+    const float* x2_a; float* x2_sum; const float* gamma2; float* bare2; float* grep2; float* norm2; float eps2;
+    // phase 5: act = steps(gate) -> silu ; silu * up -> hidden ; down matvec (+ all-reduce)
+    ZgDecVec gate, up; float* silu; float* hidden; uint32_t n_steps, F;
+    ZgDecStep steps[kZgDecMaxSteps];
+    ZgDecVec down_local, down;
+};
+constexpr uint32_t kZgDecMaxHeads = 64;   // query heads / KV heads of one layer (per rank)
+constexpr uint32_t kZgDecMaxItems = 32;   // column groups one CTA may own in one matvec phase
+// Per-layer descriptor block in device memory, copied into shared memory one layer ahead of its use:
+//   [ZgDecLayer][ZgDecPhase x 4 : qkv, o, gate|up, down][ZgDecHead x cap_heads][ZgDecKv x cap_kv]
+struct ZgDecodePlan {       // passed to the kernel by value
+    const uint8_t* blocks; uint32_t blk_bytes, cap_heads, cap_kv, n_layers;
+    float* attn_part;       // [head][max_splits][2 + part_dh]
+    uint32_t* sync;         // [0] grid barrier counter, [32] exit counter, [64] sticky error flag
+    const uint32_t* dyn;
+    uint32_t max_splits, part_dh, grid, _pad;
+    ZgPeerComm pc;
+};
+struct ZgDecodeHost {       // owned by a compiled program
+    ZgDecodePlan plan = {};
+    void* d_blocks = nullptr;
+    float* d_part = nullptr; float* d_attn_part = nullptr; uint32_t* d_sync = nullptr;
+    uint32_t* h_err = nullptr;   // pinned copy of the error flag, read after every execute
+    bool valid = false;
+};
+bool zg_decode_init(ZgCudaCtx* ctx);
+uint32_t zg_decode_grid(const ZgCudaCtx* ctx);
+uint32_t zg_decode_block_bytes();
+void zg_decode_block_fill(uint8_t* block, const ZgDecLayer& ly, const ZgDecPhase* ph4, const ZgDecHead* heads, uint32_t n_heads,
+                          const ZgDecKv* kvs, uint32_t n_kv);
+bool zg_decode_launch(ZgCudaCtx* ctx, const ZgDecodeHost& d, cudaStream_t st);
+void zg_decode_free(ZgDecodeHost* d);
+void zg_trace_set_decode(unsigned long long* d_buf);
 
 // comm.cu : NCCL through dlopen (no link-time dependency)
 bool zg_comm_allreduce(ZgCudaCtx* ctx, float* buf, size_t n, cudaStream_t st);
