@@ -56,8 +56,7 @@ def main():
     pts = kind >= 64
     if pts.any():   # fused decode kernel: named points of CTA 0 (kind = 64 + 16 * phase + point)
         PH = ["qkv", "o", "gate|up", "down"]
-        PT = {0: "begin", 1: "issued", 2: "prologue", 3: "synced", 4: "filled", 5: "staged", 6: "chunks", 7: "reduced", 8: "attn-begin", 9: "attn-end",
-              10: "end", 11: "barrier", 12: "allreduce", 13: "barrier2"}
+        PT = {0: "begin", 2: "prologue", 8: "attn-begin", 9: "attn-end", 10: "matvecs", 11: "barrier", 12: "allreduce"}
         tk, tt = kind[pts], t_in[pts]
         o2 = np.argsort(tt)
         tk, tt = tk[o2], tt[o2]

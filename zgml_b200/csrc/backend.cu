@@ -598,19 +598,21 @@ struct DecHostLayer {
     uint32_t part_elems[4];   // split-K scratch floats per phase
 };
 
-static bool plan_decode_phase(uint32_t grid, uint32_t n_kc, uint32_t n_items, bool whole_vector, uint32_t* S_out, uint32_t* slots_out) {
-    // S k-splits x (grid / S) column-group slots; cost = rounds x (records per warp + per-item overhead)
-    double best = 1e30; uint32_t bS = 0;
-    for (uint32_t S = 1; S <= n_kc && S <= grid && S <= 64; S++) {
+static bool plan_decode_phase(uint32_t grid, uint32_t n_kc, uint32_t n_items, bool whole_vector, uint32_t* S_out, uint32_t* lS_out, uint32_t* slots_out) {
+    // S = 2^lS k-splits x (grid >> lS) column-group slots; cost = rounds x (records per warp + per-item overhead)
+    double best = 1e30; uint32_t bl = UINT32_MAX;
+    for (uint32_t lS = 0; lS <= 6; lS++) {
+        const uint32_t S = 1u << lS;
+        if (S > n_kc || S > grid) break;
         const uint32_t recs = (n_kc + S - 1) / S;
         if (!whole_vector && (size_t)recs * ZG_KR > kZgDecMaxD) continue;
-        const uint32_t slots = grid / S, rounds = (n_items + slots - 1) / slots, per_warp = (recs + 15) / 16;
+        const uint32_t slots = grid >> lS, rounds = (n_items + slots - 1) / slots, per_warp = (recs + 15) / 16;
         if (rounds > kZgDecMaxItems) continue;
         const double cost = (double)rounds * ((double)per_warp + 1.5) + 0.02 * S;
-        if (cost < best) { best = cost; bS = S; }
+        if (cost < best) { best = cost; bl = lS; }
     }
-    if (!bS) return false;
-    *S_out = bS; *slots_out = grid / bS;
+    if (bl == UINT32_MAX) return false;
+    *S_out = 1u << bl; *lS_out = bl; *slots_out = grid >> bl;
     return true;
 }
 
@@ -817,6 +819,11 @@ static bool match_decode_layers(ZgCudaProgram* p, size_t i0, std::vector<DecHost
             }
         }
         if (!heads_ok) break;
+        {   // nn.silu as the lowering emits it (src/nn.zig:38-44): neg, exp, + ones, recip, * gate
+            const ZgDecStep* st = ly.steps;
+            ly.act_silu = (ly.n_steps == 5 && st[0].op == ZG_EW_NEG && st[1].op == ZG_EW_EXP && st[2].op == ZG_EW_ADD && st[2].sec_kind == 0 &&
+                           st[3].op == ZG_EW_RECIP && st[4].op == ZG_EW_MUL && st[4].sec_kind == 1) ? 1u : 0u;
+        }
         roles.insert(roles.end(), {fe.dst, me.dst}); written.insert(written.end(), {fe.dst, me.dst});
         const uint32_t hidden_buf = me.dst;
         c += 2;
@@ -846,6 +853,7 @@ static bool match_decode_layers(ZgCudaProgram* p, size_t i0, std::vector<DecHost
         // ── phases ──
         auto fill_mv = [&](ZgDecPhase& ph, std::initializer_list<const ZgOp*> mops, uint32_t K, bool whole, uint32_t* part_elems) {
             ph.n_mv = (uint32_t)mops.size(); ph.K = K;
+            for (uint32_t m2 = 0; m2 < kZgDecMaxMv; m2++) ph.mv[m2].first_item = UINT32_MAX;   // absent entries never match an item
             uint32_t items = 0, k = 0;
             for (const ZgOp* mop : mops) {
                 const auto& qm = mop->u.qmatmul;
@@ -856,7 +864,7 @@ static bool match_decode_layers(ZgCudaProgram* p, size_t i0, std::vector<DecHost
                 ph.fmt = (uint32_t)w->fmt; ph.n_kc = w->n_kc; ph.rec_bytes = w->rec_bytes;
             }
             ph.n_items = items;
-            if (!plan_decode_phase(grid, ph.n_kc, items, whole, &ph.S, &ph.n_slots)) return false;
+            if (!plan_decode_phase(grid, ph.n_kc, items, whole, &ph.S, &ph.lS, &ph.n_slots)) return false;
             *part_elems = 0;
             if (ph.S > 1) for (uint32_t m2 = 0; m2 < ph.n_mv; m2++) *part_elems += ph.S * ph.mv[m2].N;
             return true;

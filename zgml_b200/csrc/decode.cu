@@ -22,6 +22,12 @@
 // immutable, so while a CTA waits at a barrier or evaluates a prologue the next phase's first chunks are already in
 // flight (148 SMs x 144 KB of ring = 21 MB, about 3 us of HBM time).
 //
+// CODE SIZE is a first-class constraint here.  The CTAs run in lockstep and every phase's code executes once per layer,
+// so whatever does not fit the instruction caches (L1.5: 32 KB) is re-fetched from L2 by all 148 SMs for every layer:
+// the first version (everything unrolled and inlined per call site, 300 KB of SASS) spent 65 us per layer almost entirely
+// on instruction fetch.  Hence: one call site per routine (a loop over the four matvec phases), loops instead of
+// unrolling wherever latency allows, the chunk producer and the rare paths out of line, descriptor copies by cp.async.
+//
 // No spin in this kernel is unbounded: grid barrier, mbarrier and peer waits give up after ~2 s, set the sticky error
 // word (reported by zg_cuda_execute through zg_cuda_last_error) and let the kernel drain.
 #include "zg_internal.cuh"
@@ -50,9 +56,17 @@ enum { ERR_BARRIER = 1, ERR_MBAR = 2, ERR_PEER = 3 };
 constexpr uint32_t kDescLy = 0, kDescPh = 1024, kDescHeads = kDescPh + 768, kDescKvs = kDescHeads + kZgDecMaxHeads * sizeof(ZgDecHead);
 constexpr uint32_t kDescGlobalBytes = kDescKvs + kZgDecMaxHeads * sizeof(ZgDecKv);          // what device memory holds per layer
 constexpr uint32_t kDescSeq = kDescGlobalBytes, kDescKdst = kDescSeq + kZgDecMaxHeads * 4, kDescVdst = kDescKdst + kZgDecMaxHeads * 4;
-constexpr uint32_t kDescBytes = kDescVdst + kZgDecMaxHeads * 4;                // + the layer's run-time values (seq_kv, store offsets)
+constexpr uint32_t kDescBytes = kDescVdst + kZgDecMaxHeads * 4;                             // + the layer's run-time values
 static_assert(sizeof(ZgDecLayer) <= 1024 && 4 * sizeof(ZgDecPhase) <= 768 && sizeof(ZgDecHead) == 40 && sizeof(ZgDecKv) == 32, "descriptor block layout");
-static_assert(sizeof(ZgDecLayer) % 8 == 0 && sizeof(ZgDecPhase) % 8 == 0, "descriptor alignment");
+static_assert(sizeof(ZgDecLayer) % 8 == 0 && sizeof(ZgDecPhase) % 8 == 0 && kDescGlobalBytes % 16 == 0 && kDescGlobalBytes <= 16 * kT, "descriptor copy");
+
+struct StreamState {   // one warp's chunk producer (owned by its lane 0)
+    uint32_t pi, item, c, slot, outstanding, valid;      // phase index, item, chunk, ring slot to fill next, in flight, position valid
+    uint32_t L, n_chunk, G, RB, n_items, n_slots;        // this warp's share of phase pi
+    const uint8_t* src;                                  // records of (item, chunk 0)
+    uint32_t k0, n_kc;
+};
+static_assert(sizeof(StreamState) == 64, "stream state");
 
 // dynamic shared memory layout (bytes)
 constexpr uint32_t kOffXin = 0;                                  // kZgDecMaxD floats: the phase's staged input vector
@@ -63,12 +77,13 @@ constexpr uint32_t kOffPart = kOffPlanes + kW * kPlaneBytes;     // [2][warp][32
 constexpr uint32_t kOffBars = kOffPart + 2 * kW * 32 * 4;        // [warp][slot] mbarriers
 constexpr uint32_t kOffRed = kOffBars + kW * kNS * 8;            // 64 floats
 constexpr uint32_t kOffSmax = kOffRed + 64 * 4;                  // scale ceilings of this CTA's column groups in the current phase
-constexpr uint32_t kOffTrace = kOffSmax + kZgDecMaxItems * 4;  // Trace state (16 B)
-constexpr uint32_t kOffDesc = kOffTrace + 16;
+constexpr uint32_t kOffTrace = kOffSmax + kZgDecMaxItems * 4;    // Trace state (16 B)
+constexpr uint32_t kOffStream = kOffTrace + 16;                  // [warp] StreamState
+constexpr uint32_t kOffDesc = kOffStream + kW * 64;
 constexpr uint32_t kSmemBytes = kOffDesc + 3 * kDescBytes;
 static_assert((3 * kAttnMaxDh + 2 * kW + kW * kAttnMaxDh) * 4 <= kZgDecMaxD * 4, "attention scratch aliases the input vector");
 static_assert(kSmemBytes <= 227 * 1024, "decode kernel shared memory");
-static_assert(kOffDesc % 16 == 0 && kDescBytes % 16 == 0, "descriptor buffers are copied word-wise and hold pointers");
+static_assert(kOffDesc % 16 == 0 && kDescBytes % 16 == 0 && kOffStream % 8 == 0, "descriptor buffers are copied 16 bytes at a time and hold pointers");
 
 __device__ __forceinline__ void imma_s8u8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -148,7 +163,7 @@ __device__ __noinline__ void trace_pt_impl(Trace* t, uint32_t kind) {
 #define trace_pt(cx, phase, point) do { if ((cx).trace_on) trace_pt_impl((cx).tr, 64 + 16 * (phase) + (point)); } while (0)
 
 // ── grid barrier: monotonic counter, `target` arrivals expected in total ──
-__device__ __forceinline__ void grid_barrier(uint32_t* sync, uint32_t target) {
+__device__ __noinline__ void grid_barrier(uint32_t* sync, uint32_t target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -183,32 +198,12 @@ __device__ __forceinline__ Desc desc_of(uint8_t* smem, uint32_t layer) {
 __device__ __forceinline__ const ZgDecPhase* phase_of(uint8_t* smem, uint32_t pi) {
     return reinterpret_cast<const ZgDecPhase*>(smem + kOffDesc + ((pi >> 2) % 3) * kDescBytes + kDescPh) + (pi & 3);
 }
-// a layer's block: device memory -> registers (issue) -> shared memory (commit); kBlockRegs words per thread at most
-constexpr int kBlockRegs = 4;
-struct BlockRegs { uint32_t w[kBlockRegs]; };
-__device__ __forceinline__ uint32_t block_word_index(const ZgDecodePlan& P, uint32_t j) {   // j-th copied word -> word offset inside the block
-    const uint32_t hdr = kDescHeads / 4, hw = P.cap_heads * (sizeof(ZgDecHead) / 4), kw = P.cap_kv * (sizeof(ZgDecKv) / 4);
-    if (j < hdr) return j;
-    if (j < hdr + hw) return kDescHeads / 4 + (j - hdr);
-    if (j < hdr + hw + kw) return kDescKvs / 4 + (j - hdr - hw);
-    return UINT32_MAX;
-}
-__device__ __forceinline__ BlockRegs block_issue(const ZgDecodePlan& P, uint32_t layer, uint32_t tid) {
-    BlockRegs r;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.blocks + (size_t)layer * P.blk_bytes);
-#pragma unroll
-    for (int u = 0; u < kBlockRegs; u++) {
-        const uint32_t wi = block_word_index(P, tid + u * kT);
-        r.w[u] = wi != UINT32_MAX ? __ldg(src + wi) : 0u;
-    }
-    return r;
-}
-__device__ __forceinline__ void block_commit(const ZgDecodePlan& P, uint8_t* smem, uint32_t layer, uint32_t tid, const BlockRegs& r) {
-    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + kOffDesc + (layer % 3) * kDescBytes);
-#pragma unroll
-    for (int u = 0; u < kBlockRegs; u++) {
-        const uint32_t wi = block_word_index(P, tid + u * kT);
-        if (wi != UINT32_MAX) dst[wi] = r.w[u];
+// a layer's block: device memory -> shared memory, 16 bytes per thread, asynchronously (cp.async); complete after
+// cp.async.wait_all + a block barrier
+__device__ __forceinline__ void block_fetch(const ZgDecodePlan& P, uint8_t* smem, uint32_t layer, uint32_t tid) {
+    if (tid * 16 < kDescGlobalBytes) {
+        const uint32_t dst = smem_u32(smem + kOffDesc + (layer % 3) * kDescBytes) + tid * 16;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(P.blocks + (size_t)layer * P.blk_bytes + tid * 16) : "memory");
     }
 }
 // the layer's run-time values (patched per step by refresh): seq_kv per head, cache store offsets per KV head
@@ -226,66 +221,56 @@ __device__ __forceinline__ void dyn_commit(const Desc& d, uint32_t tid, uint32_t
     else if (tid >= 128 && tid < 128 + n_kv) d.v_dst[tid - 128] = v;
 }
 
-// ── the chunk stream of one warp: (phase, item, chunk) in execution order, across phases and layers ──
-struct Geo {          // this warp's share of one matvec phase
-    uint32_t S, split, slot, n_slots, n_items, n_kc, ks, ke, k0, L, n_chunk, G, RB;
-    bool cta_busy;    // the CTA owns at least one column group of the phase
-    bool busy;        // ... and this warp has records to stream
-};
+// ── work split of a matvec phase: S = 2^lS k-splits x (grid >> lS) column-group slots; a CTA owns split (cta & (S - 1)) of the
+//    column groups slot, slot + n_slots, ...; its 16 warps split the k-range ──
+struct Geo { uint32_t split, slot, ks, ke, k0, L; bool cta_busy; };
 __device__ __forceinline__ Geo phase_geo(const ZgDecPhase* ph, uint32_t cta, uint32_t warp) {
     Geo g;
-    g.S = ph->S; g.n_slots = ph->n_slots; g.n_items = ph->n_items; g.n_kc = ph->n_kc; g.RB = ph->rec_bytes;
-    g.G = (ph->fmt == ZG_QFMT_I4_F16) ? 4u : 2u;
-    g.split = cta % g.S; g.slot = cta / g.S;
-    g.ks = (g.split * g.n_kc) / g.S; g.ke = ((g.split + 1) * g.n_kc) / g.S;   // 32-bit: S <= 64 splits of n_kc < 2^20 records
-    g.k0 = g.ks + (warp * (g.ke - g.ks)) / kW;
-    const uint32_t k1 = g.ks + ((warp + 1) * (g.ke - g.ks)) / kW;
-    g.L = k1 - g.k0;
-    g.n_chunk = (g.L + g.G - 1) / g.G;
-    g.cta_busy = g.slot < g.n_slots && g.slot < g.n_items;
-    g.busy = g.cta_busy && g.L > 0;
+    const uint32_t lS = ph->lS, n_kc = ph->n_kc;
+    g.split = cta & ((1u << lS) - 1); g.slot = cta >> lS;
+    g.ks = (g.split * n_kc) >> lS; g.ke = ((g.split + 1) * n_kc) >> lS;
+    g.k0 = g.ks + ((warp * (g.ke - g.ks)) >> 4);
+    g.L = g.ks + (((warp + 1) * (g.ke - g.ks)) >> 4) - g.k0;
+    g.cta_busy = g.slot < ph->n_slots && g.slot < ph->n_items;
     return g;
 }
 __device__ __forceinline__ uint32_t item_op(const ZgDecPhase* ph, uint32_t item) {
-    uint32_t o = 0;
-    while (o + 1 < ph->n_mv && item >= ph->mv[o + 1].first_item) o++;
-    return o;
+    return (item >= ph->mv[1].first_item ? 1u : 0u) + (item >= ph->mv[2].first_item ? 1u : 0u);
 }
-__device__ __forceinline__ const uint8_t* item_records(const ZgDecPhase* ph, const Geo& g, uint32_t item) {
-    const uint32_t o = item_op(ph, item);
-    return ph->mv[o].recs + ((size_t)(item - ph->mv[o].first_item) * g.n_kc + g.k0) * g.RB;
-}
-struct Stream {
-    uint32_t pi, item, c, slot, outstanding;   // phase index, item, chunk, ring slot to fill next, chunks requested and not yet consumed
-    bool valid;                                // (pi, item, c) names a chunk that is still to be requested
-    Geo g;
-    const uint8_t* src;
-};
-// Request chunks until the ring is full, the stream ends, or the next chunk belongs to a layer whose descriptors are not in
-// shared memory yet (ready_layer).  Warp-uniform; lane 0 issues.
-__device__ __forceinline__ void stream_fill(Stream& s, uint8_t* smem, uint32_t n_ph, uint32_t ready_layer, uint32_t cta, uint32_t warp,
-                                            uint32_t lane, uint32_t ring, uint32_t bars) {
-    while (s.outstanding < kNS) {
-        while (!s.valid && s.pi < n_ph && (s.pi >> 2) <= ready_layer) {
-            const ZgDecPhase* ph = phase_of(smem, s.pi);
-            s.g = phase_geo(ph, cta, warp);
-            if (s.g.busy) { s.item = s.g.slot; s.c = 0; s.src = item_records(ph, s.g, s.item); s.valid = true; }
-            else s.pi++;
+
+// ── the chunk stream of one warp: (phase, item, chunk) in execution order, across phases and layers.  Run by lane 0 only,
+//    out of line, state in shared memory.  Requests chunks until the ring is full, the stream ends, or the next chunk belongs
+//    to a layer whose descriptors are not in shared memory yet (ready_layer). ──
+__device__ __noinline__ void stream_fill(uint8_t* smem, uint32_t cta, uint32_t warp, uint32_t n_ph, uint32_t ready_layer) {
+    StreamState* s = reinterpret_cast<StreamState*>(smem + kOffStream) + warp;
+    const uint32_t ring = smem_u32(smem + kOffRing) + warp * kNS * kSlotBytes, bars = smem_u32(smem + kOffBars) + warp * kNS * 8;
+    while (s->outstanding < kNS) {
+        while (!s->valid && s->pi < n_ph && (s->pi >> 2) <= ready_layer) {
+            const ZgDecPhase* ph = phase_of(smem, s->pi);
+            const Geo g = phase_geo(ph, cta, warp);
+            if (g.cta_busy && g.L > 0) {
+                s->G = ph->fmt == ZG_QFMT_I4_F16 ? 4u : 2u; s->RB = ph->rec_bytes; s->L = g.L; s->n_chunk = (g.L + s->G - 1) / s->G;
+                s->n_items = ph->n_items; s->n_slots = ph->n_slots; s->k0 = g.k0; s->n_kc = ph->n_kc;
+                s->item = g.slot; s->c = 0; s->valid = 1;
+                const uint32_t o = item_op(ph, s->item);
+                s->src = ph->mv[o].recs + ((size_t)(s->item - ph->mv[o].first_item) * s->n_kc + s->k0) * s->RB;
+            } else s->pi++;
         }
-        if (!s.valid) return;
-        const uint32_t cnt = min(s.g.G, s.g.L - s.c * s.g.G);
-        if (lane == 0) {
-            const uint32_t bar = bars + s.slot * 8;
-            mbar_expect_tx(bar, cnt * s.g.RB);
-            bulk_g2s(ring + s.slot * kSlotBytes, s.src + (size_t)s.c * s.g.G * s.g.RB, cnt * s.g.RB, bar);
-        }
-        s.outstanding++;
-        if (++s.slot == kNS) s.slot = 0;
-        if (++s.c == s.g.n_chunk) {
-            s.c = 0;
-            s.item += s.g.n_slots;
-            if (s.item >= s.g.n_items) { s.valid = false; s.pi++; }
-            else s.src = item_records(phase_of(smem, s.pi), s.g, s.item);
+        if (!s->valid) return;
+        const uint32_t cnt = min(s->G, s->L - s->c * s->G), bar = bars + s->slot * 8;
+        mbar_expect_tx(bar, cnt * s->RB);
+        bulk_g2s(ring + s->slot * kSlotBytes, s->src + (size_t)s->c * s->G * s->RB, cnt * s->RB, bar);
+        s->outstanding++;
+        if (++s->slot == kNS) s->slot = 0;
+        if (++s->c == s->n_chunk) {
+            s->c = 0;
+            s->item += s->n_slots;
+            if (s->item >= s->n_items) { s->valid = 0; s->pi++; }
+            else {
+                const ZgDecPhase* ph = phase_of(smem, s->pi);
+                const uint32_t o = item_op(ph, s->item);
+                s->src = ph->mv[o].recs + ((size_t)(s->item - ph->mv[o].first_item) * s->n_kc + s->k0) * s->RB;
+            }
         }
     }
 }
@@ -299,22 +284,22 @@ struct Ctx {          // per-thread constants + ring state
     uint32_t* sync;
     uint8_t* smem;
     float* xin; float* part; float* red; float* smax;
-    Trace* tr; uint32_t tr_phase; bool trace_on;
+    Trace* tr; bool trace_on;
 };
 
 // scale ceiling of the i-th column group this CTA owns in the phase (thread i < kZgDecMaxItems): issued before the prologue's
 // loads, stored to shared memory after them
 __device__ __forceinline__ float smax_issue(const ZgDecPhase* ph, const Geo& g, uint32_t tid) {
     if (!g.cta_busy || tid >= kZgDecMaxItems) return 1.0f;
-    const uint32_t item = g.slot + tid * g.n_slots;
-    if (item >= g.n_items) return 1.0f;
+    const uint32_t item = g.slot + tid * ph->n_slots;
+    if (item >= ph->n_items) return 1.0f;
     const uint32_t o = item_op(ph, item);
     return __ldg(ph->mv[o].smax + (item - ph->mv[o].first_item));
 }
 
 // ── one matvec phase: the CTA's column groups x its k-split, activations already staged in xin[] (element x_base + i) ──
 template <int FMT>
-__device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* ph, const Geo& g, uint32_t x_base) {
+__device__ __forceinline__ void mv_phase(Ctx& cx, const ZgDecPhase* ph, const Geo& g, uint32_t x_base) {
     constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
     constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
     constexpr uint32_t QB = kI4 ? 512u : 1024u;
@@ -322,6 +307,8 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
     constexpr uint32_t RB = QB + 4 * SB;
     constexpr uint32_t G = kI4 ? 4u : 2u;
     const uint32_t lane = cx.lane, gq = lane >> 2, t = lane & 3, j = gq & 3;
+    const uint32_t n_chunk = (g.L + G - 1) / G, n_items = ph->n_items, n_slots = ph->n_slots;
+    const uint32_t S = ph->S;
 
     // this warp's slice of the staged activations, scaled in place: x' = x * 0.499 / (max|x| * smax) (qgemv.cu)
     float* xw = cx.xin + ((size_t)g.k0 * ZG_KR - x_base);
@@ -329,6 +316,7 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
     float sm_prev = cx.smax[0];
     if (g.L > 0) {
         float mx = 0.0f;
+#pragma unroll 1
         for (uint32_t i = 0; i < g.L; i++) {
             const float aa = fabsf(xw[32 * i + lane]);
             mx = (aa <= 3.0e38f) ? fmaxf(mx, aa) : INFINITY;
@@ -337,17 +325,18 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         xm = mx;
         const float f = (mx <= 3.0e38f && mx >= 1.0e-30f) ? (0.499f / mx) * (1.0f / sm_prev) : 0.0f;
+#pragma unroll 1
         for (uint32_t i = 0; i < g.L; i++) xw[32 * i + lane] *= f;
         __syncwarp();
     }
-    trace_pt(cx, cx.tr_phase, 5);
     const uint32_t xs_u32 = smem_u32(xw);
     const uint32_t brow = cx.planes + j * 32 + 4 * t;
     const uint32_t q_off = lane * 16;
     const uint32_t sc_off = QB + (kF32 ? 4u : 2u) * (8 * ((lane & 15) >> 2) + 4 * (lane >> 4) + (lane & 3));
 
     uint32_t ord = 0;   // ordinal of the item among this CTA's items
-    for (uint32_t item = g.slot; item < g.n_items; item += g.n_slots, ord++) {
+#pragma unroll 1
+    for (uint32_t item = g.slot; item < n_items; item += n_slots, ord++) {
         const uint32_t o = item_op(ph, item);
         const uint32_t nb = item - ph->mv[o].first_item;
         float* part_w = cx.part + ((size_t)cx.pbuf * kW + cx.warp) * 32;
@@ -355,6 +344,7 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
             const float sm = cx.smax[ord];
             if (sm != sm_prev) {   // re-normalise for this column group's scale ceiling: exact (powers of two)
                 const float ratio = sm_prev / sm;
+#pragma unroll 1
                 for (uint32_t i = 0; i < g.L; i++) xw[32 * i + lane] *= ratio;
                 __syncwarp();
                 sm_prev = sm;
@@ -366,7 +356,8 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
 #pragma unroll
                 for (int i = 0; i < 4; i++) acc[ct][i] = 0;
             uint32_t xa = xs_u32 + lane * 4;
-            for (uint32_t c = 0; c < g.n_chunk; c++, xa += G * ZG_KR * 4) {
+#pragma unroll 1
+            for (uint32_t c = 0; c < n_chunk; c++, xa += G * ZG_KR * 4) {
                 const uint32_t cnt = min(G, g.L - c * G);
                 const uint32_t slot_u32 = cx.ring + cx.slot * kSlotBytes, bar_u32 = cx.bars + cx.slot * 8;
                 {   // bounded wait for the chunk's bytes
@@ -379,57 +370,47 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
                         }
                     }
                 }
-#pragma unroll
-                for (uint32_t r = 0; r < G; r++) {
-                    if (r < cnt) {
-                        float sc;
-                        if constexpr (kF32) {
-                            sc = __uint_as_float(lds32(slot_u32 + sc_off + r * RB));
-                        } else {
-                            unsigned short h;
-                            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(slot_u32 + sc_off + r * RB));
-                            sc = __half2float(__ushort_as_half(h));
-                        }
-                        const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + r * ZG_KR * 4)), 1.5f));
-                        const uint32_t pa = cx.planes + lane + r * kPlaneRow;
-                        sts8(pa, F);
-                        sts8(pa + 32, F >> 8);
-                        sts8(pa + 64, F >> 16);
+                // digit planes of the chunk's records: lane = k row, F = s * x' + 1.5 in (1, 2), low three bytes = base-256 digits
+#pragma unroll 1
+                for (uint32_t r = 0; r < cnt; r++) {
+                    float sc;
+                    if constexpr (kF32) {
+                        sc = __uint_as_float(lds32(slot_u32 + sc_off + r * RB));
+                    } else {
+                        unsigned short h;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(slot_u32 + sc_off + r * RB));
+                        sc = __half2float(__ushort_as_half(h));
                     }
+                    const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + r * ZG_KR * 4)), 1.5f));
+                    const uint32_t pa = cx.planes + lane + r * kPlaneRow;
+                    sts8(pa, F);
+                    sts8(pa + 32, F >> 8);
+                    sts8(pa + 64, F >> 16);
                 }
                 __syncwarp();
-#pragma unroll
-                for (uint32_t r = 0; r < G; r++) {
-                    if (r < cnt) {
-                        const uint32_t qa = slot_u32 + q_off + r * RB;
-                        uint32_t a[2][4];
-                        if constexpr (!kI4) {
-                            const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
-                            a[0][0] = q0.x; a[0][1] = q0.y; a[0][2] = q0.z; a[0][3] = q0.w;
-                            a[1][0] = q1.x; a[1][1] = q1.y; a[1][2] = q1.z; a[1][3] = q1.w;
-                        } else {
-                            const uint4 q0 = lds128(qa);
-                            a[0][0] = q0.x; a[0][1] = q0.x & 0x0F0F0F0Fu; a[0][2] = q0.y; a[0][3] = q0.y & 0x0F0F0F0Fu;
-                            a[1][0] = q0.z; a[1][1] = q0.z & 0x0F0F0F0Fu; a[1][2] = q0.w; a[1][3] = q0.w & 0x0F0F0F0Fu;
-                        }
-                        const uint32_t b0 = lds32(brow + r * kPlaneRow), b1 = lds32(brow + r * kPlaneRow + 16);
-                        if constexpr (kI4) {
-                            dsum = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum));
-                            imma_u8u8(acc[0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                            imma_u8u8(acc[1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
-                        } else {
-                            imma_s8u8(acc[0], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                            imma_s8u8(acc[1], a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
-                        }
+#pragma unroll 1
+                for (uint32_t r = 0; r < cnt; r++) {
+                    const uint32_t qa = slot_u32 + q_off + r * RB;
+                    const uint32_t b0 = lds32(brow + r * kPlaneRow), b1 = lds32(brow + r * kPlaneRow + 16);
+                    if constexpr (!kI4) {
+                        const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
+                        imma_s8u8(acc[0], q0.x, q0.y, q0.z, q0.w, b0, b1);
+                        imma_s8u8(acc[1], q1.x, q1.y, q1.z, q1.w, b0, b1);
+                    } else {
+                        const uint4 q0 = lds128(qa);
+                        dsum = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum));
+                        imma_u8u8(acc[0], q0.x, q0.x & 0x0F0F0F0Fu, q0.y, q0.y & 0x0F0F0F0Fu, b0, b1);
+                        imma_u8u8(acc[1], q0.z, q0.z & 0x0F0F0F0Fu, q0.w, q0.w & 0x0F0F0F0Fu, b0, b1);
                     }
                 }
                 __syncwarp();
                 // the slot is free: request the chunk kNS ahead in the stream (possibly of a later phase / layer)
-                st.outstanding--;
                 if (++cx.slot == kNS) { cx.slot = 0; cx.parity ^= 1; }
-                stream_fill(st, cx.smem, cx.n_ph, cx.ready_layer, cx.cta, cx.warp, lane, cx.ring, cx.bars);
+                if (lane == 0) {
+                    reinterpret_cast<StreamState*>(cx.smem + kOffStream)[cx.warp].outstanding--;
+                    stream_fill(cx.smem, cx.cta, cx.warp, cx.n_ph, cx.ready_layer);
+                }
             }
-            trace_pt(cx, cx.tr_phase, 6);
             // flush: integer sums -> this warp's float partial of the column group
             {
                 const uint32_t kcnt = g.L * ZG_KR;
@@ -478,19 +459,11 @@ __device__ __forceinline__ void mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* 
             float v = 0.0f;
 #pragma unroll
             for (int w = 0; w < kW; w++) v += pr[w * 32];
-            float* out = g.S == 1 ? ph->mv[o].out : ph->mv[o].part + (size_t)g.split * ph->mv[o].N;
+            float* out = S == 1 ? ph->mv[o].out : ph->mv[o].part + (size_t)g.split * ph->mv[o].N;
             out[nb * ZG_TN + cx.tid] = v;
         }
-        trace_pt(cx, cx.tr_phase, 7);
         cx.pbuf ^= 1;
     }
-}
-
-__device__ __forceinline__ void run_mv_phase(Ctx& cx, Stream& st, const ZgDecPhase* ph, const Geo& g, uint32_t x_base) {
-    if (!g.cta_busy) return;   // CTA-uniform: this CTA owns no column group of the phase
-    if (ph->fmt == ZG_QFMT_I4_F16) mv_phase<ZG_QFMT_I4_F16>(cx, st, ph, g, x_base);
-    else if (ph->fmt == ZG_QFMT_I8_F16) mv_phase<ZG_QFMT_I8_F16>(cx, st, ph, g, x_base);
-    else mv_phase<ZG_QFMT_I8_F32>(cx, st, ph, g, x_base);
 }
 
 // fixed-order block sum (every CTA computes the identical value)
@@ -506,60 +479,53 @@ __device__ __forceinline__ float block_sum(Ctx& cx, float v) {
 }
 
 // ── prologue of phases 1 and 4: x = a (+ b -> sum) ; bare = x * inv_rms ; grep = gamma ; norm = bare * gamma -> xin[0 .. n_pad).
-//    Every load of the prologue is issued before the first one is used (NU elements per thread).  No trailing barrier. ──
-template <int NU>
-__device__ __forceinline__ void prologue_norm(Ctx& cx, const float* a, const ZgDecVec b, float* sum, const float* gamma, float* bare,
+//    Four elements per thread and pass, their loads in flight together; the sums wait in xin[] for the scale. ──
+__device__ __forceinline__ void prologue_norm(Ctx& cx, const float* a, const ZgDecVec& b, float* sum, const float* gamma, float* bare,
                                               float* grep, float* norm, float eps, uint32_t D, uint32_t n_pad) {
+    constexpr int NU = 4;
     const bool has_b = b.full != nullptr, writer = cx.cta == 0;
-    float v[NU], gm[NU];
+    const float* bsrc = b.S ? b.part : b.full;
+    float ss = 0.0f;
+#pragma unroll 1
+    for (uint32_t e0 = 0; e0 < D; e0 += NU * kT) {
+        float v[NU];
 #pragma unroll
-    for (int u = 0; u < NU; u++) {
-        const uint32_t i = cx.tid + u * kT;
-        v[u] = i < D ? __ldcg(a + i) : 0.0f;
-        gm[u] = i < D ? __ldg(gamma + i) : 0.0f;
-    }
-    if (has_b) {
-        float t2[NU];
-        const float* src = b.S ? b.part : b.full;
+        for (int u = 0; u < NU; u++) { const uint32_t i = e0 + cx.tid + u * kT; v[u] = i < D ? __ldcg(a + i) : 0.0f; }
+        if (has_b) {
+            float t2[NU];
 #pragma unroll
-        for (int u = 0; u < NU; u++) { const uint32_t i = cx.tid + u * kT; t2[u] = i < D ? __ldcg(src + i) : 0.0f; }
-        for (uint32_t s = 1; s < b.S; s++) {
+            for (int u = 0; u < NU; u++) { const uint32_t i = e0 + cx.tid + u * kT; t2[u] = i < D ? __ldcg(bsrc + i) : 0.0f; }
+#pragma unroll 1
+            for (uint32_t s = 1; s < b.S; s++) {
 #pragma unroll
-            for (int u = 0; u < NU; u++) { const uint32_t i = cx.tid + u * kT; if (i < D) t2[u] += __ldcg(b.part + (size_t)s * b.n + i); }
+                for (int u = 0; u < NU; u++) { const uint32_t i = e0 + cx.tid + u * kT; if (i < D) t2[u] += __ldcg(b.part + (size_t)s * b.n + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const uint32_t i = e0 + cx.tid + u * kT;
+                v[u] = __fadd_rn(v[u], t2[u]);
+                if (writer && i < D) { sum[i] = v[u]; if (b.S) b.full[i] = t2[u]; }
+            }
         }
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-            const uint32_t i = cx.tid + u * kT;
-            if (i < D) {
-                v[u] = __fadd_rn(v[u], t2[u]);
-                if (writer) { sum[i] = v[u]; if (b.S) b.full[i] = t2[u]; }
-            }
+            const uint32_t i = e0 + cx.tid + u * kT;
+            if (i < D) cx.xin[i] = v[u];
+            ss = fmaf(v[u], v[u], ss);
         }
     }
-    float ss = 0.0f;
-#pragma unroll
-    for (int u = 0; u < NU; u++) ss = fmaf(v[u], v[u], ss);
     const float tot = block_sum(cx, ss);
     const float inv_rms = 1.0f / sqrtf(tot / (float)D + eps);
-#pragma unroll
-    for (int u = 0; u < NU; u++) {
-        const uint32_t i = cx.tid + u * kT;
-        if (i < n_pad) {
-            float xv = 0.0f;
-            if (i < D) {
-                const float bz = __fmul_rn(v[u], inv_rms);
-                xv = __fmul_rn(bz, gm[u]);
-                if (writer) { bare[i] = bz; grep[i] = gm[u]; norm[i] = xv; }
-            }
-            cx.xin[i] = xv;
+#pragma unroll 4
+    for (uint32_t i = cx.tid; i < n_pad; i += kT) {
+        float xv = 0.0f;
+        if (i < D) {
+            const float bz = __fmul_rn(cx.xin[i], inv_rms), gm = __ldg(gamma + i);
+            xv = __fmul_rn(bz, gm);
+            if (writer) { bare[i] = bz; grep[i] = gm; norm[i] = xv; }
         }
+        cx.xin[i] = xv;
     }
-}
-__device__ __forceinline__ void run_prologue_norm(Ctx& cx, const float* a, const ZgDecVec& b, float* sum, const float* gamma, float* bare,
-                                                  float* grep, float* norm, float eps, uint32_t D, uint32_t n_pad) {
-    if (n_pad <= 4 * kT) prologue_norm<4>(cx, a, b, sum, gamma, bare, grep, norm, eps, D, n_pad);
-    else if (n_pad <= 8 * kT) prologue_norm<8>(cx, a, b, sum, gamma, bare, grep, norm, eps, D, n_pad);
-    else prologue_norm<16>(cx, a, b, sum, gamma, bare, grep, norm, eps, D, n_pad);
 }
 
 __device__ __forceinline__ uint32_t attn_splits(uint32_t seq_kv, uint32_t max_splits) {
@@ -576,6 +542,7 @@ __device__ __forceinline__ void prologue_attn_merge(Ctx& cx, const ZgDecodePlan&
     const uint32_t k_lo = g.ks * ZG_KR, k_hi = min(k_lo + n, K);
     const uint32_t h_lo = k_lo / dh, n_h = k_hi > k_lo ? (k_hi - 1) / dh - h_lo + 1 : 0;
     float* wsm = cx.part;   // [head - h_lo][16] weights (the partial-sum buffers are idle during the prologue)
+#pragma unroll 1
     for (uint32_t p0 = 0; p0 < n_h * 16; p0 += kT) {
         const uint32_t pidx = p0 + cx.tid, h = h_lo + pidx / 16, sp = pidx & 15;
         const bool in = pidx < n_h * 16 && sp < attn_splits(d.seq_kv[min(h, ly.n_heads - 1)], P.max_splits);
@@ -592,7 +559,7 @@ __device__ __forceinline__ void prologue_attn_merge(Ctx& cx, const ZgDecodePlan&
     }
     __syncthreads();
     const bool writer = g.slot == 0;
-#pragma unroll 2
+#pragma unroll 1
     for (uint32_t i = cx.tid; i < n; i += kT) {
         const uint32_t k = k_lo + i;
         float val = 0.0f;
@@ -601,6 +568,7 @@ __device__ __forceinline__ void prologue_attn_merge(Ctx& cx, const ZgDecodePlan&
             const uint32_t splits = attn_splits(d.seq_kv[h], P.max_splits);
             const float* base = P.attn_part + (size_t)h * P.max_splits * stride + 2 + dd;
             const float* w = wsm + (h - h_lo) * 16;
+#pragma unroll 1
             for (uint32_t sp0 = 0; sp0 < splits; sp0 += 4) {
                 float a4[4];
 #pragma unroll
@@ -628,9 +596,7 @@ __device__ __noinline__ float apply_unary(uint32_t op, float v) {
         default: return v;
     }
 }
-
-// the activation chain of one element (fused_elementwise steps, src/backend/reference.zig:262-300); out of line: the
-// kernel's code has to stay small
+// the general activation chain of one element (fused_elementwise steps, src/backend/reference.zig:262-300); out of line
 __device__ __noinline__ float act_chain(const ZgDecLayer* ly, float gt, float up, float sec0, int first_ext, uint32_t k) {
     float v = gt;
     for (uint32_t s = 0; s < ly->n_steps; s++) {
@@ -644,33 +610,38 @@ __device__ __noinline__ float act_chain(const ZgDecLayer* ly, float gt, float up
     return v;
 }
 
-// ── prologue of phase 5: mid = steps(gate) ; hidden = mid * up for the CTA's k-range ──
+// ── prologue of phase 5: mid = steps(gate) ; hidden = mid * up for the CTA's k-range.  The SiLU chain of the lowering (neg,
+//    exp, + ones, recip, * gate: src/nn.zig:38-44) is evaluated inline, op by op with the same roundings; any other chain by
+//    the general interpreter. ──
 __device__ __forceinline__ void prologue_act(Ctx& cx, const Desc& d, const Geo& g) {
-    constexpr int NU = 8;   // elements per thread and pass: their loads are in flight together
+    constexpr int NU = 4;
     const ZgDecLayer& ly = *d.ly;
-    const uint32_t n = (g.ke - g.ks) * ZG_KR, F = ly.F;
+    const uint32_t n = (g.ke - g.ks) * ZG_KR, F = ly.F, k_lo = g.ks * ZG_KR;
     const bool writer = g.slot == 0;
-    // the first step that reads an external buffer (SiLU: the ones vector) is loaded with gate / up; later ones in the chain
     int first_ext = -1;
+#pragma unroll 1
     for (uint32_t s = 0; s < ly.n_steps; s++)
         if ((ly.steps[s].op == ZG_EW_ADD || ly.steps[s].op == ZG_EW_MUL) && ly.steps[s].sec_kind == 0) { first_ext = (int)s; break; }
     const float* gsrc = ly.gate.S ? ly.gate.part : ly.gate.full;
     const float* usrc = ly.up.S ? ly.up.part : ly.up.full;
     const float* esrc = first_ext >= 0 ? ly.steps[first_ext].sec : nullptr;
+    const uint32_t Smax = max(ly.gate.S, ly.up.S);
+#pragma unroll 1
     for (uint32_t e0 = 0; e0 < n; e0 += NU * kT) {
         float gt[NU], up[NU], sec0[NU];
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-            const uint32_t i = e0 + cx.tid + u * kT, k = g.ks * ZG_KR + i;
+            const uint32_t i = e0 + cx.tid + u * kT, k = k_lo + i;
             const bool in = i < n && k < F;
             gt[u] = in ? __ldcg(gsrc + k) : 0.0f;
             up[u] = in ? __ldcg(usrc + k) : 0.0f;
             sec0[u] = (in && esrc) ? __ldg(esrc + k) : 0.0f;
         }
-        for (uint32_t sx = 1; sx < max(ly.gate.S, ly.up.S); sx++) {
+#pragma unroll 1
+        for (uint32_t sx = 1; sx < Smax; sx++) {
 #pragma unroll
             for (int u = 0; u < NU; u++) {
-                const uint32_t i = e0 + cx.tid + u * kT, k = g.ks * ZG_KR + i;
+                const uint32_t i = e0 + cx.tid + u * kT, k = k_lo + i;
                 if (i < n && k < F) {
                     if (sx < ly.gate.S) gt[u] += __ldcg(ly.gate.part + (size_t)sx * ly.gate.n + k);
                     if (sx < ly.up.S) up[u] += __ldcg(ly.up.part + (size_t)sx * ly.up.n + k);
@@ -679,11 +650,13 @@ __device__ __forceinline__ void prologue_act(Ctx& cx, const Desc& d, const Geo& 
         }
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-            const uint32_t i = e0 + cx.tid + u * kT, k = g.ks * ZG_KR + i;
+            const uint32_t i = e0 + cx.tid + u * kT, k = k_lo + i;
             if (i < n) {
                 float hv = 0.0f;
                 if (k < F) {
-                    const float v = act_chain(d.ly, gt[u], up[u], sec0[u], first_ext, k);
+                    float v;
+                    if (ly.act_silu) v = __fmul_rn(gt[u], 1.0f / __fadd_rn(expf(-gt[u]), sec0[u]));
+                    else v = act_chain(d.ly, gt[u], up[u], sec0[u], first_ext, k);
                     hv = __fmul_rn(v, up[u]);
                     if (writer) {
                         ly.silu[k] = v; ly.hidden[k] = hv;
@@ -847,6 +820,7 @@ __device__ __forceinline__ void attention_item(Ctx& cx, const ZgDecodePlan& P, c
 
 __device__ __forceinline__ void attention_phase(Ctx& cx, const ZgDecodePlan& P, const Desc& d) {
     const ZgDecLayer& ly = *d.ly;
+#pragma unroll 1
     for (uint32_t it = cx.cta; it < ly.n_heads * P.max_splits; it += cx.grid) {
         const uint32_t h = it / P.max_splits, sp = it % P.max_splits;
         const uint32_t splits = attn_splits(d.seq_kv[h], P.max_splits);
@@ -860,28 +834,28 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const ZgDecodePlan& P, 
 // are final since the previous step)
 __device__ __forceinline__ void attention_prefetch(Ctx& cx, const ZgDecodePlan& P, const Desc& d) {
     const ZgDecLayer& ly = *d.ly;
-    const uint32_t row_lines = (ly.d_head * 4 + 127) / 128;
+#pragma unroll 1
     for (uint32_t it = cx.cta; it < ly.n_heads * P.max_splits; it += cx.grid) {
         const uint32_t h = it / P.max_splits, sp = it % P.max_splits;
         const uint32_t seq_kv = d.seq_kv[h], splits = attn_splits(seq_kv, P.max_splits);
-        if (sp >= splits) continue;
-        if (h > 0 && d.heads[h - 1].kv == d.heads[h].kv) continue;   // one prefetch per KV head and split
+        if (sp >= splits || (h > 0 && d.heads[h - 1].kv == d.heads[h].kv)) continue;   // one prefetch per KV head and split
         const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
         const uint32_t kv_lo = sp * chunk, kv_hi = min(kv_lo + chunk, seq_kv);
         const char* kb = reinterpret_cast<const char*>(ly.k_cache + d.heads[h].k_off);
         const char* vb = reinterpret_cast<const char*>(ly.v_cache + d.heads[h].v_off);
-        const uint32_t total = (kv_hi > kv_lo ? kv_hi - kv_lo : 0) * row_lines;
-        for (uint32_t q = cx.tid; q < total; q += kT) {
-            const uint32_t s = kv_lo + q / row_lines, b = (q % row_lines) * 128;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (size_t)s * ly.k_cs * 4 + b));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)s * ly.v_cs * 4 + b));
-        }
+#pragma unroll 1
+        for (uint32_t s = kv_lo + cx.tid; s < kv_hi; s += kT)
+#pragma unroll 1
+            for (uint32_t b = 0; b < ly.d_head * 4; b += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (size_t)s * ly.k_cs * 4 + b));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)s * ly.v_cs * 4 + b));
+            }
     }
 }
 
 // ── all-reduce phase over NVLink peer memory: the protocol of ops.cu k_allreduce_peer (16-byte cells {x, epoch, y, epoch}),
 //    run by the first kZgPeerCtas CTAs; local values come from the matvec's partial sums ──
-__device__ __forceinline__ void allreduce_phase(Ctx& cx, const ZgDecodePlan& P, const ZgDecVec& local, float* out, uint32_t& ar_seq) {
+__device__ __noinline__ void allreduce_phase(Ctx& cx, const ZgDecodePlan& P, const ZgDecVec& local, float* out, uint32_t& ar_seq) {
     if (cx.cta >= kZgPeerCtas) return;
     const ZgPeerComm& pc = P.pc;
     const uint32_t n2 = local.n >> 1;
@@ -934,12 +908,9 @@ __device__ __forceinline__ void allreduce_phase(Ctx& cx, const ZgDecodePlan& P, 
     ar_seq++;
 }
 
-// Measured and rejected: instantiating the body 8 times at different addresses (CTA i runs copy i % 8, to spread the
-// instruction fetches of the lockstepped CTAs over L2 slices) made the step 20 % SLOWER — instruction lines shared between SMs help.
-constexpr int kCodeCopies = 1;
-template <int COPY>
-__device__ __forceinline__ void decode_body(const ZgDecodePlan& P, uint8_t* smem) {
-    asm volatile("" ::"n"(COPY));
+__global__ void __launch_bounds__(kT, 1)
+k_decode_layers(const __grid_constant__ ZgDecodePlan P) {
+    extern __shared__ __align__(128) uint8_t smem[];
     Ctx cx;
     cx.tid = threadIdx.x; cx.lane = cx.tid & 31; cx.warp = cx.tid >> 5; cx.cta = blockIdx.x; cx.grid = gridDim.x;
     const uint32_t smem_base = smem_u32(smem);
@@ -954,31 +925,27 @@ __device__ __forceinline__ void decode_body(const ZgDecodePlan& P, uint8_t* smem
     cx.smax = reinterpret_cast<float*>(smem + kOffSmax);
     cx.n_ph = 4 * P.n_layers;
     const uint32_t L = P.n_layers;
-    cx.tr = reinterpret_cast<Trace*>(smem + kOffTrace); cx.tr_phase = 0;
+    cx.tr = reinterpret_cast<Trace*>(smem + kOffTrace);
     cx.trace_on = false;
-    if (cx.cta == 0 && cx.tid == 0) { trace_open(cx.tr, 64 * L + 8); cx.trace_on = cx.tr->next != nullptr; }
+    if (cx.cta == 0 && cx.tid == 0) { trace_open(cx.tr, 24 * L + 8); cx.trace_on = cx.tr->next != nullptr; }
 
-    // descriptor blocks of layers 0 and 1, then layer 0's run-time values
-    {
-        const BlockRegs b0 = block_issue(P, 0, cx.tid);
-        BlockRegs b1 = b0;
-        if (L > 1) b1 = block_issue(P, 1, cx.tid);
-        block_commit(P, smem, 0, cx.tid, b0);
-        if (L > 1) block_commit(P, smem, 1, cx.tid, b1);
-    }
-    // ring barriers and the constant ones plane (digit index 3) of every record slot
+    // descriptor blocks of layers 0 and 1
+    block_fetch(P, smem, 0, cx.tid);
+    if (L > 1) block_fetch(P, smem, 1, cx.tid);
+    // ring barriers, producer state and the constant ones plane (digit index 3) of every record slot
     if (cx.lane == 0) {
         for (uint32_t s = 0; s < kNS; s++) mbar_init(cx.bars + s * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        StreamState* st = reinterpret_cast<StreamState*>(smem + kOffStream) + cx.warp;
+        st->pi = 0; st->item = 0; st->c = 0; st->slot = 0; st->outstanding = 0; st->valid = 0;
     }
     for (uint32_t i = cx.lane; i < 4 * 8; i += 32)
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(cx.planes + (i >> 3) * kPlaneRow + 96 + (i & 7) * 4), "r"(0x01010101u) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     cx.ready_layer = L > 1 ? 1u : 0u;
-    Stream st;
-    st.pi = 0; st.item = 0; st.c = 0; st.slot = 0; st.outstanding = 0; st.valid = false; st.src = nullptr;
-    stream_fill(st, smem, cx.n_ph, cx.ready_layer, cx.cta, cx.warp, cx.lane, cx.ring, cx.bars);
-    {
+    if (cx.lane == 0) stream_fill(smem, cx.cta, cx.warp, cx.n_ph, cx.ready_layer);
+    {   // layer 0's run-time values
         const Desc d0 = desc_of(smem, 0);
         dyn_commit(d0, cx.tid, dyn_issue(P, d0, cx.tid));
         __syncthreads();
@@ -987,69 +954,65 @@ __device__ __forceinline__ void decode_body(const ZgDecodePlan& P, uint8_t* smem
     uint32_t ar_seq = 0;
     if (P.pc.world > 1 && cx.cta < kZgPeerCtas) ar_seq = ld_vol(P.pc.seq + 2 + cx.cta);
     uint32_t arrivals = 0;   // grid-barrier arrivals expected so far
-    auto barrier = [&]() { arrivals += cx.grid; grid_barrier(P.sync, arrivals); };
 
+#pragma unroll 1
     for (uint32_t l = 0; l < L; l++) {
         const Desc d = desc_of(smem, l);
         const ZgDecLayer& ly = *d.ly;
-        // One loop over the four matvec phases (0: q|k|v, 1: o, 2: gate|up, 3: down): every routine has exactly one call
-        // site, which keeps the kernel's code small enough to stay in the instruction cache.
+        // One loop over the four matvec phases (0: q|k|v, 1: o, 2: gate|up, 3: down): every routine has exactly one call site.
 #pragma unroll 1
         for (uint32_t k = 0; k < 4; k++) {
             if (k == 1) {   // phase 2: attention
                 trace_pt(cx, 3, 8);
                 attention_phase(cx, P, d);
                 trace_pt(cx, 3, 9);
-                barrier();
+                arrivals += cx.grid; grid_barrier(P.sync, arrivals);
             }
-            cx.tr_phase = k;
             trace_pt(cx, k, 0);
             const ZgDecPhase* ph = d.ph + k;
             const Geo g = phase_geo(ph, cx.cta, cx.warp);
             const float smv = smax_issue(ph, g, cx.tid);
-            BlockRegs nb = {};
             uint32_t ndyn = 0;
             uint32_t x_base = 0;
             if (k == 0 || k == 2) {
                 if (k == 0) {
                     // fetches that ride along with the prologue's loads: layer l + 2's descriptors, layer l + 1's run-time values
-                    if (l + 2 < L) nb = block_issue(P, l + 2, cx.tid);
+                    if (l + 2 < L) block_fetch(P, smem, l + 2, cx.tid);
                     if (l + 1 < L) ndyn = dyn_issue(P, desc_of(smem, l + 1), cx.tid);
                     attention_prefetch(cx, P, d);
                 }
-                trace_pt(cx, k, 1);
                 const bool first = k == 0;
-                run_prologue_norm(cx, first ? ly.x1_a : ly.x2_a, first ? ly.x1_b : ly.o, first ? ly.x1_sum : ly.x2_sum, first ? ly.gamma1 : ly.gamma2,
-                                  first ? ly.bare1 : ly.bare2, first ? ly.grep1 : ly.grep2, first ? ly.norm1 : ly.norm2, first ? ly.eps1 : ly.eps2,
-                                  ly.D, ph->n_kc * ZG_KR);
+                prologue_norm(cx, first ? ly.x1_a : ly.x2_a, first ? ly.x1_b : ly.o, first ? ly.x1_sum : ly.x2_sum, first ? ly.gamma1 : ly.gamma2,
+                              first ? ly.bare1 : ly.bare2, first ? ly.grep1 : ly.grep2, first ? ly.norm1 : ly.norm2, first ? ly.eps1 : ly.eps2,
+                              ly.D, ph->n_kc * ZG_KR);
             } else {
                 x_base = g.ks * ZG_KR;
-                trace_pt(cx, k, 1);
                 if (g.cta_busy) {
                     if (k == 1) prologue_attn_merge(cx, P, d, g, ph->K);
                     else prologue_act(cx, d, g);
                 }
             }
-            trace_pt(cx, k, 2);
             if (cx.tid < kZgDecMaxItems) cx.smax[cx.tid] = smv;
             if (k == 0) {
-                if (l + 2 < L) block_commit(P, smem, l + 2, cx.tid, nb);
                 if (l + 1 < L) dyn_commit(desc_of(smem, l + 1), cx.tid, ndyn);
+                asm volatile("cp.async.wait_all;" ::: "memory");
             }
             __syncthreads();
-            trace_pt(cx, k, 3);
             if (k == 0 && l + 2 < L) cx.ready_layer = l + 2;
-            stream_fill(st, smem, cx.n_ph, cx.ready_layer, cx.cta, cx.warp, cx.lane, cx.ring, cx.bars);
-            trace_pt(cx, k, 4);
-            run_mv_phase(cx, st, ph, g, x_base);
+            if (cx.lane == 0) stream_fill(smem, cx.cta, cx.warp, cx.n_ph, cx.ready_layer);
+            trace_pt(cx, k, 2);
+            if (g.cta_busy) {   // CTA-uniform
+                if (ph->fmt == ZG_QFMT_I4_F16) mv_phase<ZG_QFMT_I4_F16>(cx, ph, g, x_base);
+                else if (ph->fmt == ZG_QFMT_I8_F16) mv_phase<ZG_QFMT_I8_F16>(cx, ph, g, x_base);
+                else mv_phase<ZG_QFMT_I8_F32>(cx, ph, g, x_base);
+            }
             trace_pt(cx, k, 10);
-            barrier();
+            arrivals += cx.grid; grid_barrier(P.sync, arrivals);
             trace_pt(cx, k, 11);
             if ((k == 1 && ly.ar_o) || (k == 3 && ly.ar_down)) {
                 allreduce_phase(cx, P, k == 1 ? ly.o_local : ly.down_local, k == 1 ? ly.o.full : ly.down.full, ar_seq);
                 trace_pt(cx, k, 12);
-                barrier();
-                trace_pt(cx, k, 13);
+                arrivals += cx.grid; grid_barrier(P.sync, arrivals);
             }
         }
     }
@@ -1068,13 +1031,6 @@ __device__ __forceinline__ void decode_body(const ZgDecodePlan& P, uint8_t* smem
         const uint32_t old = atomicAdd(P.sync + 32, 1u);
         if (old == cx.grid - 1) { P.sync[0] = 0u; P.sync[32] = 0u; __threadfence(); }
     }
-}
-
-__global__ void __launch_bounds__(kT, 1)
-k_decode_layers(const __grid_constant__ ZgDecodePlan P) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    decode_body<0>(P, smem);
-}
 }
 
 } // namespace

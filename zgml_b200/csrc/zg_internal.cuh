@@ -240,8 +240,9 @@ struct ZgDecMv {
     uint32_t n_nb, first_item, N, _pad;
 };
 struct ZgDecPhase {
-    ZgDecMv mv[kZgDecMaxMv];
+    ZgDecMv mv[kZgDecMaxMv];       // absent entries: first_item = UINT32_MAX
     uint32_t n_mv, fmt, n_kc, K, S, n_slots, n_items, rec_bytes;
+    uint32_t lS, _pad;             // S = 1 << lS k-splits (powers of two keep the device-side geometry to shifts)
 };
 struct ZgDecHead { float* q_rot; float* attn_out; uint32_t q_src, k_off, v_off, kv, buf_off, dyn; };
 struct ZgDecKv { float* k_rot; uint32_t k_src, v_src, k_dyn, v_dyn, k_base, v_base; };
@@ -262,6 +263,7 @@ struct ZgDecLayer {
     const float* x2_a; float* x2_sum; const float* gamma2; float* bare2; float* grep2; float* norm2; float eps2;
     // phase 5: act = steps(gate) -> silu ; silu * up -> hidden ; down matvec (+ all-reduce)
     ZgDecVec gate, up; float* silu; float* hidden; uint32_t n_steps, F;
+    uint32_t act_silu, _pad2;   // the steps are exactly neg, exp, add(ext), recip, mul(gate): evaluated inline
     ZgDecStep steps[kZgDecMaxSteps];
     ZgDecVec down_local, down;
 };
