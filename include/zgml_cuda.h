@@ -253,6 +253,12 @@ ZgCudaQWeight* zg_cuda_qweight_upload(ZgCudaCtx* ctx, const ZgQWeight* w, int fm
  * rows = dims[0] = K, cols = dims[1] = N, zgml nibble order. */
 ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void* raw, size_t raw_bytes,
                                            uint32_t ggml_type, size_t rows, size_t cols);
+/* Extension for benchmarks / multi-GPU tests: random-init GGUF blocks generated IN HBM for the slab
+ * [k0, k1) x [n0, n1) of a global [rows_full, cols_full] tensor, then imported like zg_cuda_qweight_upload_gguf.
+ * Block bytes are a pure function of (seed, tensor_id, global block index): every world size holds slices of the
+ * same model, and zgml_b200/host/llama.py::synth_gguf_blocks reproduces them on the host for the CPU oracle. */
+ZgCudaQWeight* zg_cuda_qweight_synth_gguf(ZgCudaCtx* ctx, uint64_t seed, uint64_t tensor_id, uint32_t ggml_type,
+                                          size_t rows_full, size_t cols_full, size_t k0, size_t k1, size_t n0, size_t n1);
 void zg_cuda_qweight_free(ZgCudaCtx* ctx, ZgCudaQWeight* w);
 int zg_cuda_qweight_format(const ZgCudaQWeight* w);
 size_t zg_cuda_qweight_device_bytes(const ZgCudaQWeight* w);

@@ -140,3 +140,58 @@ def test_two_gpu_sharded_decode_matches_unsharded_oracle(cfg, kind, token_len, g
         assert rel(out[r], want) < 1e-3
         assert (np.argmax(out[r], axis=1) == np.argmax(want, axis=1)).all()
     assert np.array_equal(out[0], out[1])
+
+
+# ── Llama-3-70B WIDTH (d_model 8192, 64 / 8 heads, d_ff 28672), 2 layers, world 2 / 4 / 8: the shapes of BASELINE.json config 5 ──
+CFG_70B_WIDTH = LlamaConfig(vocab_size=8192, d_model=8192, n_layers=2, n_heads=64, n_kv_heads=8, d_ff=28672, max_seq_len=64,
+                            rope_base=5e5, tied_lm_head=False)
+
+
+def _rank_main_synth(rank, world, port, cfg, kind, peer, fused, context, n_tok, out):
+    import torch.distributed as dist
+    if not peer:
+        os.environ["ZG_CUDA_PEER"] = "0"          # NCCL all-reduces instead of the NVLink peer-memory kernel
+    if fused:
+        os.environ["ZG_CUDA_DECODE"] = "1"        # the persistent fused decode kernel (peer all-reduce phases inside)
+    from zgml_b200 import CudaBackend
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    be = CudaBackend(rank)
+    try:
+        be.comm_init_torch()
+        w, handles = synthetic_resident_shard(be, cfg, kind, seed=17, rank=rank, world=world)   # slices of ONE model, whatever the world size
+        sess = DeviceLlamaSession(be, cfg, w, 1)
+        sess.pos = context
+        toks, logs = greedy(sess, 1, n_tok)
+        out[rank] = (logs, be.comm_mode(), be.program_stats(sess.handle)["fused_decode_layers"])
+        sess.close()
+        for h in handles:
+            h.free()
+    finally:
+        be.close()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("path", ["peer", "nccl", "fused"])
+def test_sharded_70b_width_matches_unsharded_oracle(world, path):
+    """Every rank holds its slab of the same hashed synthetic model; rank-identical logits, 1e-3 against the unsharded oracle
+    executor on the host form of that model, identical greedy tokens.  Self-skips below `world` GPUs."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    from zgml_b200.host.llama import synthetic_model_host
+    cfg, kind, n_tok, context = CFG_70B_WIDTH, "q4_0", 3, 20
+    out = mp.Manager().dict()
+    mp.spawn(_rank_main_synth, args=(world, _free_port(), cfg, kind, path != "nccl", path == "fused", context, n_tok, out), nprocs=world, join=True)
+    ref = DeviceLlamaSession(OracleBackend(native=True), cfg, synthetic_model_host(cfg, kind, seed=17), 1)
+    ref.pos = context
+    _, want = greedy(ref, 1, n_tok)
+    ref.close()
+    for r in range(world):
+        logs, mode, fused_layers = out[r]
+        assert mode == ("nccl" if path == "nccl" else "nvlink-peer+nccl")   # the path under test really ran
+        assert fused_layers == (cfg.n_layers if path == "fused" else 0)
+        assert rel(logs, want) < 1e-3
+        assert (np.argmax(logs, axis=1) == np.argmax(want, axis=1)).all()
+        assert np.array_equal(logs, out[0][0])                 # bit-identical on every rank

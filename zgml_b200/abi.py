@@ -164,6 +164,7 @@ SYMBOLS = [
     ("zg_cuda_execute_device", None, [vp, vp]),
     ("zg_cuda_qweight_upload", vp, [vp, C.POINTER(ZgQWeight), C.c_int]),
     ("zg_cuda_qweight_upload_gguf", vp, [vp, vp, sz, u32, sz, sz]),
+    ("zg_cuda_qweight_synth_gguf", vp, [vp, C.c_uint64, C.c_uint64, u32, sz, sz, sz, sz, sz, sz]),
     ("zg_cuda_qweight_free", None, [vp, vp]),
     ("zg_cuda_qweight_format", C.c_int, [vp]),
     ("zg_cuda_qweight_device_bytes", sz, [vp]),

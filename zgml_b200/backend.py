@@ -495,6 +495,16 @@ class QuantizedWeight:
             raise BackendError(f"gguf qweight upload failed: {last_error()}")
         return cls(be, ptr, rows, cols, 32)
 
+    @classmethod
+    def synth_gguf(cls, be: CudaBackend, seed: int, tensor_id: int, ggml_type: int, rows_full: int, cols_full: int,
+                   k0: int, k1: int, n0: int, n1: int) -> "QuantizedWeight":
+        """Random-init GGUF blocks of the slab [k0, k1) x [n0, n1) of a global tensor, generated in HBM
+        (zg_cuda_qweight_synth_gguf): world-size independent, reproduced on the host by host/llama.py::synth_gguf_blocks."""
+        ptr = be.lib.zg_cuda_qweight_synth_gguf(be.ctx, seed, tensor_id, ggml_type, rows_full, cols_full, k0, k1, n0, n1)
+        if not ptr:
+            raise BackendError(f"synthetic qweight failed: {last_error()}")
+        return cls(be, ptr, k1 - k0, n1 - n0, 32)
+
     @property
     def format(self) -> int:
         return self.be.lib.zg_cuda_qweight_format(self.ptr)

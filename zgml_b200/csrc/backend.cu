@@ -175,7 +175,12 @@ extern "C" void zg_cuda_set_stream(ZgCudaCtx* ctx, void* s) {
     ctx->stream = (cudaStream_t)s;
     ctx->owns_stream = false;
 }
-extern "C" void zg_cuda_sync(ZgCudaCtx* ctx) { if (ctx) cudaStreamSynchronize(ctx->stream); }
+extern "C" void zg_cuda_sync(ZgCudaCtx* ctx) {
+    if (!ctx) return;
+    zg_peer_check_enqueue(ctx, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    zg_peer_check_result(ctx);
+}
 extern "C" void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int e) { if (ctx) ctx->graph_mode = e != 0; }
 extern "C" void zg_cuda_set_profiling(ZgCudaCtx* ctx, int e) { if (ctx) ctx->profiling = e != 0; }
 
@@ -396,6 +401,47 @@ static bool ranges_conflict(const std::vector<ZgRange>& a, const std::vector<ZgR
     return false;
 }
 
+// Offsets / extents of the run-time patched fields against the buffer sizes (the reference's CPU slices would trap on an
+// out-of-range position, src/backend/reference.zig:436-458,599-671; here it would be a silent out-of-bounds access).
+static bool dyn_extent_ok(const ZgCudaProgram* p, const ZgOp& op, size_t i) {
+    if (op.tag == ZG_OP_SLICE_ASSIGN) {
+        const auto& sa = op.u.slice_assign;
+        if (sa.rows == 0 || sa.cols == 0) return true;
+        const size_t dext = (size_t)(sa.rows - 1) * sa.dst_row_stride + (size_t)(sa.cols - 1) * sa.dst_col_stride + 1;
+        if ((size_t)sa.dst_offset + dext > p->buffer_elems[sa.dst]) {
+            zg_set_error("op %zu: slice_assign writes [%u, %zu) of a %zu-element buffer", i, sa.dst_offset, (size_t)sa.dst_offset + dext, p->buffer_elems[sa.dst]);
+            return false;
+        }
+    } else if (op.tag == ZG_OP_ATTENTION) {
+        const auto& a = op.u.attention;
+        if (a.seq_kv == 0 || a.d_head == 0 || a.seq_q == 0) return true;
+        const size_t kext = (size_t)a.k_off + (size_t)(a.seq_kv - 1) * a.k_cs + (size_t)(a.d_head - 1) * a.k_rs + 1;
+        const size_t vext = (size_t)a.v_off + (size_t)(a.seq_kv - 1) * a.v_cs + (size_t)(a.d_head - 1) * a.v_rs + 1;
+        const size_t mext = a.has_mask ? (size_t)a.mask_off + (size_t)(a.seq_kv - 1) * a.mask_rs + (size_t)(a.seq_q - 1) * a.mask_cs + 1 : 0;
+        if (kext > p->buffer_elems[a.k] || vext > p->buffer_elems[a.v] || (a.has_mask && mext > p->buffer_elems[a.mask])) {
+            zg_set_error("op %zu: attention over seq_kv = %u reads past its k / v / mask buffer", i, a.seq_kv);
+            return false;
+        }
+    }
+    return true;
+}
+// every op's static element ranges inside its buffers (compile time and structural refresh)
+static bool validate_extents(const ZgCudaProgram* p) {
+    std::vector<ZgRange> rr;
+    for (size_t i = 0; i < p->ops.size(); i++) {
+        op_ranges(p, p->ops[i], rr);
+        for (const ZgRange& r : rr) {
+            if (r.buf >= p->buffers.size() || r.dyn) continue;   // virtual ordering buffers; patched ranges are checked with their run-time value
+            if (r.hi > p->buffer_elems[r.buf] && !(p->ops[i].tag == ZG_OP_ALLGATHER)) {
+                zg_set_error("op %zu (tag %u): touches [%zu, %zu) of buffer %u which has %zu elements", i, p->ops[i].tag, r.lo, r.hi, r.buf, p->buffer_elems[r.buf]);
+                return false;
+            }
+        }
+        if (!dyn_extent_ok(p, p->ops[i], i)) return false;
+    }
+    return true;
+}
+
 extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog) {
     if (!ctx || !prog) { zg_set_error("compile: null argument"); return nullptr; }
     if (prog->n_buffers > 65535) { zg_set_error("compile: more than 65535 buffers"); return nullptr; }
@@ -437,7 +483,7 @@ extern "C" ZgCudaProgram* zg_cuda_compile(ZgCudaCtx* ctx, const ZgProgram* prog)
         if (!w) { free_program(p); return nullptr; }
         p->qweights.push_back(w); p->qweight_owned.push_back(true);
     }
-    if (!validate_ops(p, prog->ops, prog->n_ops) || !adopt_ops(p, prog->ops, prog->n_ops) || !upload_steps(p) ||
+    if (!validate_ops(p, prog->ops, prog->n_ops) || !adopt_ops(p, prog->ops, prog->n_ops) || !validate_extents(p) || !upload_steps(p) ||
         !reserve_workspace(p) || !build_schedule(p)) {
         free_program(p); return nullptr;
     }
@@ -473,6 +519,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
         cudaStreamSynchronize(ctx->stream);
         if (!validate_ops(p, ops, n_ops)) return; // keep the previous op list; error string set
         adopt_ops(p, ops, n_ops);
+        if (!validate_extents(p)) { p->ops.clear(); p->steps.clear(); n_ops = 0; }   // out-of-range op list: the program becomes a no-op (error string set)
         upload_steps(p);
         reserve_workspace(p);
         build_schedule(p);
@@ -499,6 +546,9 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
             }
             pos = q;
         }
+    }
+    for (size_t i = 0; i < n_ops; i++) {   // patched positions must stay inside their buffers: reject the refresh otherwise (old values stay)
+        if ((ops[i].tag == ZG_OP_SLICE_ASSIGN || ops[i].tag == ZG_OP_ATTENTION) && op_dyn_value(ops[i]) != p->h_dyn[i] && !dyn_extent_ok(p, ops[i], i)) return;
     }
     for (size_t i = 0; i < n_ops; i++) {
         uint32_t v = op_dyn_value(ops[i]);
@@ -1545,8 +1595,10 @@ extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in
         cudaMemcpyAsync(io.host_ptr, (uint8_t*)p->buffers[io.buf_idx] + io.offset, io.size, cudaMemcpyDeviceToHost, st);
     }
     if (p->dec.valid) cudaMemcpyAsync(p->dec.h_err, p->dec.d_sync + 64, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    zg_peer_check_enqueue(ctx, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) zg_set_error("execute: %s", cudaGetErrorString(e));
+    zg_peer_check_result(ctx);
     if (p->dec.valid && *p->dec.h_err) {   // a bounded wait inside the fused decode kernel gave up: results are invalid
         static const char* what[] = {"", "grid barrier", "weight ring (TMA)", "NVLink peer all-reduce: a peer rank never arrived"};
         zg_set_error("execute: fused decode kernel timed out in its %s wait; the step's outputs are invalid", what[*p->dec.h_err & 3]);

@@ -90,42 +90,66 @@ extern "C" int zg_cuda_comm_init(ZgCudaCtx* ctx, const void* id128, int rank, in
     return 0;
 }
 
-// Export this rank's slot region, gather everybody's IPC handle through NCCL, map the peers.
+// Export this rank's slot region, gather everybody's IPC handle through NCCL, map the peers.  COLLECTIVE: every rank runs
+// the same two NCCL calls whatever happens locally (ZG_CUDA_PEER=0 on some ranks only, a failed allocation, a failed
+// export or mapping): local failures only clear `ok`, which travels with the handle, and the decision is taken from the
+// min-reduced value — so no rank can be left waiting in a collective its peers skipped.
 static bool peer_setup(ZgCudaCtx* ctx) {
     const int world = ctx->world, rank = ctx->rank;
-    if (world > kZgMaxRanks) return false;
-    if (const char* e = getenv("ZG_CUDA_PEER")) if (e[0] == '0') return false;
+    if (world > kZgMaxRanks) return false;   // same on every rank
+    bool ok = true;
+    if (const char* e = getenv("ZG_CUDA_PEER")) if (e[0] == '0') ok = false;
     const size_t slot_bytes = (size_t)kZgPeerSets * world * kPeerSlotFloats * 2 * sizeof(float);   // every float travels with its epoch
-    const size_t flag_bytes = 0;   // readiness travels inside the data cells (epoch words)
-    const size_t total = slot_bytes + flag_bytes + (2 + kZgPeerCtas) * sizeof(uint32_t) + 64;
-    if (cudaMalloc(&ctx->peer_mem, total) != cudaSuccess) { cudaGetLastError(); return false; }
-    cudaMemset(ctx->peer_mem, 0, total);
+    const size_t total = slot_bytes + (2 + kZgPeerCtas) * sizeof(uint32_t) + 64;
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, ctx->peer_mem) != cudaSuccess) { cudaGetLastError(); cudaFree(ctx->peer_mem); ctx->peer_mem = nullptr; return false; }
+    memset(&mine, 0, sizeof(mine));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    char* d_handles = nullptr;
-    std::vector<cudaIpcMemHandle_t> all(world);
-    bool ok = cudaMalloc(&d_handles, 64 * (size_t)world) == cudaSuccess;
-    ok = ok && cudaMemcpy(d_handles + 64 * rank, &mine, 64, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && check(g_nccl.all_gather(d_handles + 64 * rank, d_handles, 64, kNcclChar, ctx->nccl_comm, ctx->stream), "ncclAllGather(ipc handles)");
-    ok = ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
-    ok = ok && cudaMemcpy(all.data(), d_handles, 64 * (size_t)world, cudaMemcpyDeviceToHost) == cudaSuccess;
-    cudaFree(d_handles);
-    int mapped_ok = ok ? 1 : 0;
+    if (ok && cudaMalloc(&ctx->peer_mem, total) != cudaSuccess) { cudaGetLastError(); ctx->peer_mem = nullptr; ok = false; }
+    if (ok) cudaMemset(ctx->peer_mem, 0, total);
+    if (ok && cudaIpcGetMemHandle(&mine, ctx->peer_mem) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    // record = 64-byte handle + 64 bytes whose first byte is this rank's ok flag
+    constexpr size_t kRec = 128;
+    std::vector<char> all(kRec * (size_t)world, 0);
+    char rec[kRec];
+    memset(rec, 0, sizeof(rec));
+    memcpy(rec, &mine, 64);
+    rec[64] = ok ? 1 : 0;
+    char* d_recs = nullptr;
+    bool xfer = cudaMalloc(&d_recs, kRec * (size_t)world) == cudaSuccess;
+    if (!xfer) { cudaGetLastError(); d_recs = nullptr; }
+    // the collectives run even when the local staging failed (with a scratch buffer the size of one record)
+    char* d_fallback = nullptr;
+    if (!xfer && cudaMalloc(&d_fallback, kRec * (size_t)world) != cudaSuccess) { cudaGetLastError(); d_fallback = nullptr; }
+    char* d_buf = xfer ? d_recs : d_fallback;
+    bool gathered = false;
+    if (d_buf) {
+        if (!xfer) rec[64] = 0;
+        cudaMemcpy(d_buf + kRec * rank, rec, kRec, cudaMemcpyHostToDevice);
+        gathered = check(g_nccl.all_gather(d_buf + kRec * rank, d_buf, kRec, kNcclChar, ctx->nccl_comm, ctx->stream), "ncclAllGather(ipc handles)") &&
+                   cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+                   cudaMemcpy(all.data(), d_buf, kRec * (size_t)world, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    int mapped_ok = (ok && gathered) ? 1 : 0;
+    for (int r = 0; r < world && mapped_ok; r++) if (!all[kRec * r + 64]) mapped_ok = 0;   // some rank opted out or failed: nobody maps
     for (int r = 0; r < world && mapped_ok; r++) {
         if (r == rank) { ctx->peer_mapped[r] = nullptr; continue; }
-        if (cudaIpcOpenMemHandle(&ctx->peer_mapped[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ctx->peer_mapped[r] = nullptr; mapped_ok = 0; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all.data() + kRec * r, 64);
+        if (cudaIpcOpenMemHandle(&ctx->peer_mapped[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ctx->peer_mapped[r] = nullptr; mapped_ok = 0; }
     }
-    // every rank must take the same path: agree through a min-reduction
+    // every rank must take the same path: agree through a min-reduction (reuses the staging buffer; a rank without one
+    // cannot take part in NCCL at all and has already failed above together with everybody else's all-gather)
     float h = (float)mapped_ok;
-    float* d_f = nullptr;
-    if (cudaMalloc(&d_f, sizeof(float)) == cudaSuccess) {
+    if (d_buf) {
+        float* d_f = reinterpret_cast<float*>(d_buf);
         cudaMemcpy(d_f, &h, sizeof(float), cudaMemcpyHostToDevice);
-        g_nccl.all_reduce(d_f, d_f, 1, kNcclFloat32, /*ncclMin*/ 3, ctx->nccl_comm, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        cudaMemcpy(&h, d_f, sizeof(float), cudaMemcpyDeviceToHost);
-        cudaFree(d_f);
+        if (!check(g_nccl.all_reduce(d_f, d_f, 1, kNcclFloat32, /*ncclMin*/ 3, ctx->nccl_comm, ctx->stream), "ncclAllReduce(peer agreement)")) h = 0.f;
+        else {
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(&h, d_f, sizeof(float), cudaMemcpyDeviceToHost);
+        }
     } else h = 0.f;
+    cudaFree(d_recs); cudaFree(d_fallback);
     if (h < 0.5f) {
         for (int r = 0; r < world; r++) if (ctx->peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->peer_mapped[r]); ctx->peer_mapped[r] = nullptr; }
         cudaFree(ctx->peer_mem); ctx->peer_mem = nullptr;
@@ -137,8 +161,25 @@ static bool peer_setup(ZgCudaCtx* ctx) {
         char* base = (char*)(r == rank ? ctx->peer_mem : ctx->peer_mapped[r]);
         pc.slots[r] = (float*)base;
     }
-    pc.seq = (uint32_t*)((char*)ctx->peer_mem + slot_bytes + flag_bytes);
+    pc.seq = (uint32_t*)((char*)ctx->peer_mem + slot_bytes);
     return true;
+}
+
+// The peer all-reduce kernels raise pc.seq[1] when a peer never arrived (their result is NaN-poisoned).  The word is
+// copied to pinned host memory behind the step's work (enqueue) and turned into an error string after the
+// synchronisation (result).  Sticky until reported.
+void zg_peer_check_enqueue(ZgCudaCtx* ctx, cudaStream_t st) {
+    if (!ctx || ctx->world <= 1 || !ctx->peer.max_n || !ctx->peer.seq) return;
+    if (!ctx->h_peer_err && cudaMallocHost(&ctx->h_peer_err, sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); ctx->h_peer_err = nullptr; return; }
+    cudaMemcpyAsync(ctx->h_peer_err, ctx->peer.seq + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+}
+bool zg_peer_check_result(ZgCudaCtx* ctx) {
+    if (!ctx || !ctx->h_peer_err || !*ctx->h_peer_err) return true;
+    zg_set_error("NVLink peer all-reduce %u timed out on rank %d: a peer rank never delivered its data; this rank's activations are NaN-poisoned",
+                 *ctx->h_peer_err, ctx->rank);
+    *ctx->h_peer_err = 0;
+    if (ctx->peer.seq) cudaMemset(ctx->peer.seq + 1, 0, sizeof(uint32_t));
+    return false;
 }
 
 bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n) {
@@ -166,6 +207,7 @@ extern "C" void zg_cuda_comm_destroy(ZgCudaCtx* ctx) {
         cudaFree(ctx->peer_mem); ctx->peer_mem = nullptr;
         ctx->peer = ZgPeerComm();
     }
+    if (ctx->h_peer_err) { cudaFreeHost(ctx->h_peer_err); ctx->h_peer_err = nullptr; }
     g_nccl.destroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr; ctx->world = 1; ctx->rank = 0;
 }

@@ -216,13 +216,15 @@ k_allreduce_peer(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc) {
         }
     }
     const uint4* mine = reinterpret_cast<const uint4*>(pc.slots[pc.rank]) + (size_t)set * pc.world * slot_pairs;
-    const long long t0 = clock64();
     for (uint32_t j = lo + tid; j < hi; j += 256) {
         uint4 got[kZgMaxRanks];
         uint32_t pending = 0;
 #pragma unroll
         for (int r = 0; r < kZgMaxRanks; r++)
             if (r < pc.world && r != pc.rank) pending |= 1u << r;
+        long long t0 = 0;   // per cell: a peer that is merely late for one cell does not shorten the others' wait
+        uint32_t spins = 0;
+        bool dead = false;
         while (pending) {   // every peer's cell is requested before any is checked; only the late ones are re-read
 #pragma unroll
             for (int r = 0; r < kZgMaxRanks; r++)
@@ -233,7 +235,13 @@ k_allreduce_peer(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc) {
 #pragma unroll
             for (int r = 0; r < kZgMaxRanks; r++)
                 if ((pending & (1u << r)) && got[r].y == epoch && got[r].w == epoch) pending &= ~(1u << r);
-            if (pending && clock64() - t0 > 8000000000LL) { pc.seq[1] = epoch; break; }   // ~4 s: a peer died; do not hang the GPU
+            if (pending && (++spins & 1023u) == 0) {
+                // A peer that never arrives (died, or its host stalled for longer than the limit) must neither hang the GPU
+                // nor let stale cells into the sum: give up after ~30 s, raise the sticky error word (zg_cuda_execute /
+                // zg_cuda_sync report it through zg_cuda_last_error) and poison this rank's result with NaN.
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > 60000000000LL || *(volatile uint32_t*)(pc.seq + 1)) { atomicExch(pc.seq + 1, epoch ? epoch : 1u); dead = true; break; }
+            }
         }
         const float2 own = b2[j];
         float2 acc = make_float2(0.f, 0.f);
@@ -243,6 +251,7 @@ k_allreduce_peer(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc) {
                 const float2 v = (r == pc.rank) ? own : make_float2(__uint_as_float(got[r].x), __uint_as_float(got[r].z));
                 acc = (r == 0) ? v : make_float2(acc.x + v.x, acc.y + v.y);
             }
+        if (dead) acc = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
         b2[j] = acc;
     }
     __syncthreads();

@@ -8,6 +8,7 @@
 //   quantizedWeightFromInfo         src/models/gguf_loader.zig:99-154 (zgml nibble order)
 //   dequantizeTo                    src/quant.zig:594-618
 #include "zg_internal.cuh"
+#include <math.h>
 
 namespace {
 
@@ -375,6 +376,68 @@ extern "C" ZgCudaQWeight* zg_cuda_qweight_upload_gguf(ZgCudaCtx* ctx, const void
         k_gguf_expand<<<grid_for(n_blocks, 128), 128, 0, ctx->stream>>>(d_raw, ggml_type, n_blocks, n_elems, d_data, d_scales);
         ZG_COUNT_LAUNCH();
     }
+    ZgCudaQWeight* w = zg_qweight_from_device_flat(ctx, d_data, d_scales, rows, cols, 32, ZG_QFMT_AUTO);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_raw); cudaFree(d_data); cudaFree(d_scales);
+    return w;
+}
+
+// ── synthetic random-init GGUF blocks, generated on the device ────────────────────────────────────────────────────
+// Benchmarks and multi-GPU tests need tens of GB of random-init weights (Llama-3-70B-shape Q4_0: 39 GB of blocks) that are
+// THE SAME MODEL at every world size.  Every byte of a tensor's block b is a pure function of (seed, tensor_id, global
+// block index), so a rank generates exactly its slab [k0, k1) x [n0, n1) of the global [K, N] tensor — in HBM, without a
+// host copy — and any other world size (or the host twin zgml_b200/host/llama.py::synth_gguf_blocks, which feeds the CPU
+// oracle) sees the same weights.  Word i (8 bytes) of block b = splitmix64-finalizer(key + 8 * b + i); Q8_0 quants are
+// clamped to >= -127 and the f16 scale keeps its random low mantissa bits under a fixed exponent e (as
+// host/llama.py::synthetic_gguf_blocks: dequantized magnitude ~ sqrt(6 / K), kaimingUniform, src/nn.zig:91-105).
+__host__ __device__ inline uint64_t zg_mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void k_synth_gguf(uint8_t* __restrict__ raw, uint64_t key, uint32_t ggml_type, uint32_t exp_bits, size_t n_full, size_t k0, size_t n0,
+                             size_t slab_blocks_per_row, size_t n_blocks) {
+    const uint32_t bb = ggml_type == 8 ? 34u : 18u, words = ggml_type == 8 ? 5u : 3u;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_blocks * words) return;
+    const size_t lb = idx / words;
+    const uint32_t wi = (uint32_t)(idx % words);
+    const size_t k = k0 + lb / slab_blocks_per_row, nblk = n0 / 32 + lb % slab_blocks_per_row;
+    const uint64_t gb = (uint64_t)k * (n_full / 32) + nblk;
+    uint64_t w = zg_mix64(key + 8ull * gb + wi);
+    uint8_t* dst = raw + lb * bb + wi * 8;
+    for (uint32_t j = 0; j < 8 && wi * 8 + j < bb; j++) {
+        uint8_t byte = (uint8_t)(w >> (8 * j));
+        const uint32_t pos = wi * 8 + j;
+        if (pos == 1) byte = (uint8_t)((byte & 3u) | (exp_bits << 2));
+        else if (pos >= 2 && ggml_type == 8 && byte == 0x80) byte = 0x81;   // int8 -128 -> -127
+        dst[j] = byte;
+    }
+}
+
+extern "C" ZgCudaQWeight* zg_cuda_qweight_synth_gguf(ZgCudaCtx* ctx, uint64_t seed, uint64_t tensor_id, uint32_t ggml_type, size_t rows_full,
+                                                     size_t cols_full, size_t k0, size_t k1, size_t n0, size_t n1) {
+    if (!ctx || (ggml_type != 8 && ggml_type != 2) || k1 <= k0 || n1 <= n0 || k1 > rows_full || n1 > cols_full || (cols_full % 32) || (n0 % 32) || (n1 % 32)) {
+        zg_set_error("qweight_synth_gguf: bad arguments (slab [%zu,%zu) x [%zu,%zu) of [%zu,%zu], column bounds must be multiples of 32)", k0, k1, n0, n1, rows_full, cols_full);
+        return nullptr;
+    }
+    cudaSetDevice(ctx->device);
+    const size_t rows = k1 - k0, cols = n1 - n0, n_elems = rows * cols, n_blocks = n_elems / 32, bb = ggml_type == 8 ? 34 : 18;
+    const double qmax = ggml_type == 8 ? 127.0 : 7.0;
+    int e = (int)floor(log2(sqrt(6.0 / (double)rows_full) / qmax)) - 1 + 15;   // biased f16 exponent, as synthetic_gguf_blocks
+    if (e < 1) e = 1;
+    if (e > 30) e = 30;
+    uint8_t* d_raw = nullptr; int8_t* d_data = nullptr; float* d_scales = nullptr;
+    if (cudaMalloc(&d_raw, n_blocks * bb) != cudaSuccess || cudaMalloc(&d_data, n_elems) != cudaSuccess || cudaMalloc(&d_scales, n_blocks * sizeof(float)) != cudaSuccess) {
+        zg_set_error("qweight_synth_gguf: staging cudaMalloc failed");
+        cudaFree(d_raw); cudaFree(d_data); cudaFree(d_scales); return nullptr;
+    }
+    const uint64_t key = zg_mix64(seed * 0x9E3779B97F4A7C15ull + tensor_id);
+    const size_t threads = n_blocks * (ggml_type == 8 ? 5 : 3);
+    k_synth_gguf<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_raw, key, ggml_type, (uint32_t)e, cols_full, k0, n0, cols / 32, n_blocks);
+    ZG_COUNT_LAUNCH();
+    k_gguf_expand<<<grid_for(n_blocks, 128), 128, 0, ctx->stream>>>(d_raw, ggml_type, n_blocks, n_elems, d_data, d_scales);
+    ZG_COUNT_LAUNCH();
     ZgCudaQWeight* w = zg_qweight_from_device_flat(ctx, d_data, d_scales, rows, cols, 32, ZG_QFMT_AUTO);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(d_raw); cudaFree(d_data); cudaFree(d_scales);

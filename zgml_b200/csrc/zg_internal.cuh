@@ -117,6 +117,7 @@ struct ZgCudaCtx {
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
     ZgPeerComm peer;             // NVLink peer-memory all-reduce state (max_n == 0: not available)
     void* peer_mem = nullptr;    // this rank's slots + counters (cudaMalloc, exported by cudaIpc)
+    uint32_t* h_peer_err = nullptr;   // pinned copy of the peer-timeout word (ZgPeerComm::seq[1])
     void* peer_mapped[kZgMaxRanks] = {};   // cudaIpcOpenMemHandle mappings to close
     void* nccl_comm = nullptr;   // ncclComm_t (comm.cu), null unless zg_cuda_comm_init ran
     int rank = 0, world = 1;
@@ -209,7 +210,9 @@ size_t zg_chain_work(const ZgOp& op);
 bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
 bool zg_launch_chain(const ZgChainOp* d_ops, uint32_t count, const uint32_t* d_dyn, cudaStream_t st);
 bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st);
-bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n);   // comm.cu: the peer path can take an n-float all-reduce
+bool zg_peer_allreduce_ok(const ZgCudaCtx* ctx, size_t n);
+void zg_peer_check_enqueue(ZgCudaCtx* ctx, cudaStream_t st);   // comm.cu: copy the peer-timeout word behind the queued work ...
+bool zg_peer_check_result(ZgCudaCtx* ctx);                      // ... and, after the sync: false (+ error string) when a peer all-reduce gave up   // comm.cu: the peer path can take an n-float all-reduce
 bool zg_op_is_batched(uint32_t tag);
 uint64_t zg_batch_signature(const ZgOp& op);
 bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, ZgBatchEntry* e);

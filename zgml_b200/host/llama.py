@@ -433,28 +433,96 @@ def synthetic_gguf_blocks(r: np.random.Generator, K: int, N: int, kind: str) -> 
     return raw.ravel()
 
 
+_MASK64 = (1 << 64) - 1
+
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    """splitmix64 finalizer on uint64 arrays (wrap-around arithmetic) — zg_mix64 in csrc/qweight.cu."""
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def tensor_id(layer: int, name: str) -> int:
+    """Identity of a linear inside a synthetic model: what `zg_cuda_qweight_synth_gguf` hashes with the seed."""
+    return 0xFFFF0000 if name == "out_proj" else layer * 16 + LINEARS.index(name)
+
+
+def synth_gguf_blocks(seed: int, tid: int, kind: str, K_full: int, N_full: int, k0: int = 0, k1: Optional[int] = None,
+                      n0: int = 0, n1: Optional[int] = None) -> np.ndarray:
+    """Host twin of `zg_cuda_qweight_synth_gguf` (csrc/qweight.cu k_synth_gguf): the raw GGUF blocks of the slab
+    [k0, k1) x [n0, n1) of the global [K_full, N_full] tensor `tid` of the synthetic model `seed`.  Every byte is a pure
+    function of (seed, tensor, global block index), so shards of any world size and the unsharded host form are slices of
+    the same weights."""
+    k1 = K_full if k1 is None else k1
+    n1 = N_full if n1 is None else n1
+    assert N_full % 32 == 0 and n0 % 32 == 0 and n1 % 32 == 0 and 0 <= k0 < k1 <= K_full and 0 <= n0 < n1 <= N_full
+    bb, words, qmax = (34, 5, 127.0) if kind == "q8_0" else (18, 3, 7.0)
+    e = int(np.floor(np.log2(np.sqrt(6.0 / K_full) / qmax))) - 1 + 15
+    e = min(max(e, 1), 30)
+    with np.errstate(over="ignore"):
+        key = _mix64(np.array([(seed * 0x9E3779B97F4A7C15 + tid) & _MASK64], dtype=np.uint64))[0]
+        k = np.arange(k0, k1, dtype=np.uint64)[:, None]
+        nb = np.arange(n0 // 32, n1 // 32, dtype=np.uint64)[None, :]
+        gb = (k * np.uint64(N_full // 32) + nb).ravel()                       # global block index of every slab block
+        w = _mix64(key + np.uint64(8) * gb[:, None] + np.arange(words, dtype=np.uint64)[None, :])
+    raw = np.ascontiguousarray(w).view(np.uint8).reshape(len(gb), words * 8)[:, :bb].copy()   # little-endian words
+    raw[:, 1] = (raw[:, 1] & 3) | np.uint8(e << 2)
+    if kind == "q8_0":
+        q = raw[:, 2:]
+        q[q == 0x80] = 0x81
+    return raw.ravel()
+
+
+def synthetic_model_host(cfg: LlamaConfig, kind: str, seed: int, embed_scale: float = 0.05) -> LlamaWeights:
+    """The WHOLE synthetic model of `synthetic_resident_shard` in the reference's host form (i8 + f32 scales per linear,
+    `quantizedWeightFromInfo` applied to `synth_gguf_blocks`): what the CPU oracle runs against any sharded GPU run."""
+    from .gguf import GGMLType, TensorInfo, quantized_weight_from_info
+    t = GGMLType.q8_0 if kind == "q8_0" else GGMLType.q4_0
+    shapes = linear_shapes(cfg)
+
+    def make(li, name, K, N):
+        raw = synth_gguf_blocks(seed, tensor_id(li, name), kind, K, N)
+        return quantized_weight_from_info(TensorInfo(name, 2, (K, N, 1, 1), t, 0), raw)
+
+    layers = [{n: make(li, n, *shapes[n]) for n in LINEARS} for li in range(cfg.n_layers)]
+    ones = [np.ones(cfg.d_model, np.float32) for _ in range(cfg.n_layers)]
+    if cfg.tied_lm_head:
+        emb = np.random.default_rng([seed, 7]).uniform(-embed_scale, embed_scale, (cfg.vocab_size, cfg.d_model)).astype(np.float32)
+        out_proj = None
+    else:
+        emb = SyntheticEmbedding(cfg.vocab_size, cfg.d_model, seed, embed_scale)
+        out_proj = make(0, "out_proj", cfg.d_model, cfg.vocab_size)
+    return LlamaWeights(cfg, emb, layers, ones, [o.copy() for o in ones], np.ones(cfg.d_model, np.float32), out_proj)
+
+
 def synthetic_resident_shard(be, cfg: LlamaConfig, kind: str, seed: int, rank: int = 0, world: int = 1,
                              embed_scale: float = 0.05):
-    """This rank's shard of a random-init GGUF model, streamed tensor by tensor straight into HBM
-    (`QuantizedWeight.from_gguf_blocks` = quantizedWeightFromInfo on device): host memory stays at one tensor,
-    which is what makes Llama-3-70B-shape Q4_0 (39 GB of blocks) loadable next to 7 other ranks.  Returns
-    (LlamaWeights of ResidentQuantizedWeight descriptors, the QuantizedWeight handles to free afterwards)."""
+    """This rank's shard of a random-init GGUF model, generated tensor by tensor IN HBM (`zg_cuda_qweight_synth_gguf` +
+    quantizedWeightFromInfo on device): no host copy at all, which is what makes Llama-3-70B-shape Q4_0 (39 GB of blocks)
+    loadable in seconds next to 7 other ranks.  The model depends on `seed` only — every world size holds slices of the SAME
+    weights (`synthetic_model_host` is their host form) — so logits and greedy tokens can be compared across world sizes
+    and against the CPU oracle.  Returns (LlamaWeights of ResidentQuantizedWeight descriptors, the handles to free)."""
     from ..backend import QuantizedWeight
     check_shardable(cfg, world)
     ggml = GGML_Q8_0 if kind == "q8_0" else GGML_Q4_0
     D, kvd, F, V = cfg.d_model, cfg.kv_dim, cfg.d_ff, cfg.vocab_size
-    local = {"wq": (D, D // world), "wk": (D, kvd // world), "wv": (D, kvd // world), "wo": (D // world, D),
-             "w_gate": (D, F // world), "w_up": (D, F // world), "w_down": (F // world, D)}
-    r = np.random.default_rng([seed, rank, world])
+    full = linear_shapes(cfg)
     handles, layers = [], []
 
-    def make(K, N):
-        h = QuantizedWeight.from_gguf_blocks(be, synthetic_gguf_blocks(r, K, N, kind), ggml, K, N)
+    def make(li, name):
+        K, N = (D, V) if name == "out_proj" else full[name]
+        if name in ("wo", "w_down"):                      # input-row slab
+            k0, k1, n0, n1 = rank * (K // world), (rank + 1) * (K // world), 0, N
+        else:                                             # output-column slab
+            k0, k1, n0, n1 = 0, K, rank * (N // world), (rank + 1) * (N // world)
+        h = QuantizedWeight.synth_gguf(be, seed, tensor_id(li, name), ggml, K, N, k0, k1, n0, n1)
         handles.append(h)
         return ResidentQuantizedWeight(h)
 
-    for _ in range(cfg.n_layers):
-        layers.append({n: make(*local[n]) for n in LINEARS})
+    for li in range(cfg.n_layers):
+        layers.append({n: make(li, n) for n in LINEARS})
     ones = [np.ones(D, np.float32) for _ in range(cfg.n_layers)]
     out_proj, head_rows = None, None
     if cfg.tied_lm_head:
@@ -462,7 +530,7 @@ def synthetic_resident_shard(be, cfg: LlamaConfig, kind: str, seed: int, rank: i
         head_rows = np.ascontiguousarray(emb[rank * (V // world):(rank + 1) * (V // world)])
     else:
         emb = SyntheticEmbedding(V, D, seed, embed_scale)
-        out_proj = make(D, V // world)
+        out_proj = make(0, "out_proj")
     w = LlamaWeights(cfg, emb, layers, ones, [o.copy() for o in ones], np.ones(D, np.float32), out_proj,
                      (rank, world) if world > 1 else None, head_rows if world > 1 else None)
     return w, handles

@@ -106,7 +106,14 @@ fn flatten(alloc: std.mem.Allocator, ops: []const backend_mod.DeviceOp) !Flat {
     for (ops, out) |op, *o| {
         o.* = switch (op) {
             .elementwise => |e| .{ .tag = 0, .u = .{ .elementwise = .{ .op = @intFromEnum(e.op), .dst = e.dst, .src0 = e.src0, .src1 = e.src1, .n = e.n, .dst_offset = e.dst_offset, .src0_offset = e.src0_offset, .src1_offset = e.src1_offset } } },
-            .matmul => |m| .{ .tag = 1, .u = .{ .matmul = .{ .dst = m.dst, .a = m.a, .b = m.b, .geom = @bitCast(m.geom) } } },
+            // MatMulGeometry is an auto-layout Zig struct (src/backend.zig:146-158): copied field by field, never bit-cast
+            .matmul => |m| .{ .tag = 1, .u = .{ .matmul = .{ .dst = m.dst, .a = m.a, .b = m.b, .geom = .{
+                .M = m.geom.M, .N = m.geom.N, .K = m.geom.K,
+                .a_row_stride = m.geom.a_row_stride, .a_col_stride = m.geom.a_col_stride,
+                .b_row_stride = m.geom.b_row_stride, .b_col_stride = m.geom.b_col_stride,
+                .a_offset = m.geom.a_offset, .b_offset = m.geom.b_offset,
+                .dst_offset = m.geom.dst_offset, .dst_row_stride = m.geom.dst_row_stride,
+            } } } },
             .qmatmul => |q| .{ .tag = 2, .u = .{ .qmatmul = .{ .dst = q.dst, .input = q.input, .weight_idx = q.weight_idx, .M = q.M, .N = q.N, .K = q.K, .input_offset = q.input_offset, .input_row_stride = q.input_row_stride, .dst_offset = q.dst_offset, .dst_row_stride = q.dst_row_stride } } },
             .softmax => |s| .{ .tag = 3, .u = .{ .softmax = .{ .dst = s.dst, .src = s.src, .rows = s.rows, .cols = s.cols, .src_offset = s.src_offset, .dst_offset = s.dst_offset } } },
             .layernorm => |l| .{ .tag = 4, .u = .{ .norm = .{ .dst = l.dst, .src = l.src, .rows = l.rows, .cols = l.cols, .eps = l.eps, .src_offset = l.src_offset, .dst_offset = l.dst_offset } } },
@@ -140,9 +147,17 @@ fn flattenIO(alloc: std.mem.Allocator, ios: []const backend_mod.ProgramIO) ![]Zg
 }
 
 // ── backend ─────────────────────────────────────────────────────────────────
+/// Per compiled program: the flattened copy of the caller's op array (kept across refreshes: only the two patched fields
+/// change between tokens, src/device_inference.zig:242-256) and the RuntimeProfile handed out by get_runtime_profile.
+const ProgramState = struct {
+    flat: Flat,
+    profile: profile_mod.RuntimeProfile = .{},
+};
+
 pub const CudaBackend = struct {
     ctx: *anyopaque,
     alloc: std.mem.Allocator,
+    programs: std.AutoHashMapUnmanaged(usize, *ProgramState) = .{},
 
     pub fn init(alloc: std.mem.Allocator, device_ordinal: u32) !CudaBackend {
         const ctx = zg_cuda_create(@intCast(device_ordinal)) orelse {
@@ -153,6 +168,12 @@ pub const CudaBackend = struct {
     }
 
     pub fn deinit(self: *CudaBackend) void {
+        var it = self.programs.valueIterator();
+        while (it.next()) |st| {
+            st.*.flat.deinit(self.alloc);
+            self.alloc.destroy(st.*);
+        }
+        self.programs.deinit(self.alloc);
         zg_cuda_destroy(self.ctx);
     }
 
@@ -174,24 +195,44 @@ fn denseMatMulF32(_: *anyopaque, _: backend_mod.DenseMatMulSpecF32) bool {
 fn compileProgram(ctx: *anyopaque, program: backend_mod.DeviceProgram) ?backend_mod.Backend.CompiledHandle {
     const be = self_(ctx);
     const flat = flatten(be.alloc, program.ops) catch return null;
-    defer flat.deinit(be.alloc);
-    const ups = flattenIO(be.alloc, program.initial_uploads) catch return null;
+    const ups = flattenIO(be.alloc, program.initial_uploads) catch { flat.deinit(be.alloc); return null; };
     defer be.alloc.free(ups);
-    const qws = be.alloc.alloc(ZgQWeight, program.qweights.len) catch return null;
+    const qws = be.alloc.alloc(ZgQWeight, program.qweights.len) catch { flat.deinit(be.alloc); return null; };
     defer be.alloc.free(qws);
     for (program.qweights, qws) |qw, *o| o.* = .{ .data = qw.data.ptr, .n_data = qw.data.len, .scales = qw.scales.ptr, .n_scales = qw.scales.len, .rows = qw.rows, .cols = qw.cols, .block_size = qw.block_size };
     const zp = ZgProgram{
         .ops = flat.ops.ptr, .n_ops = flat.ops.len, .n_buffers = program.n_buffers, .buffer_sizes = program.buffer_sizes.ptr,
         .initial_uploads = ups.ptr, .n_uploads = ups.len, .qweights = qws.ptr, .n_qweights = qws.len,
     };
-    return zg_cuda_compile(be.ctx, &zp); // the library copies ops, steps and weights: nothing here outlives the call
+    const handle = zg_cuda_compile(be.ctx, &zp) orelse { // the library copies ops, steps and weights
+        flat.deinit(be.alloc);
+        return null;
+    };
+    // keep the flattened ops: refresh_program only patches them
+    const st = be.alloc.create(ProgramState) catch { flat.deinit(be.alloc); zg_cuda_free(be.ctx, handle); return null; };
+    st.* = .{ .flat = flat };
+    be.programs.put(be.alloc, @intFromPtr(handle), st) catch { flat.deinit(be.alloc); be.alloc.destroy(st); zg_cuda_free(be.ctx, handle); return null; };
+    return handle;
 }
 
+/// Called before every execute with the caller's mutated op array.  Only `slice_assign.dst_offset` and
+/// `attention.seq_kv` change between tokens (patchSliceAssignOffset / patchAttentionSeqKV): they are copied into the
+/// cached flat array; a different op count (a re-planned program) re-flattens.
 fn refreshProgram(ctx: *anyopaque, handle: backend_mod.Backend.CompiledHandle, ops: []const backend_mod.DeviceOp) void {
     const be = self_(ctx);
-    const flat = flatten(be.alloc, ops) catch return;
-    defer flat.deinit(be.alloc);
-    zg_cuda_refresh(be.ctx, handle, flat.ops.ptr, flat.ops.len);
+    const st = be.programs.get(@intFromPtr(handle)) orelse return;
+    if (ops.len != st.flat.ops.len) {
+        const fresh = flatten(be.alloc, ops) catch return;
+        st.flat.deinit(be.alloc);
+        st.flat = fresh;
+    } else {
+        for (ops, st.flat.ops) |op, *o| switch (op) {
+            .slice_assign => |s| o.u.slice_assign.dst_offset = s.dst_offset,
+            .attention => |a| o.u.attention.seq_kv = a.seq_kv,
+            else => {},
+        };
+    }
+    zg_cuda_refresh(be.ctx, handle, st.flat.ops.ptr, st.flat.ops.len);
 }
 
 fn executeProgram(ctx: *anyopaque, handle: backend_mod.Backend.CompiledHandle, inputs: []const backend_mod.ProgramIO, outputs: []const backend_mod.ProgramIO) void {
@@ -204,11 +245,31 @@ fn executeProgram(ctx: *anyopaque, handle: backend_mod.Backend.CompiledHandle, i
 }
 
 fn freeProgram(ctx: *anyopaque, handle: backend_mod.Backend.CompiledHandle) void {
-    zg_cuda_free(self_(ctx).ctx, handle);
+    const be = self_(ctx);
+    if (be.programs.fetchRemove(@intFromPtr(handle))) |kv| {
+        kv.value.flat.deinit(be.alloc);
+        be.alloc.destroy(kv.value);
+    }
+    zg_cuda_free(be.ctx, handle);
 }
 
-fn getRuntimeProfile(_: *anyopaque, _: backend_mod.Backend.CompiledHandle) ?*profile_mod.RuntimeProfile {
-    return null; // zg_cuda_profile() exposes per-tag device times as ZgProfile; mapping it onto RuntimeProfile is optional
+/// VTable slot 6 (src/backend.zig:351): the library's ZgProfile (per-DeviceOp-tag device time + counters, filled when
+/// profiling is enabled with zg_cuda_set_profiling) mapped onto RuntimeProfile (src/profile.zig:820-842).  The program-command
+/// and schedule-region counters belong to the Metal planner (src/backend/program.zig) and stay zero.
+fn getRuntimeProfile(ctx: *anyopaque, handle: backend_mod.Backend.CompiledHandle) ?*profile_mod.RuntimeProfile {
+    const be = self_(ctx);
+    const st = be.programs.get(@intFromPtr(handle)) orelse return null;
+    const zp = zg_cuda_profile(be.ctx, handle) orelse return null; // profiling off: like cpu.zig:136-138
+    var rp = &st.profile;
+    const n = @min(rp.time_ns.len, zp.time_ns.len); // DeviceOp tags 0..11 in union declaration order on both sides
+    for (0..n) |i| rp.time_ns[i] = zp.time_ns[i];
+    rp.backend_op_count = zp.backend_op_count;
+    rp.fallback_op_count = zp.fallback_op_count; // always 0: there is no CPU fallback
+    rp.backend_dispatch_count = zp.backend_dispatch_count;
+    rp.sync_time_ns = zp.sync_time_ns;
+    rp.sync_count = zp.sync_count;
+    rp.call_count = zp.call_count;
+    return rp;
 }
 
 const vtable = backend_mod.Backend.VTable{
