@@ -62,6 +62,7 @@ def lib(native: bool = False):
         "zo_state_execute": (None, [vp, C.POINTER(abi.ZgProgram), C.POINTER(abi.ZgOp), sz,
                                     C.POINTER(abi.ZgIO), sz, C.POINTER(abi.ZgIO), sz]),
         "zo_state_destroy": (None, [vp]),
+        "zo_set_exec_threads": (None, [sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -237,6 +238,12 @@ def run_program(program, inputs=(), outputs=()):
     del keep
     if rc != 0:
         raise MemoryError("oracle program allocation failed")
+
+
+def set_exec_threads(n: int, native: bool = False):
+    """Threads the program executor splits a qmatmul's output columns over (bench.py --impl reference: all host cores;
+    default 1 like the reference, src/inference_utils.zig:192).  Results are bit-identical for any n."""
+    lib(native).zo_set_exec_threads(int(n))
 
 
 class ProgramState:

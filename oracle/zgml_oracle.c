@@ -813,24 +813,24 @@ static void zo_matmul_dense(const zo_buffer* bufs, const ZgOp* op) {
 /* qmatmul — reference.zig:499-566 (x86 path: the aarch64 W8A8 shortcut at :512-528
  * is compiled out).  Row zeroed, loop K -> N in per-row block chunks; vector path
  * d + f32(q)*(scale*x); scalar tail d += f32(q)*(scale*x) (same product order). */
-ZO_API void zo_qmatmul_op(const float* input, float* dst_ptr, const int8_t* w_data,
-                          const float* w_scales, size_t bs, size_t M, size_t N, size_t K,
-                          size_t input_offset, size_t input_row_stride, size_t dst_offset,
-                          size_t dst_row_stride) {
+static void zo_qmatmul_op_cols(const float* input, float* dst_ptr, const int8_t* w_data,
+                               const float* w_scales, size_t bs, size_t M, size_t N, size_t K,
+                               size_t input_offset, size_t input_row_stride, size_t dst_offset,
+                               size_t dst_row_stride, size_t n_lo, size_t n_hi) {
     if (input_row_stride == 0) input_row_stride = K;
     if (dst_row_stride == 0) dst_row_stride = N;
     for (size_t row = 0; row < M; row++) {
         const float* input_row = input + input_offset + row * input_row_stride;
         float* dst_row = dst_ptr + dst_offset + row * dst_row_stride;
-        for (size_t n = 0; n < N; n++) dst_row[n] = 0;
+        for (size_t n = n_lo; n < n_hi; n++) dst_row[n] = 0;
         for (size_t k = 0; k < K; k++) {
             float input_v = input_row[k];
-            size_t w_base = k * N, n = 0;
-            while (n < N) {
+            size_t w_base = k * N, n = n_lo;
+            while (n < n_hi) {
                 size_t flat = w_base + n;
                 float scale = w_scales[flat / bs] * input_v;
                 size_t block_rem = bs - (flat % bs);
-                size_t chunk = zo_min(block_rem, N - n);
+                size_t chunk = zo_min(block_rem, n_hi - n);
                 for (size_t j = 0; j < chunk; j++) {
                     float p = (float)w_data[flat + j] * scale;
                     dst_row[n + j] = dst_row[n + j] + p;
@@ -839,6 +839,40 @@ ZO_API void zo_qmatmul_op(const float* input, float* dst_ptr, const int8_t* w_da
             }
         }
     }
+}
+ZO_API void zo_qmatmul_op(const float* input, float* dst_ptr, const int8_t* w_data,
+                          const float* w_scales, size_t bs, size_t M, size_t N, size_t K,
+                          size_t input_offset, size_t input_row_stride, size_t dst_offset,
+                          size_t dst_row_stride) {
+    zo_qmatmul_op_cols(input, dst_ptr, w_data, w_scales, bs, M, N, K, input_offset, input_row_stride, dst_offset, dst_row_stride, 0, N);
+}
+
+/* All-host-cores variant for the program executor (bench.py --impl reference only): the reference runs qmatmul on one
+ * thread (src/inference_utils.zig:192); here the output columns are split over `zo_exec_threads` threads.  Every output
+ * column is accumulated by exactly the same operations in the same order, so results are bit-identical to one thread. */
+static size_t zo_exec_threads = 1;
+ZO_API void zo_set_exec_threads(size_t n) { zo_exec_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+typedef struct {
+    const float* input; float* dst; const int8_t* w; const float* s; size_t bs, M, N, K, io, irs, doff, drs, n_lo, n_hi;
+} zo_qmm_task;
+static void* zo_qmm_worker(void* arg) {
+    zo_qmm_task* t = (zo_qmm_task*)arg;
+    zo_qmatmul_op_cols(t->input, t->dst, t->w, t->s, t->bs, t->M, t->N, t->K, t->io, t->irs, t->doff, t->drs, t->n_lo, t->n_hi);
+    return NULL;
+}
+static void zo_qmatmul_op_mt(const float* input, float* dst_ptr, const int8_t* w_data, const float* w_scales, size_t bs, size_t M,
+                             size_t N, size_t K, size_t io, size_t irs, size_t doff, size_t drs) {
+    size_t nt_want = zo_exec_threads;
+    if (nt_want <= 1 || N < 256 || (bs && N % bs != 0)) { zo_qmatmul_op(input, dst_ptr, w_data, w_scales, bs, M, N, K, io, irs, doff, drs); return; }
+    pthread_t th[256];
+    zo_qmm_task tasks[256];
+    size_t chunk = (((N + nt_want - 1) / nt_want) + 31) & ~(size_t)31, nt = 0;
+    for (size_t lo = 0; lo < N; lo += chunk, nt++) {
+        tasks[nt] = (zo_qmm_task){input, dst_ptr, w_data, w_scales, bs, M, N, K, io, irs, doff, drs, lo, zo_min(lo + chunk, N)};
+        if (nt > 0) pthread_create(&th[nt], NULL, zo_qmm_worker, &tasks[nt]);
+    }
+    zo_qmm_worker(&tasks[0]);
+    for (size_t i = 1; i < nt; i++) pthread_join(th[i], NULL);
 }
 
 /* attention — reference.zig:568-672: per query row, online softmax over seq_kv;
@@ -906,7 +940,7 @@ ZO_API void zo_execute_ops(float** buf_ptrs, const size_t* buf_lens, size_t n_bu
             case ZG_OP_MATMUL: zo_matmul_dense(bufs, op); break;
             case ZG_OP_QMATMUL: {
                 const ZgQWeight* w = &qweights[op->u.qmatmul.weight_idx];
-                zo_qmatmul_op(bufs[op->u.qmatmul.input].ptr, bufs[op->u.qmatmul.dst].ptr, w->data,
+                zo_qmatmul_op_mt(bufs[op->u.qmatmul.input].ptr, bufs[op->u.qmatmul.dst].ptr, w->data,
                               w->scales, w->block_size, op->u.qmatmul.M, op->u.qmatmul.N,
                               op->u.qmatmul.K, op->u.qmatmul.input_offset,
                               op->u.qmatmul.input_row_stride, op->u.qmatmul.dst_offset,
