@@ -720,10 +720,175 @@ k_attention_fast(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restric
     ZG_TRACE_MARK(2)
 }
 
+// Prefill attention (seq_q >= 16, d_head 64 / 128, unit row strides): flash-attention tiling in fp32.  One CTA owns 64
+// query rows of one head and walks the kv positions in tiles of 64: Q, K, V tiles in shared memory, the 64 x 64 score tile
+// in registers (thread (ty, tx) of 16 x 16 holds rows 4ty.., columns 4tx..), online softmax per row (row statistics shared by
+// the 16 threads of a row through half-warp shuffles), probabilities through shared memory, output accumulators in
+// registers (rows 4ty.., DH / 16 columns per thread).  Same skip rules as reference.zig:599-671 (non-finite mask or score
+// entries are skipped, an all-masked row gives zeros); a kv tile whose mask is non-finite for every (row, position) pair of
+// the CTA — everything above the causal diagonal — is skipped without touching K or V.  The one-CTA-per-query-row kernel
+// this replaces re-read every K / V row per query: 466 ms of a 523 ms Llama-3-8B prefill of 2048 tokens.
+constexpr int kPfBQ = 64, kPfBK = 64, kPfThreads = 256;
+template <int DH>
+__global__ void __launch_bounds__(kPfThreads, 2)
+k_attention_prefill(const ZgBatchEntry* __restrict__ tab, const uint32_t* __restrict__ d_dyn) {
+    ZG_TRACE_BEGIN(7)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
+    extern __shared__ __align__(16) float pf_smem[];
+    float* Qs = pf_smem;                         // [64][DH]
+    float* Ks = Qs + kPfBQ * DH;                 // [64][DH + 4]  (+4: conflict-free column reads of four consecutive rows)
+    float* Vs = Ks + kPfBK * (DH + 4);           // [64][DH]
+    float* Ps = Ks;                              // [64][64 + 4]: the probabilities reuse the K tile (two CTAs per SM fit this way)
+    constexpr int KP = DH + 4, PP = kPfBK + 4, OC = DH / 16;
+    const ZgBatchEntry e = tab[blockIdx.y];
+    const uint32_t has_mask = e.u[0], seq_q = e.u[2];
+    const float scale = e.f;
+    const uint32_t q_off = e.u[3], k_off = e.u[4], v_off = e.u[5], mask_off = e.u[6], dst_off = e.u[7];
+    const uint32_t q_cs = e.u[9], k_cs = e.u[11], v_cs = e.u[13], mask_rs = e.u[14], mask_cs = e.u[15], dst_cs = e.u[17];
+    const float* __restrict__ q = e.s0;
+    const float* __restrict__ k = e.s1;
+    const float* __restrict__ v = e.s2;
+    const float* __restrict__ mask = e.s3;
+    const uint32_t seq_kv = d_dyn[e.dyn];
+    const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t q0 = blockIdx.x * kPfBQ;
+    // Q tile (rows past seq_q: zeros)
+    for (uint32_t i = tid; i < kPfBQ * (DH / 4); i += kPfThreads) {
+        const uint32_t r = i / (DH / 4), c4 = i % (DH / 4);
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q0 + r < seq_q) val = *reinterpret_cast<const float4*>(q + (size_t)q_off + (size_t)(q0 + r) * q_cs + 4 * c4);
+        *reinterpret_cast<float4*>(Qs + r * DH + 4 * c4) = val;
+    }
+    float o[4][OC];
+    float m_run[4], l_run[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        m_run[r] = -INFINITY; l_run[r] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < OC; c++) o[r][c] = 0.0f;
+    }
+    for (uint32_t s0 = 0; s0 < seq_kv; s0 += kPfBK) {
+        // additive mask of this thread's 4 x 4 entries; out-of-range rows / positions count as masked
+        float mk[4][4];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t qi = q0 + 4 * ty + r, sj = s0 + 4 * tx + c;
+                float mv = -INFINITY;
+                if (qi < seq_q && sj < seq_kv) mv = has_mask ? mask[(size_t)mask_off + (size_t)sj * mask_rs + (size_t)qi * mask_cs] : 0.0f;
+                mk[r][c] = mv;
+                any = any || isfinite(mv);
+            }
+        if (!__syncthreads_or(any ? 1 : 0)) continue;   // nothing attendable in the tile (also orders the previous tile's reads of Ks / Vs / Ps)
+        for (uint32_t i = tid; i < kPfBK * (DH / 4); i += kPfThreads) {
+            const uint32_t r = i / (DH / 4), c4 = i % (DH / 4);
+            float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+            if (s0 + r < seq_kv) {
+                kv4 = *reinterpret_cast<const float4*>(k + (size_t)k_off + (size_t)(s0 + r) * k_cs + 4 * c4);
+                vv4 = *reinterpret_cast<const float4*>(v + (size_t)v_off + (size_t)(s0 + r) * v_cs + 4 * c4);
+            }
+            *reinterpret_cast<float4*>(Ks + r * KP + 4 * c4) = kv4;
+            *reinterpret_cast<float4*>(Vs + r * DH + 4 * c4) = vv4;
+        }
+        __syncthreads();
+        // scores: S[4ty + r][4tx + c] = q . k
+        float sc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) sc[r][c] = 0.0f;
+#pragma unroll 4
+        for (int d = 0; d < DH; d += 4) {
+            float4 qa[4], ka[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) qa[r] = *reinterpret_cast<const float4*>(Qs + (4 * ty + r) * DH + d);
+#pragma unroll
+            for (int c = 0; c < 4; c++) ka[c] = *reinterpret_cast<const float4*>(Ks + (4 * tx + c) * KP + d);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    sc[r][c] = fmaf(qa[r].x, ka[c].x, sc[r][c]); sc[r][c] = fmaf(qa[r].y, ka[c].y, sc[r][c]);
+                    sc[r][c] = fmaf(qa[r].z, ka[c].z, sc[r][c]); sc[r][c] = fmaf(qa[r].w, ka[c].w, sc[r][c]);
+                }
+        }
+        __syncthreads();   // every thread is done with the K tile: its memory now takes the probabilities
+        // online softmax per row (16 threads of a half warp share a row)
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float rmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float sv = -INFINITY;
+                if (isfinite(mk[r][c])) { sv = sc[r][c] * scale + mk[r][c]; if (!isfinite(sv)) sv = -INFINITY; }
+                sc[r][c] = sv;
+                rmax = fmaxf(rmax, sv);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, off));
+            const float new_m = fmaxf(m_run[r], rmax);
+            const float alpha = (m_run[r] == -INFINITY || new_m == -INFINITY) ? (new_m == -INFINITY ? 1.0f : 0.0f) : expf(m_run[r] - new_m);
+            float rsum = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float pv = (sc[r][c] == -INFINITY) ? 0.0f : expf(sc[r][c] - new_m);
+                Ps[(4 * ty + r) * PP + 4 * tx + c] = pv;
+                rsum += pv;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, off);
+            l_run[r] = l_run[r] * alpha + rsum;
+            m_run[r] = new_m;
+#pragma unroll
+            for (int c = 0; c < OC; c++) o[r][c] *= alpha;
+        }
+        __syncthreads();
+        // O[4ty + r][tx + 16c] += sum_j P[4ty + r][j] V[j][tx + 16c]   (column = tx + 16c: conflict-free V reads)
+#pragma unroll 4
+        for (int j = 0; j < kPfBK; j++) {
+            float pj[4], vj[OC];
+#pragma unroll
+            for (int r = 0; r < 4; r++) pj[r] = Ps[(4 * ty + r) * PP + j];
+#pragma unroll
+            for (int c = 0; c < OC; c++) vj[c] = Vs[j * DH + tx + 16 * c];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < OC; c++) o[r][c] = fmaf(pj[r], vj[c], o[r][c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t qi = q0 + 4 * ty + r;
+        if (qi >= seq_q) continue;
+        const float inv_l = l_run[r] > 0.0f ? 1.0f / l_run[r] : 0.0f;
+#pragma unroll
+        for (int c = 0; c < OC; c++) {
+            const uint32_t col = tx + 16 * c;
+            const float val = o[r][c] * inv_l;
+            e.dst[(size_t)dst_off + (size_t)qi * dst_cs + col] = val;
+            if (e.dst2) e.dst2[(size_t)e.d2_off + (size_t)col * e.d2_rs + (size_t)qi * e.d2_cs] = val;
+        }
+    }
+    ZG_TRACE_MARK(2)
+}
+template <int DH> constexpr size_t pf_smem_bytes() { return (size_t)(kPfBQ * DH + kPfBK * (DH + 4) + kPfBK * DH) * sizeof(float); }
+static_assert(kPfBQ * (kPfBK + 4) <= kPfBK * (64 + 4), "the probability tile fits inside the K tile");
+static inline bool attn_prefill_ok(const ZgOp& op);
+
 static inline bool attn_fast_ok(const ZgOp& op) {
     const auto& a = op.u.attention;
     return a.q_rs == 1 && a.k_rs == 1 && a.v_rs == 1 && a.dst_rs == 1 && (a.d_head % 4) == 0 && a.d_head <= 256 &&
            (a.k_off % 4) == 0 && (a.k_cs % 4) == 0;
+}
+
+static inline bool attn_prefill_ok(const ZgOp& op) {
+    const auto& a = op.u.attention;
+    return attn_fast_ok(op) && a.seq_q >= 16 && (a.d_head == 64 || a.d_head == 128) && (a.q_off % 4) == 0 && (a.q_cs % 4) == 0 &&
+           (a.v_off % 4) == 0 && (a.v_cs % 4) == 0;
 }
 
 struct MMParams {
@@ -1297,7 +1462,7 @@ uint64_t zg_batch_signature(const ZgOp& op) {
     switch (op.tag) {
         case ZG_OP_SLICE_ASSIGN: return ((uint64_t)op.tag << 56) | ((uint64_t)(op.u.slice_assign.rows & 0xFFFFFFF) << 28) | (op.u.slice_assign.cols & 0xFFFFFFF);
         case ZG_OP_ROPE: return ((uint64_t)op.tag << 56) | ((uint64_t)(op.u.rope.half_d & 0xFFFFFFF) << 28) | (op.u.rope.seq_len & 0xFFFFFFF);
-        case ZG_OP_ATTENTION: return ((uint64_t)op.tag << 56) | ((uint64_t)attn_fast_ok(op) << 55) | ((uint64_t)(op.u.attention.d_head & 0x7FFFFFF) << 28) | (op.u.attention.seq_q & 0xFFFFFFF);
+        case ZG_OP_ATTENTION: return ((uint64_t)op.tag << 56) | ((uint64_t)attn_fast_ok(op) << 55) | ((uint64_t)attn_prefill_ok(op) << 54) | ((uint64_t)(op.u.attention.d_head & 0x7FFFFFF) << 28) | (op.u.attention.seq_q & 0xFFFFFFF);
         default: return 0;
     }
 }
@@ -1370,7 +1535,28 @@ bool zg_launch_batch(const ZgOp& first, const ZgBatchEntry* d_entries, uint32_t 
         case ZG_OP_ATTENTION: {
             const auto& a = first.u.attention;
             if (a.seq_q == 0 || a.d_head == 0) return true;
-            if (attn_fast_ok(first)) {
+            if (attn_prefill_ok(first)) {
+                const dim3 grid((a.seq_q + kPfBQ - 1) / kPfBQ, count);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = grid; cfg.blockDim = dim3(kPfThreads); cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = g_zg_pdl ? 1 : 0;
+                cudaError_t le;
+                if (a.d_head == 64) {
+                    static bool once64 = false;
+                    if (!once64) { cudaFuncSetAttribute(k_attention_prefill<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem_bytes<64>()); once64 = true; }
+                    cfg.dynamicSmemBytes = pf_smem_bytes<64>();
+                    le = cudaLaunchKernelEx(&cfg, k_attention_prefill<64>, d_entries, d_dyn);
+                } else {
+                    static bool once128 = false;
+                    if (!once128) { cudaFuncSetAttribute(k_attention_prefill<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem_bytes<128>()); once128 = true; }
+                    cfg.dynamicSmemBytes = pf_smem_bytes<128>();
+                    le = cudaLaunchKernelEx(&cfg, k_attention_prefill<128>, d_entries, d_dyn);
+                }
+                if (le != cudaSuccess) { zg_set_error("prefill attention launch failed: %s", cudaGetErrorString(le)); return false; }
+            } else if (attn_fast_ok(first)) {
                 const uint32_t sp = (attn_part && attn_cnt && attn_splits > 1) ? attn_splits : 1u;
                 const dim3 grid(a.seq_q, count, sp);
                 if (a.d_head <= 64) launch_k(k_attention_fast<2>, dim3(grid), dim3(kAttnFastWarps * 32), st, d_entries, d_dyn, attn_part, attn_cnt, sp);

@@ -566,7 +566,7 @@ bool launch_fmt(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cud
 } // namespace
 
 // Work split for one launch of up to 8 activation rows.
-ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M) {
+ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count) {
     ZgGemvPlan pl;
     const uint32_t rows = M > 8 ? 8 : M;
     pl.mp = rows <= 2 ? 1 : (rows <= 4 ? 2 : 4);
@@ -590,6 +590,25 @@ ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t 
     if (ctx->tune_smax && (uint32_t)ctx->tune_smax < S && (w->n_kc + ctx->tune_smax * warps * lcap_max - 1) / (ctx->tune_smax * warps * lcap_max) <= 1) S = (uint32_t)ctx->tune_smax;
     if (S > w->n_kc) S = w->n_kc;
     if (S < 1) S = 1;
+    // Wave quantisation: `count` matvecs share the launch, and a launch of slightly more CTAs than the GPU holds at once
+    // (Llama-3-70B gate|up sharded over 8 GPUs: 2 x 112 column groups x 2 splits = 448 CTAs for 444 slots) costs an
+    // extra round.  ZG_GEMV_WAVE=1 tries a few more k-splits and takes the cheapest in rounds x (records per warp + fixed
+    // per-CTA cost).  MEASURED AND REJECTED as a default (round 2, same box A/B): 2 % slower on the 70B decode step both
+    // unsharded (252.4 -> 247.2 tok/s at 24 layers) and for an 8-way shard (58.9 -> 60.5 us/layer) — every extra split adds
+    // a partial-sum round trip through global scratch that costs more than the emptier last round saves.
+    static const bool wave_aware = [] { const char* e = getenv("ZG_GEMV_WAVE"); return e && e[0] == '1'; }();
+    if (wave_aware && S >= 2 && !ctx->tune_s && count >= 1 && (uint64_t)w->n_nb * S * count > target) {
+        const double c0 = 6.0;
+        double best = 1e30; uint32_t bS = S;
+        for (uint32_t s2 = S; s2 <= S + 4 && s2 <= w->n_kc; s2++) {
+            const uint64_t ctas = (uint64_t)w->n_nb * s2 * count;
+            const double rounds = (double)((ctas + target - 1) / target);
+            const double per_warp = (double)(((w->n_kc + s2 - 1) / s2 + warps - 1) / warps);
+            const double cost = rounds * (per_warp + c0);
+            if (cost < best - 1e-9) { best = cost; bS = s2; }
+        }
+        S = bS;
+    }
     uint32_t P = ((uint64_t)w->n_nb * S + target - 1) / target;
     if (P < 1) P = 1;
     if (ctx->tune_p) P = (uint32_t)ctx->tune_p;
@@ -644,9 +663,14 @@ void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, 
                       size_t* counters) {
     *partial_elems = 0; *counters = 0;
     if (w->fmt == ZG_QFMT_GENERIC || M == 0 || M > 8) return;
-    ZgGemvPlan plan = zg_qgemv_plan(ctx, w, M);
-    if (plan.S > 1) {
-        *partial_elems = (size_t)w->n_nb * plan.S * (2 * plan.mp) * ZG_TN;
+    uint32_t S = 1, mp = 1;
+    for (uint32_t count = 1; count <= kZgGemvBatch; count++) {   // the split count depends on how many matvecs share the launch: size for the largest
+        const ZgGemvPlan plan = zg_qgemv_plan(ctx, w, M, count);
+        if (plan.S > S) S = plan.S;
+        mp = plan.mp;
+    }
+    if (S > 1) {
+        *partial_elems = (size_t)w->n_nb * S * (2 * mp) * ZG_TN;
         *counters = w->n_nb;
     }
 }
@@ -686,7 +710,7 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
                               float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
                               const ZgGemvWs* ws, cudaStream_t st, const ZgGemvPrologue* pro) {
     const ZgCudaQWeight* w0 = ws_w[0];
-    ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M);
+    ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M, count);
     QGemvBatch bt;
     memset(&bt, 0, sizeof(bt));
     for (uint32_t i = 0; i < count; i++) {

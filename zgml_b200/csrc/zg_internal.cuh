@@ -138,7 +138,7 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
 struct ZgGemvPlan {
     uint32_t grid = 0, threads = 256, P = 1, S = 1, mp = 1, G = 2, NS = 3, lcap = 1, xs_stride = 32, smem_bytes = 0;
 };
-ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M);
+ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count = 1);   // count: matvecs sharing the launch
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
                       size_t* counters);
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
