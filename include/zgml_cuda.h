@@ -331,6 +331,14 @@ int zg_cuda_attention_quantized_host(ZgCudaCtx* ctx, float* h_dst, size_t dst_co
                                      const ZgCudaKVCache* v_cache, size_t v_col_start, size_t seq_kv, const float* h_mask,
                                      size_t mask_row_stride, size_t mask_col_stride, float scale, int int8_query);
 
+/* LlamaInferenceSession.quantizeKV for a compiled program — src/llama_inference.zig:648-679 (plan side :277-328): from now on
+ * every patched slice_assign into a buffer that attention ops read as K or V stores quantized columns (storeColumn) into a
+ * Q8 cache standing in for that buffer, and those attention ops run attentionQuantized over the caches (the routing of
+ * src/llama_inference.zig:336-377).  The caches start zeroed, like the reference's; call it right after compile.
+ * int8_query != 0: the aarch64 branch of attentionQuantized (query quantized per block), 0: the portable f32-query branch.
+ * Returns 0 on success; -1 (program unchanged) when the program's cache accesses are not whole d_head columns. */
+int zg_cuda_program_quantize_kv(ZgCudaCtx* ctx, ZgCudaProgram* prog, size_t block_size, int int8_query);
+
 /* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
  * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */
 int zg_cuda_comm_unique_id(void* id128);

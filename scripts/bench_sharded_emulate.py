@@ -20,7 +20,7 @@ for _ in range(n):
     be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
 be.sync()
 dt = (time.perf_counter() - t0) / n
-print(f"emulated rank 0 of {world}: {cfg.n_layers} layers, {1e6 * dt:.1f} us/step, {1e6 * dt / cfg.n_layers:.2f} us/layer (incl. head), ZG_GEMV_WAVE={os.environ.get('ZG_GEMV_WAVE', '1')}, "
+print(f"emulated rank 0 of {world}: {cfg.n_layers} layers, {1e6 * dt:.1f} us/step, {1e6 * dt / cfg.n_layers:.2f} us/layer (incl. head), ZG_CUDA_DECODE={os.environ.get("ZG_CUDA_DECODE", "0")}, fused layers {be.program_stats(sess.handle)["fused_decode_layers"]}, "
       f"kernels {be.program_stats(sess.handle)['kernels']}")
 sess.close()
 for h in handles:

@@ -448,6 +448,12 @@ class CudaBackend:
     def launch_count(self) -> int:
         return int(self.lib.zg_cuda_launch_count())
 
+    def quantize_kv(self, handle: CompiledHandle, block_size: int = 32, int8_query: bool = False) -> None:
+        """LlamaInferenceSession.quantizeKV (src/llama_inference.zig:648-679) for a compiled program: Q8 caches replace the f32 KV
+        buffers, cache writes run storeColumn, attention runs attentionQuantized."""
+        if self.lib.zg_cuda_program_quantize_kv(self.ctx, handle.ptr, block_size, int(int8_query)) != 0:
+            raise BackendError(f"quantize_kv failed: {last_error()}")
+
     def program_stats(self, handle: CompiledHandle) -> dict:
         """Schedule facts of a compiled program: kernels per execution, DeviceOps / layers inside the fused decode kernel."""
         f = self.lib.zg_cuda_program_stats

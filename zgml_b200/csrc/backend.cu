@@ -85,6 +85,7 @@ struct ZgCudaProgram {
         std::vector<ZgGemvPrologue> pros;  // matvec batch: how each op obtains its activations
         std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
         bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false, decode = false;
+        uint32_t kvq = 0, kvq_max_warps = 0, kvq_seq_q = 0, kvq_splits = 1; size_t kvq_part_off = 0, kvq_cnt_off = 0;   // 1: batch of cache stores, 2: batch of cache-backed attentions
         ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
         ZgEwMulMacro em = {};
@@ -103,6 +104,15 @@ struct ZgCudaProgram {
     float* d_attn_part = nullptr;      // split-KV partial states, one slice per attention unit
     uint32_t* d_attn_cnt = nullptr;    // arrival counters (self re-arming)
     bool uniform_pos = true;   // every patched slice_assign sits at the same position (checked per refresh)
+    // quantized KV cache mode (zg_cuda_program_quantize_kv; LlamaInferenceSession.quantizeKV, src/llama_inference.zig:648-679):
+    // Q8 caches stand in for the f32 cache buffers; the patched slice_assigns into them run storeColumn, the attention ops
+    // over them attentionQuantized (src/llama_inference.zig:336-377)
+    bool kvq = false; size_t kvq_bs = 32; int kvq_int8 = 0;
+    std::map<uint32_t, ZgCudaKVCache*> kv_caches;   // program buffer -> the cache standing in for it
+    std::vector<char> kvq_role;                     // per op: 0 none, 1 cache store, 2 attention over the caches
+    std::vector<uint32_t> kvq_entry;                // per op: its entry in d_kvq_store / d_kvq_attn
+    ZgKvqStore* d_kvq_store = nullptr; ZgKvqAttn* d_kvq_attn = nullptr;
+    float* d_kvq_part = nullptr; uint32_t* d_kvq_cnt = nullptr;   // split-KV scratch of the cache-backed attention units
     ZgDecodeHost dec;          // fused decode kernel (decode.cu) when the program's layers match the single-token LLaMA pattern
     uint32_t dec_first = 0, dec_count = 0;   // the ops it covers
 };
@@ -160,7 +170,7 @@ extern "C" void zg_cuda_capabilities(ZgCapabilities* c) {
     memset(c, 0, sizeof(*c));
     c->compiled_programs = 1; c->host_visible_program_memory = 0;
     c->dense_matmul_f32 = 1; c->qmatmul = 1; c->fused_elementwise = 1; c->max_fused_elementwise_steps = 0;
-    c->dynamic_program_refresh = 1; c->prefill_attention = 1; c->decode_attention = 1;
+    c->dynamic_program_refresh = 1; c->prefill_attention = 1; c->decode_attention = 1; c->quantized_kv = 1;
     c->attention_supported = 1; c->attention_max_seq_kv = 0; c->attention_max_d_head = 512;
 }
 
@@ -235,6 +245,8 @@ static void free_program(ZgCudaProgram* p) {
     if (p->h_dyn) cudaFreeHost(p->h_dyn);
     zg_gemv_ws_free(&p->ws);
     zg_decode_free(&p->dec);
+    for (auto& kv : p->kv_caches) zg_cuda_kvcache_free(p->ctx, kv.second);
+    cudaFree(p->d_kvq_store); cudaFree(p->d_kvq_attn); cudaFree(p->d_kvq_part); cudaFree(p->d_kvq_cnt);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->dep_events) cudaEventDestroy(e);
     delete p;
@@ -566,7 +578,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 // every op is what the op-by-op execution gives.  Matching is deliberately strict: consecutive in program order, whole
 // contiguous vectors, all buffers distinct.
 struct ZgItem { uint32_t first = 0, count = 1, kind = 0; };   // kind 0: one op; 1: [add,] rmsnorm, repeat, mul; 2: fused_elementwise, mul; 3: attention, slice_assign
-enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3, ITEM_DECODE = 4 };
+enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3, ITEM_DECODE = 4, ITEM_KVQ = 5 };
 
 static bool distinct(std::initializer_list<uint32_t> bufs) {
     std::vector<uint32_t> v(bufs);
@@ -1022,7 +1034,7 @@ static bool build_schedule(ZgCudaProgram* p) {
     size_t dec_end = 0;
     zg_decode_free(&p->dec);
     p->dec_first = 0; p->dec_count = 0;
-    if (p->ctx->decode_fused && p->ctx->fuse && chain_max && p->uniform_pos && match_decode_layers(p, 0, dec_layers, &dec_end)) {
+    if (p->ctx->decode_fused && !p->kvq && p->ctx->fuse && chain_max && p->uniform_pos && match_decode_layers(p, 0, dec_layers, &dec_end)) {
         if (!build_decode_plan(p, dec_layers)) return false;
         p->dec_count = (uint32_t)dec_end;
     }
@@ -1036,7 +1048,8 @@ static bool build_schedule(ZgCudaProgram* p) {
         ZgItem it; it.first = (uint32_t)i;
         ZgNormMacro nm = {}; ZgEwMulMacro em = {};
         uint32_t c = 0;
-        if (chain_max && p->ctx->fuse && (c = match_norm(p, i, &nm))) it.kind = ITEM_NORM;
+        if (p->kvq && i < p->kvq_role.size() && p->kvq_role[i]) { it.kind = ITEM_KVQ; c = 1; }
+        else if (chain_max && p->ctx->fuse && (c = match_norm(p, i, &nm))) it.kind = ITEM_NORM;
         else if (p->ctx->fuse && (c = match_ewmul(p, i, &em))) it.kind = ITEM_EWMUL;
         else if (p->ctx->fuse && (c = match_attn_store(p, i))) it.kind = ITEM_ATTN_STORE;
         else c = 1;
@@ -1203,6 +1216,9 @@ static bool build_schedule(ZgCudaProgram* p) {
         const ZgOp& op = p->ops[it.first];
         return op.tag != ZG_OP_RMSNORM && op.tag != ZG_OP_ALLREDUCE && zg_chain_work(op) <= 512;
     };
+    std::vector<int> level_of_op(n, -1);
+    for (size_t k = 0; k < ni; k++) for (uint32_t j = 0; j < items[k].count; j++) level_of_op[items[k].first + j] = level[k];
+    auto level_of_unit_first = [&](const ZgCudaProgram::Unit& u) { return level_of_op[u.ops[0]]; };
     size_t pos = 0;
     while (pos < no) {
         size_t end = pos;
@@ -1263,6 +1279,19 @@ static bool build_schedule(ZgCudaProgram* p) {
                 u.ranges.insert(u.ranges.end(), item_rng[order[k]].begin(), item_rng[order[k]].end());
                 continue;
             }
+            if (it.kind == ITEM_KVQ) {   // same-level cache stores / cache-backed attentions of one shape share a launch
+                const uint32_t role = (uint32_t)p->kvq_role[it.first];
+                const uint32_t sq = role == 2 ? op.u.attention.seq_q : 0;
+                size_t ui = (size_t)-1;
+                for (size_t q = p->units.size(); q-- > 0;) {
+                    const ZgCudaProgram::Unit& u = p->units[q];
+                    if (u.kvq == role && u.kvq_seq_q == sq && !u.ops.empty() && level[order[k]] == level_of_unit_first(u)) { ui = q; break; }
+                    if (!u.kvq) break;
+                }
+                if (ui == (size_t)-1) { ZgCudaProgram::Unit u; u.kvq = role; u.kvq_seq_q = sq; p->units.push_back(u); ui = p->units.size() - 1; }
+                p->units[ui].ops.push_back(it.first);
+                continue;
+            }
             if (it.kind == ITEM_DECODE) {
                 ZgCudaProgram::Unit u; u.decode = true;
                 for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
@@ -1312,6 +1341,73 @@ static bool build_schedule(ZgCudaProgram* p) {
             entries.push_back(e);
         }
     }
+    // cache-backed ops: parameter tables in unit order
+    cudaFree(p->d_kvq_store); p->d_kvq_store = nullptr;
+    cudaFree(p->d_kvq_attn); p->d_kvq_attn = nullptr;
+    p->kvq_entry.assign(n, 0);
+    if (p->kvq) {
+        std::vector<ZgKvqStore> st_tab; std::vector<ZgKvqAttn> at_tab;
+        for (auto& u : p->units) {
+            if (!u.kvq) continue;
+            u.first_entry = (uint32_t)(u.kvq == 1 ? st_tab.size() : at_tab.size());
+            u.n_entries = (uint32_t)u.ops.size();
+            for (uint32_t i : u.ops) {
+                int8_t* cq; float* cs; uint32_t dh, bs, bpc; size_t ncols;
+                if (u.kvq == 1) {
+                    const auto& sa = p->ops[i].u.slice_assign;
+                    zg_kvq_cache_arrays(p->kv_caches[sa.dst], &cq, &cs, &dh, &bs, &bpc, &ncols);
+                    ZgKvqStore e;
+                    e.src = p->buffers[sa.src] + sa.src_offset; e.q = cq; e.s = cs; e.src_cs = sa.src_col_stride; e.n_write = sa.cols;
+                    e.dyn_idx = i; e.d_head = dh; e.bs = bs; e.bpc = bpc;
+                    u.kvq_max_warps = std::max(u.kvq_max_warps, sa.cols * bpc);
+                    p->kvq_entry[i] = (uint32_t)st_tab.size();
+                    st_tab.push_back(e);
+                } else {
+                    const auto& a = p->ops[i].u.attention;
+                    ZgKvqAttn e;
+                    memset(&e, 0, sizeof(e));
+                    e.dst = p->buffers[a.dst] + a.dst_off; e.dst_cs = a.dst_cs; e.q = p->buffers[a.q] + a.q_off; e.q_cs = a.q_cs;
+                    e.d_head = a.d_head; e.seq_kv = a.seq_kv;
+                    zg_kvq_cache_arrays(p->kv_caches[a.k], &cq, &cs, &dh, &bs, &bpc, &ncols);
+                    e.k_q = cq; e.k_s = cs; e.k_col_start = a.k_off / a.d_head; e.bs = bs; e.nb = bpc;
+                    zg_kvq_cache_arrays(p->kv_caches[a.v], &cq, &cs, &dh, &bs, &bpc, &ncols);
+                    e.v_q = cq; e.v_s = cs; e.v_col_start = a.v_off / a.d_head;
+                    e.mask = a.has_mask ? p->buffers[a.mask] + a.mask_off : nullptr; e.mask_rs = a.mask_rs; e.mask_cs = a.seq_q > 1 ? a.mask_cs : 0;
+                    e.scale = a.scale; e.int8_query = p->kvq_int8; e.dyn_idx = i;
+                    p->kvq_entry[i] = (uint32_t)at_tab.size();
+                    at_tab.push_back(e);
+                }
+            }
+        }
+        if (!st_tab.empty()) {
+            ZG_CUDA_OK(cudaMalloc(&p->d_kvq_store, st_tab.size() * sizeof(ZgKvqStore)));
+            ZG_CUDA_OK(cudaMemcpy(p->d_kvq_store, st_tab.data(), st_tab.size() * sizeof(ZgKvqStore), cudaMemcpyHostToDevice));
+        }
+        if (!at_tab.empty()) {
+            ZG_CUDA_OK(cudaMalloc(&p->d_kvq_attn, at_tab.size() * sizeof(ZgKvqAttn)));
+            ZG_CUDA_OK(cudaMemcpy(p->d_kvq_attn, at_tab.data(), at_tab.size() * sizeof(ZgKvqAttn), cudaMemcpyHostToDevice));
+        }
+        // split-KV: several CTAs per query column when the launch would otherwise leave most SMs idle (decode: one column per head)
+        cudaFree(p->d_kvq_part); p->d_kvq_part = nullptr;
+        cudaFree(p->d_kvq_cnt); p->d_kvq_cnt = nullptr;
+        size_t part_total = 0, cnt_total = 0;
+        for (auto& u : p->units) {
+            if (u.kvq != 2) continue;
+            const uint32_t rows = u.n_entries * u.kvq_seq_q;
+            uint32_t sp = rows ? (uint32_t)p->ctx->sm_count * 2 / rows : 1;
+            sp = std::max(1u, std::min(sp, 16u));
+            uint32_t dmax = 0;
+            for (uint32_t i : u.ops) dmax = std::max(dmax, p->ops[i].u.attention.d_head);
+            u.kvq_splits = sp; u.kvq_part_off = part_total; u.kvq_cnt_off = cnt_total;
+            part_total += (size_t)rows * sp * (2 + dmax);
+            cnt_total += rows;
+        }
+        if (part_total) {
+            ZG_CUDA_OK(cudaMalloc(&p->d_kvq_part, part_total * sizeof(float)));
+            ZG_CUDA_OK(cudaMalloc(&p->d_kvq_cnt, cnt_total * sizeof(uint32_t)));
+            ZG_CUDA_OK(cudaMemset(p->d_kvq_cnt, 0, cnt_total * sizeof(uint32_t)));
+        }
+    }
     // split-KV scratch of the decode attention units
     size_t part_total = 0, cnt_total = 0;
     for (auto& u : p->units) {
@@ -1357,6 +1453,11 @@ static bool build_schedule(ZgCudaProgram* p) {
 static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
     ZgCudaCtx* ctx = p->ctx;
     const ZgOp& op = p->ops[i];
+    if (p->kvq && i < p->kvq_role.size() && p->kvq_role[i] == 1) {
+        const auto& sa = op.u.slice_assign;
+        return zg_kvq_launch_stores(p->d_kvq_store + p->kvq_entry[i], 1, sa.cols * (uint32_t)(sa.rows / p->kvq_bs), p->d_dyn, st);
+    }
+    if (p->kvq && i < p->kvq_role.size() && p->kvq_role[i] == 2) return zg_kvq_launch_attention(p->d_kvq_attn + p->kvq_entry[i], 1, op.u.attention.seq_q, p->d_dyn, nullptr, nullptr, 1, st);
     if (op.tag == ZG_OP_QMATMUL) {
         const auto& q = op.u.qmatmul;
         ZgGemvWs view = p->ws;
@@ -1377,6 +1478,9 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.decode) { p->dec.plan.dyn = p->d_dyn; return zg_decode_launch(p->ctx, p->dec, st); }
+    if (u.kvq == 1) return zg_kvq_launch_stores(p->d_kvq_store + u.first_entry, u.n_entries, u.kvq_max_warps, p->d_dyn, st);
+    if (u.kvq == 2) return zg_kvq_launch_attention(p->d_kvq_attn + u.first_entry, u.n_entries, u.kvq_seq_q, p->d_dyn,
+                                                   p->d_kvq_part ? p->d_kvq_part + u.kvq_part_off : nullptr, p->d_kvq_cnt ? p->d_kvq_cnt + u.kvq_cnt_off : nullptr, u.kvq_splits, st);
     if (u.chain) return zg_launch_chain(p->d_chain + u.first_entry, u.n_entries, p->d_dyn, st);
     if (u.ewmul) return zg_launch_ewmul(u.em, st);
     if (u.norm) return zg_launch_norm_macro(u.nm, st);
@@ -1644,6 +1748,63 @@ extern "C" size_t zg_cuda_trace_read(ZgCudaCtx* ctx, unsigned long long* host, s
 extern "C" const ZgProfile* zg_cuda_profile(ZgCudaCtx* ctx, ZgCudaProgram* p) {
     if (!ctx || !p || !ctx->profiling) return nullptr;
     return &p->profile;
+}
+
+// LlamaInferenceSession.quantizeKV (src/llama_inference.zig:648-679, plan side :277-328) for a compiled program.
+extern "C" int zg_cuda_program_quantize_kv(ZgCudaCtx* ctx, ZgCudaProgram* p, size_t block_size, int int8_query) {
+    if (!ctx || !p || block_size == 0 || (block_size & 3)) { zg_set_error("program_quantize_kv: bad arguments (block_size must be a positive multiple of 4)"); return -1; }
+    if (p->kvq) return 0;   // like the reference: a second call keeps the caches
+    cudaSetDevice(ctx->device);
+    const size_t n = p->ops.size();
+    std::vector<char> role(n, 0);
+    std::map<uint32_t, uint32_t> kv_dh;   // cache buffer -> d_head
+    for (size_t i = 0; i < n; i++) {
+        if (p->ops[i].tag != ZG_OP_ATTENTION) continue;
+        const auto& a = p->ops[i].u.attention;
+        const uint32_t dh = a.d_head;
+        if (a.k_rs != 1 || a.v_rs != 1 || a.q_rs != 1 || a.dst_rs != 1 || a.k_cs != dh || a.v_cs != dh || dh == 0 || dh > 512 || (dh & 3) || dh % block_size ||
+            a.k_off % dh || a.v_off % dh || (int8_query && dh / block_size > 32)) {
+            zg_set_error("program_quantize_kv: op %zu: attention layout not expressible over a column-major Q8 cache (src/quant.zig:941-947)", i); return -1;
+        }
+        for (uint32_t b : {a.k, a.v}) {
+            if (kv_dh.count(b) && kv_dh[b] != dh) { zg_set_error("program_quantize_kv: buffer %u is read with two head sizes", b); return -1; }
+            kv_dh[b] = dh;
+        }
+        role[i] = 2;
+    }
+    if (kv_dh.empty()) { zg_set_error("program_quantize_kv: the program has no attention op"); return -1; }
+    for (size_t i = 0; i < n; i++) {
+        const ZgOp& op = p->ops[i];
+        if (op.tag == ZG_OP_SLICE_ASSIGN && kv_dh.count(op.u.slice_assign.dst)) {
+            const auto& sa = op.u.slice_assign;
+            const uint32_t dh = kv_dh[sa.dst];
+            if (sa.rows != dh || sa.dst_row_stride != 1 || sa.dst_col_stride != dh || sa.src_row_stride != 1 || sa.dst_base_offset % dh || sa.dst_offset % dh ||
+                (sa.patch_stride && sa.patch_stride % dh) || kv_dh.count(sa.src)) {
+                zg_set_error("program_quantize_kv: op %zu: cache write is not a run of whole d_head columns (src/llama_inference.zig:336-348)", i); return -1;
+            }
+            role[i] = 1;
+            continue;
+        }
+        if (role[i]) {   // attention: q / mask / dst must not be cache buffers
+            const auto& a = op.u.attention;
+            if (kv_dh.count(a.q) || kv_dh.count(a.dst) || (a.has_mask && kv_dh.count(a.mask))) { zg_set_error("program_quantize_kv: op %zu: a cache buffer is used as q / mask / dst", i); return -1; }
+            continue;
+        }
+        std::vector<ZgRange> rr;
+        op_ranges(p, op, rr);
+        for (const ZgRange& r : rr)
+            if (kv_dh.count(r.buf)) { zg_set_error("program_quantize_kv: op %zu (tag %u) touches a KV-cache buffer directly", i, op.tag); return -1; }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : kv_dh) {
+        ZgCudaKVCache* c = zg_cuda_kvcache_create(ctx, kv.second, p->buffer_elems[kv.first] / kv.second, block_size);
+        if (!c) { for (auto& q : p->kv_caches) zg_cuda_kvcache_free(ctx, q.second); p->kv_caches.clear(); return -1; }
+        p->kv_caches[kv.first] = c;
+    }
+    p->kvq = true; p->kvq_bs = block_size; p->kvq_int8 = int8_query ? 1 : 0; p->kvq_role = role;
+    p->graph_valid = false;
+    if (!build_schedule(p)) { p->kvq = false; build_schedule(p); return -1; }
+    return 0;
 }
 
 extern "C" uint64_t zg_cuda_program_stats(const ZgCudaProgram* p, int what) {

@@ -184,6 +184,9 @@ qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (uint32_t i = 0; i < NS && pf_left; i++) issue_chunk();
     }
+    // Measured and rejected (round 2): pulling the REST of the warp's weight run into L2 here with cp.async.bulk.prefetch.L2
+    // (the kernel sits resident 5-11 us before its activations exist) made every configuration slower — 70B shard of 8:
+    // 61.2 -> 62.1 us/layer, unsharded 175 -> 198, GEMV microbenchmark 5.79 -> 5.24 TB/s: the wait is not idle HBM time.
     // the constant ones plane (digit index 3) of every (record, row): B column of ones -> sum_k q
     for (uint32_t i = lane; i < G * XR * 8; i += 32) {
         const uint32_t rm = i >> 3, w4 = i & 7;

@@ -31,13 +31,13 @@ constexpr uint32_t kAttnWarps = 8, kMaxDHead = 512;
 
 __device__ __forceinline__ float byte_f(uint32_t w, int e) { return (float)(int)(int8_t)(w >> (8 * e)); }
 
-// a warp per (column, block): quantizeInput on column col_start + i (src/quant.zig:689-701, 320-341)
-__global__ void k_kv_store(const float* __restrict__ src, uint32_t d_head, uint32_t bs, uint32_t bpc, uint32_t n_write,
-                           int8_t* __restrict__ q, float* __restrict__ s, size_t col_start) {
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// a warp per (column, block): quantizeInput on column col_start + i (src/quant.zig:689-701, 320-341); source column i
+// starts at src + i * src_cs
+__device__ __forceinline__ void kv_store_body(const float* __restrict__ src, size_t src_cs, uint32_t d_head, uint32_t bs, uint32_t bpc, uint32_t n_write,
+                                              int8_t* __restrict__ q, float* __restrict__ s, size_t col_start, uint32_t wid, uint32_t lane) {
     if (wid >= n_write * bpc) return;
     const uint32_t i = wid / bpc, b = wid % bpc;
-    const float* x = src + (size_t)i * d_head + (size_t)b * bs;
+    const float* x = src + (size_t)i * src_cs + (size_t)b * bs;
     float mx = 0.0f;
     for (uint32_t k = lane; k < bs; k += 32) mx = fmaxf(mx, fabsf(x[k]));
 #pragma unroll
@@ -51,6 +51,19 @@ __global__ void k_kv_store(const float* __restrict__ src, uint32_t d_head, uint3
         v = v < -127.0f ? -127.0f : (v > 127.0f ? 127.0f : v);
         q[col * d_head + (size_t)b * bs + k] = (int8_t)(int)v;
     }
+}
+__global__ void k_kv_store(const float* __restrict__ src, uint32_t d_head, uint32_t bs, uint32_t bpc, uint32_t n_write,
+                           int8_t* __restrict__ q, float* __restrict__ s, size_t col_start) {
+    kv_store_body(src, d_head, d_head, bs, bpc, n_write, q, s, col_start, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
+}
+// the cache-backed slice_assign ops of one dependency level of a program (blockIdx.y = op): the destination column comes
+// from the op's run-time patched dst_offset (f32 elements into the cache buffer the Q8 cache stands in for)
+__global__ void k_kv_store_tab(const ZgKvqStore* __restrict__ tab, const uint32_t* __restrict__ dyn) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const ZgKvqStore e = tab[blockIdx.y];
+    kv_store_body(e.src, e.src_cs, e.d_head, e.bs, e.bpc, e.n_write, e.q, e.s, (size_t)(dyn[e.dyn_idx] / e.d_head),
+                  (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
 // dotI8I8 (src/quant.zig:764-798) of one K column with the quantized query in shared memory
@@ -95,25 +108,20 @@ __device__ float dot_f32(const uint32_t* __restrict__ kw, const float* __restric
     return total;
 }
 
-struct AttnParams {
-    float* dst; size_t dst_cs;
-    const float* q; size_t q_cs;
-    uint32_t d_head, seq_kv, bs, nb;
-    const int8_t* k_q; const float* k_s; size_t k_col_start;
-    const int8_t* v_q; const float* v_s; size_t v_col_start;
-    const float* mask; size_t mask_rs, mask_cs;
-    float scale;
-    int int8_query;
-};
+using AttnParams = ZgKvqAttn;
 
-__global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized(const AttnParams p) {
+// `split` of `splits` CTAs share one query column's kv range (tiles of 32 positions); with splits > 1 the CTA leaves its
+// (max, sum, unnormalised accumulator) state in part[(row * splits_max + split) * (2 + d_head)] and the last CTA to arrive at
+// cnt[row] merges the states in split order (deterministic) — ops.cu k_attention_fast does the same for the f32 cache.
+__device__ __forceinline__ void attention_quantized_body(const AttnParams& p, const uint32_t qi, const uint32_t split, const uint32_t splits,
+                                                         const uint32_t splits_max, float* __restrict__ part, uint32_t* __restrict__ cnt, const uint32_t row) {
     __shared__ float s_q[kMaxDHead];
     __shared__ uint32_t s_qi8[kMaxDHead / 4];
     __shared__ float s_qs[kMaxDHead / 4];
     __shared__ float s_acc[kAttnWarps][kMaxDHead];
     __shared__ float s_m[kAttnWarps], s_l[kAttnWarps];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t qi = blockIdx.x, d = p.d_head, nb = p.nb, bs = p.bs;
+    const uint32_t d = p.d_head, nb = p.nb, bs = p.bs;
     const float* q_col = p.q + (size_t)qi * p.q_cs;
     for (uint32_t r = threadIdx.x; r < d; r += blockDim.x) s_q[r] = q_col[r];
     __syncthreads();
@@ -146,7 +154,8 @@ __global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized(const A
         for (int e = 0; e < 4; e++) acc[g][e] = 0.0f;
 
     const uint32_t n_tiles = (p.seq_kv + 31) / 32;
-    for (uint32_t t = warp; t < n_tiles; t += kAttnWarps) {
+    const uint32_t tiles_per = (n_tiles + splits - 1) / splits, t_lo = split * tiles_per, t_hi = min(t_lo + tiles_per, n_tiles);
+    for (uint32_t t = t_lo + warp; t < t_hi; t += kAttnWarps) {
         const uint32_t s = t * 32 + lane;
         bool ok = s < p.seq_kv;
         float mask_add = 0.0f;
@@ -215,6 +224,46 @@ __global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized(const A
         f[w2] = (s_m[w2] == -INFINITY) ? 0.0f : expf(s_m[w2] - big_m);
         tot_l += s_l[w2] * f[w2];
     }
+    if (splits > 1) {
+        __shared__ uint32_t s_last;
+        const size_t stride = 2 + d;
+        float* mine = part + ((size_t)row * splits_max + split) * stride;
+        for (uint32_t r = threadIdx.x; r < d; r += blockDim.x) {
+            float o = 0.0f;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < kAttnWarps; w2++) o += s_acc[w2][r] * f[w2];
+            mine[2 + r] = o;
+        }
+        if (threadIdx.x == 0) { mine[0] = big_m; mine[1] = tot_l; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt + row) : "memory");
+            const uint32_t last = (old == splits - 1) ? 1u : 0u;
+            if (last) cnt[row] = 0u;   // re-arm for the next launch
+            s_last = last;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        const float* all = part + (size_t)row * splits_max * stride;
+        float G = -INFINITY;
+        for (uint32_t sp = 0; sp < splits; sp++) G = fmaxf(G, __ldcg(all + (size_t)sp * stride));
+        float Lt = 0.0f;
+        for (uint32_t sp = 0; sp < splits; sp++) {
+            const float ms = __ldcg(all + (size_t)sp * stride);
+            if (ms != -INFINITY) Lt += __ldcg(all + (size_t)sp * stride + 1) * expf(ms - G);
+        }
+        const float inv_L = Lt > 0.0f ? 1.0f / Lt : 0.0f;
+        for (uint32_t r = threadIdx.x; r < d; r += blockDim.x) {
+            float a = 0.0f;
+            for (uint32_t sp = 0; sp < splits; sp++) {
+                const float ms = __ldcg(all + (size_t)sp * stride);
+                if (ms != -INFINITY) a += __ldcg(all + (size_t)sp * stride + 2 + r) * expf(ms - G);
+            }
+            p.dst[(size_t)qi * p.dst_cs + r] = a * inv_L;
+        }
+        return;
+    }
     const float inv_l = tot_l > 0.0f ? 1.0f / tot_l : 0.0f;        // fully masked query column: zeros (src/quant.zig:1075)
     for (uint32_t r = threadIdx.x; r < d; r += blockDim.x) {
         float o = 0.0f;
@@ -223,8 +272,56 @@ __global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized(const A
         p.dst[(size_t)qi * p.dst_cs + r] = o * inv_l;
     }
 }
+__global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized(const AttnParams p) { attention_quantized_body(p, blockIdx.x, 0, 1, 1, nullptr, nullptr, 0); }
+// the cache-backed attention ops of one dependency level of a program (blockIdx.y = op); seq_kv is the op's patched value
+__global__ void __launch_bounds__(32 * kAttnWarps) k_attention_quantized_tab(const AttnParams* __restrict__ tab, const uint32_t* __restrict__ dyn,
+                                                                            float* __restrict__ part, uint32_t* __restrict__ cnt, const uint32_t splits_max) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    AttnParams p = tab[blockIdx.y];
+    p.seq_kv = dyn[p.dyn_idx];
+    // the launch provides splits_max CTAs per query column; a short context uses fewer (>= 64 positions each), the rest leave
+    const uint32_t splits = min(splits_max, max(1u, (p.seq_kv + 63u) / 64u));
+    if (blockIdx.z >= splits) return;
+    attention_quantized_body(p, blockIdx.x, blockIdx.z, splits, splits_max, part, cnt, blockIdx.y * gridDim.x + blockIdx.x);
+}
 
 } // namespace
+
+// ── cache-backed program ops (backend.cu zg_cuda_program_quantize_kv) ──
+bool zg_kvq_cache_arrays(const ZgCudaKVCache* c, int8_t** q, float** s, uint32_t* d_head, uint32_t* bs, uint32_t* bpc, size_t* n_cols) {
+    if (!c) return false;
+    *q = c->q; *s = c->s; *d_head = (uint32_t)c->d_head; *bs = (uint32_t)c->bs; *bpc = (uint32_t)c->bpc; *n_cols = c->n_cols;
+    return true;
+}
+bool zg_kvq_launch_stores(const ZgKvqStore* d_tab, uint32_t count, uint32_t max_warps, const uint32_t* d_dyn, cudaStream_t st) {
+    if (count == 0 || max_warps == 0) return true;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((max_warps * 32 + 255) / 256, count); cfg.blockDim = dim3(256); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_zg_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_kv_store_tab, d_tab, d_dyn);
+    ZG_COUNT_LAUNCH();
+    if (e != cudaSuccess) { zg_set_error("quantized KV store launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+}
+bool zg_kvq_launch_attention(const ZgKvqAttn* d_tab, uint32_t count, uint32_t seq_q, const uint32_t* d_dyn, float* part, uint32_t* cnt,
+                             uint32_t splits_max, cudaStream_t st) {
+    if (count == 0 || seq_q == 0) return true;
+    if (!part || !cnt || splits_max < 1) splits_max = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(seq_q, count, splits_max); cfg.blockDim = dim3(32 * kAttnWarps); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_zg_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_attention_quantized_tab, d_tab, d_dyn, part, cnt, splits_max);
+    ZG_COUNT_LAUNCH();
+    if (e != cudaSuccess) { zg_set_error("quantized attention launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+}
 
 extern "C" ZgCudaKVCache* zg_cuda_kvcache_create(ZgCudaCtx* ctx, size_t d_head, size_t n_cols, size_t block_size) {
     if (!ctx || d_head == 0 || n_cols == 0 || block_size == 0 || d_head % block_size != 0) {
@@ -320,7 +417,7 @@ extern "C" int zg_cuda_attention_quantized_device(ZgCudaCtx* ctx, float* d_dst, 
     p.k_q = k_cache->q; p.k_s = k_cache->s; p.k_col_start = k_col_start;
     p.v_q = v_cache->q; p.v_s = v_cache->s; p.v_col_start = v_col_start;
     p.mask = d_mask; p.mask_rs = mask_row_stride; p.mask_cs = mask_col_stride;
-    p.scale = scale; p.int8_query = int8_query ? 1 : 0;
+    p.scale = scale; p.int8_query = int8_query ? 1 : 0; p.dyn_idx = 0;
     k_attention_quantized<<<(unsigned)seq_q, 32 * kAttnWarps, 0, ctx->stream>>>(p);
     ZG_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();

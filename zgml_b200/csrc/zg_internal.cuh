@@ -298,6 +298,24 @@ bool zg_decode_launch(ZgCudaCtx* ctx, const ZgDecodeHost& d, cudaStream_t st);
 void zg_decode_free(ZgDecodeHost* d);
 void zg_trace_set_decode(unsigned long long* d_buf);
 
+// qkv.cu : quantized KV cache ops as program ops (zg_cuda_program_quantize_kv)
+struct ZgKvqStore { const float* src; int8_t* q; float* s; uint32_t src_cs, n_write, dyn_idx, d_head, bs, bpc; };
+struct ZgKvqAttn {
+    float* dst; size_t dst_cs;
+    const float* q; size_t q_cs;
+    uint32_t d_head, seq_kv, bs, nb;
+    const int8_t* k_q; const float* k_s; size_t k_col_start;
+    const int8_t* v_q; const float* v_s; size_t v_col_start;
+    const float* mask; size_t mask_rs, mask_cs;
+    float scale;
+    int int8_query;
+    uint32_t dyn_idx, _pad;
+};
+bool zg_kvq_cache_arrays(const ZgCudaKVCache* c, int8_t** q, float** s, uint32_t* d_head, uint32_t* bs, uint32_t* bpc, size_t* n_cols);
+bool zg_kvq_launch_stores(const ZgKvqStore* d_tab, uint32_t count, uint32_t max_warps, const uint32_t* d_dyn, cudaStream_t st);
+bool zg_kvq_launch_attention(const ZgKvqAttn* d_tab, uint32_t count, uint32_t seq_q, const uint32_t* d_dyn, float* part, uint32_t* cnt,
+                             uint32_t splits_max, cudaStream_t st);   // part: [count * seq_q][splits_max][2 + d_head], cnt: [count * seq_q] zeroed
+
 // comm.cu : NCCL through dlopen (no link-time dependency)
 bool zg_comm_allreduce(ZgCudaCtx* ctx, float* buf, size_t n, cudaStream_t st);
 bool zg_comm_allgather(ZgCudaCtx* ctx, const float* src, float* dst, size_t n_per_rank, cudaStream_t st);
