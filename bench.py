@@ -374,6 +374,64 @@ def gemv_leg(args, be, torch, dist, stream, rank, world, barrier):
     return gemv, roofline, int(launches)
 
 
+def w8a8_leg(be, torch, stream, cpu=True):
+    """The W8A8 decode path of `session.quantize()` models (quantizeInput + gemvRange, src/quant.zig:320-459; not on the GGUF-direct
+    program path): GPU GB/s over more distinct transposed weights than L2 holds, and the CPU port with the GemvPool partitioning
+    rule (src/quant.zig:135-196: <= 16 workers, one per 2^20 weight elements) on 1 and min(host threads, 16) workers.
+    Bytes per gemv = N*K int8 + 4*N*K/32 scales + 4K + 4N."""
+    from oracle import oracle
+    from zgml_b200 import QuantizedWeight
+    out = []
+    r = np.random.default_rng(0)
+    for (K, N) in SHAPES:
+        nbytes = N * K + N * (K // 32) * 4 + 4 * K + 4 * N
+        copies = max(2, -(-384_000_000 // nbytes))
+        data = r.integers(-127, 128, K * N, dtype=np.int8)
+        scales = r.uniform(1e-3, 1e-2, K * N // 32).astype(np.float32)
+        ws = []
+        for _ in range(copies):
+            w = QuantizedWeight.upload(be, data, scales, K, N, 32)
+            w.prepare_transposed()
+            ws.append(w)
+        x = torch.randn(K, device="cuda")
+        y = torch.empty(N, device="cuda")
+        iters = 100
+        with torch.cuda.stream(stream):
+            for w in ws[:3]:
+                w.gemv_device(x.data_ptr(), y.data_ptr())
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for i in range(iters):
+                    ws[i % copies].gemv_device(x.data_ptr(), y.data_ptr())
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        for w in ws:
+            w.free()
+        peak, _ = peaks()
+        row = {"K": K, "N": N, "block_size": 32, "us_per_gemv": round(us, 2), "gbps": round(nbytes / us / 1e3, 1),
+               "frac_of_measured_hbm": round(nbytes / us / 1e3 / peak, 4), "launches_per_gemv": 2}
+        if cpu:
+            o = oracle.QuantizedWeight(data, scales, K, N, 32)
+            o.prepare_transposed()
+            xh = r.standard_normal(K).astype(np.float32)
+            for workers in (1, min(host_threads(), 16)):
+                o.gemv_pool(xh, workers, native=True)
+                t0, n = time.perf_counter(), 0
+                while n < 3 or time.perf_counter() - t0 < 1.0:
+                    o.gemv_pool(xh, workers, native=True)
+                    n += 1
+                row[f"cpu_gbps_{workers}_workers"] = round(nbytes * n / (time.perf_counter() - t0) / 1e9, 2)
+        out.append(row)
+    return out
+
+
 def decode_leg(args, be, torch, dist, stream, rank, world, barrier, sampler):
     """configs[4]: strong-scaling Llama-3-70B-shape Q4_0 decode.  Returns the pieces of the contract line."""
     from zgml_b200.host import llama
@@ -542,6 +600,10 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         with torch.cuda.stream(stream):
             line["extras"] = run_extras(be, torch)
+        try:
+            line["gemv"]["w8a8"] = w8a8_leg(be, torch, stream, cpu=not args.no_cpu)
+        except Exception as e:
+            line["gemv"]["w8a8_error"] = repr(e)
     if rank == 0 and world == 1 and not args.no_cpu:
         t1, t2, tok_s = cpu_decode_sample(1, args.cpu_tokens)
         line["cpu_baseline"] = {"value": round(tok_s, 4), "unit": UNIT, "cores": 1, "kind": "port",

@@ -85,7 +85,8 @@ struct ZgCudaProgram {
         std::vector<ZgGemvPrologue> pros;  // matvec batch: how each op obtains its activations
         std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
         bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false, decode = false;
-        uint32_t kvq = 0, kvq_max_warps = 0, kvq_seq_q = 0, kvq_splits = 1; size_t kvq_part_off = 0, kvq_cnt_off = 0;   // 1: batch of cache stores, 2: batch of cache-backed attentions
+        uint32_t kvq = 0, kvq_max_warps = 0, kvq_seq_q = 0, kvq_splits = 1; size_t kvq_part_off = 0, kvq_cnt_off = 0;
+        int attn_blk = -1; uint32_t ab_splits = 1; size_t ab_part_off = 0, ab_cnt_off = 0;   // fused attention block of one layer   // 1: batch of cache stores, 2: batch of cache-backed attentions
         ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
         ZgEwMulMacro em = {};
@@ -113,6 +114,8 @@ struct ZgCudaProgram {
     std::vector<uint32_t> kvq_entry;                // per op: its entry in d_kvq_store / d_kvq_attn
     ZgKvqStore* d_kvq_store = nullptr; ZgKvqAttn* d_kvq_attn = nullptr;
     float* d_kvq_part = nullptr; uint32_t* d_kvq_cnt = nullptr;   // split-KV scratch of the cache-backed attention units
+    std::vector<ZgAttnBlock> attn_blocks;            // single-token attention blocks fused into one launch each (ops.cu k_attention_layer)
+    ZgAttnBlock* d_attn_blocks = nullptr; float* d_attn_blk_part = nullptr; uint32_t* d_attn_blk_cnt = nullptr;
     ZgDecodeHost dec;          // fused decode kernel (decode.cu) when the program's layers match the single-token LLaMA pattern
     uint32_t dec_first = 0, dec_count = 0;   // the ops it covers
 };
@@ -142,6 +145,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
+    if (const char* e = getenv("ZG_CUDA_ATTN_LAYER")) ctx->attn_layer = (e[0] != '0');   // 0: rope / cache stores / attention as separate launches
     if (const char* e = getenv("ZG_CUDA_DECODE")) ctx->decode_fused = (e[0] != '0');   // 0: never use the fused decode kernel
     if (!zg_qgemv_init(ctx) || !zg_qgemm_init(ctx) || !zg_decode_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
     int n_branch = 7; // capture streams for independent ops of a program (ZG_CUDA_BRANCH=0: strictly serial graphs)
@@ -247,6 +251,7 @@ static void free_program(ZgCudaProgram* p) {
     zg_decode_free(&p->dec);
     for (auto& kv : p->kv_caches) zg_cuda_kvcache_free(p->ctx, kv.second);
     cudaFree(p->d_kvq_store); cudaFree(p->d_kvq_attn); cudaFree(p->d_kvq_part); cudaFree(p->d_kvq_cnt);
+    cudaFree(p->d_attn_blocks); cudaFree(p->d_attn_blk_part); cudaFree(p->d_attn_blk_cnt);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : p->dep_events) cudaEventDestroy(e);
     delete p;
@@ -578,7 +583,7 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
 // every op is what the op-by-op execution gives.  Matching is deliberately strict: consecutive in program order, whole
 // contiguous vectors, all buffers distinct.
 struct ZgItem { uint32_t first = 0, count = 1, kind = 0; };   // kind 0: one op; 1: [add,] rmsnorm, repeat, mul; 2: fused_elementwise, mul; 3: attention, slice_assign
-enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3, ITEM_DECODE = 4, ITEM_KVQ = 5 };
+enum { ITEM_OP = 0, ITEM_NORM = 1, ITEM_EWMUL = 2, ITEM_ATTN_STORE = 3, ITEM_DECODE = 4, ITEM_KVQ = 5, ITEM_ATTN_LAYER = 6 };
 
 static bool distinct(std::initializer_list<uint32_t> bufs) {
     std::vector<uint32_t> v(bufs);
@@ -646,6 +651,93 @@ static uint32_t match_attn_store(const ZgCudaProgram* p, size_t i) {
     if (sa.patch_stride != 0 || sa.src != a.dst || sa.dst == a.dst || sa.dst == a.q || sa.dst == a.k || sa.dst == a.v || sa.dst == a.mask) return 0;
     if (sa.rows != a.d_head || sa.cols != a.seq_q || sa.src_offset != a.dst_off || sa.src_row_stride != a.dst_rs || sa.src_col_stride != a.dst_cs) return 0;
     return 2;
+}
+
+// The attention block of one layer of a single-token program, starting at op i:
+//   per KV head: rope(k_rot <- k_proj) ; slice_assign(K cache <- k_rot, patched) ; slice_assign(V cache <- v_proj, patched)
+//   per head:    rope(q_rot <- q_proj) ; attention ; slice_assign(concat <- attn_out)
+// Returns the number of ops matched (0: no match) and fills the launch descriptor.  As strict as the decode matcher.
+static uint32_t match_attention_block(const ZgCudaProgram* p, size_t i, ZgAttnBlock* B) {
+    const size_t n = p->ops.size();
+    auto elems = [&](uint32_t b) { return p->buffer_elems[b]; };
+    size_t c = i;
+    memset(B, 0, sizeof(*B));
+    if (c + 6 > n || p->ops[c].tag != ZG_OP_ROPE || p->ops[c + 1].tag != ZG_OP_SLICE_ASSIGN || p->ops[c + 1].u.slice_assign.patch_stride == 0) return 0;
+    const uint32_t k_buf = p->ops[c].u.rope.src;
+    uint32_t dh = 0, cs_buf = UINT32_MAX, kc_buf = UINT32_MAX, vc_buf = UINT32_MAX, v_buf = UINT32_MAX, patch = 0, n_kv = 0;
+    std::vector<uint32_t> written, readonly;
+    while (c + 3 <= n && n_kv < kZgDecMaxHeads && p->ops[c].tag == ZG_OP_ROPE && p->ops[c].u.rope.src == k_buf && p->ops[c + 1].tag == ZG_OP_SLICE_ASSIGN &&
+           p->ops[c + 1].u.slice_assign.patch_stride != 0) {
+        const auto& ro = p->ops[c].u.rope;
+        const ZgOp &ks = p->ops[c + 1], &vs = p->ops[c + 2];
+        if (vs.tag != ZG_OP_SLICE_ASSIGN) return 0;
+        const auto& ka = ks.u.slice_assign; const auto& va = vs.u.slice_assign;
+        const uint32_t d = 2 * ro.half_d;
+        if (dh == 0) { dh = d; cs_buf = ro.cos_sin; kc_buf = ka.dst; vc_buf = va.dst; v_buf = va.src; patch = ka.patch_stride; }
+        if (d != dh || d == 0 || ro.seq_len != 1 || ro.cos_sin != cs_buf || ro.cs_off != 0 || ro.dst_off != 0 || ro.src_rs != 1 ||
+            (size_t)ro.src_off + dh > elems(k_buf) || elems(ro.dst) < dh || elems(cs_buf) < dh) return 0;
+        if (ka.dst != kc_buf || ka.src != ro.dst || ka.rows != dh || ka.cols != 1 || ka.dst_row_stride != 1 || ka.src_offset != 0 ||
+            ka.src_row_stride != 1 || ka.patch_stride != patch) return 0;
+        if (va.dst != vc_buf || va.src != v_buf || va.rows != dh || va.cols != 1 || va.dst_row_stride != 1 || va.src_row_stride != 1 ||
+            va.patch_stride != patch || (size_t)va.src_offset + dh > elems(v_buf)) return 0;
+        ZgDecKv& kv = B->kvs[n_kv++];
+        kv.k_rot = p->buffers[ro.dst]; kv.k_src = ro.src_off; kv.v_src = va.src_offset; kv.k_dyn = (uint32_t)(c + 1); kv.v_dyn = (uint32_t)(c + 2);
+        kv.k_base = ka.dst_base_offset; kv.v_base = va.dst_base_offset;
+        written.push_back(ro.dst);
+        c += 3;
+    }
+    if (n_kv == 0 || kc_buf == vc_buf) return 0;
+    if (c + 3 > n || p->ops[c].tag != ZG_OP_ROPE) return 0;
+    const uint32_t q_buf = p->ops[c].u.rope.src;
+    uint32_t n_heads = 0, mask_buf = UINT32_MAX, cat_buf = UINT32_MAX;
+    while (c + 3 <= n && n_heads < kZgDecMaxHeads && p->ops[c].tag == ZG_OP_ROPE && p->ops[c].u.rope.src == q_buf && p->ops[c + 1].tag == ZG_OP_ATTENTION) {
+        const auto& ro = p->ops[c].u.rope;
+        const ZgOp &ao = p->ops[c + 1], &so = p->ops[c + 2];
+        if (so.tag != ZG_OP_SLICE_ASSIGN) return 0;
+        const auto& a = ao.u.attention; const auto& sa = so.u.slice_assign;
+        const uint32_t h = n_heads;
+        if (2 * ro.half_d != dh || ro.seq_len != 1 || ro.cos_sin != cs_buf || ro.cs_off != 0 || ro.dst_off != 0 || ro.src_rs != 1 ||
+            (size_t)ro.src_off + dh > elems(q_buf) || elems(ro.dst) < dh) return 0;
+        if (a.q != ro.dst || a.k != kc_buf || a.v != vc_buf || a.d_head != dh || a.seq_q != 1 || a.q_off != 0 || a.q_rs != 1 || a.k_rs != 1 ||
+            a.v_rs != 1 || a.dst_off != 0 || a.dst_rs != 1 || (dh % 4) != 0 || dh > 256 || (a.k_off % 4) != 0 || (a.k_cs % 4) != 0 ||
+            a.k_cs != patch || a.v_cs != patch || a.k_cs == 0 || elems(a.dst) < dh) return 0;
+        if (h == 0) {
+            B->has_mask = a.has_mask; mask_buf = a.mask; B->mask_off = a.mask_off; B->mask_rs = a.mask_rs; B->scale = a.scale;
+            B->k_cs = a.k_cs; B->v_cs = a.v_cs; cat_buf = sa.dst;
+        } else if (a.has_mask != B->has_mask || (a.has_mask && (a.mask != mask_buf || a.mask_off != B->mask_off || a.mask_rs != B->mask_rs)) ||
+                   a.scale != B->scale || a.k_cs != B->k_cs || a.v_cs != B->v_cs) return 0;
+        uint32_t kvi = UINT32_MAX;
+        for (uint32_t g = 0; g < n_kv; g++) if (B->kvs[g].k_base == a.k_off && B->kvs[g].v_base == a.v_off) kvi = g;
+        if (kvi == UINT32_MAX || (h > 0 && kvi < B->heads[h - 1].kv)) return 0;
+        if (sa.dst != cat_buf || sa.src != a.dst || sa.patch_stride != 0 || sa.rows != dh || sa.cols != 1 || sa.dst_row_stride != 1 ||
+            sa.src_offset != 0 || sa.src_row_stride != 1 || (size_t)sa.dst_offset + dh > elems(cat_buf)) return 0;
+        ZgDecHead& hd = B->heads[n_heads++];
+        hd.q_rot = p->buffers[ro.dst]; hd.attn_out = p->buffers[a.dst]; hd.q_src = ro.src_off; hd.k_off = a.k_off; hd.v_off = a.v_off; hd.kv = kvi;
+        hd.buf_off = sa.dst_offset; hd.dyn = (uint32_t)(c + 1);
+        written.push_back(ro.dst); written.push_back(a.dst);
+        c += 3;
+    }
+    if (n_heads == 0) return 0;
+    for (uint32_t g = 0; g < n_kv; g++) {   // every KV head is read by some query head (its first one stores the cache rows)
+        bool used = false;
+        for (uint32_t h = 0; h < n_heads; h++) used = used || B->heads[h].kv == g;
+        if (!used) return 0;
+    }
+    // distinct buffers: projections, rope table, mask, caches, concat and the per-head temporaries
+    written.push_back(kc_buf); written.push_back(vc_buf); written.push_back(cat_buf);
+    readonly = {q_buf, k_buf, v_buf, cs_buf};
+    if (B->has_mask) readonly.push_back(mask_buf);
+    std::vector<uint32_t> all(written);
+    all.insert(all.end(), readonly.begin(), readonly.end());
+    std::sort(all.begin(), all.end());
+    if (std::adjacent_find(all.begin(), all.end()) != all.end()) {
+        // q / k / v may legitimately be distinct windows of one buffer?  The lowering uses three buffers: anything else keeps the general path
+        return 0;
+    }
+    B->q_proj = p->buffers[q_buf]; B->k_proj = p->buffers[k_buf]; B->v_proj = p->buffers[v_buf]; B->cs = p->buffers[cs_buf];
+    B->mask = B->has_mask ? p->buffers[mask_buf] : nullptr; B->k_cache = p->buffers[kc_buf]; B->v_cache = p->buffers[vc_buf];
+    B->attn_buf = p->buffers[cat_buf]; B->n_heads = n_heads; B->n_kv = n_kv; B->d_head = dh;
+    return (uint32_t)(c - i);
 }
 
 // ── fused decode kernel (decode.cu): recognise the single-token layer pattern of the LLaMA lowering ───────────────
@@ -1029,6 +1121,8 @@ static bool build_schedule(ZgCudaProgram* p) {
     std::vector<ZgItem> items;
     std::vector<ZgNormMacro> norm_of;     // per item (kind ITEM_NORM)
     std::vector<ZgEwMulMacro> ewmul_of;   // per item (kind ITEM_EWMUL)
+    std::map<size_t, int> attn_of_item;   // item (kind ITEM_ATTN_LAYER) -> index into p->attn_blocks
+    p->attn_blocks.clear();
     // single-token LLaMA layers: ONE persistent kernel for all of them (decode.cu)
     std::vector<DecHostLayer> dec_layers;
     size_t dec_end = 0;
@@ -1048,7 +1142,9 @@ static bool build_schedule(ZgCudaProgram* p) {
         ZgItem it; it.first = (uint32_t)i;
         ZgNormMacro nm = {}; ZgEwMulMacro em = {};
         uint32_t c = 0;
+        ZgAttnBlock ab;
         if (p->kvq && i < p->kvq_role.size() && p->kvq_role[i]) { it.kind = ITEM_KVQ; c = 1; }
+        else if (p->ctx->fuse && p->ctx->attn_layer && !p->kvq && (c = match_attention_block(p, i, &ab))) { it.kind = ITEM_ATTN_LAYER; attn_of_item[items.size()] = (int)p->attn_blocks.size(); p->attn_blocks.push_back(ab); }
         else if (chain_max && p->ctx->fuse && (c = match_norm(p, i, &nm))) it.kind = ITEM_NORM;
         else if (p->ctx->fuse && (c = match_ewmul(p, i, &em))) it.kind = ITEM_EWMUL;
         else if (p->ctx->fuse && (c = match_attn_store(p, i))) it.kind = ITEM_ATTN_STORE;
@@ -1292,6 +1388,11 @@ static bool build_schedule(ZgCudaProgram* p) {
                 p->units[ui].ops.push_back(it.first);
                 continue;
             }
+            if (it.kind == ITEM_ATTN_LAYER) {
+                ZgCudaProgram::Unit u; u.attn_blk = attn_of_item[order[k]];
+                for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
+                p->units.push_back(u); continue;
+            }
             if (it.kind == ITEM_DECODE) {
                 ZgCudaProgram::Unit u; u.decode = true;
                 for (uint32_t j = 0; j < it.count; j++) u.ops.push_back(it.first + j);
@@ -1408,6 +1509,28 @@ static bool build_schedule(ZgCudaProgram* p) {
             ZG_CUDA_OK(cudaMemset(p->d_kvq_cnt, 0, cnt_total * sizeof(uint32_t)));
         }
     }
+    // fused attention blocks: descriptors + split-KV scratch
+    cudaFree(p->d_attn_blocks); p->d_attn_blocks = nullptr;
+    cudaFree(p->d_attn_blk_part); p->d_attn_blk_part = nullptr;
+    cudaFree(p->d_attn_blk_cnt); p->d_attn_blk_cnt = nullptr;
+    if (!p->attn_blocks.empty()) {
+        size_t pt = 0, ct = 0;
+        for (auto& u : p->units) {
+            if (u.attn_blk < 0) continue;
+            const ZgAttnBlock& B = p->attn_blocks[u.attn_blk];
+            uint32_t sp = (uint32_t)p->ctx->sm_count / std::max(B.n_heads, 1u);
+            sp = std::max(1u, std::min(sp, 8u));
+            const uint32_t ni32 = B.d_head <= 64 ? 64 : (B.d_head <= 128 ? 128 : 256);
+            u.ab_splits = sp; u.ab_part_off = pt; u.ab_cnt_off = ct;
+            pt += (size_t)B.n_heads * sp * (ni32 + 2);
+            ct += B.n_heads;
+        }
+        ZG_CUDA_OK(cudaMalloc(&p->d_attn_blocks, p->attn_blocks.size() * sizeof(ZgAttnBlock)));
+        ZG_CUDA_OK(cudaMemcpy(p->d_attn_blocks, p->attn_blocks.data(), p->attn_blocks.size() * sizeof(ZgAttnBlock), cudaMemcpyHostToDevice));
+        ZG_CUDA_OK(cudaMalloc(&p->d_attn_blk_part, std::max<size_t>(pt, 1) * sizeof(float)));
+        ZG_CUDA_OK(cudaMalloc(&p->d_attn_blk_cnt, std::max<size_t>(ct, 1) * sizeof(uint32_t)));
+        ZG_CUDA_OK(cudaMemset(p->d_attn_blk_cnt, 0, std::max<size_t>(ct, 1) * sizeof(uint32_t)));
+    }
     // split-KV scratch of the decode attention units
     size_t part_total = 0, cnt_total = 0;
     for (auto& u : p->units) {
@@ -1478,6 +1601,11 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.decode) { p->dec.plan.dyn = p->d_dyn; return zg_decode_launch(p->ctx, p->dec, st); }
+    if (u.attn_blk >= 0) {
+        const ZgAttnBlock& B = p->attn_blocks[u.attn_blk];
+        return zg_launch_attention_layer(p->d_attn_blocks + u.attn_blk, B.n_heads, B.d_head, u.ab_splits, p->d_dyn, p->d_attn_blk_part + u.ab_part_off,
+                                         p->d_attn_blk_cnt + u.ab_cnt_off, st);
+    }
     if (u.kvq == 1) return zg_kvq_launch_stores(p->d_kvq_store + u.first_entry, u.n_entries, u.kvq_max_warps, p->d_dyn, st);
     if (u.kvq == 2) return zg_kvq_launch_attention(p->d_kvq_attn + u.first_entry, u.n_entries, u.kvq_seq_q, p->d_dyn,
                                                    p->d_kvq_part ? p->d_kvq_part + u.kvq_part_off : nullptr, p->d_kvq_cnt ? p->d_kvq_cnt + u.kvq_cnt_off : nullptr, u.kvq_splits, st);

@@ -879,6 +879,236 @@ template <int DH> constexpr size_t pf_smem_bytes() { return (size_t)(kPfBQ * DH 
 static_assert(kPfBQ * (kPfBK + 4) <= kPfBK * (64 + 4), "the probability tile fits inside the K tile");
 static inline bool attn_prefill_ok(const ZgOp& op);
 
+// ── the attention block of one layer of a single-token program in ONE launch (ZgAttnBlock) ──
+// CTA = (query head, kv split).  Prologue: rope of this head's query and of its KV head's key from the projections (the
+// rotated query / key buffers, the K-cache row and the V-cache row are stored by the split-0 CTA of the head / of the KV
+// head's first query head).  The position written by this step is served from shared memory, so no CTA reads a cache row
+// another CTA writes in the same launch.  Main loop, split merge and the second store into the concatenated buffer as in
+// k_attention_fast.  Replaces rope x (n_kv + n_heads), slice_assign x (2 n_kv + n_heads) and the attention launch.
+template <int NI>
+__global__ void __launch_bounds__(kAttnFastWarps * 32)
+k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restrict__ d_dyn, float* __restrict__ part, uint32_t* __restrict__ cnt,
+                  const uint32_t max_splits) {
+    ZG_TRACE_BEGIN(7)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const ZgAttnBlock& B = *blkp;
+    const uint32_t h = blockIdx.x, sp = blockIdx.y;
+    const ZgDecHead hd = B.heads[h];
+    const ZgDecKv kv = B.kvs[hd.kv];
+    const uint32_t dh = B.d_head, hd2 = dh >> 1;
+    const uint32_t seq_kv = d_dyn[hd.dyn];
+    const uint32_t splits = min(max_splits, max(1u, (seq_kv + 127u) / 128u));
+    if (sp >= splits) return;
+    const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
+    const uint32_t kv_lo = sp * chunk, kv_hi = min(kv_lo + chunk, seq_kv);
+    const float* kbase = B.k_cache + hd.k_off;
+    const float* vbase = B.v_cache + hd.v_off;
+    {   // while the projections are still being computed: pull this CTA's cache rows into L2 (rows below the one written by
+        // this step are final since the previous step)
+        const char* kb = reinterpret_cast<const char*>(kbase);
+        const char* vb = reinterpret_cast<const char*>(vbase);
+        for (uint32_t s = kv_lo + threadIdx.x; s < kv_hi; s += blockDim.x)
+            for (uint32_t b = 0; b < dh * 4; b += 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (size_t)s * B.k_cs * 4 + b));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)s * B.v_cs * 4 + b));
+            }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ __align__(16) float sq[NI * 32];
+    __shared__ __align__(16) float sk[NI * 32];
+    __shared__ __align__(16) float sv[NI * 32];
+    __shared__ float sh_m[kAttnFastWarps], sh_l[kAttnFastWarps];
+    __shared__ float sh_acc[kAttnFastWarps][NI * 32];
+    const uint32_t k_dst = d_dyn[kv.k_dyn], v_dst = d_dyn[kv.v_dyn];
+    // the kv position this step writes, as this head's attention op numbers its rows (UINT32_MAX: not one of its rows)
+    uint32_t s_new = UINT32_MAX;
+    if (k_dst >= hd.k_off && (k_dst - hd.k_off) % B.k_cs == 0 && v_dst >= hd.v_off && (v_dst - hd.v_off) % B.v_cs == 0 &&
+        (k_dst - hd.k_off) / B.k_cs == (v_dst - hd.v_off) / B.v_cs)
+        s_new = (k_dst - hd.k_off) / B.k_cs;
+    const bool store = sp == 0 && ((h == 0) || (B.heads[h - 1].kv != hd.kv));
+    if (tid < NI * 32) {
+        const uint32_t r = tid;
+        float qv = 0.0f, kvv = 0.0f, vv = 0.0f;
+        if (r < dh) {
+            const bool lo = r < hd2;
+            const uint32_t pair = lo ? r : r - hd2, other = lo ? r + hd2 : pair;
+            const float c = B.cs[pair], sn = B.cs[pair + hd2];
+            const float q_me = B.q_proj[hd.q_src + r], q_pt = B.q_proj[hd.q_src + other];
+            const float k_me = B.k_proj[kv.k_src + r], k_pt = B.k_proj[kv.k_src + other];
+            vv = B.v_proj[kv.v_src + r];
+            // separate roundings like the reference (reference.zig:474-475)
+            qv = lo ? __fsub_rn(__fmul_rn(q_me, c), __fmul_rn(q_pt, sn)) : __fadd_rn(__fmul_rn(q_me, c), __fmul_rn(q_pt, sn));
+            kvv = lo ? __fsub_rn(__fmul_rn(k_me, c), __fmul_rn(k_pt, sn)) : __fadd_rn(__fmul_rn(k_me, c), __fmul_rn(k_pt, sn));
+            if (sp == 0) hd.q_rot[r] = qv;
+            if (store) {
+                kv.k_rot[r] = kvv;
+                B.k_cache[(size_t)k_dst + r] = kvv;
+                B.v_cache[(size_t)v_dst + r] = vv;
+            }
+        }
+        sq[r] = qv; sk[r] = kvv; sv[r] = vv;
+    }
+    __syncthreads();
+    const uint32_t dh4 = dh >> 2;
+    float acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) acc[i] = 0.0f;
+    float m_val = -INFINITY, l = 0.0f;
+    uint32_t lpp = 1;
+    {
+        const uint32_t len = kv_hi > kv_lo ? kv_hi - kv_lo : 0;
+        while (lpp < 8 && len <= (kAttnFastWarps * 32u) / (2 * lpp) && (dh4 % (2 * lpp)) == 0) lpp *= 2;
+    }
+    const uint32_t pw = 32 / lpp, seg = lane & (lpp - 1), pos_in_warp = lane / lpp;
+    const uint32_t f4 = dh4 / lpp;
+    for (uint32_t s0 = kv_lo + warp * pw; s0 < kv_hi; s0 += kAttnFastWarps * pw) {
+        const uint32_t s = s0 + pos_in_warp;
+        float mask_add = -INFINITY;
+        if (s < kv_hi) mask_add = B.has_mask ? B.mask[(size_t)B.mask_off + (size_t)s * B.mask_rs] : 0.0f;
+        bool ok = isfinite(mask_add);
+        float score = -INFINITY;
+        {
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+            if (ok) {
+                const float4* kr = reinterpret_cast<const float4*>(s == s_new ? sk : kbase + (size_t)s * B.k_cs) + seg * f4;
+                const float4* q4 = reinterpret_cast<const float4*>(sq) + seg * f4;
+                uint32_t d = 0;
+                for (; d + 8 <= f4; d += 8) {
+                    float4 kk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) kk[u] = kr[d + u];
+#pragma unroll
+                    for (int u = 0; u < 8; u += 4) {
+                        const float4 qa = q4[d + u], qb = q4[d + u + 1], qc = q4[d + u + 2], qf = q4[d + u + 3];
+                        d0 = fmaf(qa.x, kk[u].x, d0); d0 = fmaf(qa.y, kk[u].y, d0); d0 = fmaf(qa.z, kk[u].z, d0); d0 = fmaf(qa.w, kk[u].w, d0);
+                        d1 = fmaf(qb.x, kk[u + 1].x, d1); d1 = fmaf(qb.y, kk[u + 1].y, d1); d1 = fmaf(qb.z, kk[u + 1].z, d1); d1 = fmaf(qb.w, kk[u + 1].w, d1);
+                        d2 = fmaf(qc.x, kk[u + 2].x, d2); d2 = fmaf(qc.y, kk[u + 2].y, d2); d2 = fmaf(qc.z, kk[u + 2].z, d2); d2 = fmaf(qc.w, kk[u + 2].w, d2);
+                        d3 = fmaf(qf.x, kk[u + 3].x, d3); d3 = fmaf(qf.y, kk[u + 3].y, d3); d3 = fmaf(qf.z, kk[u + 3].z, d3); d3 = fmaf(qf.w, kk[u + 3].w, d3);
+                    }
+                }
+                if (d + 4 <= f4) {
+                    float4 kk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) kk[u] = kr[d + u];
+                    const float4 qa = q4[d], qb = q4[d + 1], qc = q4[d + 2], qf = q4[d + 3];
+                    d0 = fmaf(qa.x, kk[0].x, d0); d0 = fmaf(qa.y, kk[0].y, d0); d0 = fmaf(qa.z, kk[0].z, d0); d0 = fmaf(qa.w, kk[0].w, d0);
+                    d1 = fmaf(qb.x, kk[1].x, d1); d1 = fmaf(qb.y, kk[1].y, d1); d1 = fmaf(qb.z, kk[1].z, d1); d1 = fmaf(qb.w, kk[1].w, d1);
+                    d2 = fmaf(qc.x, kk[2].x, d2); d2 = fmaf(qc.y, kk[2].y, d2); d2 = fmaf(qc.z, kk[2].z, d2); d2 = fmaf(qc.w, kk[2].w, d2);
+                    d3 = fmaf(qf.x, kk[3].x, d3); d3 = fmaf(qf.y, kk[3].y, d3); d3 = fmaf(qf.z, kk[3].z, d3); d3 = fmaf(qf.w, kk[3].w, d3);
+                    d += 4;
+                }
+                for (; d < f4; d++) {
+                    const float4 a = kr[d], qa = q4[d];
+                    d0 = fmaf(qa.x, a.x, d0); d0 = fmaf(qa.y, a.y, d0); d0 = fmaf(qa.z, a.z, d0); d0 = fmaf(qa.w, a.w, d0);
+                }
+            }
+            float dot = (d0 + d1) + (d2 + d3);
+            for (uint32_t o = 1; o < lpp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (ok) {
+                score = dot * B.scale + mask_add;
+                ok = isfinite(score);
+                if (!ok) score = -INFINITY;
+            }
+        }
+        float bm = score;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+        if (bm == -INFINITY) continue;
+        const float new_m = fmaxf(m_val, bm);
+        const float alpha = (m_val == -INFINITY) ? 0.0f : expf(m_val - new_m);
+        const float wgt = ok ? expf(score - new_m) : 0.0f;
+        l = l * alpha + warp_sum(seg == 0 ? wgt : 0.0f);
+        m_val = new_m;
+#pragma unroll
+        for (int i = 0; i < NI; i++) acc[i] *= alpha;
+        const uint32_t nj = min(pw, kv_hi - s0);
+#pragma unroll 1
+        for (uint32_t j0 = 0; j0 < nj; j0 += 8) {
+            float vv[8][NI];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const bool in = j0 + jj < nj;
+                const uint32_t sj = s0 + j0 + jj;
+                const float* vr = (sj == s_new) ? sv : vbase + (size_t)sj * B.v_cs;
+#pragma unroll
+                for (int i = 0; i < NI; i++) vv[jj][i] = (in && lane + 32 * i < dh) ? vr[lane + 32 * i] : 0.0f;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const float wj = __shfl_sync(0xffffffffu, wgt, ((j0 + jj) * lpp) & 31);
+#pragma unroll
+                for (int i = 0; i < NI; i++) acc[i] = fmaf(wj, vv[jj][i], acc[i]);
+            }
+        }
+    }
+    if (lane == 0) { sh_m[warp] = m_val; sh_l[warp] = l; }
+#pragma unroll
+    for (int i = 0; i < NI; i++) sh_acc[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    float gm = -INFINITY;
+    for (int w = 0; w < kAttnFastWarps; w++) gm = fmaxf(gm, sh_m[w]);
+    float gl = 0.0f;
+    float wscale[kAttnFastWarps];
+#pragma unroll
+    for (int w = 0; w < kAttnFastWarps; w++) {
+        wscale[w] = (sh_m[w] == -INFINITY) ? 0.0f : expf(sh_m[w] - gm);
+        gl += sh_l[w] * wscale[w];
+    }
+    float* out1 = hd.attn_out;
+    float* out2 = B.attn_buf + hd.buf_off;
+    if (splits > 1) {
+        __shared__ uint32_t s_last;
+        float* mine = part + ((size_t)h * max_splits + sp) * (NI * 32 + 2);
+        for (uint32_t r = tid; r < dh; r += blockDim.x) {
+            float a = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
+            mine[2 + r] = a;
+        }
+        if (tid == 0) { mine[0] = gm; mine[1] = gl; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cnt + h) : "memory");
+            const uint32_t last = (old == splits - 1) ? 1u : 0u;
+            if (last) cnt[h] = 0u;   // re-arm for the next launch
+            s_last = last;
+        }
+        __syncthreads();
+        if (s_last) {
+            const float* all = part + (size_t)h * max_splits * (NI * 32 + 2);
+            float G = -INFINITY;
+            for (uint32_t q = 0; q < splits; q++) G = fmaxf(G, __ldcg(all + (size_t)q * (NI * 32 + 2)));
+            float L = 0.0f;
+            for (uint32_t q = 0; q < splits; q++) {
+                const float ms = __ldcg(all + (size_t)q * (NI * 32 + 2));
+                L += (ms == -INFINITY) ? 0.0f : __ldcg(all + (size_t)q * (NI * 32 + 2) + 1) * expf(ms - G);
+            }
+            const float inv_L = L > 0.0f ? 1.0f / L : 0.0f;
+            for (uint32_t r = tid; r < dh; r += blockDim.x) {
+                float a = 0.0f;
+                for (uint32_t q = 0; q < splits; q++) {
+                    const float ms = __ldcg(all + (size_t)q * (NI * 32 + 2));
+                    if (ms != -INFINITY) a += __ldcg(all + (size_t)q * (NI * 32 + 2) + 2 + r) * expf(ms - G);
+                }
+                out1[r] = a * inv_L; out2[r] = a * inv_L;
+            }
+        }
+        ZG_TRACE_MARK(2)
+        return;
+    }
+    const float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
+    for (uint32_t r = tid; r < dh; r += blockDim.x) {
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
+        out1[r] = a * inv_l; out2[r] = a * inv_l;
+    }
+    ZG_TRACE_MARK(2)
+}
+
 static inline bool attn_fast_ok(const ZgOp& op) {
     const auto& a = op.u.attention;
     return a.q_rs == 1 && a.k_rs == 1 && a.v_rs == 1 && a.dst_rs == 1 && (a.d_head % 4) == 0 && a.d_head <= 256 &&
@@ -1498,6 +1728,17 @@ bool zg_fill_batch_entry(const ZgOp& op, float* const* bufs, uint32_t op_index, 
         }
         default: zg_set_error("internal: op kind %u has no batch entry", op.tag); return false;
     }
+}
+
+bool zg_launch_attention_layer(const ZgAttnBlock* d_blk, uint32_t n_heads, uint32_t d_head, uint32_t max_splits, const uint32_t* d_dyn, float* part,
+                               uint32_t* cnt, cudaStream_t st) {
+    if (n_heads == 0) return true;
+    const dim3 grid(n_heads, max_splits), block(kAttnFastWarps * 32);
+    if (d_head <= 64) launch_k(k_attention_layer<2>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
+    else if (d_head <= 128) launch_k(k_attention_layer<4>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
+    else launch_k(k_attention_layer<8>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
+    ZG_COUNT_LAUNCH();
+    return true;
 }
 
 // `first` = any op of the batch (all share the work shape); `d_entries` = `count` consecutive table entries.

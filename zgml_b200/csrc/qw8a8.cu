@@ -128,6 +128,11 @@ k_gemv_w8a8(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const
 // but ran at 1.39 / 1.88 TB/s against 2.23 / 3.61 TB/s for the two-kernel form below (every CTA repeats the activation
 // quantization, and its 16 dependent rounds sit in front of the first weight byte).
 
+// Measured and rejected (round 2, same-box A/B): two output rows per warp (half as many CTAs per gemv so that the next gemv's
+// CTAs fit beside it) with the quantize kernel also launched programmatically dependent: 2.56 / 3.47 TB/s at 4096 x 4096 /
+// 4096 x 14336 against 2.23 / 3.61 for this form — a wash; the pair of dependent launches per gemv (about 4 us of latency
+// for 2.9 us of HBM time at 4096 x 4096) bounds it either way.
+
 // Any block size / K: one thread per output, the reference loop as written.
 __global__ void k_gemv_w8a8_generic(const int8_t* __restrict__ t_d, const float* __restrict__ t_s, const int8_t* __restrict__ xq,
                                     const float* __restrict__ xs, float* __restrict__ dst, uint32_t N, uint32_t K, uint32_t bs,

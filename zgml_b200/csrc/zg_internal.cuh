@@ -112,6 +112,7 @@ struct ZgCudaCtx {
     int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
+    bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
     size_t chain_max = 8200;     // small ops up to this many element visits join single-CTA chains (0 = off, ZG_CUDA_CHAIN)
@@ -230,6 +231,7 @@ bool zg_launch_op(ZgCudaCtx* ctx, const ZgOp& op, float* const* bufs, const uint
 // matvecs] [SiLU*up + down matvec] (+ an NVLink peer all-reduce phase after o / down when sharded).  Every DeviceOp's
 // output buffer is still written.  Weights stream through per-warp TMA rings that run AHEAD across phase and layer
 // boundaries (weights are immutable), so barrier and prologue latencies overlap with HBM traffic.
+constexpr uint32_t kZgDecMaxHeads = 64;   // query heads / KV heads of one layer (per rank)
 constexpr uint32_t kZgDecMaxMv = 3;       // matvecs per phase (q|k|v, gate|up)
 constexpr uint32_t kZgDecMaxSteps = 8;    // fused_elementwise steps of the activation chain
 constexpr uint32_t kZgDecMaxD = 8192;     // floats a CTA stages per phase (norm phases: the whole d_model vector)
@@ -270,7 +272,6 @@ struct ZgDecLayer {
     ZgDecStep steps[kZgDecMaxSteps];
     ZgDecVec down_local, down;
 };
-constexpr uint32_t kZgDecMaxHeads = 64;   // query heads / KV heads of one layer (per rank)
 constexpr uint32_t kZgDecMaxItems = 32;   // column groups one CTA may own in one matvec phase
 // Per-layer descriptor block in device memory, copied into shared memory one layer ahead of its use:
 //   [ZgDecLayer][ZgDecPhase x 4 : qkv, o, gate|up, down][ZgDecHead x cap_heads][ZgDecKv x cap_kv]
@@ -289,6 +290,19 @@ struct ZgDecodeHost {       // owned by a compiled program
     uint32_t* h_err = nullptr;   // pinned copy of the error flag, read after every execute
     bool valid = false;
 };
+// ── ops.cu k_attention_layer: the whole attention block of one layer of a single-token program in ONE launch ──
+// rope(k) -> K-cache store, V-cache store, rope(q), split-KV attention, merge, copy into the concatenated buffer — 3 * (n_kv +
+// n_heads) DeviceOps (src/device_inference.zig lowering of llama_transformer.zig:192-253).  Every op's buffer is still written.
+struct ZgAttnBlock {
+    const float* q_proj; const float* k_proj; const float* v_proj; const float* cs; const float* mask;
+    float* k_cache; float* v_cache; float* attn_buf;
+    uint32_t n_heads, n_kv, d_head, has_mask, mask_off, mask_rs, k_cs, v_cs;
+    float scale; uint32_t _pad;
+    ZgDecHead heads[kZgDecMaxHeads];
+    ZgDecKv kvs[kZgDecMaxHeads];
+};
+bool zg_launch_attention_layer(const ZgAttnBlock* d_blk, uint32_t n_heads, uint32_t d_head, uint32_t max_splits, const uint32_t* d_dyn, float* part,
+                               uint32_t* cnt, cudaStream_t st);   // part: [n_heads][max_splits][2 + pad32(d_head)], cnt: [n_heads] zeroed
 bool zg_decode_init(ZgCudaCtx* ctx);
 uint32_t zg_decode_grid(const ZgCudaCtx* ctx);
 uint32_t zg_decode_block_bytes();
