@@ -373,3 +373,64 @@ def test_matmul_bias_matches_reference(cuda_backend, M):   # reference test: src
     b = r.standard_normal(N).astype(np.float32)
     assert rel_err(w.matmul_bias(x, b, M), o.matmul_bias(x, b, M)) < 5e-5
     w.free()
+
+
+# ── gate | up matvec pair + activation epilogue in ONE launch (csrc/qgemv.cu qgemv_pair_kernel) ──────────────────
+@pytest.mark.parametrize("K,N", [(128, 192), (576, 1536), (2048, 8192), (8192, 1024), (4096, 64)],
+                         ids=["tiny", "smollm-135m", "smollm-1.7b", "long-k-split", "one-group-many-splits"])
+@pytest.mark.parametrize("kind", ["i8_f32", "q8_0", "q4_0"])
+@pytest.mark.parametrize("chain", ["silu", "bias-relu"])
+def test_gate_up_pair_epilogue_matches_oracle_and_unpaired_path(cuda_backend, K, N, kind, chain):
+    """The MLP head of a single-token program (reference src/nn.zig:38-44 lowered by src/device_inference.zig): two matvecs from
+    one input, an elementwise chain on the first, times the second.  The pair launch must leave ALL FOUR buffers (gate, up,
+    chain output, product) as the oracle executor does (1e-5 relative), and bit-identical to the unpaired schedule."""
+    from zgml_b200 import CudaBackend
+    r = rng(K * 3 + N)
+    if kind == "i8_f32":
+        oa = oracle.QuantizedWeight.from_slice(r.uniform(-1, 1, K * N).astype(np.float32), K, N, 32)
+        ob = oracle.QuantizedWeight.from_slice(r.uniform(-1, 1, K * N).astype(np.float32), K, N, 32)
+    else:
+        t, mk = (8, make_q8_0_raw) if kind == "q8_0" else (2, make_q4_0_raw)
+        oa, ob = oracle.QuantizedWeight.from_gguf(mk(K, N, 1), t, K, N), oracle.QuantizedWeight.from_gguf(mk(K, N, 2), t, K, N)
+    x = r.standard_normal(K).astype(np.float32)
+    bias = r.standard_normal(N).astype(np.float32)
+    ones = np.ones(N, np.float32)
+    # buffers: 0 x, 1 gate, 2 up, 3 chain output, 4 product, 5 ones, 6 bias
+    if chain == "silu":      # gate * recip(exp(-gate) + 1)
+        steps = [("neg", False, 0, 0), ("exp", False, 0, 0), ("add", False, 5, 0), ("recip", False, 0, 0), ("mul", True, 1, 0)]
+    else:                    # relu(gate + bias) * up-in-chain, secondaries from an external buffer and from the second matvec
+        steps = [("add", False, 6, 0), ("relu", False, 0, 0), ("mul", False, 2, 0)]
+    ops = [DeviceOp.qmatmul(1, 0, 0, 1, N, K), DeviceOp.qmatmul(2, 0, 1, 1, N, K),
+           DeviceOp.fused_elementwise(steps, N, 3, 1), DeviceOp.elementwise("mul", 4, 3, 2, N)]
+    prog = DeviceProgram(ops, [K, N, N, N, N, N, N], [ProgramIO(0, x), ProgramIO(5, ones), ProgramIO(6, bias)],
+                         [QuantizedWeightUpload(oa.data, oa.scales, K, N, 32), QuantizedWeightUpload(ob.data, ob.scales, K, N, 32)])
+    want = [np.zeros(N, np.float32) for _ in range(4)]
+    oracle.run_program(prog, [], [ProgramIO(1 + i, want[i]) for i in range(4)])
+
+    def run(be):
+        h = be.compile_program(prog)
+        assert h is not None
+        got = [np.zeros(N, np.float32) for _ in range(4)]
+        for _ in range(2):   # twice: the split-K arrival counters must come back to zero
+            be.execute_program(h, [], [ProgramIO(1 + i, got[i]) for i in range(4)])
+        n_kernels = be.program_stats(h)["kernels"]   # counted when the step's graph is captured
+        be.free_program(h)
+        return got, n_kernels
+
+    got, n_kernels = run(cuda_backend)
+    assert n_kernels == 1
+    for g, w_ in zip(got, want):
+        assert rel_err(g, w_) < 1e-5
+    import os
+    os.environ["ZG_CUDA_GEMV_PAIR"] = "0"
+    try:
+        plain = CudaBackend(0)
+    finally:
+        del os.environ["ZG_CUDA_GEMV_PAIR"]
+    try:
+        got0, n0 = run(plain)
+    finally:
+        plain.close()
+    assert n0 == 2
+    for g, g0 in zip(got, got0):
+        assert np.array_equal(g.view(np.uint32), g0.view(np.uint32))

@@ -86,6 +86,7 @@ struct ZgCudaProgram {
         std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
         bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false, decode = false;
         uint32_t kvq = 0, kvq_max_warps = 0, kvq_seq_q = 0, kvq_splits = 1; size_t kvq_part_off = 0, kvq_cnt_off = 0;
+        bool gemv_pair = false; ZgGemvEpilogue epi;   // gate | up matvec pair + activation epilogue (qgemv.cu qgemv_pair_kernel)
         int attn_blk = -1; uint32_t ab_splits = 1; size_t ab_part_off = 0, ab_cnt_off = 0;   // fused attention block of one layer   // 1: batch of cache stores, 2: batch of cache-backed attentions
         ZgNormMacro nm = {};
         uint32_t attn_splits = 1; size_t attn_part_off = 0, attn_cnt_off = 0;   // split-KV decode attention scratch (per unit)
@@ -145,6 +146,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
+    if (const char* e = getenv("ZG_CUDA_GEMV_PAIR")) ctx->gemv_pair = (e[0] != '0');   // 0: gate | up as a plain batch, the activation chain as its own launch
     if (const char* e = getenv("ZG_CUDA_ATTN_LAYER")) ctx->attn_layer = (e[0] != '0');   // 0: rope / cache stores / attention as separate launches
     if (const char* e = getenv("ZG_CUDA_DECODE")) ctx->decode_fused = (e[0] != '0');   // 0: never use the fused decode kernel
     if (!zg_qgemv_init(ctx) || !zg_qgemm_init(ctx) || !zg_decode_init(ctx)) { cudaStreamDestroy(ctx->stream); delete ctx; return nullptr; }
@@ -1160,6 +1162,40 @@ static bool build_schedule(ZgCudaProgram* p) {
     std::vector<ZgGemvPrologue> pro_of(ni);      // per consumer item
     std::vector<int> absorbed_by(ni, -1);        // macro item -> first consumer item
     std::vector<int> macro_of(ni, -1);           // consumer item -> macro item
+    // ── gate | up pair + activation epilogue: qmatmul(gate), qmatmul(up), fused_elementwise(steps(gate)), mul(. * up) of a
+    //    single-token program become ONE launch (the pair kernel evaluates the chain on the finished sums) ──
+    std::vector<char> pair_lead(ni, 0), pair_absorbed(ni, 0);
+    std::vector<ZgGemvEpilogue> epi_of(ni);
+    if (p->ctx->fuse && p->ctx->gemv_pair && !p->ctx->gemv_fuse) {
+        for (size_t k = 0; k + 2 < ni; k++) {
+            const ZgItem &ia = items[k], &ib = items[k + 1], &ie = items[k + 2];
+            if (ia.kind != ITEM_OP || ib.kind != ITEM_OP || ie.kind != ITEM_EWMUL) continue;
+            const ZgOp &oa = p->ops[ia.first], &ob = p->ops[ib.first];
+            if (oa.tag != ZG_OP_QMATMUL || ob.tag != ZG_OP_QMATMUL) continue;
+            const auto& qa = oa.u.qmatmul; const auto& qb = ob.u.qmatmul;
+            const ZgCudaQWeight *wa = p->qweights[qa.weight_idx], *wb = p->qweights[qb.weight_idx];
+            if (qa.M != 1 || qb.M != 1 || qa.input != qb.input || qa.input_offset != qb.input_offset || qa.dst_offset || qb.dst_offset || qa.dst == qb.dst ||
+                wa->fmt == ZG_QFMT_GENERIC || wa->fmt != wb->fmt || wa->K != wb->K || wa->N != wb->N) continue;
+            const ZgEwMulMacro& em = ewmul_of[k + 2];
+            if (em.src != p->buffers[qa.dst] || em.other != p->buffers[qb.dst] || em.n != wa->N || em.n_steps > 6 ||
+                em.mid == p->buffers[qa.input] || em.dst == p->buffers[qa.input]) continue;   // other CTAs still read the input vector
+            ZgGemvEpilogue ep;
+            ep.n_steps = em.n_steps; ep.o_mid = em.mid; ep.o_dst = em.dst;
+            const auto& st = p->steps[ie.first];
+            bool ok = true;
+            for (uint32_t q = 0; q < em.n_steps && ok; q++) {
+                ep.steps[q].op = st[q].op; ep.steps[q].is_swapped = st[q].is_swapped; ep.steps[q].sec = nullptr; ep.sec_kind[q] = 0;
+                if (st[q].op == ZG_EW_ADD || st[q].op == ZG_EW_MUL) {
+                    if (st[q].secondary_buf == qa.dst) { ep.sec_kind[q] = 1; ok = st[q].secondary_offset == 0; }
+                    else if (st[q].secondary_buf == qb.dst) { ep.sec_kind[q] = 2; ok = st[q].secondary_offset == 0; }
+                    else { ep.steps[q].sec = p->buffers[st[q].secondary_buf] + st[q].secondary_offset; ok = (size_t)st[q].secondary_offset + em.n <= p->buffer_elems[st[q].secondary_buf]; }
+                }
+            }
+            if (!ok) continue;
+            pair_lead[k] = 1; pair_absorbed[k + 1] = 1; pair_absorbed[k + 2] = 1; epi_of[k] = ep;
+            k += 2;
+        }
+    }
     if (p->ctx->fuse && p->ctx->gemv_fuse) {
         for (size_t k = 0; k + 1 < ni; k++) {
             const ZgItem& it = items[k];
@@ -1214,8 +1250,11 @@ static bool build_schedule(ZgCudaProgram* p) {
     {
         std::vector<ZgRange> tmp;
         for (size_t k = 0; k < ni; k++) {
-            if (absorbed_by[k] >= 0) continue;
+            if (absorbed_by[k] >= 0 || pair_absorbed[k]) continue;
             for (uint32_t j = 0; j < items[k].count; j++) { op_ranges(p, p->ops[items[k].first + j], tmp); item_rng[k].insert(item_rng[k].end(), tmp.begin(), tmp.end()); }
+            if (pair_lead[k])   // the launch also runs the up matvec and the activation chain
+                for (size_t k2 = k + 1; k2 <= k + 2; k2++)
+                    for (uint32_t j = 0; j < items[k2].count; j++) { op_ranges(p, p->ops[items[k2].first + j], tmp); item_rng[k].insert(item_rng[k].end(), tmp.begin(), tmp.end()); }
             if (macro_of[k] < 0) continue;
             const ZgItem& mi = items[macro_of[k]];
             const uint32_t in_buf = p->ops[items[k].first].u.qmatmul.input;
@@ -1238,7 +1277,7 @@ static bool build_schedule(ZgCudaProgram* p) {
     std::vector<std::vector<Access>> acc(p->buffers.size() + 2);   // + the virtual GEMM-scratch and communicator buffers
     std::vector<int> level(ni, 0);
     for (size_t k = 0; k < ni; k++) {
-        if (absorbed_by[k] >= 0) { level[k] = -1; continue; }
+        if (absorbed_by[k] >= 0 || pair_absorbed[k]) { level[k] = -1; continue; }
         const std::vector<ZgRange>& rng = item_rng[k];
         int lvl = 0;
         for (const ZgRange& r : rng)
@@ -1252,7 +1291,7 @@ static bool build_schedule(ZgCudaProgram* p) {
         }
     }
     std::vector<uint32_t> order;
-    for (size_t k = 0; k < ni; k++) if (absorbed_by[k] < 0) order.push_back((uint32_t)k);
+    for (size_t k = 0; k < ni; k++) if (absorbed_by[k] < 0 && !pair_absorbed[k]) order.push_back((uint32_t)k);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return level[a] < level[b]; });
     const size_t no = order.size();
     p->units.clear();
@@ -1346,6 +1385,14 @@ static bool build_schedule(ZgCudaProgram* p) {
             const ZgItem& it = items[order[k]];
             if (in_chain(it)) continue;   // chained above
             const ZgOp& op = p->ops[it.first];
+            if (pair_lead[order[k]]) {
+                ZgCudaProgram::Unit u; u.gemv_pair = true; u.epi = epi_of[order[k]];
+                u.entry_ops.push_back(it.first); u.entry_ops.push_back(items[order[k] + 1].first);
+                for (size_t k2 = order[k]; k2 <= (size_t)order[k] + 2; k2++)
+                    for (uint32_t j = 0; j < items[k2].count; j++) u.ops.push_back(items[k2].first + j);
+                u.ranges = item_rng[order[k]];
+                p->units.push_back(u); continue;
+            }
             if (it.kind == ITEM_OP && op.tag == ZG_OP_QMATMUL && op.u.qmatmul.M >= 1 && op.u.qmatmul.M <= 8 &&
                 (p->ctx->gemv_batch > 1 || pro_of[order[k]].kind != 0) && p->qweights[op.u.qmatmul.weight_idx]->fmt != ZG_QFMT_GENERIC) {
                 // independent matvecs of one shape / format / row count (and prologue kind) share a launch (q|k|v, gate|up)
@@ -1601,6 +1648,15 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.decode) { p->dec.plan.dyn = p->d_dyn; return zg_decode_launch(p->ctx, p->dec, st); }
+    if (u.gemv_pair) {
+        const uint32_t ia = u.entry_ops[0], ib = u.entry_ops[1];
+        const auto& qa = p->ops[ia].u.qmatmul; const auto& qb = p->ops[ib].u.qmatmul;
+        ZgGemvWs va = p->ws, vb = p->ws;
+        if (va.partials) { va.partials += p->ws_part_off[ia]; va.partials_elems -= p->ws_part_off[ia]; vb.partials += p->ws_part_off[ib]; vb.partials_elems -= p->ws_part_off[ib]; }
+        if (va.counters) { va.counters += p->ws_cnt_off[ia]; va.counters_n -= p->ws_cnt_off[ia]; vb.counters += p->ws_cnt_off[ib]; vb.counters_n -= p->ws_cnt_off[ib]; }
+        return zg_qgemv_launch_pair(p->ctx, p->qweights[qa.weight_idx], p->qweights[qb.weight_idx], p->buffers[qa.input] + qa.input_offset,
+                                    p->buffers[qa.dst], p->buffers[qb.dst], &va, &vb, u.epi, st);
+    }
     if (u.attn_blk >= 0) {
         const ZgAttnBlock& B = p->attn_blocks[u.attn_blk];
         return zg_launch_attention_layer(p->d_attn_blocks + u.attn_blk, B.n_heads, B.d_head, u.ab_splits, p->d_dyn, p->d_attn_blk_part + u.ab_part_off,

@@ -965,8 +965,19 @@ k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restri
     const uint32_t f4 = dh4 / lpp;
     for (uint32_t s0 = kv_lo + warp * pw; s0 < kv_hi; s0 += kAttnFastWarps * pw) {
         const uint32_t s = s0 + pos_in_warp;
+        const uint32_t nj = min(pw, kv_hi - s0);
+        // every global load of the step is issued before the first one is used: mask, the first eight V rows (all of them when
+        // the range is spread over the 16 warps), then K — one memory round trip per step instead of two
         float mask_add = -INFINITY;
         if (s < kv_hi) mask_add = B.has_mask ? B.mask[(size_t)B.mask_off + (size_t)s * B.mask_rs] : 0.0f;
+        float vv[8][NI];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const uint32_t sj = s0 + jj;
+            const float* vr = (sj == s_new) ? sv : vbase + (size_t)sj * B.v_cs;
+#pragma unroll
+            for (int i = 0; i < NI; i++) vv[jj][i] = ((uint32_t)jj < nj && lane + 32 * i < dh) ? vr[lane + 32 * i] : 0.0f;
+        }
         bool ok = isfinite(mask_add);
         float score = -INFINITY;
         {
@@ -1023,10 +1034,14 @@ k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restri
         m_val = new_m;
 #pragma unroll
         for (int i = 0; i < NI; i++) acc[i] *= alpha;
-        const uint32_t nj = min(pw, kv_hi - s0);
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            const float wj = __shfl_sync(0xffffffffu, wgt, (jj * lpp) & 31);
+#pragma unroll
+            for (int i = 0; i < NI; i++) acc[i] = fmaf(wj, vv[jj][i], acc[i]);   // rows past nj were loaded as zeros
+        }
 #pragma unroll 1
-        for (uint32_t j0 = 0; j0 < nj; j0 += 8) {
-            float vv[8][NI];
+        for (uint32_t j0 = 8; j0 < nj; j0 += 8) {
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
                 const bool in = j0 + jj < nj;

@@ -503,6 +503,277 @@ qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
     ZG_TRACE_MARK(2)
 }
 
+// ── gate | up pair with the activation epilogue (M == 1) ─────────────────────────────────────────────────────────────
+// The decode matvec above, specialised to one activation row, walking its column groups twice per group — first the
+// `a` weight (gate), then the `b` weight (up) — through the same TMA ring and the same staged activations.  When the second
+// sum of a column group is final (S == 1: right away; S > 1: in the CTA that arrives last for `b` — every CTA passes `a`
+// before `b`, so `a`'s final values are visible to it), the epilogue evaluates mid = steps(gate), dst = mid * up.
+struct QGemvPair { QGemvParams a, b; ZgGemvEpilogue epi; };
+struct QGemvPairBatch { QGemvPair p[2]; };
+
+__device__ __forceinline__ float epi_unary(uint32_t op, float v) {
+    switch (op) {
+        case ZG_EW_NEG: return -v;
+        case ZG_EW_ABS: return fabsf(v);
+        case ZG_EW_RELU: return fmaxf(v, 0.0f);
+        case ZG_EW_SQRT: return sqrtf(v);
+        case ZG_EW_RECIP: return 1.0f / v;
+        case ZG_EW_EXP: return expf(v);
+        case ZG_EW_LOG: return logf(v);
+        default: return v;
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 3)
+qgemv_pair_kernel(const __grid_constant__ QGemvPairBatch bt) {
+    const QGemvPair& pp = bt.p[blockIdx.y];
+    const QGemvParams& pa = pp.a;
+    const QGemvParams& pb = pp.b;
+    constexpr bool kI4 = (FMT == ZG_QFMT_I4_F16);
+    constexpr bool kF32 = (FMT == ZG_QFMT_I8_F32);
+    constexpr uint32_t QB = kI4 ? 512u : 1024u;
+    constexpr uint32_t SB = kF32 ? 32u : 16u;
+    constexpr uint32_t RB = QB + 4 * SB;
+    constexpr uint32_t G = kI4 ? 4u : 2u;
+
+    __shared__ float part[2][kMaxWarps][ZG_TN];
+    __shared__ uint32_t s_last;
+    extern __shared__ __align__(128) uint8_t dsm[];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const uint32_t g = lane >> 2, t = lane & 3, j = g & 3;
+    const uint32_t split = blockIdx.x % pa.S, grp = blockIdx.x / pa.S;
+    const uint32_t nb_begin = grp * pa.P;
+    const uint32_t nb_end = min(nb_begin + pa.P, pa.n_nb);
+    const uint32_t ks = (uint32_t)(((uint64_t)split * pa.n_kc) / pa.S);
+    const uint32_t ke = (uint32_t)(((uint64_t)(split + 1) * pa.n_kc) / pa.S);
+    const uint32_t k0 = ks + (warp * (ke - ks)) / W, k1 = ks + ((warp + 1) * (ke - ks)) / W;
+    const uint32_t L = k1 - k0;
+    const uint32_t NS = pa.NS;
+    const uint32_t n_chunk = (L + G - 1) / G;
+    const uint32_t n_virtual = 2 * (nb_end - nb_begin);          // (column group, weight) pairs this CTA walks: a, b, a, b, ...
+    const uint32_t total_chunks = n_chunk * n_virtual;
+    constexpr uint32_t slot_bytes = G * RB;
+
+    const uint32_t dsm_u32 = smem_u32(dsm);
+    const uint32_t xs_bytes = W * pa.xs_stride * 4, ring_bytes = W * NS * slot_bytes, plane_bytes = G * kPlaneRow;
+    float* xs_w = reinterpret_cast<float*>(dsm) + (size_t)warp * pa.xs_stride;
+    const uint32_t xs_u32 = dsm_u32 + warp * pa.xs_stride * 4;
+    const uint32_t ring = dsm_u32 + xs_bytes + warp * NS * slot_bytes;
+    const uint32_t planes = dsm_u32 + xs_bytes + ring_bytes + warp * plane_bytes;
+    const uint32_t bars = dsm_u32 + xs_bytes + ring_bytes + W * plane_bytes + warp * NS * 8;
+
+    ZG_TRACE_BEGIN(10)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    uint32_t pf_c = 0, pf_v = 0, pf_slot = 0, pf_left = total_chunks;
+    auto issue_chunk = [&]() {   // lane 0 only
+        const uint8_t* base = ((pf_v & 1) ? pb.recs : pa.recs) + ((size_t)(nb_begin + (pf_v >> 1)) * pa.n_kc + k0) * RB;
+        const uint32_t cnt = min(G, L - pf_c * G);
+        const uint32_t bar = bars + pf_slot * 8;
+        mbar_expect_tx(bar, cnt * RB);
+        bulk_g2s(ring + pf_slot * slot_bytes, base + (size_t)pf_c * G * RB, cnt * RB, bar);
+        pf_left--;
+        if (++pf_c == n_chunk) { pf_c = 0; pf_v++; }
+        if (++pf_slot == NS) pf_slot = 0;
+    };
+    if (lane == 0) {
+        for (uint32_t s = 0; s < NS; s++) mbar_init(bars + s * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (uint32_t i = 0; i < NS && pf_left; i++) issue_chunk();
+    }
+    for (uint32_t i = lane; i < G * 8; i += 32) {
+        const uint32_t rm = i >> 3, w4 = i & 7;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(planes + rm * kPlaneRow + 96 + w4 * 4), "r"(0x01010101u) : "memory");
+    }
+    __syncwarp();
+    float sm_prev = __ldg(pa.smax + nb_begin);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
+
+    float xm = 0.0f;
+    {
+        const uint32_t kb = k0 * ZG_KR;
+        const float rsm = 1.0f / sm_prev;
+        const float* xr = pa.x + kb + lane;
+        float* xd = xs_w + lane;
+        float v[kLcap];
+        float mx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < (int)kLcap; i++) {
+            v[i] = ((uint32_t)i < L && kb + lane + 32 * i < pa.K) ? xr[32 * i] : 0.0f;
+            const float aa = fabsf(v[i]);
+            mx = (aa <= 3.0e38f) ? fmaxf(mx, aa) : INFINITY;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        xm = mx;
+        const float f = (mx <= 3.0e38f && mx >= 1.0e-30f) ? (0.499f / mx) * rsm : 0.0f;
+#pragma unroll
+        for (int i = 0; i < (int)kLcap; i++)
+            if ((uint32_t)i < L) xd[32 * i] = v[i] * f;
+        __syncwarp();
+    }
+    const uint32_t brow = planes + j * 32 + 4 * t;
+    const uint32_t q_off = lane * 16;
+    const uint32_t sc_off = QB + (kF32 ? 4u : 2u) * (8 * ((lane & 15) >> 2) + 4 * (lane >> 4) + (lane & 3));
+
+    uint32_t buf = 0, slot = 0, parity = 0, slot_u32 = ring, bar_u32 = bars;
+    float v_a = 0.0f;   // tid < 32: the finished `a` sum of the current column group (S == 1)
+
+    for (uint32_t vi = 0; vi < n_virtual; vi++) {
+        const uint32_t nb = nb_begin + (vi >> 1);
+        const bool is_b = (vi & 1) != 0;
+        const QGemvParams& cur = is_b ? pb : pa;
+        const float sm = __ldg(cur.smax + nb);
+        if (sm != sm_prev) {
+            const float ratio = sm_prev / sm;
+            float* xd = xs_w + lane;
+            for (uint32_t i = 0; i < L; i++) xd[32 * i] *= ratio;
+            __syncwarp();
+            sm_prev = sm;
+        }
+        int acc[2][4];
+        uint32_t dsum = 0;
+#pragma unroll
+        for (int ct = 0; ct < 2; ct++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) acc[ct][i] = 0;
+        uint32_t xa = xs_u32 + lane * 4;
+        for (uint32_t c = 0; c < n_chunk; c++, xa += G * ZG_KR * 4) {
+            const uint32_t cnt = min(G, L - c * G);
+            mbar_wait(bar_u32, parity);
+#pragma unroll
+            for (uint32_t r = 0; r < G; r++) {
+                if (r < cnt) {
+                    float sc;
+                    if constexpr (kF32) {
+                        sc = __uint_as_float(lds32(slot_u32 + sc_off + r * RB));
+                    } else {
+                        unsigned short h;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(slot_u32 + sc_off + r * RB));
+                        sc = __half2float(__ushort_as_half(h));
+                    }
+                    const uint32_t F = __float_as_uint(fmaf(sc, __uint_as_float(lds32(xa + r * ZG_KR * 4)), 1.5f));
+                    const uint32_t pa2 = planes + lane + r * kPlaneRow;
+                    sts8(pa2, F);
+                    sts8(pa2 + 32, F >> 8);
+                    sts8(pa2 + 64, F >> 16);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (uint32_t r = 0; r < G; r++) {
+                if (r < cnt) {
+                    const uint32_t qa = slot_u32 + q_off + r * RB;
+                    const uint32_t b0 = lds32(brow + r * kPlaneRow), b1 = lds32(brow + r * kPlaneRow + 16);
+                    if constexpr (!kI4) {
+                        const uint4 q0 = lds128(qa), q1 = lds128(qa + 512);
+                        imma_s8u8(acc[0], q0.x, q0.y, q0.z, q0.w, b0, b1);
+                        imma_s8u8(acc[1], q1.x, q1.y, q1.z, q1.w, b0, b1);
+                    } else {
+                        const uint4 q0 = lds128(qa);
+                        dsum = __dp4a(b0, 0x01010101u, __dp4a(b1, 0x01010101u, dsum));
+                        imma_u8u8(acc[0], q0.x, q0.x & 0x0F0F0F0Fu, q0.y, q0.y & 0x0F0F0F0Fu, b0, b1);
+                        imma_u8u8(acc[1], q0.z, q0.z & 0x0F0F0F0Fu, q0.w, q0.w & 0x0F0F0F0Fu, b0, b1);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && pf_left) issue_chunk();
+            slot_u32 += slot_bytes; bar_u32 += 8;
+            if (++slot == NS) { slot = 0; slot_u32 = ring; bar_u32 = bars; parity ^= 1; }
+        }
+        {   // flush: integer sums -> this warp's float partial
+            const uint32_t kcnt = L * ZG_KR;
+            float* dstp = &part[buf][warp][0];
+            const float esc = (xm <= 3.0e38f) ? ((xm >= 1.0e-30f) ? (xm * (2.004008016f * 1.1920928955078125e-07f)) * sm : 0.0f)
+                                              : __int_as_float(0x7fc00000);
+            long long dS = 0;
+            if constexpr (kI4) {
+                uint32_t ds = dsum;
+                ds += __shfl_xor_sync(0xffffffffu, ds, 1);
+                ds += __shfl_xor_sync(0xffffffffu, ds, 2);
+                const uint32_t D0 = __shfl_sync(0xffffffffu, ds, 0);
+                const uint32_t D1 = __shfl_sync(0xffffffffu, ds, 4);
+                const uint32_t D2 = __shfl_sync(0xffffffffu, ds, 8);
+                dS = (long long)D0 + ((long long)D1 << 8) + ((long long)D2 << 16);
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ct++) {
+                int pz[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) pz[i] = __shfl_xor_sync(0xffffffffu, acc[ct][i], 1);
+                if (t == 0) {
+                    const int* o = acc[ct];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        long long T;
+                        if constexpr (!kI4) {
+                            T = (long long)o[2 * h] + ((long long)o[2 * h + 1] << 8) + ((long long)pz[2 * h] << 16) - 12582912LL * (long long)pz[2 * h + 1];
+                        } else {
+                            long long u0, u1, u2, us;
+                            if (h == 0) { u0 = o[2]; u1 = o[3]; u2 = pz[2]; us = pz[3]; }
+                            else { u0 = (o[0] - o[2]) >> 4; u1 = (o[1] - o[3]) >> 4; u2 = (pz[0] - pz[2]) >> 4; us = (pz[1] - pz[3]) >> 4; }
+                            T = u0 + (u1 << 8) + (u2 << 16) - 8 * dS - 12582912LL * (us - 8LL * (long long)kcnt);
+                        }
+                        dstp[ct * 16 + g + 8 * h] = __ll2float_rn(T) * esc;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        float fin = 0.0f;
+        bool have = false;
+        const uint32_t n = nb * ZG_TN + tid;
+        if (tid < ZG_TN) {
+            float v = 0.0f;
+            for (uint32_t w = 0; w < W; w++) v += part[buf][w][tid];
+            if (cur.S == 1) { fin = v; have = true; }
+            else cur.partials[(((size_t)nb * cur.S + split) * 2) * ZG_TN + tid] = v;
+        }
+        if (cur.S > 1) {
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t old;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(cur.counters + nb) : "memory");
+                const uint32_t last = (old == cur.S - 1) ? 1u : 0u;
+                if (last) cur.counters[nb] = 0u;
+                s_last = last;
+            }
+            __syncthreads();
+            if (s_last && tid < ZG_TN) {
+                float v = 0.0f;
+                for (uint32_t s2 = 0; s2 < cur.S; s2++) v += __ldcg(cur.partials + (((size_t)nb * cur.S + s2) * 2) * ZG_TN + tid);
+                fin = v; have = true;
+            }
+        }
+        if (have) {
+            cur.out[n] = fin;
+            if (!is_b) v_a = fin;
+            else {
+                const float gt = (pa.S == 1) ? v_a : __ldcg(pa.out + n), up = fin;
+                float v = gt;
+                for (uint32_t st = 0; st < pp.epi.n_steps; st++) {
+                    const uint32_t sop = pp.epi.steps[st].op, sw = pp.epi.steps[st].is_swapped;
+                    if (sop == ZG_EW_ADD || sop == ZG_EW_MUL) {
+                        const uint32_t kd = pp.epi.sec_kind[st];
+                        const float o2 = kd == 1 ? gt : (kd == 2 ? up : pp.epi.steps[st].sec[n]);
+                        if (sop == ZG_EW_ADD) v = sw ? __fadd_rn(o2, v) : __fadd_rn(v, o2);
+                        else v = sw ? __fmul_rn(o2, v) : __fmul_rn(v, o2);
+                    } else v = epi_unary(sop, v);
+                }
+                pp.epi.o_mid[n] = v;
+                pp.epi.o_dst[n] = __fmul_rn(v, up);
+            }
+        }
+        buf ^= 1;
+    }
+    ZG_TRACE_MARK(2)
+}
+
 // Generic block size / ragged N: one thread per output column, exact scale lookup
 // per element ((k*N+n)/bs) like src/backend/reference.zig:540-563.
 __global__ void qmatmul_generic_kernel(const int8_t* __restrict__ data, const float* __restrict__ scales,
@@ -766,4 +1037,70 @@ bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* 
         if (!launch_batch_rows(ctx, count, ws_w, xin, xout, std::min(rpp, M - m0), in_rs, out_rs, ws, st, nullptr)) return false;
     }
     return true;
+}
+
+
+// gate | up pair with the activation epilogue: see qgemv_pair_kernel.  M == 1, identical fast-format shapes, one input vector.
+template <int FMT>
+static bool launch_pair_fmt(const ZgGemvPlan& plan, const QGemvPairBatch& bt, cudaStream_t st, bool pdl) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(qgemv_pair_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { zg_set_error("cudaFuncSetAttribute(qgemv pair) failed"); return false; }
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid, 1);
+    cfg.blockDim = dim3(plan.threads);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_pair_kernel<FMT>, bt);
+    ZG_COUNT_LAUNCH();
+    if (e != cudaSuccess) { zg_set_error("qgemv pair launch failed: %s", cudaGetErrorString(e)); return false; }
+    return true;
+}
+
+bool zg_qgemv_launch_pair(ZgCudaCtx* ctx, const ZgCudaQWeight* wa, const ZgCudaQWeight* wb, const float* d_in, float* d_out_a, float* d_out_b,
+                          const ZgGemvWs* ws_a, const ZgGemvWs* ws_b, const ZgGemvEpilogue& epi, cudaStream_t st) {
+    if (wa->fmt != wb->fmt || wa->K != wb->K || wa->N != wb->N || wa->fmt == ZG_QFMT_GENERIC) { zg_set_error("internal: mismatched matvec pair"); return false; }
+    // the pair is planned like a batch of two: same column groups and k-splits, each CTA walks both weights
+    ZgGemvPlan plan = zg_qgemv_plan(ctx, wa, 1, 2);
+    {   // each warp requests twice as many chunks: the ring depth may use them
+        const uint32_t chunks = ((plan.lcap + plan.G - 1) / plan.G) * plan.P * 2;
+        const uint32_t want = ctx->tune_u ? (uint32_t)ctx->tune_u : 2;
+        if (plan.NS < want && plan.NS < chunks) {
+            plan.NS = std::min(want, chunks);
+            const uint32_t warps = kThreads / 32;
+            plan.smem_bytes = warps * plan.xs_stride * 4 + warps * plan.NS * plan.G * wa->rec_bytes + warps * plan.G * kPlaneRow + warps * plan.NS * 8;
+        }
+    }
+    QGemvPairBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    const ZgCudaQWeight* ws_w[2] = {wa, wb};
+    float* outs[2] = {d_out_a, d_out_b};
+    const ZgGemvWs* wss[2] = {ws_a, ws_b};
+    for (int i = 0; i < 2; i++) {
+        QGemvParams& q = i ? bt.p[0].b : bt.p[0].a;
+        const ZgCudaQWeight* w = ws_w[i];
+        size_t pe = 0, nc = 0;
+        zg_qgemv_ws_need(ctx, w, 1, &pe, &nc);
+        if (plan.S > 1 && (!wss[i] || wss[i]->partials_elems < pe || wss[i]->counters_n < nc)) { zg_set_error("internal: pair split workspace too small"); return false; }
+        q.recs = w->recs; q.smax = w->smax; q.n_kc = w->n_kc; q.n_nb = w->n_nb;
+        q.K = (uint32_t)w->K; q.N = (uint32_t)w->N; q.M = 1;
+        q.x = d_in; q.x_rs = (uint32_t)w->K; q.xs_stride = plan.xs_stride;
+        q.out = outs[i]; q.out_rs = (uint32_t)w->N;
+        q.P = plan.P; q.S = plan.S; q.NS = plan.NS;
+        q.partials = wss[i] ? wss[i]->partials : nullptr; q.counters = wss[i] ? wss[i]->counters : nullptr;
+    }
+    bt.p[0].epi = epi;
+    switch (wa->fmt) {
+        case ZG_QFMT_I8_F32: return launch_pair_fmt<ZG_QFMT_I8_F32>(plan, bt, st, ctx->pdl);
+        case ZG_QFMT_I8_F16: return launch_pair_fmt<ZG_QFMT_I8_F16>(plan, bt, st, ctx->pdl);
+        case ZG_QFMT_I4_F16: return launch_pair_fmt<ZG_QFMT_I4_F16>(plan, bt, st, ctx->pdl);
+        default: return false;
+    }
 }

@@ -112,6 +112,7 @@ struct ZgCudaCtx {
     int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
+    bool gemv_pair = true;       // single-token programs: gate | up matvecs + SiLU * up chain in ONE launch (ZG_CUDA_GEMV_PAIR=0: off)
     bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
     bool fuse = true;            // evaluate the lowering's fixed op patterns (norm+gamma, SiLU*up, attention+store) in one pass
@@ -159,6 +160,18 @@ struct ZgGemvPrologue {
     float* o_sum = nullptr; float* o_mid = nullptr; float* o_grep = nullptr; float* o_x = nullptr;   // o_mid: bare (1) / mid (2)
     ZgDevStepC steps[6] = {};
 };
+// Epilogue of a gate | up matvec PAIR (M == 1): both matvecs run in one launch, every CTA computes the same column groups of
+// both weights, and the activation chain that consumes them — fused_elementwise(mid = steps(gate)) ; mul(dst = mid * up), the
+// SiLU * up of src/nn.zig:38-44 — is evaluated on the finished sums: one launch less on the decode critical path
+// (src/backend/metal.zig:2533 fuses the same pair).  Every DeviceOp's buffer is still written.
+struct ZgGemvEpilogue {
+    uint32_t n_steps = 0, _pad = 0;
+    ZgDevStepC steps[6] = {};
+    uint32_t sec_kind[6] = {};     // 0: steps[i].sec[n] ; 1: the gate value ; 2: the up value
+    float* o_mid = nullptr; float* o_dst = nullptr;
+};
+bool zg_qgemv_launch_pair(ZgCudaCtx* ctx, const ZgCudaQWeight* wa, const ZgCudaQWeight* wb, const float* d_in, float* d_out_a, float* d_out_b,
+                          const ZgGemvWs* ws_a, const ZgGemvWs* ws_b, const ZgGemvEpilogue& epi, cudaStream_t st);
 constexpr uint32_t kZgGemvBatch = 8;   // independent same-shape matvecs of one dependency level per launch
 bool zg_qgemv_launch_batch(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeight* const* w, const float* const* d_in,
                            float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
