@@ -15,7 +15,7 @@ for i in range(4):
     sess.execute_at([1], 512 + i)
 be.sync()
 t0 = time.perf_counter()
-n = 200
+n = int(os.environ.get("N_REPLAY", "200"))
 for _ in range(n):
     be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
 be.sync()

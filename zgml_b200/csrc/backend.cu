@@ -1176,6 +1176,7 @@ static bool build_schedule(ZgCudaProgram* p) {
             const ZgCudaQWeight *wa = p->qweights[qa.weight_idx], *wb = p->qweights[qb.weight_idx];
             if (qa.M != 1 || qb.M != 1 || qa.input != qb.input || qa.input_offset != qb.input_offset || qa.dst_offset || qb.dst_offset || qa.dst == qb.dst ||
                 wa->fmt == ZG_QFMT_GENERIC || wa->fmt != wb->fmt || wa->K != wb->K || wa->N != wb->N) continue;
+            if (zg_qgemv_stream_plan(p->ctx, wa, 2).use) continue;   // large pairs: the streamed batch + a chain launch is faster than the pair kernel
             const ZgEwMulMacro& em = ewmul_of[k + 2];
             if (em.src != p->buffers[qa.dst] || em.other != p->buffers[qb.dst] || em.n != wa->N || em.n_steps > 6 ||
                 em.mid == p->buffers[qa.input] || em.dst == p->buffers[qa.input]) continue;   // other CTAs still read the input vector
@@ -1914,6 +1915,7 @@ extern "C" int zg_cuda_trace(ZgCudaCtx* ctx, int enable) {
     if (g_trace_buf) cudaMemset(g_trace_buf, 0, (1 + 3 * 16000) * 8);
     zg_trace_set_ops(enable ? g_trace_buf : nullptr);
     zg_trace_set_gemv(enable ? g_trace_buf : nullptr);
+    zg_trace_set_gemv_stream(enable ? g_trace_buf : nullptr);
     zg_trace_set_decode(enable ? g_trace_buf : nullptr);
     return 0;
 }

@@ -930,7 +930,7 @@ bool zg_qgemv_init(ZgCudaCtx* ctx) {
     if (ctx->tune_u < 2 || ctx->tune_u > 16) ctx->tune_u = 0;
     if (ctx->tune_g < 1 || ctx->tune_g > 16) ctx->tune_g = 0;
     // opt every instantiation into its dynamic shared memory once per context, outside any stream capture
-    return set_smem_attrs<ZG_QFMT_I8_F32>() && set_smem_attrs<ZG_QFMT_I8_F16>() && set_smem_attrs<ZG_QFMT_I4_F16>();
+    return set_smem_attrs<ZG_QFMT_I8_F32>() && set_smem_attrs<ZG_QFMT_I8_F16>() && set_smem_attrs<ZG_QFMT_I4_F16>() && zg_qgemv_stream_init(ctx);
 }
 
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
@@ -947,6 +947,13 @@ void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, 
         *partial_elems = (size_t)w->n_nb * S * (2 * mp) * ZG_TN;
         *counters = w->n_nb;
     }
+    if (M == 1)   // the streamed form cuts column groups at CTA boundaries: one partial slot per piece
+        for (uint32_t count = 1; count <= kZgGemvBatch; count++) {
+            const ZgGemvStreamPlan sp = zg_qgemv_stream_plan(ctx, w, count);
+            if (!sp.use) continue;
+            *partial_elems = std::max(*partial_elems, (size_t)w->n_nb * sp.slots * ZG_TN);
+            *counters = w->n_nb;
+        }
 }
 
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
@@ -984,6 +991,10 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
                               float* const* d_out, uint32_t M, const uint32_t* in_rs, const uint32_t* out_rs,
                               const ZgGemvWs* ws, cudaStream_t st, const ZgGemvPrologue* pro) {
     const ZgCudaQWeight* w0 = ws_w[0];
+    if (M == 1 && !(pro && pro[0].kind)) {
+        const ZgGemvStreamPlan sp = zg_qgemv_stream_plan(ctx, w0, count);
+        if (sp.use) return zg_qgemv_stream_launch(ctx, sp, count, ws_w, d_in, d_out, ws, st);
+    }
     ZgGemvPlan plan = zg_qgemv_plan(ctx, w0, M, count);
     QGemvBatch bt;
     memset(&bt, 0, sizeof(bt));

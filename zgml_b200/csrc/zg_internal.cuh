@@ -112,6 +112,7 @@ struct ZgCudaCtx {
     int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
+    int gemv_stream = 1, stream_min_chunks = 0, stream_early = 0, stream_ns = 0, stream_waves = 0, stream_chunks = 0;   // ZG_GEMV_STREAM / ZG_GEMV_STREAM_MIN (qgemv_stream.cu)
     bool gemv_pair = true;       // single-token programs: gate | up matvecs + SiLU * up chain in ONE launch (ZG_CUDA_GEMV_PAIR=0: off)
     bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
@@ -140,7 +141,14 @@ ZgCudaQWeight* zg_qweight_from_device_flat(ZgCudaCtx* ctx, const int8_t* d_data,
 struct ZgGemvPlan {
     uint32_t grid = 0, threads = 256, P = 1, S = 1, mp = 1, G = 2, NS = 3, lcap = 1, xs_stride = 32, smem_bytes = 0;
 };
-ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count = 1);   // count: matvecs sharing the launch
+ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count = 1);
+// qgemv_stream.cu: the large-launch form of the single-row matvec (one column group per warp, evenly sliced work)
+struct ZgGemvStreamPlan { bool use = false; uint32_t grid = 0, GB = 0, nq = 0, TQ = 0, Lq = 0, NS = 2, slots = 0, smem_bytes = 0; };
+ZgGemvStreamPlan zg_qgemv_stream_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t count);
+bool zg_qgemv_stream_init(ZgCudaCtx* ctx);
+bool zg_qgemv_stream_launch(ZgCudaCtx* ctx, const ZgGemvStreamPlan& pl, uint32_t count, const ZgCudaQWeight* const* w, const float* const* d_in,
+                            float* const* d_out, const ZgGemvWs* ws, cudaStream_t st);
+void zg_trace_set_gemv_stream(unsigned long long* d_buf);   // count: matvecs sharing the launch
 void zg_qgemv_ws_need(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, size_t* partial_elems,
                       size_t* counters);
 bool zg_qmatmul_launch(ZgCudaCtx* ctx, const ZgCudaQWeight* w, const float* d_in, float* d_out,
