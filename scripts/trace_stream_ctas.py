@@ -4,6 +4,8 @@ is the tail of a launch a few slow SMs, a second round of CTAs, or late starters
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import zgml_b200.backend as _zb
+_zb._LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libzgml_cuda_trace.so")   # built with -DZG_STREAM_TRACE_ALL (see scripts/README.md)
 from zgml_b200 import CudaBackend, DeviceOp, DeviceProgram, ProgramIO, QuantizedWeight
 from zgml_b200.backend import ResidentQuantizedWeight
 K, N, copies = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])

@@ -8,8 +8,8 @@
 // for 444 resident slots leaves SMs with 3 CTAs running 1.4x longer than SMs with 2.  Here
 //
 //  * the launch is ONE linear space: (matvec of the batch, block of 8 column groups, k) measured in chunks of G
-//    records; CTA c of the grid takes chunks [c T / grid, (c + 1) T / grid) — every CTA the same amount whatever the
-//    shape, grid = 3 CTAs per SM, no wave quantisation;
+//    records; CTA c takes chunks [c per, (c + 1) per) — every CTA the same amount whatever the shape, one round of
+//    CTAs, `per` snapped to a divisor / multiple of a column group's chunk count so that cuts fall on few, aligned places;
 //  * inside a CTA each warp owns ONE column group of the block and walks the CTA's whole k-range for it (a contiguous
 //    run of records -> one TMA bulk copy per chunk into the warp's ring): no cross-warp reduction, no CTA barrier in
 //    the streaming loop, one flush per (column group, segment) instead of one per 16 records;
@@ -45,9 +45,11 @@ struct QGemvSParams {
     uint32_t GB;       // blocks of 8 column groups per matvec
     uint32_t nq;       // chunks per column group = ceil(n_kc / G)
     uint32_t TQ;       // chunks of the whole launch = count * GB * nq
+    uint32_t per;      // chunks per CTA: CTA c takes [c * per, (c + 1) * per)
     uint32_t Lq;       // chunks per segment at most
     uint32_t NS;       // ring slots per warp
     uint32_t slots;    // partial slots per column group
+    uint32_t rev;      // debug: CTA c takes the range of CTA grid - 1 - c
     uint32_t early;    // 1: release the dependent launch at kernel entry (its CTAs then compete for this kernel's SM slots)
 };
 
@@ -112,8 +114,9 @@ qgemv_stream_kernel(const __grid_constant__ QGemvSParams P) {
     const uint32_t g = lane >> 2, t = lane & 3, j = g & 3;
     const uint32_t NS = P.NS;
     const uint32_t n_cta = gridDim.x;
-    const uint32_t q_lo = (uint32_t)(((uint64_t)blockIdx.x * P.TQ) / n_cta);
-    const uint32_t q_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1) * P.TQ) / n_cta);
+    const uint32_t cta = P.rev ? n_cta - 1 - blockIdx.x : blockIdx.x;   // rev: debug (is a slow CTA slow by index or by address?)
+    const uint32_t q_lo = cta * P.per;
+    const uint32_t q_hi = min(q_lo + P.per, P.TQ);
 
     const uint32_t dsm_u32 = smem_u32(dsm);
     float* xs = reinterpret_cast<float*>(dsm);
@@ -335,8 +338,7 @@ qgemv_stream_kernel(const __grid_constant__ QGemvSParams P) {
             uint32_t qq = gbl * P.nq, cntp = 0;
             const uint32_t end = qq + P.nq, q_mine = qq + qi;
             while (qq < end) {
-                const uint32_t cc = (uint32_t)((((uint64_t)qq + 1) * n_cta - 1) / P.TQ);
-                const uint32_t hi = min((uint32_t)(((uint64_t)(cc + 1) * P.TQ) / n_cta), end);
+                const uint32_t hi = min((qq / P.per + 1) * P.per, end);   // the CTA that holds chunk qq ends here
                 if (q_mine >= qq && q_mine < hi) ord = cntp + (q_mine - qq) / P.Lq;
                 cntp += (hi - qq + P.Lq - 1) / P.Lq;
                 qq = hi;
@@ -438,9 +440,9 @@ bool zg_qgemv_stream_init(ZgCudaCtx* ctx) {
     if (const char* e = getenv("ZG_GEMV_STREAM")) ctx->gemv_stream = atoi(e);            // 0: never, 1: when a launch has the work (default), 2: every M == 1 launch
     if (const char* e = getenv("ZG_GEMV_STREAM_EARLY")) ctx->stream_early = atoi(e);     // 1: griddepcontrol.launch_dependents at kernel entry (A/B)
     if (const char* e = getenv("ZG_GEMV_STREAM_NS")) ctx->stream_ns = atoi(e);           // ring slots per warp (2: three CTAs per SM; 4: two)
-    if (const char* e = getenv("ZG_GEMV_STREAM_WAVES")) ctx->stream_waves = atoi(e);
     if (const char* e = getenv("ZG_GEMV_STREAM_MIN")) ctx->stream_min_chunks = atoi(e);  // chunks in a launch below which the k-split kernel keeps it
-    if (const char* e = getenv("ZG_GEMV_STREAM_CHUNKS")) ctx->stream_chunks = atoi(e);   // chunks per warp and CTA aimed for
+    if (const char* e = getenv("ZG_GEMV_STREAM_ALIGN")) ctx->stream_align = atoi(e);     // 1: always snap, 2: never, 0: snap below two column groups per CTA
+    if (const char* e = getenv("ZG_GEMV_STREAM_CHUNKS")) ctx->stream_chunks = atoi(e);   // chunks per warp and CTA at least
     return set_stream_attr<ZG_QFMT_I8_F32>() && set_stream_attr<ZG_QFMT_I8_F16>() && set_stream_attr<ZG_QFMT_I4_F16>();
 }
 
@@ -454,21 +456,31 @@ ZgGemvStreamPlan zg_qgemv_stream_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight*
     pl.nq = (w->n_kc + G - 1) / G;
     pl.TQ = count * pl.GB * pl.nq;
     pl.Lq = kSegRecs / G;
-    pl.NS = ctx->stream_ns > 0 ? (uint32_t)ctx->stream_ns : 2;
+    pl.NS = ctx->stream_ns > 0 ? (uint32_t)ctx->stream_ns : 4;   // 4 slots: two CTAs per SM, 147 KB in flight per SM
     pl.smem_bytes = kSegRecs * ZG_KR * 4 + kWarps * pl.NS * G * w->rec_bytes + kWarps * G * kPlaneRow + kWarps * pl.NS * 8;
     const uint32_t occ = std::max(1u, std::min(3u, (227u * 1024u) / (pl.smem_bytes + 1024u + 256u)));   // CTAs per SM (80 registers allow 3)
     const uint32_t slots_max = (uint32_t)ctx->sm_count * occ;
-    // CTAs of `per` chunks per warp: long enough to amortise the staging, the flush and the split pieces (measured: 32 chunks
-    // and 224 CTAs beat 16 chunks and 444 CTAs on the 132 MB Llama-3-70B matvecs — HBM is saturated either way, and every CTA
-    // boundary inside a column group is one more partial + arrival); launches with less than `min_total` chunks keep the k-split kernel
-    const uint32_t per = ctx->stream_chunks > 0 ? (uint32_t)ctx->stream_chunks : 32u;
-    const uint32_t min_total = ctx->stream_min_chunks > 0 ? (uint32_t)ctx->stream_min_chunks : 4096u;
+    // CTAs of `per` chunks per warp, ONE round of CTAs (grid <= resident slots).  `per` is snapped up to a divisor of a column
+    // group's chunk count nq (or a multiple of it): CTA boundaries then fall on the same few places of every column group
+    // (per == nq: none at all — whole groups, direct stores) and a CTA never straddles two blocks of column groups.  Measured
+    // (132 MB Llama-3-70B matvec in a dependent chain): 224 aligned CTAs of 32 chunks 31.3 us, 444 CTAs of 16.1 chunks 36 us
+    // (three CTAs per SM stream at unequal speed under saturation and the slow quarter finishes latency-bound).
+    const uint32_t per_min = ctx->stream_chunks > 0 ? (uint32_t)ctx->stream_chunks : 16u;
+    const uint32_t min_total = ctx->stream_min_chunks > 0 ? (uint32_t)ctx->stream_min_chunks : 3072u;
     if (ctx->gemv_stream == 1 && pl.TQ < min_total) return pl;
-    const uint32_t waves = ctx->stream_waves > 0 ? (uint32_t)ctx->stream_waves : 1u;
-    pl.grid = std::min(slots_max * waves, std::max(1u, pl.TQ / std::min(per, pl.TQ)));
+    // batches of three or more int8 matvecs already stream at 92-97 % of HBM through the k-split kernel's many short CTAs
+    // (measured, 8 x 4096x4096 / 4096x14336: 6.0-6.4 TB/s against 5.7-6.2 here); the int4 batches do not (5.0 -> 5.6 TB/s here)
+    if (ctx->gemv_stream == 1 && count >= 3 && w->fmt != ZG_QFMT_I4_F16) return pl;
+    uint32_t per = std::max(per_min, (pl.TQ + slots_max - 1) / slots_max);
+    if (ctx->stream_align == 1 || (ctx->stream_align == 0 && per < 2 * pl.nq)) {
+        if (per < pl.nq && pl.TQ / pl.nq >= 128) per = pl.nq;       // whole column groups still give >= 128 CTAs: no cuts, no partials
+        else if (per < pl.nq) { while (pl.nq % per) per++; }          // smallest divisor of nq that is >= per (nq itself at the latest)
+        else per = ((per + pl.nq - 1) / pl.nq) * pl.nq;
+    }
+    pl.per = per;
+    pl.grid = (pl.TQ + per - 1) / per;
     // pieces a column group can be cut into: staging capacity + CTA boundaries inside its nq chunks
-    const uint32_t per_cta = pl.TQ / pl.grid;   // >= 1
-    pl.slots = (pl.nq + pl.Lq - 1) / pl.Lq + (pl.nq + per_cta - 1) / per_cta + 2;
+    pl.slots = (pl.nq + pl.Lq - 1) / pl.Lq + (pl.nq + per - 1) / per + 2;
     pl.use = true;
     return pl;
 }
@@ -489,7 +501,7 @@ bool zg_qgemv_stream_launch(ZgCudaCtx* ctx, const ZgGemvStreamPlan& pl, uint32_t
         p.op[i] = QGemvSOp{w->recs, w->smax, d_in[i], d_out[i], ws[i].partials, ws[i].counters};
     }
     p.n_kc = w0->n_kc; p.n_nb = w0->n_nb; p.K = (uint32_t)w0->K; p.N = (uint32_t)w0->N;
-    p.GB = pl.GB; p.nq = pl.nq; p.TQ = pl.TQ; p.Lq = pl.Lq; p.NS = pl.NS; p.slots = pl.slots; p.early = ctx->stream_early ? 1u : 0u;
+    p.GB = pl.GB; p.nq = pl.nq; p.TQ = pl.TQ; p.per = pl.per; p.Lq = pl.Lq; p.NS = pl.NS; p.slots = pl.slots; p.early = ctx->stream_early ? 1u : 0u; p.rev = getenv("ZG_GEMV_STREAM_REV") ? 1u : 0u;
     switch (w0->fmt) {
         case ZG_QFMT_I8_F32: return launch_stream<ZG_QFMT_I8_F32>(p, pl.grid, pl.smem_bytes, st, ctx->pdl);
         case ZG_QFMT_I8_F16: return launch_stream<ZG_QFMT_I8_F16>(p, pl.grid, pl.smem_bytes, st, ctx->pdl);

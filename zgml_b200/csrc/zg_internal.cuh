@@ -112,7 +112,7 @@ struct ZgCudaCtx {
     int gemv_fuse = 0;           // evaluate norm (bit 0) / SiLU*up (bit 1) blocks inside the consuming matvecs' prologues (ZG_CUDA_GEMV_FUSE).
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
-    int gemv_stream = 1, stream_min_chunks = 0, stream_early = 0, stream_ns = 0, stream_waves = 0, stream_chunks = 0;   // ZG_GEMV_STREAM / ZG_GEMV_STREAM_MIN (qgemv_stream.cu)
+    int gemv_stream = 1, stream_min_chunks = 0, stream_early = 0, stream_ns = 0, stream_waves = 0, stream_chunks = 0, stream_align = 0;   // ZG_GEMV_STREAM / ZG_GEMV_STREAM_MIN (qgemv_stream.cu)
     bool gemv_pair = true;       // single-token programs: gate | up matvecs + SiLU * up chain in ONE launch (ZG_CUDA_GEMV_PAIR=0: off)
     bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
@@ -143,7 +143,7 @@ struct ZgGemvPlan {
 };
 ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count = 1);
 // qgemv_stream.cu: the large-launch form of the single-row matvec (one column group per warp, evenly sliced work)
-struct ZgGemvStreamPlan { bool use = false; uint32_t grid = 0, GB = 0, nq = 0, TQ = 0, Lq = 0, NS = 2, slots = 0, smem_bytes = 0; };
+struct ZgGemvStreamPlan { bool use = false; uint32_t grid = 0, GB = 0, nq = 0, TQ = 0, per = 0, Lq = 0, NS = 2, slots = 0, smem_bytes = 0; };
 ZgGemvStreamPlan zg_qgemv_stream_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t count);
 bool zg_qgemv_stream_init(ZgCudaCtx* ctx);
 bool zg_qgemv_stream_launch(ZgCudaCtx* ctx, const ZgGemvStreamPlan& pl, uint32_t count, const ZgCudaQWeight* const* w, const float* const* d_in,
