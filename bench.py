@@ -357,7 +357,8 @@ def gemv_leg(args, be, torch, dist, stream, rank, world, barrier):
                 traffic = int(t) * per_launch
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"qgemv_kernel<{domc['format']}> {domc['K']}x{domc['N']} batch 1, {per_launch} matvecs per launch "
+    kname = "qgemv_stream_kernel" if be.program_stats(domc["h"])["streamed_matvec_launches"] else "qgemv_kernel"
+    roofline = {"bound": "hbm", "kernel": f"{kname}<{domc['format']}> {domc['K']}x{domc['N']} batch 1, {per_launch} matvecs per launch "
                                           "(dominant kernel of the GEMV leg; the same kernel carries the decode step's linears)",
                 "achieved": dom["gbps"], "peak": peak, "peak_kind": f"{peak_kind} copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
                 "unit": "GB/s", "frac": round(dom["gbps"] / peak, 4), "frac_all_cases": round(value / world / peak, 4),

@@ -232,7 +232,7 @@ void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int enabled);
 void* zg_cuda_program_buffer(ZgCudaProgram* prog, uint32_t buf_idx);
 /* Schedule introspection (tests / benches assert that the fast paths are the ones that run): what == 0: kernels one
  * execution launches (graph nodes); 1: DeviceOps covered by the fused single-token decode kernel (0: general schedule);
- * 2: layers inside that kernel. */
+ * 2: layers inside that kernel; 3: launches of the streamed single-row matvec kernel (csrc/qgemv_stream.cu) among them. */
 uint64_t zg_cuda_program_stats(const ZgCudaProgram* prog, int what);
 /* Run the program's ops with no host<->device copies (inputs already resident);
  * asynchronous on the ctx stream. */

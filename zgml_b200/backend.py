@@ -457,7 +457,8 @@ class CudaBackend:
     def program_stats(self, handle: CompiledHandle) -> dict:
         """Schedule facts of a compiled program: kernels per execution, DeviceOps / layers inside the fused decode kernel."""
         f = self.lib.zg_cuda_program_stats
-        return {"kernels": int(f(handle.ptr, 0)), "fused_decode_ops": int(f(handle.ptr, 1)), "fused_decode_layers": int(f(handle.ptr, 2))}
+        return {"kernels": int(f(handle.ptr, 0)), "fused_decode_ops": int(f(handle.ptr, 1)), "fused_decode_layers": int(f(handle.ptr, 2)),
+                "streamed_matvec_launches": int(f(handle.ptr, 3))}
 
 
 class QuantizedWeight:

@@ -13,6 +13,7 @@
 #include <string>
 
 std::atomic<uint64_t> g_zg_launches{0};
+std::atomic<uint64_t> g_zg_stream_launches{0};   // launches of the streamed matvec kernel (qgemv_stream.cu)
 static char g_err[1024] = "";
 
 void zg_set_error(const char* fmt, ...) {
@@ -70,6 +71,7 @@ struct ZgCudaProgram {
     cudaGraphExec_t exec = nullptr;
     bool graph_valid = false;
     uint64_t graph_kernels = 0; // kernel nodes captured in `graph` (added to the launch counter per replay)
+    uint64_t graph_streamed = 0; // of those: streamed matvec launches
     ZgProfile profile;
     std::vector<cudaEvent_t> prof_events;
     std::vector<cudaEvent_t> dep_events; // capture-time fork/join markers of the concurrent graph branches
@@ -1794,9 +1796,10 @@ static bool run_ops(ZgCudaProgram* p) {
         if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
         if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
         ZG_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const uint64_t before = g_zg_launches.load();
+        const uint64_t before = g_zg_launches.load(), before_s = g_zg_stream_launches.load();
         bool ok = ctx->branch.empty() ? launch_all(p, st, false) : launch_all_branched(p, st);
         p->graph_kernels = g_zg_launches.load() - before;
+        p->graph_streamed = g_zg_stream_launches.load() - before_s;
         g_zg_launches.store(before); // captured, not launched: counted per replay below
         cudaError_t e = cudaStreamEndCapture(st, &p->graph);
         if (!ok) { if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; } return false; }
@@ -1999,6 +2002,7 @@ extern "C" uint64_t zg_cuda_program_stats(const ZgCudaProgram* p, int what) {
         case 0: return p->graph_kernels;
         case 1: return p->dec.valid ? p->dec_count : 0;
         case 2: return p->dec.valid ? p->dec.plan.n_layers : 0;
+        case 3: return p->graph_streamed;
         default: return 0;
     }
 }

@@ -421,6 +421,7 @@ bool launch_stream(const QGemvSParams& p, uint32_t grid, uint32_t smem, cudaStre
     cfg.numAttrs = pdl ? 1 : 0;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_stream_kernel<FMT>, p);
     ZG_COUNT_LAUNCH();
+    g_zg_stream_launches.fetch_add(1, std::memory_order_relaxed);
     if (e != cudaSuccess) { zg_set_error("qgemv stream launch failed: %s (grid %u, %u B shared)", cudaGetErrorString(e), grid, smem); return false; }
     return true;
 }

@@ -15,6 +15,7 @@
 
 void zg_set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_zg_launches;
+extern std::atomic<uint64_t> g_zg_stream_launches;
 #define ZG_COUNT_LAUNCH() (g_zg_launches.fetch_add(1, std::memory_order_relaxed))
 
 #define ZG_CUDA_OK(expr)                                                                     \
