@@ -696,6 +696,27 @@ def run_extras(be, torch):
         out["decode_smollm_1p7b_q4_0_ctx512"] = {"tok_s": round(n / dt, 1), "device_tok_s": round(n / dd, 1), "ms_per_token_device": round(1e3 * dd / n, 3),
                                                  "hbm_bytes_per_token": int(qb), "frac_of_hbm_floor": round(qb / (peak * 1e9) / (dd / n), 4),
                                                  "kernels_per_token": be.program_stats(sess.handle)["kernels"]}
+        # the tied f32 LM head as an argmax-safe f16 copy (zg_cuda_program_promote_dense), same greedy tokens
+        toks_f32 = []
+        sess.pos = 512
+        t = 1
+        for _ in range(8):
+            t = int(np.argmax(sess.step(t))); toks_f32.append(t)
+        be.promote_dense_weights(sess.handle, "f16")
+        sess.pos = 512
+        t, toks_f16 = 1, []
+        for _ in range(8):
+            t = int(np.argmax(sess.step(t))); toks_f16.append(t)
+        be.sync()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            be.lib.zg_cuda_execute_device(be.ctx, sess.handle.ptr)
+        be.sync()
+        d16 = time.perf_counter() - t0
+        out["decode_smollm_1p7b_q4_0_ctx512"]["f16_lm_head"] = {
+            "device_tok_s": round(n / d16, 1), "ms_per_token_device": round(1e3 * d16 / n, 3),
+            "head_bytes_saved_per_token": be.program_stats(sess.handle)["dense_bytes_saved_per_execution"],
+            "greedy_tokens_equal_f32_head": toks_f16 == toks_f32}
         sess.close()
         for h in handles:
             h.free()

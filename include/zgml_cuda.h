@@ -232,7 +232,8 @@ void zg_cuda_set_graph_mode(ZgCudaCtx* ctx, int enabled);
 void* zg_cuda_program_buffer(ZgCudaProgram* prog, uint32_t buf_idx);
 /* Schedule introspection (tests / benches assert that the fast paths are the ones that run): what == 0: kernels one
  * execution launches (graph nodes); 1: DeviceOps covered by the fused single-token decode kernel (0: general schedule);
- * 2: layers inside that kernel; 3: launches of the streamed single-row matvec kernel (csrc/qgemv_stream.cu) among them. */
+ * 2: layers inside that kernel; 3: launches of the streamed single-row matvec kernel (csrc/qgemv_stream.cu) among them;
+ * 4: HBM bytes per execution saved by promoted dense operands (zg_cuda_program_promote_dense). */
 uint64_t zg_cuda_program_stats(const ZgCudaProgram* prog, int what);
 /* Run the program's ops with no host<->device copies (inputs already resident);
  * asynchronous on the ctx stream. */
@@ -338,6 +339,17 @@ int zg_cuda_attention_quantized_host(ZgCudaCtx* ctx, float* h_dst, size_t dst_co
  * int8_query != 0: the aarch64 branch of attentionQuantized (query quantized per block), 0: the portable f32-query branch.
  * Returns 0 on success; -1 (program unchanged) when the program's cache accesses are not whole d_head columns. */
 int zg_cuda_program_quantize_kv(ZgCudaCtx* ctx, ZgCudaProgram* prog, size_t block_size, int int8_query);
+
+/* Format hint for dense matmul operands (precedent: the WGPU backend's f16 promotion of matmul B buffers that
+ * have initial uploads, src/backend/wgpu.zig:1068-1106).  Every matmul op of the program with M == 1 and a k-contiguous B
+ * operand that no op writes (the tied LM head x @ token_embed^T, src/models/llama.zig:162-165) gets a 16-bit copy of that operand;
+ * the op then streams the copy (half the bytes), bounds each output's error by ||x|| * ||w - round16(w)|| and recomputes every
+ * column that could still be the maximum from the f32 original, with the exact kernel's arithmetic.  The argmax — and the
+ * winning logits bit for bit — equal the unpromoted program's; the other outputs carry the 16-bit weight rounding.
+ * An execute() input that overwrites a promoted operand refreshes its copy.  Returns the number of ops promoted, -1 on error. */
+#define ZG_DENSE_BF16 1   /* f32's range, 8 significant bits: other logits within ~2e-3 of the output scale */
+#define ZG_DENSE_F16 2    /* the WGPU backend's choice, 11 significant bits: other logits within ~2e-4; |w| > 65504 falls back to the exact row */
+int zg_cuda_program_promote_dense(ZgCudaCtx* ctx, ZgCudaProgram* prog, int format);
 
 /* Multi-GPU (one process per GPU): a 128-byte NCCL unique id made on rank 0, distributed by the host
  * (torch.distributed / MPI / file), then one communicator per context.  Returns 0 on success. */

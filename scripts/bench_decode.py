@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--context", type=int, default=0, help="decode starts at this position (KV cache below it holds zeros)")
     ap.add_argument("--cpu-tokens", type=int, default=0)
     ap.add_argument("--profile", action="store_true", help="per-DeviceOp-tag device time (one launch per op, program order)")
+    ap.add_argument("--head", default="f32", choices=["f32", "f16", "bf16"], help="tied LM head operand format (promote_dense_weights: argmax-safe 16-bit copy)")
     ap.add_argument("--layers", type=int, default=0, help="override n_layers (memory-bounded experiments only)")
     ap.add_argument("--gguf", default="", help="decode a GGUF file (Q8_0 / Q4_0 linears) instead of in-memory synthetic weights: memory-mapped, "
                     "raw blocks go tensor by tensor to HBM (host/gguf.py::load_resident)")
@@ -56,6 +57,7 @@ def main():
     t0 = time.perf_counter()
     sess = llama.DeviceLlamaSession(be, cfg, w, 1)
     t_compile = time.perf_counter() - t0
+    promoted = be.promote_dense_weights(sess.handle, args.head) if args.head != "f32" else 0
     sess.pos = args.context
     tok = 1
     lg = sess.step(tok)  # warm-up (captures the graph)
@@ -83,6 +85,7 @@ def main():
             "device_tok_s": round(args.tokens / dt_dev, 1), "tokens": args.tokens, "context": args.context,
             "ops_per_token": sess.n_ops, "kernels_per_token": launches // args.tokens, "schedule": be.program_stats(sess.handle),
             "weight_bytes_per_token": qbytes + head_bytes, "hbm_gbps_on_weights": round((qbytes + head_bytes) / (dt / args.tokens) / 1e9, 1),
+            "lm_head": args.head, "dense_ops_promoted": promoted, "head_bytes_saved_per_token": be.program_stats(sess.handle)["dense_bytes_saved_per_execution"],
             "gen_s": round(t_gen, 1), "compile_s": round(t_compile, 1), "data": "synthetic random-init GGUF-direct weights"}
     if args.profile:
         be.set_profiling(True)

@@ -186,6 +186,7 @@ SYMBOLS = [
     ("zg_cuda_attention_quantized_device", C.c_int, [vp, vp, sz, vp, sz, sz, sz, vp, sz, vp, sz, sz, vp, sz, sz, C.c_float, C.c_int]),
     ("zg_cuda_attention_quantized_host", C.c_int, [vp, vp, sz, vp, sz, sz, sz, vp, sz, vp, sz, sz, vp, sz, sz, C.c_float, C.c_int]),
     ("zg_cuda_program_quantize_kv", C.c_int, [vp, vp, sz, C.c_int]),
+    ("zg_cuda_program_promote_dense", C.c_int, [vp, vp, C.c_int]),
     ("zg_cuda_comm_unique_id", C.c_int, [vp]),
     ("zg_cuda_comm_init", C.c_int, [vp, vp, C.c_int, C.c_int]),
     ("zg_cuda_comm_destroy", None, [vp]),

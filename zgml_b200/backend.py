@@ -454,11 +454,22 @@ class CudaBackend:
         if self.lib.zg_cuda_program_quantize_kv(self.ctx, handle.ptr, block_size, int(int8_query)) != 0:
             raise BackendError(f"quantize_kv failed: {last_error()}")
 
+    def promote_dense_weights(self, handle: CompiledHandle, fmt: str = "f16") -> int:
+        """Format hint for dense matmul operands (include/zgml_cuda.h zg_cuda_program_promote_dense; precedent
+        src/backend/wgpu.zig:1068-1106): single-row matmuls against a constant k-contiguous operand (the tied LM head) stream a
+        16-bit copy (f16: 11 significant bits, bf16: 8) and recompute every possible argmax from the f32 original.  Returns the number of ops promoted."""
+        if fmt not in ("bf16", "f16"):
+            raise BackendError("promote_dense_weights: format must be 'f16' or 'bf16'")
+        n = self.lib.zg_cuda_program_promote_dense(self.ctx, handle.ptr, 1 if fmt == "bf16" else 2)
+        if n < 0:
+            raise BackendError(f"promote_dense_weights failed: {last_error()}")
+        return int(n)
+
     def program_stats(self, handle: CompiledHandle) -> dict:
         """Schedule facts of a compiled program: kernels per execution, DeviceOps / layers inside the fused decode kernel."""
         f = self.lib.zg_cuda_program_stats
         return {"kernels": int(f(handle.ptr, 0)), "fused_decode_ops": int(f(handle.ptr, 1)), "fused_decode_layers": int(f(handle.ptr, 2)),
-                "streamed_matvec_launches": int(f(handle.ptr, 3))}
+                "streamed_matvec_launches": int(f(handle.ptr, 3)), "dense_bytes_saved_per_execution": int(f(handle.ptr, 4))}
 
 
 class QuantizedWeight:

@@ -113,6 +113,7 @@ struct ZgCudaProgram {
     // over them attentionQuantized (src/llama_inference.zig:336-377)
     bool kvq = false; size_t kvq_bs = 32; int kvq_int8 = 0;
     std::map<uint32_t, ZgCudaKVCache*> kv_caches;   // program buffer -> the cache standing in for it
+    std::map<uint32_t, ZgDenseHead*> dense;         // matmul op index -> bf16 copy of its B operand (zg_cuda_program_promote_dense)
     std::vector<char> kvq_role;                     // per op: 0 none, 1 cache store, 2 attention over the caches
     std::vector<uint32_t> kvq_entry;                // per op: its entry in d_kvq_store / d_kvq_attn
     ZgKvqStore* d_kvq_store = nullptr; ZgKvqAttn* d_kvq_attn = nullptr;
@@ -254,6 +255,7 @@ static void free_program(ZgCudaProgram* p) {
     zg_gemv_ws_free(&p->ws);
     zg_decode_free(&p->dec);
     for (auto& kv : p->kv_caches) zg_cuda_kvcache_free(p->ctx, kv.second);
+    for (auto& d : p->dense) zg_dense_head_free(d.second);
     cudaFree(p->d_kvq_store); cudaFree(p->d_kvq_attn); cudaFree(p->d_kvq_part); cudaFree(p->d_kvq_cnt);
     cudaFree(p->d_attn_blocks); cudaFree(p->d_attn_blk_part); cudaFree(p->d_attn_blk_cnt);
     for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
@@ -1645,6 +1647,14 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
     if (op.tag == ZG_OP_ALLGATHER)
         return zg_comm_allgather(ctx, p->buffers[op.u.allgather.src] + op.u.allgather.src_offset,
                                  p->buffers[op.u.allgather.dst] + op.u.allgather.dst_offset, op.u.allgather.n, st);
+    if (op.tag == ZG_OP_MATMUL && !p->dense.empty()) {
+        auto d = p->dense.find((uint32_t)i);
+        if (d != p->dense.end()) {
+            const auto& m = op.u.matmul; const ZgMatMulGeometry& g = m.geom;
+            return zg_dense_head_launch(ctx, d->second, p->buffers[m.a] + g.a_offset, p->buffers[m.b], g.b_offset, g.b_col_stride,
+                                        p->buffers[m.dst] + g.dst_offset, st);
+        }
+    }
     if (zg_op_is_batched(op.tag)) return zg_launch_batch(op, p->d_batch + p->single_entry[i], 1, p->d_dyn, st);
     return zg_launch_op(ctx, op, p->buffers.data(), p->d_dyn, (uint32_t)i, p->d_steps + p->step_off[i], st);
 }
@@ -1878,6 +1888,11 @@ extern "C" void zg_cuda_execute(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgIO* in
     if (!upload_inputs_staged(p, in, n_in, st))
         for (size_t i = 0; i < n_in; i++)
             cudaMemcpyAsync((uint8_t*)p->buffers[in[i].buf_idx] + in[i].offset, in[i].host_ptr, in[i].size, cudaMemcpyHostToDevice, st);
+    for (auto& d : p->dense) {   // an input that overwrites a promoted operand refreshes its bf16 copy
+        const auto& m = p->ops[d.first].u.matmul;
+        for (size_t i = 0; i < n_in; i++)
+            if (in[i].buf_idx == m.b) { zg_dense_head_refresh(ctx, d.second, p->buffers[m.b], m.geom.b_offset, m.geom.b_col_stride, st); break; }
+    }
     if (!run_ops(p)) { cudaStreamSynchronize(st); return; }
     for (size_t i = 0; i < n_out; i++) {
         const ZgIO& io = out[i];
@@ -1996,6 +2011,36 @@ extern "C" int zg_cuda_program_quantize_kv(ZgCudaCtx* ctx, ZgCudaProgram* p, siz
     return 0;
 }
 
+// Dense B operands of single-row matmuls (the tied LM head) stored as bf16 next to the f32 original; see dense_head.cu.
+// Returns the number of matmul ops promoted (0: none qualified), -1 on error.
+extern "C" int zg_cuda_program_promote_dense(ZgCudaCtx* ctx, ZgCudaProgram* p, int format) {
+    if (!ctx || !p || (format != ZG_DENSE_BF16 && format != ZG_DENSE_F16)) { zg_set_error("program_promote_dense: bad arguments (format must be ZG_DENSE_BF16 or ZG_DENSE_F16)"); return -1; }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    int n_promoted = 0;
+    std::vector<ZgRange> rr;
+    for (size_t i = 0; i < p->ops.size(); i++) {
+        const ZgOp& op = p->ops[i];
+        if (op.tag != ZG_OP_MATMUL || p->dense.count((uint32_t)i)) continue;
+        const auto& m = op.u.matmul; const ZgMatMulGeometry& g = m.geom;
+        // one activation row (staged in <= 32 KB of shared memory) against a k-contiguous operand with 16-byte aligned rows; small heads stay exact
+        if (g.M != 1 || g.b_row_stride != 1 || g.a_col_stride != 1 || (g.K & 7) || g.K < 64 || g.K > 8192 || g.N < 1024 || (g.b_col_stride & 3) || (g.b_offset & 3) ||
+            (g.a_offset & 3) || (g.dst_offset & 3) || g.b_col_stride < g.K) continue;
+        bool written = false;   // the operand must be a constant of the program: no op writes it
+        for (size_t k = 0; k < p->ops.size() && !written; k++) {
+            op_ranges(p, p->ops[k], rr);
+            for (const ZgRange& r : rr) if (r.write && r.buf == m.b) { written = true; break; }
+        }
+        if (written) continue;
+        ZgDenseHead* h = zg_dense_head_create(ctx, format, p->buffers[m.b], g.b_offset, g.b_col_stride, (uint32_t)g.N, (uint32_t)g.K);
+        if (!h) return -1;
+        p->dense[(uint32_t)i] = h;
+        n_promoted++;
+    }
+    if (n_promoted) { cudaStreamSynchronize(ctx->stream); p->graph_valid = false; }
+    return n_promoted;
+}
+
 extern "C" uint64_t zg_cuda_program_stats(const ZgCudaProgram* p, int what) {
     if (!p) return 0;
     switch (what) {
@@ -2003,6 +2048,7 @@ extern "C" uint64_t zg_cuda_program_stats(const ZgCudaProgram* p, int what) {
         case 1: return p->dec.valid ? p->dec_count : 0;
         case 2: return p->dec.valid ? p->dec.plan.n_layers : 0;
         case 3: return p->graph_streamed;
+        case 4: { uint64_t b = 0; for (auto& d : p->dense) b += (uint64_t)d.second->N * d.second->K * 2 - (uint64_t)d.second->N * 6; return b; }   // HBM bytes per execution saved by the bf16 operands
         default: return 0;
     }
 }

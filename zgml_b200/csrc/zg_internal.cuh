@@ -143,6 +143,13 @@ struct ZgGemvPlan {
     uint32_t grid = 0, threads = 256, P = 1, S = 1, mp = 1, G = 2, NS = 3, lcap = 1, xs_stride = 32, smem_bytes = 0;
 };
 ZgGemvPlan zg_qgemv_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t M, uint32_t count = 1);
+// dense_head.cu: bf16 copy of a dense matmul B operand (the tied LM head) with the argmax-safe exact recompute
+struct ZgDenseHead { int format = 0; void* w16 = nullptr; float* err = nullptr; float* part_max = nullptr; float* glob = nullptr; uint32_t N = 0, K = 0, n_part = 0; };
+ZgDenseHead* zg_dense_head_create(ZgCudaCtx* ctx, int format, const float* d_w, size_t w_off, size_t row_stride, uint32_t N, uint32_t K);
+bool zg_dense_head_refresh(ZgCudaCtx* ctx, ZgDenseHead* h, const float* d_w, size_t w_off, size_t row_stride, cudaStream_t st);
+void zg_dense_head_free(ZgDenseHead* h);
+bool zg_dense_head_launch(ZgCudaCtx* ctx, const ZgDenseHead* h, const float* d_x, const float* d_w, size_t w_off, size_t row_stride,
+                          float* d_dst, cudaStream_t st);
 // qgemv_stream.cu: the large-launch form of the single-row matvec (one column group per warp, evenly sliced work)
 struct ZgGemvStreamPlan { bool use = false; uint32_t grid = 0, GB = 0, nq = 0, TQ = 0, per = 0, Lq = 0, NS = 2, slots = 0, smem_bytes = 0; };
 ZgGemvStreamPlan zg_qgemv_stream_plan(const ZgCudaCtx* ctx, const ZgCudaQWeight* w, uint32_t count);
