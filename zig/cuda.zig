@@ -78,6 +78,8 @@ extern fn zg_cuda_kvcache_free(ctx: *anyopaque, cache: *anyopaque) void;
 extern fn zg_cuda_kvcache_clear(ctx: *anyopaque, cache: *anyopaque) c_int;
 extern fn zg_cuda_kvcache_store_device(ctx: *anyopaque, cache: *anyopaque, col_start: usize, n_write: usize, d_src: *const anyopaque) c_int;
 extern fn zg_cuda_attention_quantized_device(ctx: *anyopaque, d_dst: *anyopaque, dst_col_stride: usize, d_q: *const anyopaque, q_col_stride: usize, d_head: usize, seq_q: usize, k_cache: *const anyopaque, k_col_start: usize, v_cache: *const anyopaque, v_col_start: usize, seq_kv: usize, d_mask: ?*const anyopaque, mask_row_stride: usize, mask_col_stride: usize, scale: f32, int8_query: c_int) c_int;
+extern fn zg_cuda_program_quantize_kv(ctx: *anyopaque, prog: *anyopaque, block_size: usize, int8_query: c_int) c_int;
+extern fn zg_cuda_program_promote_dense(ctx: *anyopaque, prog: *anyopaque, format: c_int) c_int;
 extern fn zg_cuda_gemv_w8a8_host(ctx: *anyopaque, w: *const anyopaque, h_input: [*]const f32, h_dst: [*]f32) c_int;
 pub const ZG_QWEIGHT_RESIDENT: usize = std.math.maxInt(usize); // ZgQWeight.block_size marker: `data` is a handle from zg_cuda_qweight_upload*
 
@@ -177,9 +179,24 @@ pub const CudaBackend = struct {
         zg_cuda_destroy(self.ctx);
     }
 
+    /// LlamaInferenceSession.quantizeKV (src/llama_inference.zig:648-679) for a compiled program: Q8 caches replace the f32 KV
+    /// buffers, cache writes run storeColumn, attention runs attentionQuantized.  int8_query = the aarch64 branch.
+    pub fn quantizeKV(self: *CudaBackend, handle: backend_mod.Backend.CompiledHandle, block_size: usize, int8_query: bool) !void {
+        if (zg_cuda_program_quantize_kv(self.ctx, handle, block_size, @intFromBool(int8_query)) != 0) return error.UnsupportedCacheLayout;
+    }
+
+    /// Format hint for dense matmul operands (the tied LM head): the WGPU backend's f16 promotion (src/backend/wgpu.zig:1068-1106),
+    /// opt-in and argmax-safe.  format: 1 = bf16, 2 = f16.  Returns the number of matmul ops promoted.
+    pub fn promoteDenseWeights(self: *CudaBackend, handle: backend_mod.Backend.CompiledHandle, format: c_int) !usize {
+        const n = zg_cuda_program_promote_dense(self.ctx, handle, format);
+        if (n < 0) return error.PromotionFailed;
+        return @intCast(n);
+    }
+
     pub fn backend(self: *CudaBackend) backend_mod.Backend {
         var caps = backend_mod.Capabilities.reference_cpu; // src/backend.zig:60-70
         caps.host_visible_program_memory = false;
+        caps.quantized_kv = true; // src/backend.zig:26: zg_cuda_program_quantize_kv
         return .{ .ctx = self, .vtable = &vtable, .name_str = "cuda-b200", .device_type = .cuda, .capabilities = caps };
     }
 };
