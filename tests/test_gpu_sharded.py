@@ -151,7 +151,9 @@ def _rank_main_synth(rank, world, port, cfg, kind, peer, fused, context, n_tok, 
     import torch.distributed as dist
     if not peer:
         os.environ["ZG_CUDA_PEER"] = "0"          # NCCL all-reduces instead of the NVLink peer-memory kernel
-    if fused:
+    if fused == "arnorm":
+        os.environ["ZG_CUDA_AR_NORM"] = "1"       # all-reduce + the norm block behind it in one launch (ops.cu k_allreduce_norm)
+    elif fused:
         os.environ["ZG_CUDA_DECODE"] = "1"        # the persistent fused decode kernel (peer all-reduce phases inside)
     from zgml_b200 import CudaBackend
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -173,7 +175,7 @@ def _rank_main_synth(rank, world, port, cfg, kind, peer, fused, context, n_tok, 
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("path", ["peer", "nccl", "fused"])
+@pytest.mark.parametrize("path", ["peer", "nccl", "fused", "arnorm"])
 def test_sharded_70b_width_matches_unsharded_oracle(world, path):
     """Every rank holds its slab of the same hashed synthetic model; rank-identical logits, 1e-3 against the unsharded oracle
     executor on the host form of that model, identical greedy tokens.  Self-skips below `world` GPUs."""
@@ -183,7 +185,7 @@ def test_sharded_70b_width_matches_unsharded_oracle(world, path):
     from zgml_b200.host.llama import synthetic_model_host
     cfg, kind, n_tok, context = CFG_70B_WIDTH, "q4_0", 3, 20
     out = mp.Manager().dict()
-    mp.spawn(_rank_main_synth, args=(world, _free_port(), cfg, kind, path != "nccl", path == "fused", context, n_tok, out), nprocs=world, join=True)
+    mp.spawn(_rank_main_synth, args=(world, _free_port(), cfg, kind, path != "nccl", "arnorm" if path == "arnorm" else path == "fused", context, n_tok, out), nprocs=world, join=True)
     ref = DeviceLlamaSession(OracleBackend(native=True), cfg, synthetic_model_host(cfg, kind, seed=17), 1)
     ref.pos = context
     _, want = greedy(ref, 1, n_tok)

@@ -88,6 +88,7 @@ struct ZgCudaProgram {
         std::vector<ZgRange> ranges;       // dependency footprint when it differs from the union of the ops' own ranges
         bool batched = false, chain = false, ewmul = false, gemv_batch = false, norm = false, decode = false;
         uint32_t kvq = 0, kvq_max_warps = 0, kvq_seq_q = 0, kvq_splits = 1; size_t kvq_part_off = 0, kvq_cnt_off = 0;
+        bool ar_norm = false;   // peer all-reduce + the norm block that consumes it (ops.cu k_allreduce_norm); nm holds the block
         bool gemv_pair = false; ZgGemvEpilogue epi;   // gate | up matvec pair + activation epilogue (qgemv.cu qgemv_pair_kernel)
         int attn_blk = -1; uint32_t ab_splits = 1; size_t ab_part_off = 0, ab_cnt_off = 0;   // fused attention block of one layer   // 1: batch of cache stores, 2: batch of cache-backed attentions
         ZgNormMacro nm = {};
@@ -149,6 +150,7 @@ extern "C" ZgCudaCtx* zg_cuda_create(int device_ordinal) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         zg_set_error("cudaStreamCreate failed"); delete ctx; return nullptr;
     }
+    if (const char* e = getenv("ZG_CUDA_AR_NORM")) ctx->ar_norm = (e[0] != '0');       // 1: the all-reduce and the norm block behind it as ONE launch (measured slower, off by default)
     if (const char* e = getenv("ZG_CUDA_GEMV_PAIR")) ctx->gemv_pair = (e[0] != '0');   // 0: gate | up as a plain batch, the activation chain as its own launch
     if (const char* e = getenv("ZG_CUDA_ATTN_LAYER")) ctx->attn_layer = (e[0] != '0');   // 0: rope / cache stores / attention as separate launches
     if (const char* e = getenv("ZG_CUDA_DECODE")) ctx->decode_fused = (e[0] != '0');   // 0: never use the fused decode kernel
@@ -1168,8 +1170,22 @@ static bool build_schedule(ZgCudaProgram* p) {
     std::vector<int> macro_of(ni, -1);           // consumer item -> macro item
     // ── gate | up pair + activation epilogue: qmatmul(gate), qmatmul(up), fused_elementwise(steps(gate)), mul(. * up) of a
     //    single-token program become ONE launch (the pair kernel evaluates the chain on the finished sums) ──
-    std::vector<char> pair_lead(ni, 0), pair_absorbed(ni, 0);
+    std::vector<char> pair_lead(ni, 0), pair_absorbed(ni, 0), arn_lead(ni, 0);
     std::vector<ZgGemvEpilogue> epi_of(ni);
+    // ── all-reduce + the norm block right behind it (every sharded layer has two): ONE launch ──
+    if (p->ctx->fuse && p->ctx->ar_norm && p->ctx->world > 1) {
+        for (size_t k = 0; k + 1 < ni; k++) {
+            if (items[k].kind != ITEM_OP || items[k + 1].kind != ITEM_NORM) continue;
+            const ZgOp& ao = p->ops[items[k].first];
+            if (ao.tag != ZG_OP_ALLREDUCE) continue;
+            const auto& ar = ao.u.allreduce;
+            const ZgNormMacro& nm = norm_of[k + 1];
+            float* ptr = p->buffers[ar.buf];
+            if (ar.offset || (ar.n & 1) || !zg_peer_allreduce_ok(p->ctx, ar.n) || (((size_t)ptr) & 15) || nm.rows != 1 || nm.cols != ar.n) continue;
+            if (nm.b ? (nm.a != ptr && nm.b != ptr) || nm.a == nm.b : nm.a != ptr) continue;
+            arn_lead[k] = 1; pair_absorbed[k + 1] = 1;
+        }
+    }
     if (p->ctx->fuse && p->ctx->gemv_pair && !p->ctx->gemv_fuse) {
         for (size_t k = 0; k + 2 < ni; k++) {
             const ZgItem &ia = items[k], &ib = items[k + 1], &ie = items[k + 2];
@@ -1257,8 +1273,8 @@ static bool build_schedule(ZgCudaProgram* p) {
         for (size_t k = 0; k < ni; k++) {
             if (absorbed_by[k] >= 0 || pair_absorbed[k]) continue;
             for (uint32_t j = 0; j < items[k].count; j++) { op_ranges(p, p->ops[items[k].first + j], tmp); item_rng[k].insert(item_rng[k].end(), tmp.begin(), tmp.end()); }
-            if (pair_lead[k])   // the launch also runs the up matvec and the activation chain
-                for (size_t k2 = k + 1; k2 <= k + 2; k2++)
+            if (pair_lead[k] || arn_lead[k])   // the launch also runs the up matvec and the activation chain / the norm block
+                for (size_t k2 = k + 1; k2 <= k + (pair_lead[k] ? 2 : 1); k2++)
                     for (uint32_t j = 0; j < items[k2].count; j++) { op_ranges(p, p->ops[items[k2].first + j], tmp); item_rng[k].insert(item_rng[k].end(), tmp.begin(), tmp.end()); }
             if (macro_of[k] < 0) continue;
             const ZgItem& mi = items[macro_of[k]];
@@ -1390,6 +1406,13 @@ static bool build_schedule(ZgCudaProgram* p) {
             const ZgItem& it = items[order[k]];
             if (in_chain(it)) continue;   // chained above
             const ZgOp& op = p->ops[it.first];
+            if (arn_lead[order[k]]) {
+                ZgCudaProgram::Unit u; u.ar_norm = true; u.nm = norm_of[order[k] + 1];
+                for (size_t k2 = order[k]; k2 <= (size_t)order[k] + 1; k2++)
+                    for (uint32_t j = 0; j < items[k2].count; j++) u.ops.push_back(items[k2].first + j);
+                u.ranges = item_rng[order[k]];
+                p->units.push_back(u); continue;
+            }
             if (pair_lead[order[k]]) {
                 ZgCudaProgram::Unit u; u.gemv_pair = true; u.epi = epi_of[order[k]];
                 u.entry_ops.push_back(it.first); u.entry_ops.push_back(items[order[k] + 1].first);
@@ -1661,6 +1684,10 @@ static bool launch_one(ZgCudaProgram* p, size_t i, cudaStream_t st) {
 
 static bool launch_unit(ZgCudaProgram* p, const ZgCudaProgram::Unit& u, cudaStream_t st) {
     if (u.decode) { p->dec.plan.dyn = p->d_dyn; return zg_decode_launch(p->ctx, p->dec, st); }
+    if (u.ar_norm) {
+        const auto& ar = p->ops[u.ops[0]].u.allreduce;
+        return zg_launch_peer_allreduce_norm(p->buffers[ar.buf], ar.n, p->ctx->peer, u.nm, st);
+    }
     if (u.gemv_pair) {
         const uint32_t ia = u.entry_ops[0], ib = u.entry_ops[1];
         const auto& qa = p->ops[ia].u.qmatmul; const auto& qb = p->ops[ib].u.qmatmul;

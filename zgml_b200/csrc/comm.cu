@@ -100,7 +100,9 @@ static bool peer_setup(ZgCudaCtx* ctx) {
     bool ok = true;
     if (const char* e = getenv("ZG_CUDA_PEER")) if (e[0] == '0') ok = false;
     const size_t slot_bytes = (size_t)kZgPeerSets * world * kPeerSlotFloats * 2 * sizeof(float);   // every float travels with its epoch
-    const size_t total = slot_bytes + (2 + kZgPeerCtas) * sizeof(uint32_t) + 64;
+    const size_t seq_bytes = ((2 + kZgPeerCtas) * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t cell_bytes = (size_t)kZgPeerSets * kZgPeerCtas * sizeof(unsigned long long);
+    const size_t total = slot_bytes + seq_bytes + cell_bytes + 64;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -162,6 +164,7 @@ static bool peer_setup(ZgCudaCtx* ctx) {
         pc.slots[r] = (float*)base;
     }
     pc.seq = (uint32_t*)((char*)ctx->peer_mem + slot_bytes);
+    pc.cells = (unsigned long long*)((char*)ctx->peer_mem + slot_bytes + seq_bytes);
     return true;
 }
 

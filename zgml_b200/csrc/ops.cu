@@ -259,6 +259,127 @@ k_allreduce_peer(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc) {
     ZG_TRACE_MARK(2)
 }
 
+// All-reduce over peer memory (k_allreduce_peer) + the block that consumes it in every sharded layer — [sum = a + b,]
+// bare = rmsnorm(sum), gamma_rep = gamma, norm = bare * gamma_rep (ZgNormMacro, one row) — in ONE launch.  Each of the 16 CTAs
+// reduces its slice exactly as k_allreduce_peer does, keeps going on the slice, and the sum of squares of the whole row is
+// exchanged through 16 local {partial, epoch} cells (8-byte volatile stores, polled; added in CTA order -> identical on
+// every CTA and every rank).  One kernel boundary less on the critical path of every all-reduce — and MEASURED SLOWER (round 2,
+// same box A/B of the 80-layer 70B decode: 2 GPUs 131.0 -> 128.5 tok/s, 8 GPUs 191.8 -> 187.3): the separate norm kernel is
+// resident and has its operands' addresses ready when the all-reduce ends (programmatic dependent launch), while here every
+// CTA waits for the slowest CTA's peers and then for an L2 round trip of the partial exchange.  Off by default (ZG_CUDA_AR_NORM=1).
+__global__ void __launch_bounds__(256)
+k_allreduce_norm(float* __restrict__ buf, uint32_t n2, const ZgPeerComm pc, const ZgNormMacro m) {
+    ZG_TRACE_BEGIN(11)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ float sh[32];
+    __shared__ float s_tot;
+    const uint32_t tid = threadIdx.x, c = blockIdx.x;
+    uint32_t* my_seq = pc.seq + 2 + c;
+    const uint32_t chunk = (n2 + gridDim.x - 1) / gridDim.x, lo = c * chunk, hi = min(lo + chunk, n2);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    ZG_TRACE_MARK(1)
+    const uint32_t seq = *(volatile uint32_t*)my_seq, set = seq % kZgPeerSets, epoch = seq + 1;
+    float2* b2 = reinterpret_cast<float2*>(buf);
+    const size_t slot_pairs = pc.max_n >> 1;
+    const size_t my_cell = ((size_t)set * pc.world + pc.rank) * slot_pairs;
+    for (uint32_t j = lo + tid; j < hi; j += 256) {
+        const float2 v = b2[j];
+        for (int pr = 0; pr < pc.world; pr++) {
+            if (pr == pc.rank) continue;
+            uint4* cell = reinterpret_cast<uint4*>(pc.slots[pr]) + my_cell + j;
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"(__float_as_uint(v.x)), "r"(epoch),
+                         "r"(__float_as_uint(v.y)), "r"(epoch) : "memory");
+        }
+    }
+    const uint4* mine = reinterpret_cast<const uint4*>(pc.slots[pc.rank]) + (size_t)set * pc.world * slot_pairs;
+    // the other operand of the residual add (nullptr: the macro has no add and normalises the all-reduced vector itself)
+    const float2* other = nullptr;
+    if (m.b) other = reinterpret_cast<const float2*>(m.a == buf ? m.b : m.a);
+    float ss = 0.0f;
+    for (uint32_t j = lo + tid; j < hi; j += 256) {
+        uint4 got[kZgMaxRanks];
+        uint32_t pending = 0;
+#pragma unroll
+        for (int r = 0; r < kZgMaxRanks; r++)
+            if (r < pc.world && r != pc.rank) pending |= 1u << r;
+        long long t0 = 0;
+        uint32_t spins = 0;
+        bool dead = false;
+        while (pending) {
+#pragma unroll
+            for (int r = 0; r < kZgMaxRanks; r++)
+                if (pending & (1u << r)) {
+                    const uint4* cell = mine + (size_t)r * slot_pairs + j;
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(got[r].x), "=r"(got[r].y), "=r"(got[r].z), "=r"(got[r].w) : "l"(cell) : "memory");
+                }
+#pragma unroll
+            for (int r = 0; r < kZgMaxRanks; r++)
+                if ((pending & (1u << r)) && got[r].y == epoch && got[r].w == epoch) pending &= ~(1u << r);
+            if (pending && (++spins & 1023u) == 0) {
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > 60000000000LL || *(volatile uint32_t*)(pc.seq + 1)) { atomicExch(pc.seq + 1, epoch ? epoch : 1u); dead = true; break; }
+            }
+        }
+        const float2 own = b2[j];
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kZgMaxRanks; r++)
+            if (r < pc.world) {
+                const float2 v = (r == pc.rank) ? own : make_float2(__uint_as_float(got[r].x), __uint_as_float(got[r].z));
+                acc = (r == 0) ? v : make_float2(acc.x + v.x, acc.y + v.y);
+            }
+        if (dead) acc = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+        b2[j] = acc;
+        float2 sv = acc;
+        if (other) {
+            const float2 o = other[j];
+            sv = make_float2(acc.x + o.x, acc.y + o.y);
+            reinterpret_cast<float2*>(m.sum)[j] = sv;
+        }
+        ss += sv.x * sv.x + sv.y * sv.y;
+    }
+    ss = block_reduce<false>(ss, sh);
+    // exchange the CTA partials: cell = {partial, epoch}, one 8-byte volatile store; every CTA adds the 16 in CTA order
+    if (tid == 0) {
+        unsigned long long* cell = pc.cells + (size_t)set * kZgPeerCtas + c;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(cell), "r"(__float_as_uint(ss)), "r"(epoch) : "memory");
+    }
+    if (tid < 32) {
+        float part = 0.0f;
+        if (tid < gridDim.x) {
+            const unsigned long long* cell = pc.cells + (size_t)set * kZgPeerCtas + tid;
+            uint32_t vx = 0, ve = 0, spins = 0;
+            long long t0 = 0;
+            for (;;) {
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(ve) : "l"(cell) : "memory");
+                if (ve == epoch) break;
+                if ((++spins & 1023u) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 60000000000LL || *(volatile uint32_t*)(pc.seq + 1)) { atomicExch(pc.seq + 1, epoch ? epoch : 1u); vx = 0x7fc00000u; break; }
+                }
+            }
+            part = __uint_as_float(vx);
+        }
+        float tot = 0.0f;
+        for (uint32_t i = 0; i < gridDim.x; i++) tot += __shfl_sync(0xffffffffu, part, i);   // CTA order
+        if (tid == 0) s_tot = tot;
+    }
+    __syncthreads();
+    const float inv_rms = 1.0f / sqrtf(s_tot / (float)m.cols + m.eps);
+    const float2* src = reinterpret_cast<const float2*>(other ? m.sum : buf);
+    const float2* g2 = reinterpret_cast<const float2*>(m.gamma);
+    for (uint32_t j = lo + tid; j < hi; j += 256) {
+        const float2 sv = src[j], g = g2[j];      // this thread's own stores above
+        const float2 bz = make_float2(sv.x * inv_rms, sv.y * inv_rms);
+        reinterpret_cast<float2*>(m.bare)[j] = bz;
+        reinterpret_cast<float2*>(m.gamma_rep)[j] = g;
+        reinterpret_cast<float2*>(m.norm)[j] = make_float2(bz.x * g.x, bz.y * g.y);
+    }
+    __syncthreads();
+    if (tid == 0) *(volatile uint32_t*)my_seq = epoch;
+    ZG_TRACE_MARK(2)
+}
+
 // one block per row
 __global__ void k_softmax(float* __restrict__ dst, const float* __restrict__ src, uint32_t cols) {
     pdl_enter();
@@ -1674,6 +1795,13 @@ bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c) {
 bool zg_launch_peer_allreduce(float* buf, size_t n, const ZgPeerComm& pc, cudaStream_t st) {
     if (n == 0) return true;
     launch_k(k_allreduce_peer, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 1), pc);
+    ZG_COUNT_LAUNCH();
+    return true;
+}
+
+bool zg_launch_peer_allreduce_norm(float* buf, size_t n, const ZgPeerComm& pc, const ZgNormMacro& m, cudaStream_t st) {
+    if (n == 0) return true;
+    launch_k(k_allreduce_norm, dim3(kZgPeerCtas), dim3(256), st, buf, (uint32_t)(n >> 1), pc, m);
     ZG_COUNT_LAUNCH();
     return true;
 }

@@ -97,6 +97,7 @@ struct ZgPeerComm {
     uint32_t max_n = 0;                 // floats per slot; 0 = peer path unavailable (NCCL is used instead)
     float* slots[kZgMaxRanks] = {};     // slot base of every rank (own entry = local pointer)
     uint32_t* seq = nullptr;            // local: [1] = timeout marker, [2 + c] = all-reduces CTA c has completed
+    unsigned long long* cells = nullptr;   // local: [set][CTA] {partial sum of squares, epoch} of the fused all-reduce + norm kernel
 };
 
 struct ZgCudaCtx {
@@ -114,6 +115,7 @@ struct ZgCudaCtx {
                                  // Off: measured SLOWER in-graph (the prologue's extra dependent L2 round trips cost what the removed kernel did)
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
     int gemv_stream = 1, stream_min_chunks = 0, stream_early = 0, stream_ns = 0, stream_waves = 0, stream_chunks = 0, stream_align = 0;   // ZG_GEMV_STREAM / ZG_GEMV_STREAM_MIN (qgemv_stream.cu)
+    bool ar_norm = false;        // sharded programs: all-reduce + the [add,] rmsnorm, gamma, mul block that consumes it in ONE launch (ZG_CUDA_AR_NORM=1; measured 2 % slower)
     bool gemv_pair = true;       // single-token programs: gate | up matvecs + SiLU * up chain in ONE launch (ZG_CUDA_GEMV_PAIR=0: off)
     bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
@@ -235,6 +237,7 @@ struct ZgEwMulMacro { const float* src; float* mid; const float* other; float* d
 bool zg_fill_chain_norm(const ZgNormMacro& m, bool sync, ZgChainOp* c);
 bool zg_fill_chain_ewmul(const ZgEwMulMacro& m, bool sync, ZgChainOp* c);
 bool zg_launch_ewmul(const ZgEwMulMacro& m, cudaStream_t st);
+bool zg_launch_peer_allreduce_norm(float* buf, size_t n, const ZgPeerComm& pc, const ZgNormMacro& m, cudaStream_t st);
 bool zg_launch_norm_macro(const ZgNormMacro& m, cudaStream_t st);   // rows longer than 4096: one 1024-thread CTA per row   // the same pair as one multi-CTA launch   // ops per chain launch (the table lives in shared memory)
 size_t zg_chain_work(const ZgOp& op);
 bool zg_fill_chain_op(const ZgOp& op, float* const* bufs, uint32_t op_index, const ZgDevStep* d_steps, bool sync, ZgChainOp* c);
