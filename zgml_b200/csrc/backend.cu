@@ -711,6 +711,7 @@ static uint32_t match_attention_block(const ZgCudaProgram* p, size_t i, ZgAttnBl
             a.k_cs != patch || a.v_cs != patch || a.k_cs == 0 || elems(a.dst) < dh) return 0;
         if (h == 0) {
             B->has_mask = a.has_mask; mask_buf = a.mask; B->mask_off = a.mask_off; B->mask_rs = a.mask_rs; B->scale = a.scale;
+            { static const uint32_t mp = [] { const char* e = getenv("ZG_CUDA_ATTN_MIN_POS"); const int v = e ? atoi(e) : 64; return (uint32_t)(v >= 32 ? v : 64); }(); B->min_pos = mp; }   // 64: an 8-head shard at 512 positions uses 8 splits (56.1 -> 54.4 us per layer); more CTAs than SMs is slower (ZG_CUDA_ATTN_SPLIT_MULT)
             B->k_cs = a.k_cs; B->v_cs = a.v_cs; cat_buf = sa.dst;
         } else if (a.has_mask != B->has_mask || (a.has_mask && (a.mask != mask_buf || a.mask_off != B->mask_off || a.mask_rs != B->mask_rs)) ||
                    a.scale != B->scale || a.k_cs != B->k_cs || a.v_cs != B->v_cs) return 0;
@@ -1593,7 +1594,8 @@ static bool build_schedule(ZgCudaProgram* p) {
         for (auto& u : p->units) {
             if (u.attn_blk < 0) continue;
             const ZgAttnBlock& B = p->attn_blocks[u.attn_blk];
-            uint32_t sp = (uint32_t)p->ctx->sm_count / std::max(B.n_heads, 1u);
+            static const uint32_t mult = [] { const char* e = getenv("ZG_CUDA_ATTN_SPLIT_MULT"); return e ? (uint32_t)atoi(e) : 1u; }();
+            uint32_t sp = (uint32_t)p->ctx->sm_count * std::max(mult, 1u) / std::max(B.n_heads, 1u);
             sp = std::max(1u, std::min(sp, 8u));
             const uint32_t ni32 = B.d_head <= 64 ? 64 : (B.d_head <= 128 ? 128 : 256);
             u.ab_splits = sp; u.ab_part_off = pt; u.ab_cnt_off = ct;

@@ -1018,7 +1018,7 @@ k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restri
     const ZgDecKv kv = B.kvs[hd.kv];
     const uint32_t dh = B.d_head, hd2 = dh >> 1;
     const uint32_t seq_kv = d_dyn[hd.dyn];
-    const uint32_t splits = min(max_splits, max(1u, (seq_kv + 127u) / 128u));
+    const uint32_t splits = min(max_splits, max(1u, seq_kv / B.min_pos));   // every split at least min_pos positions: a short tail split only adds a merge
     if (sp >= splits) return;
     const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
     const uint32_t kv_lo = sp * chunk, kv_hi = min(kv_lo + chunk, seq_kv);

@@ -1082,7 +1082,8 @@ bool zg_qgemv_launch_pair(ZgCudaCtx* ctx, const ZgCudaQWeight* wa, const ZgCudaQ
     ZgGemvPlan plan = zg_qgemv_plan(ctx, wa, 1, 2);
     {   // each warp requests twice as many chunks: the ring depth may use them
         const uint32_t chunks = ((plan.lcap + plan.G - 1) / plan.G) * plan.P * 2;
-        const uint32_t want = ctx->tune_u ? (uint32_t)ctx->tune_u : 2;
+        static const uint32_t pair_ns = [] { const char* e = getenv("ZG_GEMV_PAIR_NS"); const int v = e ? atoi(e) : 2; return (uint32_t)(v >= 2 && v <= 8 ? v : 2); }();
+        const uint32_t want = ctx->tune_u ? (uint32_t)ctx->tune_u : pair_ns;
         if (plan.NS < want && plan.NS < chunks) {
             plan.NS = std::min(want, chunks);
             const uint32_t warps = kThreads / 32;

@@ -329,7 +329,7 @@ struct ZgAttnBlock {
     const float* q_proj; const float* k_proj; const float* v_proj; const float* cs; const float* mask;
     float* k_cache; float* v_cache; float* attn_buf;
     uint32_t n_heads, n_kv, d_head, has_mask, mask_off, mask_rs, k_cs, v_cs;
-    float scale; uint32_t _pad;
+    float scale; uint32_t min_pos;   // KV positions per split at least (64)
     ZgDecHead heads[kZgDecMaxHeads];
     ZgDecKv kvs[kZgDecMaxHeads];
 };
