@@ -161,6 +161,69 @@ k_norm_macro(const ZgNormMacro m) {
     ZG_TRACE_MARK(2)
 }
 
+// The same block for a long row spread over a thread-block CLUSTER of 8 CTAs x 256 threads (one float4 per thread): the single
+// 1024-thread CTA above moves 96 KB in and 128 KB out through one SM's L2 port (~3 us of work on a launch that sits on the
+// critical path twice per layer); here every CTA moves an eighth and the row's sum of squares crosses the cluster through
+// distributed shared memory (each CTA publishes its partial, cluster barrier, everyone adds the 8 partials in rank order).
+constexpr int kNormClusterCtas = 8;
+__global__ void __launch_bounds__(256)
+k_norm_macro_cluster(const ZgNormMacro m) {
+    ZG_TRACE_BEGIN(3)
+    pdl_enter();
+    ZG_TRACE_MARK(1)
+    __shared__ float sh[8];
+    __shared__ float s_part;
+    const uint32_t tid = threadIdx.x, rank = blockIdx.x % kNormClusterCtas, r = blockIdx.x / kNormClusterCtas, c4 = m.cols >> 2;
+    const size_t ro = (size_t)r * c4;
+    const uint32_t j = rank * 256 + tid;
+    const bool live = j < c4;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), g = x;
+    if (live) {
+        x = reinterpret_cast<const float4*>(m.a)[ro + j];
+        g = reinterpret_cast<const float4*>(m.gamma)[j];
+        if (m.b) {
+            const float4 t = reinterpret_cast<const float4*>(m.b)[ro + j];
+            x = make_float4(x.x + t.x, x.y + t.y, x.z + t.z, x.w + t.w);
+            reinterpret_cast<float4*>(m.sum)[ro + j] = x;
+        }
+    }
+    float ss = (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) sh[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += sh[i];
+        s_part = t;
+    }
+    // cluster barrier (release / acquire): every CTA's partial is visible in its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    float tot = 0.0f;
+    {
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_part);
+#pragma unroll
+        for (uint32_t c = 0; c < kNormClusterCtas; c++) {
+            uint32_t remote; float v;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+            tot += v;
+        }
+    }
+    // nobody may exit (and release its shared memory) while a peer still reads it
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    const float inv_rms = 1.0f / sqrtf(tot / (float)m.cols + m.eps);
+    if (live) {
+        const float4 bz = make_float4(x.x * inv_rms, x.y * inv_rms, x.z * inv_rms, x.w * inv_rms);
+        reinterpret_cast<float4*>(m.bare)[ro + j] = bz;
+        reinterpret_cast<float4*>(m.gamma_rep)[ro + j] = g;
+        reinterpret_cast<float4*>(m.norm)[ro + j] = make_float4(bz.x * g.x, bz.y * g.y, bz.z * g.z, bz.w * g.w);
+    }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    ZG_TRACE_MARK(2)
+}
+
 // fused_elementwise chain -> mid, then mid * other -> dst (SiLU(gate) * up): one launch for the two ops
 __global__ void k_fused_ew_mul(const ZgDevStep* __restrict__ steps, uint32_t n_steps, float* __restrict__ mid,
                                const float* __restrict__ src, uint32_t n, const float* __restrict__ other, float* __restrict__ dst) {
@@ -1808,6 +1871,20 @@ bool zg_launch_peer_allreduce_norm(float* buf, size_t n, const ZgPeerComm& pc, c
 
 bool zg_launch_norm_macro(const ZgNormMacro& m, cudaStream_t st) {
     if (m.rows == 0) return true;
+    static const bool use_cluster = [] { const char* e = getenv("ZG_CUDA_NORM_CLUSTER"); return !(e && e[0] == '0'); }();
+    if (use_cluster && (m.cols >> 2) <= kNormClusterCtas * 256) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(m.rows * kNormClusterCtas); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kNormClusterCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_zg_pdl ? 2 : 1;
+        if (cudaLaunchKernelEx(&cfg, k_norm_macro_cluster, m) == cudaSuccess) { ZG_COUNT_LAUNCH(); return true; }
+        cudaGetLastError();   // fall through to the single-CTA form
+    }
     launch_k(k_norm_macro, dim3(m.rows), dim3(1024), st, m);
     ZG_COUNT_LAUNCH();
     return true;
