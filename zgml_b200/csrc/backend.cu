@@ -1325,7 +1325,8 @@ static bool build_schedule(ZgCudaProgram* p) {
     // them: they may consume the chain's earlier levels, and nothing in the chain depends on them (same level = no
     // conflict; later levels start a new chain).  The unit order stays a topological order of the dependency DAG.
     auto chain_work = [&](const ZgItem& it) -> size_t {
-        if (it.kind == ITEM_NORM) return norm_of[&it - items.data()].cols <= 4096 ? 1 : 0;   // longer rows: their own 1024-thread kernel
+        static const uint32_t norm_chain_max = [] { const char* e = getenv("ZG_CUDA_NORM_CHAIN_MAX"); return e ? (uint32_t)atoi(e) : 256u; }();   // measured: the cluster kernel beats the chain CTA from SmolLM-135M (576) up: +4 % / +2 % / +7 % tok/s on 135M / 1.7B / Llama-3-8B
+        if (it.kind == ITEM_NORM) return norm_of[&it - items.data()].cols <= norm_chain_max ? 1 : 0;   // longer rows: their own cluster kernel (ops.cu k_norm_macro_cluster)
         if (it.kind == ITEM_EWMUL) return ewmul_of[&it - items.data()].n <= 1024 ? 1 : 0;   // transcendental chains: one CTA only when tiny
         if (it.kind != ITEM_OP) return 0;
         const ZgOp& op = p->ops[it.first];

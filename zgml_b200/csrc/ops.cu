@@ -173,7 +173,9 @@ k_norm_macro_cluster(const ZgNormMacro m) {
     ZG_TRACE_MARK(1)
     __shared__ float sh[8];
     __shared__ float s_part;
-    const uint32_t tid = threadIdx.x, rank = blockIdx.x % kNormClusterCtas, r = blockIdx.x / kNormClusterCtas, c4 = m.cols >> 2;
+    uint32_t n_cta;   // CTAs of this row's cluster (1, 2, 4 or 8: 256 float4 each)
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(n_cta));
+    const uint32_t tid = threadIdx.x, rank = blockIdx.x % n_cta, r = blockIdx.x / n_cta, c4 = m.cols >> 2;
     const size_t ro = (size_t)r * c4;
     const uint32_t j = rank * 256 + tid;
     const bool live = j < c4;
@@ -203,8 +205,7 @@ k_norm_macro_cluster(const ZgNormMacro m) {
     float tot = 0.0f;
     {
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(&s_part);
-#pragma unroll
-        for (uint32_t c = 0; c < kNormClusterCtas; c++) {
+        for (uint32_t c = 0; c < n_cta; c++) {
             uint32_t remote; float v;
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(c));
             asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
@@ -1873,11 +1874,13 @@ bool zg_launch_norm_macro(const ZgNormMacro& m, cudaStream_t st) {
     if (m.rows == 0) return true;
     static const bool use_cluster = [] { const char* e = getenv("ZG_CUDA_NORM_CLUSTER"); return !(e && e[0] == '0'); }();
     if (use_cluster && (m.cols >> 2) <= kNormClusterCtas * 256) {
+        uint32_t n_cta = 1;
+        while (n_cta * 256 < (m.cols >> 2)) n_cta *= 2;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(m.rows * kNormClusterCtas); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.gridDim = dim3(m.rows * n_cta); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = kNormClusterCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = n_cta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
