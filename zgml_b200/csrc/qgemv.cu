@@ -56,6 +56,7 @@ struct QGemvParams {
     float* out;
     uint32_t out_rs;
     uint32_t P, S, NS;
+    uint32_t cl;           // 1: the S k-splits of a column group are the CTAs of one thread-block cluster; partial sums meet in distributed shared memory
     float* partials;
     uint32_t* counters;
 };
@@ -98,6 +99,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(const float* local, uint32_t rank) {
+    uint32_t remote; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -130,6 +141,7 @@ qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
     constexpr uint32_t RB = QB + 4 * SB;       // record bytes
 
     __shared__ float part[2][kMaxWarps][MR][ZG_TN];
+    __shared__ float xpart[2][MR][ZG_TN];   // cluster split-K: this CTA's partial of the current column group, read by the split-0 CTA
     __shared__ uint32_t s_last;
     // dynamic: [warp][row][xs_stride] scaled activations | [warp][slot][G records] weight ring |
     //          [warp][G][MR][kPlaneRow] digit planes | [warp][slot] mbarriers
@@ -474,11 +486,24 @@ qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
             for (uint32_t w = 0; w < W; w++) v += part[buf][w][m][col];
             if (p.S == 1) {
                 if (m < p.M) p.out[(size_t)m * p.out_rs + nb * ZG_TN + col] = v;
+            } else if (p.cl) {
+                xpart[buf][m][col] = v;
             } else {
                 p.partials[(((size_t)nb * p.S + split) * MR + m) * ZG_TN + col] = v;
             }
         }
-        if (p.S > 1) {
+        if (p.S > 1 && p.cl) {
+            // the S splits of this column group are the CTAs of one cluster (rank = split): one cluster barrier publishes the
+            // partials, the split-0 CTA adds them in split order through distributed shared memory — no global scratch, no atomic.
+            // The next group uses the other buffer, and rank 0 reaches that group's barrier only after this read.
+            cluster_sync_all();
+            if (split == 0 && tid < MR * ZG_TN) {
+                const uint32_t m = tid >> 5, col = tid & 31;
+                float v = 0.0f;
+                for (uint32_t s2 = 0; s2 < p.S; s2++) v += ld_cluster_f32(&xpart[buf][m][col], s2);
+                if (m < p.M) p.out[(size_t)m * p.out_rs + nb * ZG_TN + col] = v;
+            }
+        } else if (p.S > 1) {
             __syncthreads();
             if (tid == 0) {
                 // release: publishes the whole CTA's partials (ordered before this thread by the barrier above);
@@ -500,6 +525,7 @@ qgemv_kernel(const __grid_constant__ QGemvBatchT<PRO != 0> bt) {
         }
         buf ^= 1;
     }
+    if (p.S > 1 && p.cl) cluster_sync_all();   // nobody leaves while the split-0 CTA may still read its partials
     ZG_TRACE_MARK(2)
 }
 
@@ -538,6 +564,7 @@ qgemv_pair_kernel(const __grid_constant__ QGemvPairBatch bt) {
     constexpr uint32_t G = kI4 ? 4u : 2u;
 
     __shared__ float part[2][kMaxWarps][ZG_TN];
+    __shared__ float xpart[2][ZG_TN];   // cluster split-K (see qgemv_kernel)
     __shared__ uint32_t s_last;
     extern __shared__ __align__(128) uint8_t dsm[];
 
@@ -732,9 +759,17 @@ qgemv_pair_kernel(const __grid_constant__ QGemvPairBatch bt) {
             float v = 0.0f;
             for (uint32_t w = 0; w < W; w++) v += part[buf][w][tid];
             if (cur.S == 1) { fin = v; have = true; }
+            else if (cur.cl) xpart[buf][tid] = v;
             else cur.partials[(((size_t)nb * cur.S + split) * 2) * ZG_TN + tid] = v;
         }
-        if (cur.S > 1) {
+        if (cur.S > 1 && cur.cl) {
+            cluster_sync_all();
+            if (split == 0 && tid < ZG_TN) {
+                float v = 0.0f;
+                for (uint32_t s2 = 0; s2 < cur.S; s2++) v += ld_cluster_f32(&xpart[buf][tid], s2);
+                fin = v; have = true;
+            }
+        } else if (cur.S > 1) {
             __syncthreads();
             if (tid == 0) {
                 uint32_t old;
@@ -754,7 +789,7 @@ qgemv_pair_kernel(const __grid_constant__ QGemvPairBatch bt) {
             cur.out[n] = fin;
             if (!is_b) v_a = fin;
             else {
-                const float gt = (pa.S == 1) ? v_a : __ldcg(pa.out + n), up = fin;
+                const float gt = (pa.S == 1 || pa.cl) ? v_a : __ldcg(pa.out + n), up = fin;   // cluster split-K: the same (split-0) CTA finishes both
                 float v = gt;
                 for (uint32_t st = 0; st < pp.epi.n_steps; st++) {
                     const uint32_t sop = pp.epi.steps[st].op, sw = pp.epi.steps[st].is_swapped;
@@ -771,6 +806,7 @@ qgemv_pair_kernel(const __grid_constant__ QGemvPairBatch bt) {
         }
         buf ^= 1;
     }
+    if (pa.S > 1 && pa.cl) cluster_sync_all();   // nobody leaves while the split-0 CTA may still read its partials
     ZG_TRACE_MARK(2)
 }
 
@@ -800,11 +836,15 @@ bool launch_fast(const ZgGemvPlan& plan, const QGemvBatch& p, uint32_t count, cu
     cfg.blockDim = dim3(plan.threads);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (p.p[0].cl) {   // the k-splits of a column group = one cluster (consecutive blockIdx.x)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = plan.S; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     cudaError_t e;
     if constexpr (PRO != 0) {
         e = cudaLaunchKernelEx(&cfg, qgemv_kernel<FMT, MP, XR, PRO>, p);
@@ -925,6 +965,7 @@ bool zg_qgemv_init(ZgCudaCtx* ctx) {
     if (const char* e = getenv("ZG_GEMV_P")) ctx->tune_p = atoi(e);
     if (const char* e = getenv("ZG_GEMV_SMAX")) ctx->tune_smax = atoi(e);
     if (const char* e = getenv("ZG_GEMV_NS")) ctx->tune_u = atoi(e);
+    if (const char* e = getenv("ZG_GEMV_CLUSTER")) ctx->gemv_cluster = (e[0] != '0');   // 0: split-K through global scratch + arrival counters
     if (const char* e = getenv("ZG_GEMV_G")) ctx->tune_g = atoi(e);
     if (const char* e = getenv("ZG_GEMV_ROWS")) { ctx->tune_rows = atoi(e); if (ctx->tune_rows < 1 || ctx->tune_rows > 8) ctx->tune_rows = 0; }
     if (ctx->tune_u < 2 || ctx->tune_u > 16) ctx->tune_u = 0;
@@ -1015,6 +1056,7 @@ static bool launch_batch_rows(ZgCudaCtx* ctx, uint32_t count, const ZgCudaQWeigh
         p.xs_stride = plan.xs_stride;
         p.out = d_out[i]; p.out_rs = out_rs[i] ? out_rs[i] : (uint32_t)w->N;
         p.P = plan.P; p.S = plan.S; p.NS = plan.NS;
+        p.cl = (ctx->gemv_cluster && (plan.S == 2 || plan.S == 4 || plan.S == 8)) ? 1u : 0u;
         p.partials = ws[i].partials; p.counters = ws[i].counters;
         if (pro) {
             if (pro[i].kind != pro[0].kind || (pro[i].kind && (M > 2 || p.x_rs != p.K))) { zg_set_error("internal: mixed or unsupported matvec prologue"); return false; }
@@ -1064,11 +1106,15 @@ static bool launch_pair_fmt(const ZgGemvPlan& plan, const QGemvPairBatch& bt, cu
     cfg.blockDim = dim3(plan.threads);
     cfg.dynamicSmemBytes = plan.smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (bt.p[0].a.cl) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = plan.S; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1; na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = na;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, qgemv_pair_kernel<FMT>, bt);
     ZG_COUNT_LAUNCH();
     if (e != cudaSuccess) { zg_set_error("qgemv pair launch failed: %s", cudaGetErrorString(e)); return false; }
@@ -1106,6 +1152,7 @@ bool zg_qgemv_launch_pair(ZgCudaCtx* ctx, const ZgCudaQWeight* wa, const ZgCudaQ
         q.x = d_in; q.x_rs = (uint32_t)w->K; q.xs_stride = plan.xs_stride;
         q.out = outs[i]; q.out_rs = (uint32_t)w->N;
         q.P = plan.P; q.S = plan.S; q.NS = plan.NS;
+        q.cl = (ctx->gemv_cluster && (plan.S == 2 || plan.S == 4 || plan.S == 8)) ? 1u : 0u;
         q.partials = wss[i] ? wss[i]->partials : nullptr; q.counters = wss[i] ? wss[i]->counters : nullptr;
     }
     bt.p[0].epi = epi;

@@ -116,6 +116,7 @@ struct ZgCudaCtx {
     bool attn_split = true;      // decode attention: several CTAs per head over the kv range (ZG_CUDA_ATTN_SPLIT=0: one)
     int gemv_stream = 1, stream_min_chunks = 0, stream_early = 0, stream_ns = 0, stream_waves = 0, stream_chunks = 0, stream_align = 0;   // ZG_GEMV_STREAM / ZG_GEMV_STREAM_MIN (qgemv_stream.cu)
     bool ar_norm = false;        // sharded programs: all-reduce + the [add,] rmsnorm, gamma, mul block that consumes it in ONE launch (ZG_CUDA_AR_NORM=1; measured 2 % slower)
+    bool gemv_cluster = true;    // k-split matvec: S in {2, 4, 8} splits of a column group form one cluster, partial sums meet in DSMEM (ZG_GEMV_CLUSTER=0: global scratch)
     bool gemv_pair = true;       // single-token programs: gate | up matvecs + SiLU * up chain in ONE launch (ZG_CUDA_GEMV_PAIR=0: off)
     bool attn_layer = true;      // single-token programs: rope + KV-cache stores + attention + concat of a layer in ONE launch (ZG_CUDA_ATTN_LAYER=0: off)
     bool decode_fused = false;   // single-token LLaMA layers run in the persistent fused decode kernel (decode.cu; ZG_CUDA_DECODE=1: on)
