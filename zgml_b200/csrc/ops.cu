@@ -1073,7 +1073,7 @@ static inline bool attn_prefill_ok(const ZgOp& op);
 template <int NI>
 __global__ void __launch_bounds__(kAttnFastWarps * 32)
 k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restrict__ d_dyn, float* __restrict__ part, uint32_t* __restrict__ cnt,
-                  const uint32_t max_splits) {
+                  const uint32_t max_splits, const uint32_t cl) {
     ZG_TRACE_BEGIN(7)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const ZgAttnBlock& B = *blkp;
@@ -1083,7 +1083,15 @@ k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restri
     const uint32_t dh = B.d_head, hd2 = dh >> 1;
     const uint32_t seq_kv = d_dyn[hd.dyn];
     const uint32_t splits = min(max_splits, max(1u, seq_kv / B.min_pos));   // every split at least min_pos positions: a short tail split only adds a merge
-    if (sp >= splits) return;
+    if (sp >= splits) {
+        // cl: the max_splits CTAs of a head are one cluster (rank = split) and merge through distributed shared memory; the
+        // splits this step does not use still take part in the two cluster barriers of the merge
+        if (cl) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        return;
+    }
     const uint32_t chunk = ((seq_kv + splits - 1) / splits + 31) & ~31u;
     const uint32_t kv_lo = sp * chunk, kv_hi = min(kv_lo + chunk, seq_kv);
     const float* kbase = B.k_cache + hd.k_off;
@@ -1258,6 +1266,55 @@ k_attention_layer(const ZgAttnBlock* __restrict__ blkp, const uint32_t* __restri
     }
     float* out1 = hd.attn_out;
     float* out2 = B.attn_buf + hd.buf_off;
+    if (cl) {
+        __shared__ float s_part[NI * 32 + 2];   // {m, l, acc[d_head]} of this split
+        if (splits > 1) {
+            for (uint32_t r = tid; r < dh; r += blockDim.x) {
+                float a = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
+                s_part[2 + r] = a;
+            }
+            if (tid == 0) { s_part[0] = gm; s_part[1] = gl; }
+        } else {
+            const float inv_l = gl > 0.0f ? 1.0f / gl : 0.0f;
+            for (uint32_t r = tid; r < dh; r += blockDim.x) {
+                float a = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kAttnFastWarps; w++) a += sh_acc[w][r] * wscale[w];
+                out1[r] = a * inv_l; out2[r] = a * inv_l;
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (splits > 1 && sp == 0) {   // same merge, same order as the last arriver of the scratch path
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_part);
+            auto rd = [&](uint32_t q, uint32_t idx) -> float {
+                uint32_t remote; float v;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(base + idx * 4), "r"(q));
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+                return v;
+            };
+            float G = -INFINITY;
+            for (uint32_t q = 0; q < splits; q++) G = fmaxf(G, rd(q, 0));
+            float L = 0.0f;
+            for (uint32_t q = 0; q < splits; q++) {
+                const float ms = rd(q, 0);
+                L += (ms == -INFINITY) ? 0.0f : rd(q, 1) * expf(ms - G);
+            }
+            const float inv_L = L > 0.0f ? 1.0f / L : 0.0f;
+            for (uint32_t r = tid; r < dh; r += blockDim.x) {
+                float a = 0.0f;
+                for (uint32_t q = 0; q < splits; q++) {
+                    const float ms = rd(q, 0);
+                    if (ms != -INFINITY) a += rd(q, 2 + r) * expf(ms - G);
+                }
+                out1[r] = a * inv_L; out2[r] = a * inv_L;
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        ZG_TRACE_MARK(2)
+        return;
+    }
     if (splits > 1) {
         __shared__ uint32_t s_last;
         float* mine = part + ((size_t)h * max_splits + sp) * (NI * 32 + 2);
@@ -1957,9 +2014,20 @@ bool zg_launch_attention_layer(const ZgAttnBlock* d_blk, uint32_t n_heads, uint3
                                uint32_t* cnt, cudaStream_t st) {
     if (n_heads == 0) return true;
     const dim3 grid(n_heads, max_splits), block(kAttnFastWarps * 32);
-    if (d_head <= 64) launch_k(k_attention_layer<2>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
-    else if (d_head <= 128) launch_k(k_attention_layer<4>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
-    else launch_k(k_attention_layer<8>, grid, block, st, d_blk, d_dyn, part, cnt, max_splits);
+    static const bool want_cl = [] { const char* e = getenv("ZG_CUDA_ATTN_CLUSTER"); return !(e && e[0] == '0'); }();
+    const uint32_t cl = (want_cl && max_splits >= 2 && max_splits <= 8) ? 1u : 0u;   // the splits of a head = one cluster, merged in DSMEM
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (g_zg_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+    if (cl) { attr[na].id = cudaLaunchAttributeClusterDimension; attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = max_splits; attr[na].val.clusterDim.z = 1; na++; }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t le;
+    if (d_head <= 64) le = cudaLaunchKernelEx(&cfg, k_attention_layer<2>, d_blk, d_dyn, part, cnt, max_splits, cl);
+    else if (d_head <= 128) le = cudaLaunchKernelEx(&cfg, k_attention_layer<4>, d_blk, d_dyn, part, cnt, max_splits, cl);
+    else le = cudaLaunchKernelEx(&cfg, k_attention_layer<8>, d_blk, d_dyn, part, cnt, max_splits, cl);
+    if (le != cudaSuccess) { zg_set_error("attention layer launch failed: %s", cudaGetErrorString(le)); return false; }
     ZG_COUNT_LAUNCH();
     return true;
 }
