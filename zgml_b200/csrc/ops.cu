@@ -2015,7 +2015,10 @@ bool zg_launch_attention_layer(const ZgAttnBlock* d_blk, uint32_t n_heads, uint3
     if (n_heads == 0) return true;
     const dim3 grid(n_heads, max_splits), block(kAttnFastWarps * 32);
     static const bool want_cl = [] { const char* e = getenv("ZG_CUDA_ATTN_CLUSTER"); return !(e && e[0] == '0'); }();
-    const uint32_t cl = (want_cl && max_splits >= 2 && max_splits <= 8) ? 1u : 0u;   // the splits of a head = one cluster, merged in DSMEM
+    // the splits of a head = one cluster, merged in DSMEM.  Clusters of up to 4 only: 16 clusters of 8 CTAs (a 4-way 70B shard)
+    // were measured 13 % slower per layer than the scratch merge — a cluster needs all its slots in one GPC at once, and the
+    // neighbouring kernels' resident CTAs delay that — while clusters of 2 and 4 gain 1-3 %.
+    const uint32_t cl = (want_cl && max_splits >= 2 && max_splits <= 4) ? 1u : 0u;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
     cudaLaunchAttribute attr[2];
