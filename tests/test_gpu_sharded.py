@@ -92,6 +92,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _spawn(fn, world, args_after_port):
+    """mp.spawn with a fresh rendezvous port; a port that another process grabbed between the probe and rank 0's listen
+    (EADDRINUSE, seen once on a busy 2-GPU box) is retried with a new one."""
+    import torch.multiprocessing as mp
+    for attempt in range(3):
+        try:
+            mp.spawn(fn, args=(world, _free_port()) + tuple(args_after_port), nprocs=world, join=True)
+            return
+        except Exception as e:  # ProcessRaisedException carries the child's traceback as text
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
+
+
 def _rank_main(rank, world, port, cfg, kind, token_len, graph, out):
     import torch.distributed as dist
     from zgml_b200 import CudaBackend
@@ -128,7 +141,7 @@ def test_two_gpu_sharded_decode_matches_unsharded_oracle(cfg, kind, token_len, g
     import torch.multiprocessing as mp
     world = 2
     out = mp.Manager().dict()
-    mp.spawn(_rank_main, args=(world, _free_port(), cfg, kind, token_len, graph, out), nprocs=world, join=True)
+    _spawn(_rank_main, world, (cfg, kind, token_len, graph, out))
     w = synthetic_weights(cfg, kind, seed=11, embed_scale=1.0)
     ref = DeviceLlamaSession(OracleBackend(), cfg, w, token_len)
     if token_len == 1:
@@ -185,7 +198,7 @@ def test_sharded_70b_width_matches_unsharded_oracle(world, path):
     from zgml_b200.host.llama import synthetic_model_host
     cfg, kind, n_tok, context = CFG_70B_WIDTH, "q4_0", 3, 20
     out = mp.Manager().dict()
-    mp.spawn(_rank_main_synth, args=(world, _free_port(), cfg, kind, path != "nccl", "arnorm" if path == "arnorm" else path == "fused", context, n_tok, out), nprocs=world, join=True)
+    _spawn(_rank_main_synth, world, (cfg, kind, path != "nccl", "arnorm" if path == "arnorm" else path == "fused", context, n_tok, out))
     ref = DeviceLlamaSession(OracleBackend(native=True), cfg, synthetic_model_host(cfg, kind, seed=17), 1)
     ref.pos = context
     _, want = greedy(ref, 1, n_tok)
