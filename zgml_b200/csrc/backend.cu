@@ -527,16 +527,23 @@ extern "C" void zg_cuda_refresh(ZgCudaCtx* ctx, ZgCudaProgram* p, const ZgOp* op
         for (size_t i = 0; i < n_ops && !structural; i++) {
             const ZgOp& old = p->ops[i];
             if (ops[i].tag != old.tag) { structural = true; break; }
-            ZgOp tmp = ops[i];
-            if (tmp.tag == ZG_OP_SLICE_ASSIGN) tmp.u.slice_assign.dst_offset = old.u.slice_assign.dst_offset;
-            else if (tmp.tag == ZG_OP_ATTENTION) tmp.u.attention.seq_kv = old.u.attention.seq_kv;
-            else if (tmp.tag == ZG_OP_FUSED_ELEMENTWISE) {
+            // everything but the per-step field must be unchanged; compared in place (no copy: an 80-layer program has ~9 k ops
+            // and this runs every token)
+            auto same_except = [&](size_t off, size_t len) {
+                const char* a = reinterpret_cast<const char*>(&ops[i]);
+                const char* b = reinterpret_cast<const char*>(&old);
+                return memcmp(a, b, off) == 0 && memcmp(a + off + len, b + off + len, sizeof(ZgOp) - off - len) == 0;
+            };
+            if (ops[i].tag == ZG_OP_SLICE_ASSIGN) {
+                if (!same_except(offsetof(ZgOp, u.slice_assign.dst_offset), sizeof(old.u.slice_assign.dst_offset))) structural = true;
+            } else if (ops[i].tag == ZG_OP_ATTENTION) {
+                if (!same_except(offsetof(ZgOp, u.attention.seq_kv), sizeof(old.u.attention.seq_kv))) structural = true;
+            } else if (ops[i].tag == ZG_OP_FUSED_ELEMENTWISE) {
                 const auto& f = ops[i].u.fused_elementwise;
                 if (f.n_steps != p->steps[i].size() ||
                     (f.n_steps && memcmp(f.steps, p->steps[i].data(), f.n_steps * sizeof(ZgFusedEwStep)) != 0)) { structural = true; break; }
-                tmp.u.fused_elementwise.steps = old.u.fused_elementwise.steps;
-            }
-            if (memcmp(&tmp, &old, sizeof(ZgOp)) != 0) structural = true;
+                if (!same_except(offsetof(ZgOp, u.fused_elementwise.steps), sizeof(old.u.fused_elementwise.steps))) structural = true;
+            } else if (memcmp(&ops[i], &old, sizeof(ZgOp)) != 0) structural = true;
         }
     }
     if (structural) {
